@@ -1,0 +1,13 @@
+"""Import shim: ``import adaprox_b200`` loads the package that lives in the
+directory ``adaptive-proximal-algorithms_b200/`` (the hyphens in the mandated
+directory name make it unimportable by a plain ``import`` statement)."""
+import importlib.util as _u
+import os as _os
+import sys as _sys
+
+_dir = _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "adaptive-proximal-algorithms_b200")
+_spec = _u.spec_from_file_location("adaprox_b200", _os.path.join(_dir, "__init__.py"),
+                                   submodule_search_locations=[_dir])
+_mod = _u.module_from_spec(_spec)
+_sys.modules["adaprox_b200"] = _mod
+_spec.loader.exec_module(_mod)

@@ -1,0 +1,667 @@
+// api.cu -- the C ABI of libadaprox_cuda.so (include/adaprox.h).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <numeric>
+#include "context.hpp"
+#include "ops.cuh"
+#include "solver_pd.cuh"
+#include "solver_pg.cuh"
+#include "comm.hpp"
+
+using namespace adaprox;
+
+// ---------------------------------------------------------------------------
+// helpers
+// ---------------------------------------------------------------------------
+static int64_t round_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+static int ws_reset(adaprox_ctx* h, size_t need) {
+  if (need > h->ws_bytes) {
+    if (h->ws) cudaFree(h->ws);
+    h->ws = nullptr; h->ws_bytes = 0;
+    size_t want = need + (need >> 3) + (1u << 20);
+    cudaError_t e = cudaMalloc(&h->ws, want);
+    if (e != cudaSuccess) return fail(h, ADAPROX_ERR_NOMEM, std::string("workspace cudaMalloc: ") + cudaGetErrorString(e));
+    h->ws_bytes = want;
+  }
+  h->ws_used = 0;
+  return ADAPROX_OK;
+}
+static double* ws_doubles(adaprox_ctx* h, int64_t count) {
+  size_t bytes = (size_t)round_up(std::max<int64_t>(count, 1) * 8, 256);
+  double* p = reinterpret_cast<double*>(h->ws + h->ws_used);
+  h->ws_used += bytes;
+  return p;
+}
+static size_t ws_size_doubles(int64_t count) { return (size_t)round_up(std::max<int64_t>(count, 1) * 8, 256); }
+
+static int get_mat(adaprox_ctx* h, adaprox_id id, HostMatrix** out) {
+  auto it = h->mats.find(id);
+  if (it == h->mats.end()) return fail(h, ADAPROX_ERR_INVALID, "unknown matrix id " + std::to_string(id));
+  *out = &it->second;
+  return ADAPROX_OK;
+}
+static int get_vec(adaprox_ctx* h, adaprox_id id, int64_t min_len, const double** out) {
+  if (id == 0) { *out = nullptr; return ADAPROX_OK; }
+  auto it = h->vecs.find(id);
+  if (it == h->vecs.end()) return fail(h, ADAPROX_ERR_INVALID, "unknown vector id " + std::to_string(id));
+  if (it->second.len < min_len) return fail(h, ADAPROX_ERR_INVALID, "vector " + std::to_string(id) + " is too short");
+  *out = it->second.p;
+  return ADAPROX_OK;
+}
+
+template <typename K>
+static int coop_launch(adaprox_ctx* h, K kernel, void** args) {
+  cudaError_t e = cudaLaunchCooperativeKernel((const void*)kernel, dim3(h->grid), dim3(kThreads), args, 0, h->stream);
+  if (e != cudaSuccess) return fail(h, ADAPROX_ERR_CUDA, std::string("cooperative launch: ") + cudaGetErrorString(e));
+  h->launches++;
+  return ADAPROX_OK;
+}
+
+// choose the work partition of a dense matrix for a grid of G CTAs
+static void plan_dense(DMat& d, int G) {
+  d.nchunks = (int)((d.n + kChunk - 1) / kChunk);
+  d.npad = (int64_t)d.nchunks * kChunk;
+  int rb = 64;
+  while (rb > 8 && (int64_t)d.nchunks * ((d.m + rb - 1) / rb) < 16LL * G) rb >>= 1;
+  d.rb = rb;
+  d.nrb = (d.m + rb - 1) / rb;
+}
+
+static int alloc_dense(adaprox_ctx* h, int64_t m, int64_t n, HostMatrix& hm) {
+  DMat& d = hm.d;
+  d = DMat{};
+  d.kind = MAT_DENSE; d.m = m; d.n = n; d.ld = round_up(n, 16);
+  plan_dense(d, h->grid);
+  double *a = nullptr, *zp = nullptr, *gp = nullptr;
+  AP_CUDA(h, cudaMalloc(&a, (size_t)m * d.ld * 8));
+  hm.allocs.push_back(a);
+  AP_CUDA(h, cudaMalloc(&zp, (size_t)d.nchunks * m * 8));
+  hm.allocs.push_back(zp);
+  AP_CUDA(h, cudaMalloc(&gp, (size_t)h->grid * d.npad * 8));
+  hm.allocs.push_back(gp);
+  AP_CUDA(h, cudaMemsetAsync(gp, 0, (size_t)h->grid * d.npad * 8, h->stream));
+  d.a = a; d.zpart = zp; d.gpart = gp;
+  hm.m_global = m; hm.row0 = 0; hm.sharded = false;
+  return ADAPROX_OK;
+}
+
+static void free_matrix(HostMatrix& hm) {
+  for (void* p : hm.allocs) cudaFree(p);
+  hm.allocs.clear();
+}
+
+// device-pointer operator calls (shared by the public ops and the generator)
+static int run_ops(adaprox_ctx* h, OpArgs& a, DWork& W) {
+  void* args[] = {&a, &W};
+  return coop_launch(h, k_ops, args);
+}
+
+static int op_mul_dev(adaprox_ctx* h, const DMat& M, const double* x_dev, double* out_dev) {
+  OpArgs a{}; a.op = OP_MUL; a.M = M; a.in = x_dev; a.out = out_dev;
+  DWork W{};
+  return run_ops(h, a, W);
+}
+static int op_amul_dev(adaprox_ctx* h, const DMat& M, const double* y_dev, double* out_dev) {
+  OpArgs a{}; a.op = OP_AMUL; a.M = M; a.in = y_dev; a.out = out_dev;
+  DWork W{};
+  return run_ops(h, a, W);
+}
+
+static int fill_prox(adaprox_ctx* h, const adaprox_prox& p, int64_t len, DProx* out) {
+  DProx d{};
+  d.kind = p.kind; d.conjugate = p.conjugate; d.lambda = p.lambda; d.lo = p.lo; d.hi = p.hi;
+  if (p.kind < ADAPROX_P_ZERO || p.kind > ADAPROX_P_IND_BOX) return fail(h, ADAPROX_ERR_INVALID, "unknown prox kind");
+  int rc;
+  if ((rc = get_vec(h, p.lo_vec, len, &d.lo_vec))) return rc;
+  if ((rc = get_vec(h, p.hi_vec, len, &d.hi_vec))) return rc;
+  if ((rc = get_vec(h, p.shift, len, &d.shift))) return rc;
+  *out = d;
+  return ADAPROX_OK;
+}
+
+static int fill_problem(adaprox_ctx* h, const adaprox_problem* p, DProblem* out, HostMatrix** fmat, HostMatrix** amat) {
+  DProblem P{};
+  P.f_kind = p->f_kind; P.f_ipar = p->f_ipar; P.f_c = p->f_c; P.n = p->n; P.md = p->m_dual;
+  *fmat = nullptr; *amat = nullptr;
+  int rc;
+  if (p->n <= 0) return fail(h, ADAPROX_ERR_INVALID, "problem.n must be positive");
+  int64_t vec_len = 0;
+  switch (p->f_kind) {
+    case ADAPROX_F_ZERO: break;
+    case ADAPROX_F_LEAST_SQUARES:
+    case ADAPROX_F_LOGISTIC:
+    case ADAPROX_F_QUADRATIC:
+    case ADAPROX_F_CUBIC: {
+      if ((rc = get_mat(h, p->f_mat, fmat))) return rc;
+      P.F = (*fmat)->d;
+      const int64_t ncols = (p->f_kind == ADAPROX_F_LOGISTIC) ? p->n - 1 : p->n;
+      if (P.F.n != ncols) return fail(h, ADAPROX_ERR_INVALID, "f matrix has " + std::to_string(P.F.n) + " columns, expected " + std::to_string(ncols));
+      if ((p->f_kind == ADAPROX_F_QUADRATIC || p->f_kind == ADAPROX_F_CUBIC) && P.F.m != p->n)
+        return fail(h, ADAPROX_ERR_INVALID, "Q must be square");
+      vec_len = (p->f_kind == ADAPROX_F_QUADRATIC || p->f_kind == ADAPROX_F_CUBIC) ? p->n : P.F.m;
+      P.f_N = (double)((*fmat)->m_global);
+      if (p->f_vec == 0) return fail(h, ADAPROX_ERR_INVALID, "f_vec (b / y / q) is required");
+    } break;
+    case ADAPROX_F_WORST_QUADRATIC:
+      if (p->f_ipar < 2 || p->f_ipar > p->n) return fail(h, ADAPROX_ERR_INVALID, "WorstQuadratic needs 2 <= k <= n");
+      break;
+    case ADAPROX_F_SIMPLE2D:
+      if (p->n != 2) return fail(h, ADAPROX_ERR_INVALID, "Simple2D needs n = 2");
+      break;
+    default:
+      return fail(h, ADAPROX_ERR_UNSUPPORTED, "eval_with_pullback not defined for f_kind " + std::to_string(p->f_kind));
+  }
+  if ((rc = get_vec(h, p->f_vec, vec_len, &P.fvec))) return rc;
+  if ((rc = fill_prox(h, p->g, p->n, &P.g))) return rc;
+  if (p->A_mat != 0) {
+    if ((rc = get_mat(h, p->A_mat, amat))) return rc;
+    P.A = (*amat)->d;
+    if (P.A.n != p->n) return fail(h, ADAPROX_ERR_INVALID, "A has the wrong number of columns");
+    if (P.A.m != p->m_dual) return fail(h, ADAPROX_ERR_INVALID, "A has the wrong number of rows (m_dual)");
+    if ((rc = fill_prox(h, p->h, p->m_dual, &P.h))) return rc;
+  } else {
+    P.A.kind = MAT_NONE;
+    P.h = DProx{};
+  }
+  *out = P;
+  return ADAPROX_OK;
+}
+
+// ---------------------------------------------------------------------------
+// life cycle
+// ---------------------------------------------------------------------------
+extern "C" int adaprox_version(void) { return 100; }
+
+extern "C" int adaprox_create(adaprox_handle* out, int device) {
+  if (!out) return ADAPROX_ERR_INVALID;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return ADAPROX_ERR_CUDA;   // no CPU fallback
+  if (device < 0 || device >= ndev) return ADAPROX_ERR_INVALID;
+  if (cudaSetDevice(device) != cudaSuccess) return ADAPROX_ERR_CUDA;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return ADAPROX_ERR_CUDA;
+  if (!prop.cooperativeLaunch) return ADAPROX_ERR_UNSUPPORTED;
+  adaprox_ctx* h = new adaprox_ctx();
+  h->device = device; h->sm_count = prop.multiProcessorCount; h->cc_major = prop.major; h->cc_minor = prop.minor;
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return ADAPROX_ERR_CUDA; }
+  cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1);
+  // resident CTAs per SM: the minimum over the persistent kernels
+  int per_sm = 2, nb = 0;
+  const void* kernels[] = {(const void*)k_primal_dual<false>, (const void*)k_primal_dual<true>, (const void*)k_ops,
+                           (const void*)k_proxgrad_family};
+  for (const void* k : kernels) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k, kThreads, 0) != cudaSuccess || nb < 1) {
+      delete h; return ADAPROX_ERR_CUDA;
+    }
+    per_sm = std::min(per_sm, nb);
+  }
+  h->grid = per_sm * h->sm_count;
+  *out = h;
+  return ADAPROX_OK;
+}
+
+extern "C" int adaprox_destroy(adaprox_handle h) {
+  if (!h) return ADAPROX_OK;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  comm_destroy(h);
+  for (auto& kv : h->mats) free_matrix(kv.second);
+  for (auto& kv : h->vecs) cudaFree(kv.second.p);
+  if (h->ws) cudaFree(h->ws);
+  cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
+  cudaStreamDestroy(h->stream);
+  delete h;
+  return ADAPROX_OK;
+}
+
+extern "C" const char* adaprox_last_error(adaprox_handle h) { return h ? h->err.c_str() : "null handle"; }
+
+extern "C" int adaprox_device_info(adaprox_handle h, int* sm_count, int* cc_major, int* cc_minor, int64_t* free_bytes) {
+  if (!h) return ADAPROX_ERR_INVALID;
+  if (sm_count) *sm_count = h->sm_count;
+  if (cc_major) *cc_major = h->cc_major;
+  if (cc_minor) *cc_minor = h->cc_minor;
+  if (free_bytes) { size_t f = 0, t = 0; AP_CUDA(h, cudaMemGetInfo(&f, &t)); *free_bytes = (int64_t)f; }
+  return ADAPROX_OK;
+}
+
+// ---------------------------------------------------------------------------
+// device-resident data
+// ---------------------------------------------------------------------------
+extern "C" int adaprox_matrix_upload_colmajor(adaprox_handle h, const double* A, int64_t m, int64_t n, int64_t lda, adaprox_id* out) {
+  if (!h || !A || !out || m <= 0 || n <= 0 || lda < m) return fail(h, ADAPROX_ERR_INVALID, "matrix_upload_colmajor: bad arguments");
+  AP_CUDA(h, cudaSetDevice(h->device));
+  HostMatrix hm;
+  int rc = alloc_dense(h, m, n, hm);
+  if (rc) { free_matrix(hm); return rc; }
+  double* stage = nullptr;
+  AP_CUDA(h, cudaMalloc(&stage, (size_t)lda * n * 8));
+  cudaError_t e = cudaMemcpyAsync(stage, A, (size_t)lda * n * 8, cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess) {
+    dim3 grid((unsigned)((m + 31) / 32), (unsigned)((hm.d.ld + 31) / 32)), block(32, 8);
+    k_colmajor_to_rowmajor<<<grid, block, 0, h->stream>>>(stage, m, n, lda, const_cast<double*>(hm.d.a), hm.d.ld);
+    h->launches++;
+    e = cudaStreamSynchronize(h->stream);
+  }
+  cudaFree(stage);
+  if (e != cudaSuccess) { free_matrix(hm); return fail(h, ADAPROX_ERR_CUDA, std::string("matrix upload: ") + cudaGetErrorString(e)); }
+  const int64_t id = h->next_id++;
+  h->mats[id] = hm;
+  *out = id;
+  return ADAPROX_OK;
+}
+
+extern "C" int adaprox_matrix_upload_rowmajor(adaprox_handle h, const double* A, int64_t m, int64_t n, int64_t lda, adaprox_id* out) {
+  if (!h || !A || !out || m <= 0 || n <= 0 || lda < n) return fail(h, ADAPROX_ERR_INVALID, "matrix_upload_rowmajor: bad arguments");
+  AP_CUDA(h, cudaSetDevice(h->device));
+  HostMatrix hm;
+  int rc = alloc_dense(h, m, n, hm);
+  if (rc) { free_matrix(hm); return rc; }
+  cudaError_t e = cudaMemsetAsync(const_cast<double*>(hm.d.a), 0, (size_t)m * hm.d.ld * 8, h->stream);
+  if (e == cudaSuccess)
+    e = cudaMemcpy2DAsync(const_cast<double*>(hm.d.a), (size_t)hm.d.ld * 8, A, (size_t)lda * 8, (size_t)n * 8, (size_t)m,
+                          cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  if (e != cudaSuccess) { free_matrix(hm); return fail(h, ADAPROX_ERR_CUDA, std::string("matrix upload: ") + cudaGetErrorString(e)); }
+  const int64_t id = h->next_id++;
+  h->mats[id] = hm;
+  *out = id;
+  return ADAPROX_OK;
+}
+
+extern "C" int adaprox_matrix_upload_csr(adaprox_handle h, int64_t m, int64_t n, int64_t nnz, const int64_t* rowptr,
+                                         const int32_t* colind, const double* vals, adaprox_id* out) {
+  if (!h || !rowptr || !out || m <= 0 || n <= 0 || nnz < 0 || (nnz > 0 && (!colind || !vals)))
+    return fail(h, ADAPROX_ERR_INVALID, "matrix_upload_csr: bad arguments");
+  if (rowptr[0] != 0 || rowptr[m] != nnz) return fail(h, ADAPROX_ERR_INVALID, "matrix_upload_csr: rowptr does not span nnz");
+  for (int64_t k = 0; k < nnz; ++k)
+    if (colind[k] < 0 || colind[k] >= n) return fail(h, ADAPROX_ERR_INVALID, "matrix_upload_csr: column index out of range");
+  AP_CUDA(h, cudaSetDevice(h->device));
+  // CSR of the transpose (counting sort by column; rows stay sorted inside each column)
+  std::vector<int64_t> tptr(n + 1, 0);
+  for (int64_t k = 0; k < nnz; ++k) tptr[colind[k] + 1]++;
+  for (int64_t j = 0; j < n; ++j) tptr[j + 1] += tptr[j];
+  std::vector<int32_t> tind(std::max<int64_t>(nnz, 1));
+  std::vector<double> tval(std::max<int64_t>(nnz, 1));
+  {
+    std::vector<int64_t> cur(tptr.begin(), tptr.end() - 1);
+    for (int64_t i = 0; i < m; ++i)
+      for (int64_t k = rowptr[i]; k < rowptr[i + 1]; ++k) {
+        const int64_t pos = cur[colind[k]]++;
+        tind[pos] = (int32_t)i; tval[pos] = vals[k];
+      }
+  }
+  HostMatrix hm;
+  DMat& d = hm.d;
+  d.kind = MAT_CSR; d.m = m; d.n = n; d.ld = 0; d.nnz = nnz; d.nchunks = 1; d.rb = 0; d.nrb = 0; d.npad = n;
+  auto up = [&](const void* src, size_t bytes, void** dst) -> cudaError_t {
+    cudaError_t e = cudaMalloc(dst, std::max<size_t>(bytes, 8));
+    if (e != cudaSuccess) return e;
+    hm.allocs.push_back(*dst);
+    return bytes ? cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice) : cudaSuccess;
+  };
+  void *p_rp, *p_ci, *p_v, *p_trp, *p_tci, *p_tv, *p_zp, *p_gp;
+  cudaError_t e = up(rowptr, (size_t)(m + 1) * 8, &p_rp);
+  if (e == cudaSuccess) e = up(colind, (size_t)nnz * 4, &p_ci);
+  if (e == cudaSuccess) e = up(vals, (size_t)nnz * 8, &p_v);
+  if (e == cudaSuccess) e = up(tptr.data(), (size_t)(n + 1) * 8, &p_trp);
+  if (e == cudaSuccess) e = up(tind.data(), (size_t)nnz * 4, &p_tci);
+  if (e == cudaSuccess) e = up(tval.data(), (size_t)nnz * 8, &p_tv);
+  if (e == cudaSuccess) { e = cudaMalloc(&p_zp, (size_t)m * 8); if (e == cudaSuccess) hm.allocs.push_back(p_zp); }
+  if (e == cudaSuccess) { e = cudaMalloc(&p_gp, (size_t)n * 8); if (e == cudaSuccess) hm.allocs.push_back(p_gp); }
+  if (e != cudaSuccess) { free_matrix(hm); return fail(h, ADAPROX_ERR_CUDA, std::string("csr upload: ") + cudaGetErrorString(e)); }
+  d.rowptr = (const int64_t*)p_rp; d.colind = (const int*)p_ci; d.vals = (const double*)p_v;
+  d.t_rowptr = (const int64_t*)p_trp; d.t_colind = (const int*)p_tci; d.t_vals = (const double*)p_tv;
+  d.zpart = (double*)p_zp; d.gpart = (double*)p_gp;
+  hm.m_global = m;
+  const int64_t id = h->next_id++;
+  h->mats[id] = hm;
+  *out = id;
+  return ADAPROX_OK;
+}
+
+extern "C" int adaprox_matrix_free(adaprox_handle h, adaprox_id mat) {
+  if (!h) return ADAPROX_ERR_INVALID;
+  auto it = h->mats.find(mat);
+  if (it == h->mats.end()) return fail(h, ADAPROX_ERR_INVALID, "matrix_free: unknown id");
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  free_matrix(it->second);
+  h->mats.erase(it);
+  return ADAPROX_OK;
+}
+
+extern "C" int adaprox_matrix_shape(adaprox_handle h, adaprox_id mat, int64_t* m, int64_t* n, int64_t* nnz) {
+  if (!h) return ADAPROX_ERR_INVALID;
+  HostMatrix* hm;
+  int rc = get_mat(h, mat, &hm);
+  if (rc) return rc;
+  if (m) *m = hm->d.m;
+  if (n) *n = hm->d.n;
+  if (nnz) *nnz = hm->d.kind == MAT_CSR ? hm->d.nnz : hm->d.m * hm->d.n;
+  return ADAPROX_OK;
+}
+
+extern "C" int adaprox_vector_upload(adaprox_handle h, const double* v, int64_t len, adaprox_id* out) {
+  if (!h || !v || !out || len <= 0) return fail(h, ADAPROX_ERR_INVALID, "vector_upload: bad arguments");
+  AP_CUDA(h, cudaSetDevice(h->device));
+  HostVector hv;
+  hv.len = len;
+  AP_CUDA(h, cudaMalloc(&hv.p, (size_t)len * 8));
+  cudaError_t e = cudaMemcpy(hv.p, v, (size_t)len * 8, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { cudaFree(hv.p); return fail(h, ADAPROX_ERR_CUDA, cudaGetErrorString(e)); }
+  const int64_t id = h->next_id++;
+  h->vecs[id] = hv;
+  *out = id;
+  return ADAPROX_OK;
+}
+
+extern "C" int adaprox_vector_download(adaprox_handle h, adaprox_id vec, double* out, int64_t len) {
+  if (!h || !out) return fail(h, ADAPROX_ERR_INVALID, "vector_download: bad arguments");
+  auto it = h->vecs.find(vec);
+  if (it == h->vecs.end() || it->second.len < len) return fail(h, ADAPROX_ERR_INVALID, "vector_download: unknown id or too short");
+  AP_CUDA(h, cudaSetDevice(h->device));
+  AP_CUDA(h, cudaStreamSynchronize(h->stream));
+  AP_CUDA(h, cudaMemcpy(out, it->second.p, (size_t)len * 8, cudaMemcpyDeviceToHost));
+  return ADAPROX_OK;
+}
+
+extern "C" int adaprox_vector_free(adaprox_handle h, adaprox_id vec) {
+  if (!h) return ADAPROX_ERR_INVALID;
+  auto it = h->vecs.find(vec);
+  if (it == h->vecs.end()) return fail(h, ADAPROX_ERR_INVALID, "vector_free: unknown id");
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  cudaFree(it->second.p);
+  h->vecs.erase(it);
+  return ADAPROX_OK;
+}
+
+extern "C" int adaprox_matrix_set_shard(adaprox_handle h, adaprox_id mat, int64_t m_global, int64_t row0) {
+  if (!h) return ADAPROX_ERR_INVALID;
+  HostMatrix* hm;
+  int rc = get_mat(h, mat, &hm);
+  if (rc) return rc;
+  if (m_global < hm->d.m || row0 < 0 || row0 + hm->d.m > m_global) return fail(h, ADAPROX_ERR_INVALID, "matrix_set_shard: bad row range");
+  hm->m_global = m_global; hm->row0 = row0; hm->sharded = (m_global != hm->d.m);
+  return ADAPROX_OK;
+}
+
+// ---------------------------------------------------------------------------
+// operator protocol, one call each
+// ---------------------------------------------------------------------------
+extern "C" int adaprox_mul(adaprox_handle h, adaprox_id mat, const double* x, double* out) {
+  if (!h || !x || !out) return fail(h, ADAPROX_ERR_INVALID, "mul: bad arguments");
+  HostMatrix* hm;
+  int rc = get_mat(h, mat, &hm);
+  if (rc) return rc;
+  AP_CUDA(h, cudaSetDevice(h->device));
+  const DMat& M = hm->d;
+  if ((rc = ws_reset(h, ws_size_doubles(M.n) + ws_size_doubles(M.m)))) return rc;
+  double* dx = ws_doubles(h, M.n);
+  double* dz = ws_doubles(h, M.m);
+  AP_CUDA(h, cudaMemcpyAsync(dx, x, (size_t)M.n * 8, cudaMemcpyHostToDevice, h->stream));
+  if ((rc = op_mul_dev(h, M, dx, dz))) return rc;
+  AP_CUDA(h, cudaMemcpyAsync(out, dz, (size_t)M.m * 8, cudaMemcpyDeviceToHost, h->stream));
+  AP_CUDA(h, cudaStreamSynchronize(h->stream));
+  return ADAPROX_OK;
+}
+
+extern "C" int adaprox_amul(adaprox_handle h, adaprox_id mat, const double* y, double* out) {
+  if (!h || !y || !out) return fail(h, ADAPROX_ERR_INVALID, "amul: bad arguments");
+  HostMatrix* hm;
+  int rc = get_mat(h, mat, &hm);
+  if (rc) return rc;
+  AP_CUDA(h, cudaSetDevice(h->device));
+  const DMat& M = hm->d;
+  if ((rc = ws_reset(h, ws_size_doubles(M.n) + ws_size_doubles(M.m)))) return rc;
+  double* dy = ws_doubles(h, M.m);
+  double* dg = ws_doubles(h, M.n);
+  AP_CUDA(h, cudaMemcpyAsync(dy, y, (size_t)M.m * 8, cudaMemcpyHostToDevice, h->stream));
+  if ((rc = op_amul_dev(h, M, dy, dg))) return rc;
+  if (hm->sharded && h->comm) { if ((rc = comm_allreduce_sum(h, dg, M.n))) return rc; }
+  AP_CUDA(h, cudaMemcpyAsync(out, dg, (size_t)M.n * 8, cudaMemcpyDeviceToHost, h->stream));
+  AP_CUDA(h, cudaStreamSynchronize(h->stream));
+  return ADAPROX_OK;
+}
+
+extern "C" int adaprox_eval_f(adaprox_handle h, const adaprox_problem* p, const double* x, double* f_x, double* grad) {
+  if (!h || !p || !x) return fail(h, ADAPROX_ERR_INVALID, "eval_f: bad arguments");
+  AP_CUDA(h, cudaSetDevice(h->device));
+  DProblem P;
+  HostMatrix *fm, *am;
+  adaprox_problem q = *p;
+  q.A_mat = 0;
+  int rc = fill_problem(h, &q, &P, &fm, &am);
+  if (rc) return rc;
+  if (fm && fm->sharded) return fail(h, ADAPROX_ERR_UNSUPPORTED, "eval_f on a row shard: use the solver entry points");
+  const int64_t mf = std::max<int64_t>(P.F.kind != MAT_NONE ? P.F.m : 0, P.n);
+  if ((rc = ws_reset(h, 2 * ws_size_doubles(P.n) + ws_size_doubles(mf) + ws_size_doubles((int64_t)kMaxRed * h->grid) + ws_size_doubles(4)))) return rc;
+  double* dx = ws_doubles(h, P.n);
+  double* dg = ws_doubles(h, P.n);
+  DWork W{};
+  W.r = ws_doubles(h, mf);
+  W.red = ws_doubles(h, (int64_t)kMaxRed * h->grid);
+  double* scal = ws_doubles(h, 4);
+  AP_CUDA(h, cudaMemcpyAsync(dx, x, (size_t)P.n * 8, cudaMemcpyHostToDevice, h->stream));
+  OpArgs a{}; a.op = OP_EVALF; a.P = P; a.in = dx; a.out = dg; a.scal = scal; a.want_grad = grad ? 1 : 0;
+  if ((rc = run_ops(h, a, W))) return rc;
+  double fx = 0.0;
+  AP_CUDA(h, cudaMemcpyAsync(&fx, scal, 8, cudaMemcpyDeviceToHost, h->stream));
+  if (grad) AP_CUDA(h, cudaMemcpyAsync(grad, dg, (size_t)P.n * 8, cudaMemcpyDeviceToHost, h->stream));
+  AP_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (f_x) *f_x = fx;
+  return ADAPROX_OK;
+}
+
+extern "C" int adaprox_prox_eval(adaprox_handle h, const adaprox_prox* g, const double* x, int64_t len, double gamma,
+                                 double* y, double* g_y) {
+  if (!h || !g || !x || !y || len <= 0) return fail(h, ADAPROX_ERR_INVALID, "prox_eval: bad arguments");
+  AP_CUDA(h, cudaSetDevice(h->device));
+  DProx px;
+  int rc = fill_prox(h, *g, len, &px);
+  if (rc) return rc;
+  if ((rc = ws_reset(h, 2 * ws_size_doubles(len) + ws_size_doubles((int64_t)kMaxRed * h->grid) + ws_size_doubles(4)))) return rc;
+  double* dx = ws_doubles(h, len);
+  double* dy = ws_doubles(h, len);
+  DWork W{};
+  W.red = ws_doubles(h, (int64_t)kMaxRed * h->grid);
+  double* scal = ws_doubles(h, 4);
+  AP_CUDA(h, cudaMemcpyAsync(dx, x, (size_t)len * 8, cudaMemcpyHostToDevice, h->stream));
+  OpArgs a{}; a.op = OP_PROX; a.px = px; a.gamma = gamma; a.len = len; a.in = dx; a.out = dy; a.scal = scal;
+  if ((rc = run_ops(h, a, W))) return rc;
+  double gy = 0.0;
+  AP_CUDA(h, cudaMemcpyAsync(&gy, scal, 8, cudaMemcpyDeviceToHost, h->stream));
+  AP_CUDA(h, cudaMemcpyAsync(y, dy, (size_t)len * 8, cudaMemcpyDeviceToHost, h->stream));
+  AP_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (g_y) *g_y = gy;
+  return ADAPROX_OK;
+}
+
+static void fill_opts(const adaprox_options* o, DOpts* d) {
+  d->solver = o->solver; d->rule = o->rule; d->gamma = o->gamma; d->t = o->t; d->norm_A = o->norm_A; d->delta = o->delta;
+  d->Theta = o->Theta; d->xi = o->xi; d->nu = o->nu; d->r = o->r; d->R = o->R; d->eta = o->eta; d->shrink = o->shrink;
+  d->sigma = o->sigma; d->muf = o->muf; d->mug = o->mug; d->theta = o->theta; d->gamma_max = o->gamma_max; d->phi = o->phi;
+  d->tol = o->tol; d->maxit = o->maxit; d->max_records = o->max_records; d->want_objective = o->want_objective;
+}
+
+extern "C" int adaprox_stepsize(const adaprox_options* o, double gamma1, double gamma0_or_rho, double dgg, double dgx,
+                                double dxx, double* gamma, double* sigma, double* state1) {
+  if (!o || !gamma || !sigma) return ADAPROX_ERR_INVALID;
+  DOpts d{};
+  fill_opts(o, &d);
+  double g = 0, s = 0, s0 = gamma1, s1 = gamma0_or_rho;
+  rule_step(d, dgg, dgx, dxx, g, s, s0, s1);
+  *gamma = g; *sigma = s;
+  if (state1) *state1 = s1;
+  return ADAPROX_OK;
+}
+
+// ---------------------------------------------------------------------------
+// solvers
+// ---------------------------------------------------------------------------
+static int validate_options(adaprox_ctx* h, const adaprox_problem* p, const adaprox_options* o) {
+  if (o->maxit < 0) return fail(h, ADAPROX_ERR_INVALID, "maxit must be >= 0");
+  const bool pd = (o->solver == ADAPROX_S_ADAPTIVE_PRIMAL_DUAL || o->solver == ADAPROX_S_LINESEARCH_PRIMAL_DUAL ||
+                   o->solver == ADAPROX_S_MALITSKY_POCK);
+  if (pd && p->A_mat == 0) return fail(h, ADAPROX_ERR_INVALID, "primal-dual solvers need A (use adaptive_proxgrad for A = 0)");
+  if (!pd && p->A_mat != 0) return fail(h, ADAPROX_ERR_INVALID, "proximal-gradient solvers take no A");
+  if (p->g.kind == ADAPROX_P_NORM_L2 || p->g.conjugate)
+    return fail(h, ADAPROX_ERR_UNSUPPORTED, "g = NormL2 / conjugate g has no fused kernel");
+  switch (o->solver) {
+    case ADAPROX_S_ADAPTIVE_PRIMAL_DUAL:
+    case ADAPROX_S_ADAPTIVE_PROXGRAD:
+      if (o->rule < ADAPROX_RULE_FIXED || o->rule > ADAPROX_RULE_OUR_PLUS) return fail(h, ADAPROX_ERR_INVALID, "unknown stepsize rule");
+      if (!(o->gamma > 0)) return fail(h, ADAPROX_ERR_INVALID, "you must provide gamma > 0 if norm_A = 0");   // :246,:288
+      break;
+    case ADAPROX_S_LINESEARCH_PRIMAL_DUAL:
+      if (!(o->eta > 0)) return fail(h, ADAPROX_ERR_INVALID, "eta must be positive");                          // :481
+      if (!(o->Theta > o->delta + 1)) return fail(h, ADAPROX_ERR_INVALID, "must be Theta > (delta + 1)");       // :482
+      if (!(o->gamma <= 1.0 / (2.0 * o->Theta * o->t * o->eta))) return fail(h, ADAPROX_ERR_INVALID, "gamma is too large");   // :488
+      break;
+    case ADAPROX_S_BACKTRACKING_PROXGRAD:
+    case ADAPROX_S_BACKTRACKING_NESTEROV:
+      if (!(o->gamma > 0) || !(o->shrink > 0 && o->shrink < 1)) return fail(h, ADAPROX_ERR_INVALID, "backtracking needs gamma0 > 0, 0 < shrink < 1");
+      break;
+    case ADAPROX_S_FIXED_NESTEROV: {
+      if (!(o->gamma > 0)) return fail(h, ADAPROX_ERR_INVALID, "fixed_nesterov needs gamma (or Lf) > 0");
+      const double mu = o->muf + o->mug, q = o->gamma * mu / (1 + o->gamma * o->mug);
+      if (!(q < 1)) return fail(h, ADAPROX_ERR_INVALID, "fixed_nesterov: q < 1 violated");                    // :110
+    } break;
+    case ADAPROX_S_AGRAAL:          // gamma <= 0 means `gamma0 = nothing` (:168-170)
+      if (!(o->phi > 1)) return fail(h, ADAPROX_ERR_INVALID, "agraal needs phi > 1");
+      break;
+    case ADAPROX_S_MALITSKY_POCK:
+      if (!(o->sigma > 0)) return fail(h, ADAPROX_ERR_INVALID, "malitsky_pock needs sigma > 0");
+      break;
+    default:
+      return fail(h, ADAPROX_ERR_INVALID, "unknown solver");
+  }
+  return ADAPROX_OK;
+}
+
+extern "C" int adaprox_solve(adaprox_handle h, const adaprox_problem* p, const adaprox_options* o, const double* x0,
+                             const double* y0, double* x_out, double* y_out, adaprox_record* records, adaprox_result* res) {
+  if (!h || !p || !o || !x0 || !x_out || !res) return fail(h, ADAPROX_ERR_INVALID, "solve: bad arguments");
+  AP_CUDA(h, cudaSetDevice(h->device));
+  int rc;
+  if ((rc = validate_options(h, p, o))) return rc;
+  DProblem P;
+  HostMatrix *fm, *am;
+  if ((rc = fill_problem(h, p, &P, &fm, &am))) return rc;
+  DOpts O{};
+  fill_opts(o, &O);
+  if (!records) O.max_records = 0;
+  const bool sharded = (fm && fm->sharded) || (am && am->sharded);
+  if (sharded) return solve_sharded(h, p, o, P, O, fm, am, x0, y0, x_out, y_out, records, res);
+
+  const int64_t n = P.n, md = std::max<int64_t>(P.md, 1);
+  const int64_t mf = std::max<int64_t>(P.F.kind != MAT_NONE ? P.F.m : 0, n);
+  const int64_t nrec = std::min<int64_t>(O.max_records, O.maxit);
+  const int G = h->grid;
+  size_t need = 11 * ws_size_doubles(n) + 6 * ws_size_doubles(md) + ws_size_doubles(mf) +
+                ws_size_doubles((int64_t)kMaxRed * G) + ws_size_doubles((nrec * (int64_t)sizeof(adaprox_record) + 7) / 8) +
+                ws_size_doubles((sizeof(DResult) + 7) / 8);
+  if ((rc = ws_reset(h, need))) return rc;
+  DWork W{};
+  for (int k = 0; k < 3; ++k) W.xb[k] = ws_doubles(h, n);
+  for (int k = 0; k < 2; ++k) W.gb[k] = ws_doubles(h, n);
+  W.v = ws_doubles(h, n);
+  for (int k = 0; k < 2; ++k) W.Aty[k] = ws_doubles(h, n);
+  for (int k = 0; k < 3; ++k) W.aux[k] = ws_doubles(h, n);
+  for (int k = 0; k < 2; ++k) W.yb[k] = ws_doubles(h, md);
+  W.w = ws_doubles(h, md);
+  for (int k = 0; k < 2; ++k) W.Axb[k] = ws_doubles(h, md);
+  W.yout = ws_doubles(h, md);
+  W.r = ws_doubles(h, mf);
+  W.red = ws_doubles(h, (int64_t)kMaxRed * G);
+  W.rec = nrec > 0 ? reinterpret_cast<adaprox_record*>(ws_doubles(h, (nrec * (int64_t)sizeof(adaprox_record) + 7) / 8)) : nullptr;
+  W.res = reinterpret_cast<DResult*>(ws_doubles(h, (sizeof(DResult) + 7) / 8));
+  W.xout = W.aux[2];
+  O.max_records = nrec;
+
+  AP_CUDA(h, cudaMemcpyAsync(W.xb[0], x0, (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
+  if (P.md > 0) {
+    if (y0) AP_CUDA(h, cudaMemcpyAsync(W.yb[0], y0, (size_t)P.md * 8, cudaMemcpyHostToDevice, h->stream));
+    else AP_CUDA(h, cudaMemsetAsync(W.yb[0], 0, (size_t)P.md * 8, h->stream));
+  }
+  if (o->solver == ADAPROX_S_AGRAAL) {      // y0 carries agraal's second start point x0 (:154,165)
+    if (!y0) return fail(h, ADAPROX_ERR_INVALID, "agraal needs the second start point (pass it as y0)");
+    AP_CUDA(h, cudaMemcpyAsync(W.aux[0], y0, (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
+  }
+  AP_CUDA(h, cudaMemsetAsync(W.red, 0, (size_t)kMaxRed * G * 8, h->stream));
+  const int64_t launches0 = h->launches;
+  AP_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+  void* args[] = {&P, &O, &W};
+  switch (o->solver) {
+    case ADAPROX_S_ADAPTIVE_PRIMAL_DUAL:
+    case ADAPROX_S_ADAPTIVE_PROXGRAD:
+      rc = coop_launch(h, k_primal_dual<false>, args);
+      break;
+    case ADAPROX_S_LINESEARCH_PRIMAL_DUAL:
+      rc = coop_launch(h, k_primal_dual<true>, args);
+      break;
+    case ADAPROX_S_BACKTRACKING_PROXGRAD:
+    case ADAPROX_S_BACKTRACKING_NESTEROV:
+    case ADAPROX_S_FIXED_NESTEROV:
+    case ADAPROX_S_AGRAAL:
+      rc = coop_launch(h, k_proxgrad_family, args);
+      break;
+    default:
+      return fail(h, ADAPROX_ERR_UNSUPPORTED, "solver has no device kernel yet");
+  }
+  if (rc) return rc;
+  AP_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+  DResult dr{};
+  AP_CUDA(h, cudaMemcpyAsync(&dr, W.res, sizeof(DResult), cudaMemcpyDeviceToHost, h->stream));
+  AP_CUDA(h, cudaMemcpyAsync(x_out, W.xout, (size_t)n * 8, cudaMemcpyDeviceToHost, h->stream));
+  if (y_out && P.md > 0) AP_CUDA(h, cudaMemcpyAsync(y_out, W.yout, (size_t)P.md * 8, cudaMemcpyDeviceToHost, h->stream));
+  AP_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (records && dr.n_records > 0)
+    AP_CUDA(h, cudaMemcpy(records, W.rec, (size_t)dr.n_records * sizeof(adaprox_record), cudaMemcpyDeviceToHost));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+  std::memset(res, 0, sizeof(*res));
+  res->iters = dr.iters; res->flags = dr.flags;
+  res->f_evals = dr.f_evals; res->grad_f_evals = dr.grad_f_evals; res->prox_g_evals = dr.prox_g_evals;
+  res->prox_h_evals = dr.prox_h_evals; res->A_evals = dr.A_evals; res->At_evals = dr.At_evals;
+  res->n_records = dr.n_records;
+  res->final_gamma = dr.final_gamma; res->final_sigma = dr.final_sigma; res->final_norm_res = dr.final_norm_res;
+  res->solve_ms = ms; res->kernel_launches = h->launches - launches0;
+  return ADAPROX_OK;
+}
+
+// ---------------------------------------------------------------------------
+// measurement hook
+// ---------------------------------------------------------------------------
+extern "C" int adaprox_time_kernel(adaprox_handle h, adaprox_id mat, int which, int reps, double* ms_per_pass) {
+  if (!h || !ms_per_pass || reps <= 0 || (which != 0 && which != 1)) return fail(h, ADAPROX_ERR_INVALID, "time_kernel: bad arguments");
+  HostMatrix* hm;
+  int rc = get_mat(h, mat, &hm);
+  if (rc) return rc;
+  AP_CUDA(h, cudaSetDevice(h->device));
+  DMat M = hm->d;
+  const int64_t len = which == 0 ? M.n : M.m;
+  if ((rc = ws_reset(h, ws_size_doubles(len)))) return rc;
+  double* in = ws_doubles(h, len);
+  std::vector<double> ones((size_t)len, 1.0);
+  AP_CUDA(h, cudaMemcpyAsync(in, ones.data(), (size_t)len * 8, cudaMemcpyHostToDevice, h->stream));
+  double* out = nullptr;
+  k_gemv_pass<<<h->grid, kThreads, 0, h->stream>>>(M, which, in, out);   // warm-up
+  h->launches++;
+  AP_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+  for (int r = 0; r < reps; ++r) { k_gemv_pass<<<h->grid, kThreads, 0, h->stream>>>(M, which, in, out); h->launches++; }
+  AP_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+  AP_CUDA(h, cudaStreamSynchronize(h->stream));
+  AP_CUDA(h, cudaGetLastError());
+  float ms = 0.f;
+  AP_CUDA(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  *ms_per_pass = (double)ms / reps;
+  return ADAPROX_OK;
+}
+
+#include "comm.inl"
+#include "generate.inl"

@@ -1,0 +1,15 @@
+// comm.hpp -- row-sharded multi-GPU support: NCCL (loaded lazily with dlopen so a
+// single-GPU user needs no NCCL at all) and the split-phase sharded solver.
+#pragma once
+#include "context.hpp"
+
+namespace adaprox {
+
+int comm_allreduce_sum(adaprox_ctx* h, double* buf_dev, int64_t count);
+void comm_destroy(adaprox_ctx* h);
+
+int solve_sharded(adaprox_ctx* h, const adaprox_problem* p, const adaprox_options* o, const DProblem& P, const DOpts& O,
+                  HostMatrix* fm, HostMatrix* am, const double* x0, const double* y0, double* x_out, double* y_out,
+                  adaprox_record* records, adaprox_result* res);
+
+}  // namespace adaprox

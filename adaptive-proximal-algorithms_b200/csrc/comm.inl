@@ -1,0 +1,347 @@
+// comm.inl -- included at the end of api.cu (same translation unit).
+//
+// Row-sharded AdaPGM: rows of A (and b / labels) are split
+// in contiguous blocks over the ranks, x / grad / stepsize state are replicated.
+// Per iteration every rank streams its shard twice (A*x is purely local, A'r
+// yields a partial n-vector) and ONE all-reduce of n+2 doubles combines the
+// A'r partials with the value sums.  NCCL delivers bit-identical sums on every
+// rank, so the replicated prox / stepsize arithmetic stays in lock step with no
+// second collective.  A persistent kernel cannot call NCCL, so the iteration is
+// split at the all-reduce into ordinary launches on one stream; convergence is
+// a device flag polled by the host once per batch of iterations, so there is
+// still no host round trip per iteration.
+#include <dlfcn.h>
+#include <nccl.h>
+
+namespace adaprox {
+
+struct NcclApi {
+  void* lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  std::string err;
+};
+
+static NcclApi* nccl_api() {
+  static NcclApi api;
+  if (api.lib) return &api;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* nm : names) {
+    api.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+    if (api.lib) break;
+  }
+  if (!api.lib) { api.err = std::string("dlopen(libnccl.so.2) failed: ") + dlerror(); return &api; }
+  api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(api.lib, "ncclGetUniqueId");
+  api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.lib, "ncclCommInitRank");
+  api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.lib, "ncclCommDestroy");
+  api.AllReduce = (decltype(api.AllReduce))dlsym(api.lib, "ncclAllReduce");
+  api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.lib, "ncclGetErrorString");
+  if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.AllReduce || !api.GetErrorString) {
+    api.err = "libnccl is missing a required symbol";
+    dlclose(api.lib);
+    api.lib = nullptr;
+  }
+  return &api;
+}
+
+struct Comm {
+  ncclComm_t comm = nullptr;
+  int nranks = 1, rank = 0;
+};
+
+int comm_allreduce_sum(adaprox_ctx* h, double* buf_dev, int64_t count) {
+  if (!h->comm) return fail(h, ADAPROX_ERR_COMM, "no communicator attached");
+  NcclApi* api = nccl_api();
+  ncclResult_t r = api->AllReduce(buf_dev, buf_dev, (size_t)count, ncclDouble, ncclSum, h->comm->comm, h->stream);
+  if (r != ncclSuccess) return fail(h, ADAPROX_ERR_COMM, std::string("ncclAllReduce: ") + api->GetErrorString(r));
+  return ADAPROX_OK;
+}
+
+void comm_destroy(adaprox_ctx* h) {
+  if (h->comm) {
+    NcclApi* api = nccl_api();
+    if (api->lib && h->comm->comm) api->CommDestroy(h->comm->comm);
+    delete h->comm;
+    h->comm = nullptr;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// split-phase kernels of the sharded AdaPGM iteration
+// ---------------------------------------------------------------------------
+struct ShState {
+  double gamma, sigma, s0, s1, norm_res;
+  long long it;            // on `done`: the iteration at which the loop stopped
+  int done;
+  unsigned flags;
+  long long n_eval, n_grad, n_proxg, n_rec;
+};
+
+struct ShArgs {
+  DProblem P; DOpts O; DWork W;
+  ShState* st;             // [2]: the kernels of iteration `it` read st[it & 1], k_sh_F writes st[(it + 1) & 1]
+  long long it;            // iteration being enqueued (host-side counter; 0 = prologue)
+  double* gbuf;            // [n + 2]: A'r sums, value sums  (all-reduced in place)
+};
+
+__device__ __forceinline__ const ShState& sh_state(const ShArgs& a, long long it) { return a.st[it & 1]; }
+__device__ __forceinline__ long long sh_current(const ShArgs& a, bool& done) {
+  done = a.st[a.it & 1].done != 0;
+  return a.it;
+}
+
+__global__ void __launch_bounds__(kThreads, 2) k_sh_A(ShArgs a) {
+  __shared__ __align__(16) double s_x[kChunk];
+  __shared__ double s_scr[kWarps * 8 + kMaxRed];
+  bool done; const long long it = sh_current(a, done);
+  if (done) return;
+  f_phase_A(a.P, a.W, a.W.xb[it % 3], s_x, s_scr, blockIdx.x, gridDim.x);
+}
+__global__ void __launch_bounds__(kThreads, 2) k_sh_B(ShArgs a) {
+  __shared__ double s_scr[kWarps * 8 + kMaxRed];
+  bool done; const long long it = sh_current(a, done);
+  if (done) return;
+  f_phase_B(a.P, a.W, a.W.xb[it % 3], s_scr, blockIdx.x, gridDim.x);
+}
+__global__ void __launch_bounds__(kThreads, 2) k_sh_C(ShArgs a) {
+  bool done; sh_current(a, done);
+  if (done) return;
+  f_phase_C(a.P, a.W, blockIdx.x, gridDim.x);
+}
+// local partial sums -> the all-reduce buffer
+__global__ void __launch_bounds__(kThreads, 2) k_sh_D(ShArgs a) {
+  __shared__ double s_scr[kWarps * 8 + kMaxRed];
+  bool done; sh_current(a, done);
+  if (done) return;
+  const int b = blockIdx.x, G = gridDim.x;
+  const int64_t nmat = a.P.F.n;
+  int64_t j0, j1;
+  cta_slice(nmat, b, G, j0, j1);
+  gsum_slice(a.P.F, j0, j1, a.gbuf, G);
+  double tot[2];
+  grid_totals<2>(a.W.red, G, SLOT_F0, tot, s_scr);
+  if (b == 0 && threadIdx.x == 0) { a.gbuf[a.P.n] = tot[0]; a.gbuf[a.P.n + 1] = tot[1]; }
+}
+// after the all-reduce: gradient, primal residual, stepsize reductions (P4)
+__global__ void __launch_bounds__(kThreads, 2) k_sh_E(ShArgs a) {
+  __shared__ double s_scr[kWarps * 8 + kMaxRed];
+  bool done; const long long it = sh_current(a, done);
+  if (done) return;
+  const DProblem& P = a.P;
+  const int b = blockIdx.x, G = gridDim.x;
+  const ShState& st = sh_state(a, it);
+  int64_t j0, j1;
+  cta_slice(P.n, b, G, j0, j1);
+  double* grad = a.W.gb[it & 1];
+  const double* grad_prev = a.W.gb[(it + 1) & 1];
+  const double* x = a.W.xb[it % 3];
+  const double* x_prev = a.W.xb[(it + 2) % 3];
+  const double f1 = a.gbuf[P.n + 1];
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int64_t j = j0 + threadIdx.x; j < j1; j += kThreads) {
+    double gj = a.gbuf[j];
+    if (P.f_kind == ADAPROX_F_LOGISTIC) gj = (j == P.n - 1) ? f1 / P.f_N : gj / P.f_N;
+    grad[j] = gj;
+    if (it > 0) {
+      const double xj = x[j];
+      const double pr = (a.W.v[j] - xj) / st.gamma + gj;
+      const double dg = gj - grad_prev[j], dx = xj - x_prev[j];
+      acc[0] = fma(pr, pr, acc[0]);
+      acc[1] = fma(dg, dg, acc[1]);
+      acc[2] = fma(dg, dx, acc[2]);
+      acc[3] = fma(dx, dx, acc[3]);
+    }
+  }
+  block_reduce_store<4>(acc, a.W.red, G, SLOT_PR, s_scr);
+}
+// stepsize, residual, record, convergence, prox step (P5 + P7); advances the state
+__global__ void __launch_bounds__(kThreads, 2) k_sh_F(ShArgs a) {
+  __shared__ double s_scr[kWarps * 8 + kMaxRed];
+  bool done; const long long it = sh_current(a, done);
+  if (done) {          // keep the final state alive in both slots
+    if (blockIdx.x == 0 && threadIdx.x == 0) a.st[(it + 1) & 1] = a.st[it & 1];
+    return;
+  }
+  const DProblem& P = a.P;
+  const DOpts& O = a.O;
+  const int b = blockIdx.x, G = gridDim.x;
+  const ShState st = sh_state(a, it);
+  ShState nx = st;
+  int64_t j0, j1;
+  cta_slice(P.n, b, G, j0, j1);
+  double gamma = st.gamma, sigma = st.sigma, s0 = st.s0, s1 = st.s1;
+  bool stop = false;
+  if (it > 0) {
+    double t4[4], tg[1] = {0.0};
+    grid_totals<4>(a.W.red, G, SLOT_PR, t4, s_scr);
+    if (O.want_objective) grid_totals<1>(a.W.red, G, gval_slot(it), tg, s_scr);
+    rule_step(O, t4[1], t4[2], t4[3], gamma, sigma, s0, s1);
+    const double norm_res = sqrt(norm_sq_jl(t4[0]));
+    nx.norm_res = norm_res;
+    if (!(gamma == gamma) || !(norm_res == norm_res) || isinf(gamma)) nx.flags |= ADAPROX_FLAG_NONFINITE;
+    if (b == 0 && threadIdx.x == 0 && a.W.rec != nullptr && it <= O.max_records) {
+      adaprox_record rc;
+      rc.it = it; rc.gamma = gamma; rc.sigma = sigma; rc.norm_res = norm_res;
+      rc.f_x = f_value(P, a.gbuf[P.n], a.gbuf[P.n + 1], 0.0);
+      rc.g_x = O.want_objective ? prox_value_finish(P.g.kind, P.g.lambda, tg[0]) : NAN;
+      rc.h_Ax = O.want_objective ? 0.0 : NAN;
+      rc.f_evals = st.n_eval; rc.grad_f_evals = st.n_grad; rc.prox_g_evals = st.n_proxg; rc.prox_h_evals = 0;
+      rc.A_evals = 0; rc.At_evals = 0;
+      a.W.rec[it - 1] = rc;
+    }
+    if (it <= O.max_records) nx.n_rec = it;
+    if (norm_res <= O.tol) { stop = true; nx.flags |= ADAPROX_FLAG_CONVERGED; }
+  }
+  nx.gamma = gamma; nx.sigma = sigma; nx.s0 = s0; nx.s1 = s1;
+  if (!stop) {
+    const double* x = a.W.xb[it % 3];
+    const double* grad = a.W.gb[it & 1];
+    double* xn = a.W.xb[(it + 1) % 3];
+    double acc[1] = {0.0};
+    for (int64_t j = j0 + threadIdx.x; j < j1; j += kThreads) {
+      const double vj = x[j] - gamma * grad[j];
+      a.W.v[j] = vj;
+      const double xj = prox_elem(P.g, vj, gamma, j, 0.0);
+      xn[j] = xj;
+      if (O.want_objective) acc[0] += prox_value_elem(P.g, xj, j);
+    }
+    block_reduce_store<1>(acc, a.W.red, G, gval_slot(it + 1), s_scr);
+    nx.n_proxg = st.n_proxg + 1;
+    if (it >= O.maxit) { nx.done = 1; nx.it = it; }           // maxit reached: x is the last prox, xb[(it + 1) % 3]
+    else { nx.n_eval = st.n_eval + 1; nx.n_grad = st.n_grad + 1; }
+  } else {
+    nx.done = 1; nx.it = it;                                  // converged: x is xb[it % 3]
+  }
+  if (b == 0 && threadIdx.x == 0) a.st[(it + 1) & 1] = nx;
+}
+
+int solve_sharded(adaprox_ctx* h, const adaprox_problem* p, const adaprox_options* o, const DProblem& P, const DOpts& Oin,
+                  HostMatrix* fm, HostMatrix* am, const double* x0, const double* y0, double* x_out, double* y_out,
+                  adaprox_record* records, adaprox_result* res) {
+  (void)p; (void)y0; (void)y_out; (void)am;
+  if (!h->comm) return fail(h, ADAPROX_ERR_COMM, "matrix is a row shard but no communicator is attached (adaprox_comm_init)");
+  if (o->solver != ADAPROX_S_ADAPTIVE_PROXGRAD)
+    return fail(h, ADAPROX_ERR_UNSUPPORTED, "row-sharded solves support adaptive_proxgrad / fixed_proxgrad only");
+  if (P.f_kind != ADAPROX_F_LEAST_SQUARES && P.f_kind != ADAPROX_F_LOGISTIC)
+    return fail(h, ADAPROX_ERR_UNSUPPORTED, "row-sharded solves support least-squares and logistic smooth terms only");
+  if (!fm || fm->d.kind == MAT_NONE) return fail(h, ADAPROX_ERR_INVALID, "sharded solve without a matrix");
+  DOpts O = Oin;
+  const int64_t n = P.n, mf = P.F.m;
+  const int64_t nrec = std::min<int64_t>(O.max_records, O.maxit);
+  O.max_records = nrec;
+  const int G = h->grid;
+  size_t need = 7 * ws_size_doubles(n) + ws_size_doubles(n + 2) + ws_size_doubles(mf) + ws_size_doubles((int64_t)kMaxRed * G) +
+                ws_size_doubles((nrec * (int64_t)sizeof(adaprox_record) + 7) / 8) + ws_size_doubles(2 * (sizeof(ShState) + 7) / 8);
+  int rc;
+  if ((rc = ws_reset(h, need))) return rc;
+  ShArgs a{};
+  a.P = P; a.O = O;
+  DWork& W = a.W;
+  for (int k = 0; k < 3; ++k) W.xb[k] = ws_doubles(h, n);
+  for (int k = 0; k < 2; ++k) W.gb[k] = ws_doubles(h, n);
+  W.v = ws_doubles(h, n);
+  W.xout = ws_doubles(h, n);
+  a.gbuf = ws_doubles(h, n + 2);
+  W.r = ws_doubles(h, mf);
+  W.red = ws_doubles(h, (int64_t)kMaxRed * G);
+  W.rec = nrec > 0 ? reinterpret_cast<adaprox_record*>(ws_doubles(h, (nrec * (int64_t)sizeof(adaprox_record) + 7) / 8)) : nullptr;
+  a.st = reinterpret_cast<ShState*>(ws_doubles(h, 2 * (sizeof(ShState) + 7) / 8));
+
+  ShState init[2];
+  std::memset(init, 0, sizeof(init));
+  rule_init(O, init[0].gamma, init[0].sigma, init[0].s0, init[0].s1);
+  init[0].it = 0; init[0].n_eval = 1; init[0].n_grad = 1; init[0].norm_res = INFINITY;
+  init[1] = init[0];
+  AP_CUDA(h, cudaMemcpyAsync(a.st, init, sizeof(init), cudaMemcpyHostToDevice, h->stream));
+  AP_CUDA(h, cudaMemcpyAsync(W.xb[0], x0, (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
+  AP_CUDA(h, cudaMemsetAsync(W.red, 0, (size_t)kMaxRed * G * 8, h->stream));
+  AP_CUDA(h, cudaMemsetAsync(a.gbuf, 0, (size_t)(n + 2) * 8, h->stream));
+  const int64_t launches0 = h->launches;
+  AP_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+
+  auto one_iteration = [&](int64_t it) -> int {
+    a.it = it;
+    k_sh_A<<<G, kThreads, 0, h->stream>>>(a);
+    k_sh_B<<<G, kThreads, 0, h->stream>>>(a);
+    k_sh_C<<<G, kThreads, 0, h->stream>>>(a);
+    k_sh_D<<<G, kThreads, 0, h->stream>>>(a);
+    int r = comm_allreduce_sum(h, a.gbuf, n + 2);
+    if (r) return r;
+    k_sh_E<<<G, kThreads, 0, h->stream>>>(a);
+    k_sh_F<<<G, kThreads, 0, h->stream>>>(a);
+    h->launches += 6;
+    return ADAPROX_OK;
+  };
+
+  ShState live[2];
+  int64_t enqueued = 0;               // gradient evaluations enqueued (prologue + iterations)
+  const int64_t total = O.maxit + 1;
+  bool finished = false;
+  while (!finished) {
+    const int64_t batch = std::min<int64_t>(32, total - enqueued);
+    for (int64_t k = 0; k < batch; ++k) if ((rc = one_iteration(enqueued + k))) return rc;
+    enqueued += batch;
+    AP_CUDA(h, cudaMemcpyAsync(live, a.st, sizeof(live), cudaMemcpyDeviceToHost, h->stream));
+    AP_CUDA(h, cudaStreamSynchronize(h->stream));
+    AP_CUDA(h, cudaGetLastError());
+    if (live[enqueued & 1].done || enqueued >= total) finished = true;
+  }
+  AP_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+  const ShState& cur = live[enqueued & 1];          // written by the last k_sh_F
+  const bool converged = (cur.flags & ADAPROX_FLAG_CONVERGED) != 0;
+  // converged at iteration k: x is xb[k % 3]; maxit: the last prox, xb[(maxit + 1) % 3]
+  const int64_t it_final = converged ? cur.it : O.maxit;
+  const double* xres = converged ? W.xb[it_final % 3] : W.xb[(O.maxit + 1) % 3];
+  AP_CUDA(h, cudaMemcpyAsync(x_out, xres, (size_t)n * 8, cudaMemcpyDeviceToHost, h->stream));
+  AP_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (records && cur.n_rec > 0)
+    AP_CUDA(h, cudaMemcpy(records, W.rec, (size_t)cur.n_rec * sizeof(adaprox_record), cudaMemcpyDeviceToHost));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+  std::memset(res, 0, sizeof(*res));
+  res->iters = it_final; res->flags = cur.flags;
+  res->f_evals = cur.n_eval; res->grad_f_evals = cur.n_grad; res->prox_g_evals = cur.n_proxg;
+  res->n_records = cur.n_rec;
+  res->final_gamma = cur.gamma; res->final_sigma = cur.sigma; res->final_norm_res = cur.norm_res;
+  res->solve_ms = ms; res->kernel_launches = h->launches - launches0;
+  return ADAPROX_OK;
+}
+
+}  // namespace adaprox
+
+extern "C" int adaprox_comm_unique_id(void* id128) {
+  if (!id128) return ADAPROX_ERR_INVALID;
+  adaprox::NcclApi* api = adaprox::nccl_api();
+  if (!api->lib) return ADAPROX_ERR_COMM;
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  ncclUniqueId id;
+  if (api->GetUniqueId(&id) != ncclSuccess) return ADAPROX_ERR_COMM;
+  std::memcpy(id128, &id, 128);
+  return ADAPROX_OK;
+}
+
+extern "C" int adaprox_comm_init(adaprox_handle h, int nranks, int rank, const void* id128) {
+  if (!h || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return adaprox::fail(h, ADAPROX_ERR_INVALID, "comm_init: bad arguments");
+  adaprox::NcclApi* api = adaprox::nccl_api();
+  if (!api->lib) return adaprox::fail(h, ADAPROX_ERR_COMM, api->err);
+  AP_CUDA(h, cudaSetDevice(h->device));
+  adaprox::comm_destroy(h);
+  ncclUniqueId id;
+  std::memcpy(&id, id128, 128);
+  adaprox::Comm* c = new adaprox::Comm();
+  c->nranks = nranks; c->rank = rank;
+  ncclResult_t r = api->CommInitRank(&c->comm, nranks, id, rank);
+  if (r != ncclSuccess) { delete c; return adaprox::fail(h, ADAPROX_ERR_COMM, std::string("ncclCommInitRank: ") + api->GetErrorString(r)); }
+  h->comm = c;
+  return ADAPROX_OK;
+}
+
+extern "C" int adaprox_comm_info(adaprox_handle h, int* nranks, int* rank) {
+  if (!h) return ADAPROX_ERR_INVALID;
+  if (nranks) *nranks = h->comm ? h->comm->nranks : 1;
+  if (rank) *rank = h->comm ? h->comm->rank : 0;
+  return ADAPROX_OK;
+}

@@ -1,0 +1,149 @@
+// common.cuh -- device-side descriptors and helpers shared by every kernel.
+//
+// Layout in HBM:
+//   dense matrices are ROW-major with the leading dimension padded to a
+//   multiple of 16 doubles (128 B) and zero-filled padding, so every row
+//   starts on a 128-byte line and 16-byte vector loads never straddle a row;
+//   CSR matrices keep both CSR(X) and CSR(X') so X'v is a gather, not a
+//   scatter (no fp64 atomics anywhere: all reductions are fixed-order).
+#pragma once
+#include <cuda_runtime.h>
+#include <cooperative_groups.h>
+#include <stdint.h>
+#include <math.h>
+
+namespace cg = cooperative_groups;
+
+namespace adaprox {
+
+constexpr int kThreads = 256;           // threads per CTA of every solver kernel
+constexpr int kWarps = kThreads / 32;
+constexpr int kV = 8;                    // matrix elements per thread per row of a chunk
+constexpr int kChunk = kThreads * kV;    // 2048 columns per column chunk (16 KB per row)
+constexpr int kRowBatch = 4;             // rows in flight per thread (16 x LDG.128)
+constexpr int kMaxRed = 16;              // reduction slots
+
+enum { MAT_NONE = 0, MAT_DENSE = 1, MAT_CSR = 2 };
+
+struct DMat {
+  int kind;
+  int64_t m, n, ld;          // local rows, columns, leading dimension (dense)
+  const double* a;           // dense row-major [m][ld]
+  // CSR(X) and CSR(X')
+  const int64_t* rowptr; const int* colind; const double* vals;
+  const int64_t* t_rowptr; const int* t_colind; const double* t_vals;
+  int64_t nnz;
+  // dense work partition: units = (column chunk c, row block rb), chunk-major
+  int nchunks;               // ceil(n / kChunk)
+  int rb;                    // rows per unit (multiple of kRowBatch)
+  int64_t nrb;               // ceil(m / rb)
+  // partial-result buffers owned by the matrix
+  double* zpart;             // [nchunks][m]    A*x partials
+  double* gpart;             // [grid][npad]    A'r partials, one row per CTA
+  int64_t npad;              // n rounded up to kChunk
+};
+
+struct DProx {
+  int kind, conjugate;
+  double lambda, lo, hi;
+  const double* lo_vec; const double* hi_vec; const double* shift;
+};
+
+// ---------------------------------------------------------------------------
+// Julia scalar semantics
+// ---------------------------------------------------------------------------
+__host__ __device__ inline double jl_min(double a, double b) {
+  // Julia's min propagates NaN; C fmin does not (src/AdaProx.jl:228,263,303,517)
+  if (a != a || b != b) return NAN;
+  return b < a ? b : a;
+}
+__host__ __device__ inline double jl_max(double a, double b) {
+  if (a != a || b != b) return NAN;
+  return b > a ? b : a;
+}
+__host__ __device__ inline double nan_to_zero(double v) { return v != v ? 0.0 : v; }   // src/AdaProx.jl:24
+__host__ __device__ inline double sq(double v) { return v * v; }
+// norm(v)^2 as Julia evaluates it: a square root followed by a square.
+__host__ __device__ inline double norm_sq_jl(double sumsq) { double nrm = sqrt(sumsq); return nrm * nrm; }
+
+// ---------------------------------------------------------------------------
+// loads
+// ---------------------------------------------------------------------------
+// Streaming 128-bit load of matrix data that is read-only for the whole kernel:
+// non-coherent path, no L1 allocation (each element is used exactly once).
+__device__ __forceinline__ double2 ld_stream(const double* p) {
+  double2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+  return r;
+}
+// Data produced by other CTAs earlier in the same (persistent) kernel: read
+// through L2 (ld.global.cg) so a stale L1 line can never be observed.
+__device__ __forceinline__ double ldcg(const double* p) { return __ldcg(p); }
+__device__ __forceinline__ double2 ldcg2(const double* p) { return __ldcg(reinterpret_cast<const double2*>(p)); }
+
+// ---------------------------------------------------------------------------
+// deterministic reductions
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;     // xor butterfly: every lane holds the same bits
+}
+
+// Block-reduce K values and store them as this CTA's partials:
+//   red[(slot0 + k) * G + blockIdx.x]
+template <int K>
+__device__ __forceinline__ void block_reduce_store(double (&v)[K], double* red, int G, int slot0, double* s_scratch) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    double s = warp_sum(v[k]);
+    if (lane == 0) s_scratch[warp * K + k] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < K) {
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) s += s_scratch[w * K + threadIdx.x];
+    red[(int64_t)(slot0 + threadIdx.x) * G + blockIdx.x] = s;
+  }
+  __syncthreads();
+}
+
+// Sum the per-CTA partials of K slots in a fixed order; every thread of every
+// CTA obtains bit-identical totals.  Must follow a grid-wide sync (or a kernel
+// boundary) after the block_reduce_store that produced the partials.
+template <int K>
+__device__ __forceinline__ void grid_totals(const double* red, int G, int slot0, double (&out)[K], double* s_scratch) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int k = warp; k < K; k += kWarps) {
+    const double* p = red + (int64_t)(slot0 + k) * G;
+    double s = 0.0;
+    for (int b = lane; b < G; b += 32) s += ldcg(p + b);
+    s = warp_sum(s);
+    if (lane == 0) s_scratch[k] = s;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < K; ++k) out[k] = s_scratch[k];
+  __syncthreads();
+}
+
+// contiguous slice [lo, hi) of `len` items owned by CTA b of G
+__device__ __forceinline__ void cta_slice(int64_t len, int b, int G, int64_t& lo, int64_t& hi) {
+  lo = (len * b) / G;
+  hi = (len * (b + 1)) / G;
+}
+
+// First unit of CTA b when U units are dealt out contiguously to G CTAs.
+__host__ __device__ inline int64_t unit_begin(int64_t U, int b, int G) { return (U * (int64_t)b) / G; }
+// The CTA that owns unit u.
+__host__ __device__ inline int unit_owner(int64_t U, int64_t u, int G) {
+  int b = (int)(((u + 1) * (int64_t)G - 1) / U);
+  if (b >= G) b = G - 1;
+  while (b + 1 < G && unit_begin(U, b + 1, G) <= u) ++b;
+  while (b > 0 && unit_begin(U, b, G) > u) --b;
+  return b;
+}
+
+}  // namespace adaprox

@@ -1,0 +1,245 @@
+// gemv.cuh -- the two matrix passes of an iteration as grid-wide device phases.
+//
+//   gemv_n_phase : zpart[c][i]  = sum_{j in chunk c} A[i][j] x[j]       (A*x,  lasso/runme.jl:22)
+//   gemv_t_phase : gpart[b][j]  = sum_{i in CTA b's rows} A[i][j] r[i]  (A'*r, lasso/runme.jl:23)
+//
+// Both stream the row-major matrix exactly once with 128-bit non-allocating
+// loads, 16 of them in flight per thread.  Work units are (column chunk of
+// 2048, block of `rb` rows), dealt out contiguously (chunk-major) to the CTAs
+// of the persistent grid, so every CTA streams one long contiguous-by-rows
+// slab and x / the accumulators stay on chip for the whole slab:
+//   A*x : the x chunk lives in shared memory (16 KB), one warp owns one row
+//         of the unit at a time -> one shuffle reduction per row, no barrier.
+//   A'r : each thread owns 8 columns of the chunk in registers for the whole
+//         slab -> no reduction at all; r[i] is a warp-uniform load.
+// Partials are combined in a fixed order by the finalize helpers below
+// (no atomics: results are reproducible run to run).
+#pragma once
+#include "common.cuh"
+
+namespace adaprox {
+
+// ---------------------------------------------------------------------------
+// dense A*x partials
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void load_x_chunk(const DMat& M, const double* x, int c, double* s_x) {
+  const int64_t col0 = (int64_t)c * kChunk;
+  for (int k = threadIdx.x; k < kChunk; k += kThreads) {
+    const int64_t j = col0 + k;
+    s_x[k] = (j < M.n) ? ldcg(x + j) : 0.0;
+  }
+}
+
+__device__ __forceinline__ double row_chunk_dot(const double* __restrict__ arow, const double* s_x, int nvec, int lane) {
+  // arow: start of this row's chunk; nvec: number of valid double2 in the chunk
+  double acc0 = 0.0, acc1 = 0.0;
+  constexpr int kU = 16;
+  int k = 0;
+  for (; k + kU * 32 <= nvec; k += kU * 32) {
+    double2 a[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) a[u] = ld_stream(arow + 2 * (k + u * 32 + lane));
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const double2 xv = *reinterpret_cast<const double2*>(s_x + 2 * (k + u * 32 + lane));
+      acc0 = fma(a[u].x, xv.x, acc0);
+      acc1 = fma(a[u].y, xv.y, acc1);
+    }
+  }
+  if (k < nvec) {   // ragged tail of the last chunk
+    double2 a[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const int idx = k + u * 32 + lane;
+      a[u] = (idx < nvec) ? ld_stream(arow + 2 * idx) : make_double2(0.0, 0.0);
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const int idx = k + u * 32 + lane;
+      if (idx < nvec) {
+        const double2 xv = *reinterpret_cast<const double2*>(s_x + 2 * idx);
+        acc0 = fma(a[u].x, xv.x, acc0);
+        acc1 = fma(a[u].y, xv.y, acc1);
+      }
+    }
+  }
+  return warp_sum(acc0 + acc1);
+}
+
+__device__ __forceinline__ void gemv_n_dense(const DMat& M, const double* x, double* s_x, int b, int G) {
+  const int64_t U = (int64_t)M.nchunks * M.nrb;
+  const int64_t u0 = unit_begin(U, b, G), u1 = unit_begin(U, b + 1, G);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int cur_c = -1;
+  for (int64_t u = u0; u < u1; ++u) {
+    const int c = (int)(u / M.nrb);
+    const int64_t rbi = u - (int64_t)c * M.nrb;
+    if (c != cur_c) {
+      __syncthreads();
+      load_x_chunk(M, x, c, s_x);
+      __syncthreads();
+      cur_c = c;
+    }
+    const int64_t col0 = (int64_t)c * kChunk;
+    const int64_t width = (M.ld - col0 < kChunk) ? (M.ld - col0) : kChunk;   // ld is padded -> even
+    const int nvec = (int)(width >> 1);
+    const int64_t r0 = rbi * M.rb;
+    const int64_t r1 = (r0 + M.rb < M.m) ? r0 + M.rb : M.m;
+    for (int64_t row = r0 + warp; row < r1; row += kWarps) {
+      const double s = row_chunk_dot(M.a + row * M.ld + col0, s_x, nvec, lane);
+      if (lane == 0) M.zpart[(int64_t)c * M.m + row] = s;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// dense A'r partials
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void gemv_t_dense(const DMat& M, const double* r, int b, int G) {
+  const int64_t U = (int64_t)M.nchunks * M.nrb;
+  const int64_t u0 = unit_begin(U, b, G), u1 = unit_begin(U, b + 1, G);
+  constexpr int kH = kV / 2;    // double2 per thread per row
+  double2 acc[kH];
+  int cur_c = -1;
+  double* gout = M.gpart + (int64_t)b * M.npad;
+
+  auto flush = [&](int c) {
+    const int64_t col0 = (int64_t)c * kChunk;
+#pragma unroll
+    for (int k = 0; k < kH; ++k) {
+      const int64_t col = col0 + 2 * (k * kThreads + threadIdx.x);
+      if (col < M.ld) *reinterpret_cast<double2*>(gout + col) = acc[k];
+    }
+  };
+
+  for (int64_t u = u0; u < u1; ++u) {
+    const int c = (int)(u / M.nrb);
+    const int64_t rbi = u - (int64_t)c * M.nrb;
+    if (c != cur_c) {
+      if (cur_c >= 0) flush(cur_c);
+#pragma unroll
+      for (int k = 0; k < kH; ++k) acc[k] = make_double2(0.0, 0.0);
+      cur_c = c;
+    }
+    const int64_t col0 = (int64_t)c * kChunk;
+    const int64_t r0 = rbi * M.rb;
+    const int64_t r1 = (r0 + M.rb < M.m) ? r0 + M.rb : M.m;
+    const double* base = M.a + col0 + 2 * threadIdx.x;
+    bool ok[kH];
+#pragma unroll
+    for (int k = 0; k < kH; ++k) ok[k] = (col0 + 2 * (k * kThreads + threadIdx.x)) < M.ld;
+    int64_t row = r0;
+    for (; row + kRowBatch <= r1; row += kRowBatch) {
+      double2 a[kRowBatch][kH];
+      double rv[kRowBatch];
+#pragma unroll
+      for (int q = 0; q < kRowBatch; ++q) {
+        const double* p = base + (row + q) * M.ld;
+#pragma unroll
+        for (int k = 0; k < kH; ++k) a[q][k] = ok[k] ? ld_stream(p + 2 * k * kThreads) : make_double2(0.0, 0.0);
+      }
+#pragma unroll
+      for (int q = 0; q < kRowBatch; ++q) rv[q] = ldcg(r + row + q);
+#pragma unroll
+      for (int q = 0; q < kRowBatch; ++q)
+#pragma unroll
+        for (int k = 0; k < kH; ++k) {
+          acc[k].x = fma(a[q][k].x, rv[q], acc[k].x);
+          acc[k].y = fma(a[q][k].y, rv[q], acc[k].y);
+        }
+    }
+    for (; row < r1; ++row) {       // row remainder
+      const double* p = base + row * M.ld;
+      const double rv = ldcg(r + row);
+      double2 a[kH];
+#pragma unroll
+      for (int k = 0; k < kH; ++k) a[k] = ok[k] ? ld_stream(p + 2 * k * kThreads) : make_double2(0.0, 0.0);
+#pragma unroll
+      for (int k = 0; k < kH; ++k) {
+        acc[k].x = fma(a[k].x, rv, acc[k].x);
+        acc[k].y = fma(a[k].y, rv, acc[k].y);
+      }
+    }
+  }
+  if (cur_c >= 0) flush(cur_c);
+}
+
+// ---------------------------------------------------------------------------
+// CSR: one warp per row, lanes stride over the row's nonzeros.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void spmv_rows(int64_t nrows, const int64_t* __restrict__ rowptr, const int* __restrict__ colind,
+                                          const double* __restrict__ vals, const double* x, double* out, int b, int G) {
+  const int lane = threadIdx.x & 31;
+  const int64_t gw = (int64_t)b * kWarps + (threadIdx.x >> 5);
+  const int64_t nw = (int64_t)G * kWarps;
+  for (int64_t row = gw; row < nrows; row += nw) {
+    const int64_t k0 = rowptr[row], k1 = rowptr[row + 1];
+    double s = 0.0;
+    for (int64_t k = k0 + lane; k < k1; k += 32) s = fma(vals[k], ldcg(x + colind[k]), s);
+    s = warp_sum(s);
+    if (lane == 0) out[row] = s;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// phases
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void gemv_n_phase(const DMat& M, const double* x, double* s_x, int b, int G) {
+  if (M.kind == MAT_DENSE) gemv_n_dense(M, x, s_x, b, G);
+  else if (M.kind == MAT_CSR) spmv_rows(M.m, M.rowptr, M.colind, M.vals, x, M.zpart, b, G);
+}
+__device__ __forceinline__ void gemv_t_phase(const DMat& M, const double* r, int b, int G) {
+  if (M.kind == MAT_DENSE) gemv_t_dense(M, r, b, G);
+  else if (M.kind == MAT_CSR) spmv_rows(M.n, M.t_rowptr, M.t_colind, M.t_vals, r, M.gpart, b, G);
+}
+
+// (A*x)_i from the partials (fixed chunk order)
+__device__ __forceinline__ double zsum(const DMat& M, int64_t i) {
+  if (M.kind == MAT_CSR) return ldcg(M.zpart + i);
+  double s = 0.0;
+  for (int c = 0; c < M.nchunks; ++c) s += ldcg(M.zpart + (int64_t)c * M.m + i);
+  return s;
+}
+
+// (A'r)_j for j in [j0, j1) from the per-CTA partials (fixed CTA order), written
+// to out[j].  Cooperative over the calling CTA; ends with a __syncthreads so the
+// caller may read out[j0..j1) back.
+__device__ __forceinline__ void gsum_slice(const DMat& M, int64_t j0, int64_t j1, double* out, int G) {
+  if (M.kind == MAT_CSR) {
+    for (int64_t j = j0 + threadIdx.x; j < j1; j += kThreads) out[j] = ldcg(M.gpart + j);
+    __syncthreads();
+    return;
+  }
+  const int64_t U = (int64_t)M.nchunks * M.nrb;
+  const bool warp_per_col = (G > 16 * M.nchunks);
+  if (!warp_per_col) {
+    int cur_c = -1, blo = 0, bhi = -1;
+    for (int64_t j = j0 + threadIdx.x; j < j1; j += kThreads) {
+      const int c = (int)(j / kChunk);
+      if (c != cur_c) {
+        blo = unit_owner(U, (int64_t)c * M.nrb, G);
+        bhi = unit_owner(U, (int64_t)(c + 1) * M.nrb - 1, G);
+        cur_c = c;
+      }
+      double s = 0.0;
+      for (int bb = blo; bb <= bhi; ++bb)
+        if (unit_begin(U, bb + 1, G) > unit_begin(U, bb, G)) s += ldcg(M.gpart + (int64_t)bb * M.npad + j);
+      out[j] = s;
+    }
+  } else {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int64_t j = j0 + warp; j < j1; j += kWarps) {
+      const int c = (int)(j / kChunk);
+      const int blo = unit_owner(U, (int64_t)c * M.nrb, G);
+      const int bhi = unit_owner(U, (int64_t)(c + 1) * M.nrb - 1, G);
+      double s = 0.0;
+      for (int bb = blo + lane; bb <= bhi; bb += 32)
+        if (unit_begin(U, bb + 1, G) > unit_begin(U, bb, G)) s += ldcg(M.gpart + (int64_t)bb * M.npad + j);
+      s = warp_sum(s);
+      if (lane == 0) out[j] = s;
+    }
+  }
+  __syncthreads();
+}
+
+}  // namespace adaprox

@@ -1,0 +1,316 @@
+// solver_pd.cuh -- the generic adaptive primal-dual loop as ONE persistent
+// cooperative kernel (src/AdaProx.jl:312-364), plus its linesearch variant
+// AdaPDM+ (src/AdaProx.jl:463-550).
+//
+// AdaPGM (:418-421), fixed-step PGM (:457-459) and Condat-Vu (:367-416) are
+// this kernel with A = none / a fixed rule, exactly as in the reference.
+// One grid of (SMs x 2) CTAs stays resident for the whole solve; phases are
+// separated by grid syncs; every scalar of the stepsize rule is recomputed
+// redundantly and bit-identically by every CTA from fixed-order reductions, so
+// there is no host round trip and no single-thread serial section.
+//
+// Per iteration (reference line numbers on the right):
+//   P1  F*x partials, A*x partials                               :335-336
+//   P2  rows: residual r, f(x) sums, A_x                         :336
+//   P3  F'*r partials                                            :336 (pullback)
+//   P4  slice: grad, primal_res, |dgrad|^2 <dgrad,dx> |dx|^2     :338, :260-261
+//   P5  stepsize (all threads); rows: w, y+ = prox_{sigma h*}    :341-347
+//   P6  norm_res, record, convergence; A'*y+ partials            :348-358
+//   P7  slice: A'y, v, x+ = prox_{gamma g}(v)                    :359-361
+#pragma once
+#include "phases.cuh"
+
+namespace adaprox {
+
+// g(x) partials are produced in P7 and consumed in P5 of the next iteration with
+// no grid sync between P5 and P7 of the same iteration (AdaPGM): alternate slots.
+__device__ __forceinline__ int gval_slot(int64_t it) { return (it & 1) ? SLOT_GVAL : SLOT_AUX0; }
+
+// dual step on this CTA's rows.  Returns via reductions: |dual_res|^2, h(A_x) sum.
+// For the NormL2 prox the caller has already reduced |w/sigma + shift|^2 (l2sum).
+__device__ __forceinline__ void dual_rows(const DProblem& P, const DWork& W, const double* w, const double* Ax,
+                                          double* ynew, double sigma, double l2sum, bool want_h, const double* yold,
+                                          double* s_scr, int b, int G, bool linesearch) {
+  double acc[3] = {0.0, 0.0, 0.0};
+  const double l2scale = (P.h.kind == ADAPROX_P_NORM_L2) ? prox_l2_scale(P.h.lambda, 1.0 / sigma, l2sum) : 0.0;
+  const int64_t tid = (int64_t)b * kThreads + threadIdx.x, nt = (int64_t)G * kThreads;
+  for (int64_t i = tid; i < P.md; i += nt) {
+    const double wi = ldcg(w + i), axi = ldcg(Ax + i);
+    const double yi = prox_conj_elem(P.h, wi, sigma, i, l2scale);                // :345
+    ynew[i] = yi;
+    const double dr = (wi - yi) / sigma - axi;                                   // :347
+    acc[0] = fma(dr, dr, acc[0]);
+    if (want_h) acc[1] += prox_value_elem(P.h, axi, i);
+    if (linesearch) { const double dy = yi - ldcg(yold + i); acc[2] = fma(dy, dy, acc[2]); }
+  }
+  double a2[2] = {acc[0], acc[1]};
+  block_reduce_store<2>(a2, W.red, G, SLOT_DR, s_scr);
+  if (linesearch) { double a1[1] = {acc[2]}; block_reduce_store<1>(a1, W.red, G, SLOT_DY, s_scr); }
+}
+
+template <bool LINESEARCH>
+__global__ void __launch_bounds__(kThreads, 2) k_primal_dual(DProblem P, DOpts O, DWork W) {
+  cg::grid_group grid = cg::this_grid();
+  const int b = blockIdx.x, G = gridDim.x;
+  __shared__ __align__(16) double s_x[kChunk];
+  __shared__ double s_scr[kWarps * 8 + kMaxRed];
+
+  const bool hasA = (P.A.kind != MAT_NONE);
+  const bool h_l2 = hasA && (P.h.kind == ADAPROX_P_NORM_L2);
+  const bool want_obj = O.want_objective != 0;
+  const int64_t tid = (int64_t)b * kThreads + threadIdx.x, nt = (int64_t)G * kThreads;
+  int64_t j0, j1;
+  cta_slice(P.n, b, G, j0, j1);
+
+  // ---- rule initialisation (:324 / :484-491) ------------------------------
+  double gamma, sigma, s0, s1;
+  double eta = O.eta, gamma_prev_ls = 0.0;
+  if (LINESEARCH) {
+    gamma = O.gamma; sigma = O.t * O.t * gamma; s0 = s1 = 0.0;
+    gamma_prev_ls = gamma;                                                       // :491
+  } else {
+    rule_init(O, gamma, sigma, s0, s1);
+  }
+
+  int xc = 0, gc = 0, axc = 0, yc = 0, atc = 0;       // ring positions
+  double* x = W.xb[0];                                // holds x0
+  double* y = W.yb[0];                                // holds y0
+  int64_t n_eval = 0, n_grad = 0, n_proxg = 0, n_proxh = 0, n_mul = 0, n_amul = 0, n_rec = 0;
+  unsigned flags = 0;
+
+  // ---- prologue (:327-332) --------------------------------------------------
+  f_phase_A(P, W, x, s_x, s_scr, b, G);
+  if (hasA) gemv_n_phase(P.A, x, s_x, b, G);
+  grid.sync();
+  f_phase_B(P, W, x, s_scr, b, G);
+  if (hasA) for (int64_t i = tid; i < P.md; i += nt) W.Axb[axc][i] = zsum(P.A, i);
+  grid.sync();
+  f_phase_C(P, W, b, G);
+  if (hasA) gemv_t_phase(P.A, y, b, G);
+  grid.sync();
+  {
+    double tot[2];
+    grid_totals<2>(W.red, G, SLOT_F0, tot, s_scr);
+    grad_slice(P, W, j0, j1, W.gb[gc], tot[1], G);
+    if (hasA) gsum_slice(P.A, j0, j1, W.Aty[atc], G);
+    double acc[1] = {0.0};
+    double* xn = W.xb[1];
+    for (int64_t j = j0 + threadIdx.x; j < j1; j += kThreads) {
+      const double aty = hasA ? W.Aty[atc][j] : 0.0;
+      const double vj = x[j] - gamma * (W.gb[gc][j] + aty);                      // :330
+      W.v[j] = vj;
+      const double xj = prox_elem(P.g, vj, gamma, j, 0.0);                       // :332
+      xn[j] = xj;
+      if (want_obj) acc[0] += prox_value_elem(P.g, xj, j);
+    }
+    block_reduce_store<1>(acc, W.red, G, gval_slot(1), s_scr);
+  }
+  n_eval = 1; n_grad = 1; n_proxg = 1; n_mul = 1; n_amul = 1;
+  grid.sync();
+  double* x_prev = W.xb[0];
+  x = W.xb[1]; xc = 1;
+  double* grad_prev = W.gb[0];
+  double norm_res = INFINITY;
+  int64_t it_done = O.maxit;
+  bool converged = false;
+
+  for (int64_t it = 1; it <= O.maxit; ++it) {
+    // ---- P1 ---------------------------------------------------------------
+    f_phase_A(P, W, x, s_x, s_scr, b, G);                                        // :336
+    if (hasA) gemv_n_phase(P.A, x, s_x, b, G);                                   // :335
+    grid.sync();
+    // ---- P2 ---------------------------------------------------------------
+    f_phase_B(P, W, x, s_scr, b, G);
+    double* Ax_prev = W.Axb[axc];
+    double* Ax = W.Axb[axc ^ 1];
+    if (hasA) for (int64_t i = tid; i < P.md; i += nt) Ax[i] = zsum(P.A, i);
+    n_eval++; n_mul++;
+    grid.sync();
+    // ---- P3 ---------------------------------------------------------------
+    f_phase_C(P, W, b, G);
+    n_grad++;
+    grid.sync();
+    // ---- P4 ---------------------------------------------------------------
+    double ftot[2];
+    grid_totals<2>(W.red, G, SLOT_F0, ftot, s_scr);
+    double* grad = W.gb[gc ^ 1];
+    grad_slice(P, W, j0, j1, grad, ftot[1], G);
+    {
+      double acc[4] = {0.0, 0.0, 0.0, 0.0};
+      const double* aty = W.Aty[atc];
+      for (int64_t j = j0 + threadIdx.x; j < j1; j += kThreads) {
+        const double xj = x[j], gj = grad[j];
+        const double pr = (W.v[j] - xj) / gamma + gj + (hasA ? aty[j] : 0.0);    // :338
+        const double dg = gj - grad_prev[j], dx = xj - x_prev[j];
+        acc[0] = fma(pr, pr, acc[0]);
+        acc[1] = fma(dg, dg, acc[1]);
+        acc[2] = fma(dg, dx, acc[2]);
+        acc[3] = fma(dx, dx, acc[3]);
+      }
+      block_reduce_store<4>(acc, W.red, G, SLOT_PR, s_scr);
+    }
+    grid.sync();
+    // ---- P5: stepsize, dual step ---------------------------------------------
+    double t5[5];                                   // PR, GG, GX, DXX, GVAL
+    {
+      double t4[4], tg[1] = {0.0};
+      grid_totals<4>(W.red, G, SLOT_PR, t4, s_scr);
+      if (want_obj) grid_totals<1>(W.red, G, gval_slot(it), tg, s_scr);
+      t5[0] = t4[0]; t5[1] = t4[1]; t5[2] = t4[2]; t5[3] = t4[3]; t5[4] = tg[0];
+    }
+    double xx0[1] = {0.0};
+    if (P.f_kind == ADAPROX_F_CUBIC) grid_totals<1>(W.red, G, SLOT_XX0, xx0, s_scr);
+    const double f_x = f_value(P, ftot[0], ftot[1], xx0[0]);
+    const double g_x = want_obj ? prox_value_finish(P.g.kind, P.g.lambda, t5[4]) : NAN;
+    const double gamma_old = gamma;                                              // :340
+    double dr_sum = 0.0, h_sum = 0.0;
+    double* ynew = y;
+    double* w = W.w;
+
+    if (!LINESEARCH) {
+      rule_step(O, t5[1], t5[2], t5[3], gamma, sigma, s0, s1);                   // :341
+      const double rho = gamma / gamma_old;                                      // :342
+      if (hasA) {
+        ynew = W.yb[yc ^ 1];
+        double l2acc[1] = {0.0};
+        for (int64_t i = tid; i < P.md; i += nt) {
+          const double wi = y[i] + sigma * ((1.0 + rho) * Ax[i] - rho * Ax_prev[i]);   // :344
+          w[i] = wi;
+          if (h_l2) { const double z = prox_l2_arg(P.h, wi / sigma, i); l2acc[0] = fma(z, z, l2acc[0]); }
+        }
+        double l2tot[1] = {0.0};
+        if (h_l2) {
+          block_reduce_store<1>(l2acc, W.red, G, SLOT_L2, s_scr);
+          grid.sync();
+          grid_totals<1>(W.red, G, SLOT_L2, l2tot, s_scr);
+        }
+        // each thread re-reads only the w[i] it wrote itself (same stride) -> no sync needed
+        dual_rows(P, W, w, Ax, ynew, sigma, l2tot[0], want_obj, y, s_scr, b, G, false);
+        n_proxh++;
+        grid.sync();
+        double t2[2];
+        grid_totals<2>(W.red, G, SLOT_DR, t2, s_scr);
+        dr_sum = t2[0]; h_sum = t2[1];
+      }
+    } else {
+      // ---- AdaPDM+ linesearch (:507-533) ----------------------------------------
+      const double delta1 = 1.0 + O.delta;
+      const double C = nan_to_zero(norm_sq_jl(t5[1]) / t5[2]);                   // :507
+      const double L = nan_to_zero(t5[2] / norm_sq_jl(t5[3]));                   // :508
+      const double Delta = gamma * L * (gamma * C - 1.0);                        // :509
+      const double xi_bar = (O.t * O.t) * (gamma * gamma) * (eta * eta) * (delta1 * delta1);   // :510
+      const double m4xim1 = 1.0 - 4.0 * xi_bar;                                  // :511
+      eta = O.R * eta;                                                           // :513
+      ynew = W.yb[yc ^ 1];
+      double* aty_next = W.Aty[atc ^ 1];
+      double gamma_next = gamma;
+      for (int trial = 0;; ++trial) {
+        gamma_next = jl_min(jl_min(gamma * sqrt(1.0 + gamma / gamma_prev_ls), 1.0 / (2.0 * O.Theta * O.t * eta)),
+                            gamma * sqrt(m4xim1 / (2.0 * delta1 * (Delta + sqrt(Delta * Delta + m4xim1 * sq(O.t * eta * gamma))))));   // :517-521
+        const double rho = gamma_next / gamma;                                   // :522
+        sigma = (O.t * O.t) * gamma_next;                                        // :523
+        double l2acc[1] = {0.0};
+        for (int64_t i = tid; i < P.md; i += nt) {
+          const double wi = y[i] + sigma * ((1.0 + rho) * Ax[i] - rho * Ax_prev[i]);   // :524
+          w[i] = wi;
+          if (h_l2) { const double z = prox_l2_arg(P.h, wi / sigma, i); l2acc[0] = fma(z, z, l2acc[0]); }
+        }
+        double l2tot[1] = {0.0};
+        if (h_l2) {
+          block_reduce_store<1>(l2acc, W.red, G, SLOT_L2, s_scr);
+          grid.sync();
+          grid_totals<1>(W.red, G, SLOT_L2, l2tot, s_scr);
+        }
+        dual_rows(P, W, w, Ax, ynew, sigma, l2tot[0], want_obj, y, s_scr, b, G, true);   // :525
+        n_proxh++;
+        grid.sync();
+        gemv_t_phase(P.A, ynew, b, G);                                           // :526
+        n_amul++;
+        grid.sync();
+        gsum_slice(P.A, j0, j1, aty_next, G);
+        {
+          double acc[1] = {0.0};
+          const double* aty = W.Aty[atc];
+          for (int64_t j = j0 + threadIdx.x; j < j1; j += kThreads) {
+            const double d = aty_next[j] - aty[j];
+            acc[0] = fma(d, d, acc[0]);
+          }
+          block_reduce_store<1>(acc, W.red, G, SLOT_DATY, s_scr);
+        }
+        grid.sync();
+        double tl[2];                               // DY, DATY
+        grid_totals<2>(W.red, G, SLOT_DY, tl, s_scr);
+        const bool accept = eta >= sqrt(tl[1]) / sqrt(tl[0]);                    // :527
+        if (accept || trial >= 200) {
+          if (!accept) flags |= ADAPROX_FLAG_LS_CAP;
+          gamma_prev_ls = gamma; gamma = gamma_next;                             // :528
+          break;
+        }
+        eta *= O.r;                                                              // :532
+        grid.sync();          // the retry rewrites reduction slots other CTAs may still be reading
+      }
+      double t2[2];
+      grid_totals<2>(W.red, G, SLOT_DR, t2, s_scr);
+      dr_sum = t2[0]; h_sum = t2[1];
+      atc ^= 1;                                                                  // :529  At_y = At_y_next
+    }
+
+    // ---- P6: residual, record, convergence (:348-356) ----------------------------
+    norm_res = sqrt(norm_sq_jl(t5[0]) + (hasA ? norm_sq_jl(dr_sum) : 0.0));
+    if (!(gamma == gamma) || !(norm_res == norm_res) || isinf(gamma)) flags |= ADAPROX_FLAG_NONFINITE;
+    if (b == 0 && threadIdx.x == 0 && W.rec != nullptr && it <= O.max_records) {
+      adaprox_record rc;
+      rc.it = it; rc.gamma = gamma; rc.sigma = sigma; rc.norm_res = norm_res;
+      rc.f_x = f_x; rc.g_x = g_x;
+      rc.h_Ax = (want_obj && hasA) ? prox_value_finish(P.h.kind, P.h.lambda, h_sum) : (want_obj ? 0.0 : NAN);
+      rc.f_evals = n_eval; rc.grad_f_evals = n_grad; rc.prox_g_evals = n_proxg; rc.prox_h_evals = n_proxh;
+      rc.A_evals = n_mul; rc.At_evals = n_amul;
+      W.rec[it - 1] = rc;
+    }
+    if (it <= O.max_records) n_rec = it;
+    if (hasA) { y = ynew; yc ^= 1; }
+    if (norm_res <= O.tol) { converged = true; it_done = it; break; }            // :354-356
+
+    if (hasA && !LINESEARCH) {
+      gemv_t_phase(P.A, y, b, G);                                                // :358
+      n_amul++;
+      grid.sync();
+      gsum_slice(P.A, j0, j1, W.Aty[atc], G);
+    }
+    // ---- P7 (:359-361) ---------------------------------------------------------------
+    {
+      double acc[1] = {0.0};
+      double* xn = W.xb[(xc + 1) % 3];
+      const double* aty = W.Aty[atc];
+      for (int64_t j = j0 + threadIdx.x; j < j1; j += kThreads) {
+        const double vj = x[j] - gamma * (grad[j] + (hasA ? aty[j] : 0.0));      // :359
+        W.v[j] = vj;
+        const double xj = prox_elem(P.g, vj, gamma, j, 0.0);                     // :361
+        xn[j] = xj;
+        if (want_obj) acc[0] += prox_value_elem(P.g, xj, j);
+      }
+      block_reduce_store<1>(acc, W.red, G, gval_slot(it + 1), s_scr);   // read in P5 of the next iteration
+    }
+    n_proxg++;
+    x_prev = x; xc = (xc + 1) % 3; x = W.xb[xc];                                 // :360
+    grad_prev = grad; gc ^= 1;
+    if (hasA) axc ^= 1;
+    grid.sync();
+  }
+
+  // ---- epilogue: copy out -----------------------------------------------------
+  for (int64_t j = tid; j < P.n; j += nt) W.xout[j] = x[j];
+  if (hasA && W.yout) for (int64_t i = tid; i < P.md; i += nt) W.yout[i] = y[i];
+  if (b == 0 && threadIdx.x == 0) {
+    DResult r;
+    r.iters = it_done;
+    r.flags = flags | (converged ? ADAPROX_FLAG_CONVERGED : 0u);
+    r.xbuf = 0;
+    r.f_evals = n_eval; r.grad_f_evals = n_grad; r.prox_g_evals = n_proxg; r.prox_h_evals = n_proxh;
+    r.A_evals = n_mul; r.At_evals = n_amul; r.n_records = n_rec;
+    r.final_gamma = gamma; r.final_sigma = sigma; r.final_norm_res = norm_res;
+    *W.res = r;
+  }
+}
+
+}  // namespace adaprox

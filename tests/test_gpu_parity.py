@@ -1,0 +1,453 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle.
+
+Tolerances (BASELINE.json north_star): iterates and objective 1e-10 relative,
+stepsize sequences 1e-12 relative, identical oracle-call counts.  The AdaPGM
+trajectory is chaotic w.r.t. summation order, so whole runs are
+compared by (a) single-call operator parity, (b) the free-running prefix of the
+trajectory, (c) final objective / iterate / iteration count.
+"""
+import numpy as np
+import pytest
+
+from oracle import adaprox_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+RTOL_OP = 1e-13
+
+
+def rel(a, b):
+    a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+# ---------------------------------------------------------------- operators
+@pytest.mark.parametrize("m,n,order", [(1, 5, "C"), (7, 13, "F"), (400, 1000, "F"), (50, 2001, "C"),
+                                       (33, 4100, "F"), (1000, 37, "C"), (9, 6200, "C")])
+def test_mul_amul_dense(AdaProx, m, n, order):
+    rng = np.random.default_rng(m * 1000 + n)
+    A = np.asarray(rng.standard_normal((m, n)), order=order)
+    x, y = rng.standard_normal(n), rng.standard_normal(m)
+    M = AdaProx.DeviceMatrix(A)
+    assert rel(M @ x, A @ x) < RTOL_OP * np.sqrt(n)
+    assert rel(M.T @ y, A.T @ y) < RTOL_OP * np.sqrt(m)
+    M.free()
+
+
+def test_mul_amul_csr(AdaProx):
+    import scipy.sparse as sp
+    S = sp.random(300, 500, density=0.03, random_state=1, format="csc")
+    S = S + sp.csr_matrix(([1.0], ([299], [499])), shape=(300, 500))
+    rng = np.random.default_rng(2)
+    x, y = rng.standard_normal(500), rng.standard_normal(300)
+    M = AdaProx.DeviceMatrix(S)
+    assert rel(M @ x, S @ x) < 1e-13
+    assert rel(M.T @ y, S.T @ y) < 1e-13
+
+
+def _pair(AdaProx, name, rng):
+    import scipy.sparse as sp
+    if name == "ls":
+        A, b = np.asfortranarray(rng.standard_normal((60, 90))), rng.standard_normal(60)
+        return AdaProx.LinearLeastSquares(A, b), O.LinearLeastSquares(A, b), 90
+    if name == "ls_wide":
+        A, b = rng.standard_normal((37, 4500)), rng.standard_normal(37)
+        return AdaProx.LinearLeastSquares(A, b), O.LinearLeastSquares(A, b), 4500
+    if name == "logistic_csr":
+        X = sp.random(200, 80, density=0.1, random_state=3, format="csr")
+        y = (rng.random(200) < 0.5).astype(float)
+        return AdaProx.LogisticLoss(X, y), O.LogisticLoss(X, y), 81
+    if name == "logistic_dense":
+        X = rng.standard_normal((120, 30))
+        y = (rng.random(120) < 0.5).astype(float)
+        return AdaProx.LogisticLoss(X, y), O.LogisticLoss(X, y), 31
+    if name == "quadratic":
+        B = rng.standard_normal((70, 70)); Q = B @ B.T; q = rng.standard_normal(70)
+        return AdaProx.Quadratic(Q, q), O.Quadratic(Q, q), 70
+    if name == "cubic":
+        B = rng.standard_normal((40, 40)); Q = B @ B.T / 40; q = rng.standard_normal(40)
+        return AdaProx.Cubic(Q, q, 0.7), O.Cubic(Q, q, 0.7), 40
+    if name == "worst":
+        return AdaProx.WorstQuadratic(100, 100.0), O.WorstQuadratic(100, 100.0), 120
+    if name == "simple2d":
+        return AdaProx.Simple2DObjective(), O.Simple2DObjective(), 2
+    raise KeyError(name)
+
+
+@pytest.mark.parametrize("name", ["ls", "ls_wide", "logistic_csr", "logistic_dense", "quadratic", "cubic", "worst", "simple2d"])
+def test_eval_with_pullback(AdaProx, name):
+    rng = np.random.default_rng(5)
+    fd, fo, n = _pair(AdaProx, name, rng)
+    for _ in range(2):
+        x = rng.standard_normal(n)
+        vd, pbd = AdaProx.eval_with_pullback(fd, x)
+        vo, pbo = O.eval_with_pullback(fo, x)
+        assert abs(vd - vo) <= 1e-12 * max(abs(vo), 1.0)
+        assert rel(pbd(), pbo()) < 1e-12
+
+
+def test_prox_operators(AdaProx):
+    rng = np.random.default_rng(7)
+    x = rng.standard_normal(257) * 2
+    b = rng.standard_normal(257)
+    cases = [
+        (AdaProx.NormL1(0.7), O.NormL1(0.7)),
+        (AdaProx.NormL2(1.3), O.NormL2(1.3)),
+        (AdaProx.NormL2(100.0), O.NormL2(100.0)),
+        (AdaProx.IndBox(-0.3, 0.9), O.IndBox(-0.3, 0.9)),
+        (AdaProx.Zero(), O.Zero()),
+        (AdaProx.IndZero(), O.IndZero()),
+        (AdaProx.Translate(AdaProx.NormL1(), -b), O.Translate(O.NormL1(), -b)),
+        (AdaProx.Translate(AdaProx.NormL2(), -b), O.Translate(O.NormL2(), -b)),
+    ]
+    for gd, go in cases:
+        for gamma in (0.05, 1.0, 3.7):
+            yd, vd = AdaProx.prox(gd, x, gamma)
+            yo, vo = O.prox(go, x, gamma)
+            assert np.max(np.abs(yd - yo)) <= 1e-14 * max(1.0, np.max(np.abs(yo))), type(go).__name__
+            assert abs(vd - vo) <= 1e-12 * max(1.0, abs(vo))
+            # conjugates (Moreau), as the primal-dual loops use them
+            yd, _ = AdaProx.prox(AdaProx.convex_conjugate(gd), x, gamma)
+            yo, _ = O.prox(O.convex_conjugate(go), x, gamma)
+            assert np.max(np.abs(yd - yo)) <= 1e-14 * max(1.0, np.max(np.abs(yo))), "conj " + type(go).__name__
+
+
+def test_stepsize_rules(AdaProx):
+    rng = np.random.default_rng(11)
+    rules = [
+        (AdaProx.FixedStepsize(0.3, 2.0), O.FixedStepsize(0.3, 2.0)),
+        (AdaProx.MalitskyMishchenkoRule(0.3, 1.5), O.MalitskyMishchenkoRule(0.3, 1.5)),
+        (AdaProx.OurRule(gamma=0.3), O.OurRule(gamma=0.3)),
+        (AdaProx.OurRule(t=0.5, norm_A=2.0, delta=0.01), O.OurRule(t=0.5, norm_A=2.0, delta=0.01)),
+        (AdaProx.OurRulePlus(gamma=0.3, nu=1.2, xi=0.9, r=0.6), O.OurRulePlus(gamma=0.3, nu=1.2, xi=0.9, r=0.6)),
+    ]
+    for rd, ro in rules:
+        (g_d, s_d), st_d = AdaProx.stepsize(rd)
+        (g_o, s_o), st_o = O.stepsize(ro)
+        assert g_d == g_o and s_d == s_o
+        for trial in range(20):
+            x1, x0 = rng.standard_normal(50), rng.standard_normal(50)
+            g1 = 3.0 * x1 + 0.1 * rng.standard_normal(50)
+            g0 = 3.0 * x0 + 0.1 * rng.standard_normal(50)
+            if trial == 7:
+                g1 = g0.copy()               # dgrad = 0 -> NaN -> 0, third candidate Inf
+            if st_o is None:
+                continue
+            (g_o, s_o), st_o2 = O.stepsize(ro, st_o, x1, g1, x0, g0)
+            dg, dx = g1 - g0, x1 - x0
+            (g_d, s_d), st_d2 = AdaProx.stepsize(rd, st_d, np.dot(dg, dg), np.dot(dg, dx), np.dot(dx, dx))
+            assert abs(g_d - g_o) <= 1e-13 * abs(g_o), (type(ro).__name__, trial)
+            assert abs(s_d - s_o) <= 1e-13 * abs(s_o)
+            st_o, st_d = st_o2, st_d2
+
+
+# ---------------------------------------------------------------- AdaPGM on the planted lasso (config C1)
+def _run_both(AdaProx, P, rule_d, rule_o, tol, maxit=10_000):
+    n = P["A"].shape[1]
+    fd = AdaProx.Counting(AdaProx.LinearLeastSquares(P["A"], P["b"]))
+    fo = O.Counting(O.LinearLeastSquares(P["A"], P["b"]))
+    gd, go = AdaProx.Counting(AdaProx.NormL1(P["lam"])), O.Counting(O.NormL1(P["lam"]))
+    logd, logo = [], []
+    xd, itd = AdaProx.adaptive_proxgrad(np.zeros(n), f=fd, g=gd, rule=rule_d, tol=tol, maxit=maxit, log=logd)
+    xo, ito = O.adaptive_proxgrad(np.zeros(n), f=fo, g=go, rule=rule_o, tol=tol, maxit=maxit, log=logo)
+    return (xd, itd, logd, fd, gd), (xo, ito, logo, fo, go)
+
+
+@pytest.mark.parametrize("rule", ["our", "mm", "fixed", "plus"])
+def test_adapgm_lasso_c1(AdaProx, lasso_small, rule):
+    P = lasso_small
+    g0 = 1.0 / P["Lf"]
+    rd, ro = {
+        "our": (AdaProx.OurRule(gamma=g0), O.OurRule(gamma=g0)),
+        "mm": (AdaProx.MalitskyMishchenkoRule(gamma=g0), O.MalitskyMishchenkoRule(gamma=g0)),
+        "fixed": (AdaProx.FixedStepsize(g0), O.FixedStepsize(g0)),
+        "plus": (AdaProx.OurRulePlus(gamma=g0), O.OurRulePlus(gamma=g0)),
+    }[rule]
+    maxit = 10_000 if rule != "fixed" else 600
+    (xd, itd, logd, fd, gd), (xo, ito, logo, fo, go) = _run_both(AdaProx, P, rd, ro, 1e-6, maxit)
+    # (b) free-running prefix: stepsizes 1e-12, records 1e-10
+    K = 40
+    gam_d = np.array([r["gamma"] for r in logd[:K]]); gam_o = np.array([r["gamma"] for r in logo[:K]])
+    assert np.max(np.abs(gam_d / gam_o - 1)) < 1e-12
+    for key in ("norm_res", "objective"):
+        a = np.array([r[key] for r in logd[:K]]); b_ = np.array([r[key] for r in logo[:K]])
+        assert np.max(np.abs(a / b_ - 1)) < 1e-10, key
+    # (c) final result
+    obj_d = logd[-1]["objective"]; obj_o = logo[-1]["objective"]
+    assert abs(obj_d - obj_o) <= 1e-10 * abs(obj_o)
+    assert abs(itd - ito) <= max(2, 0.03 * ito)
+    if rule != "fixed":
+        assert logd[-1]["norm_res"] <= 1e-6
+        assert abs(obj_d - P["optimum"]) <= 1e-9 * P["optimum"]
+        assert np.linalg.norm(xd - P["x_star"]) < 1e-5
+    # counter identities -- exact
+    assert fd.eval_count == itd + 1 and fd.grad_count == itd + 1
+    assert gd.prox_count == (itd if logd[-1]["norm_res"] <= 1e-6 else itd + 1)
+    assert [r["f_evals"] for r in logd[:5]] == [r["f_evals"] for r in logo[:5]] == [2, 3, 4, 5, 6]
+    assert [r["prox_g_evals"] for r in logd[:5]] == [r["prox_g_evals"] for r in logo[:5]]
+
+
+def test_adapgm_no_logger_same_result(AdaProx, lasso_small):
+    """Without a logger the objective is never computed (src/AdaProx.jl:350-352) -- same iterates."""
+    P = lasso_small
+    f = AdaProx.LinearLeastSquares(P["A"], P["b"]); g = AdaProx.NormL1(1.0)
+    rule = AdaProx.OurRule(gamma=1.0 / P["Lf"])
+    log = []
+    x1, it1 = AdaProx.adaptive_proxgrad(np.zeros(1000), f=f, g=g, rule=rule, tol=1e-5, maxit=300, log=log)
+    x2, it2 = AdaProx.adaptive_proxgrad(np.zeros(1000), f=f, g=g, rule=rule, tol=1e-5, maxit=300)
+    assert it1 == it2 == 300 and np.array_equal(x1, x2)          # deterministic reductions: bit-identical reruns
+    assert log[0]["f_evals"] is None                              # f not wrapped in Counting -> `nothing`
+
+
+# ---------------------------------------------------------------- reference test-suite mirror (test/runtests.jl)
+def test_simple_2d_problem(AdaProx):
+    f, g = AdaProx.Simple2DObjective(), AdaProx.Simple2DBox()
+    fo = O.Simple2DObjective()
+    obj_tol = 1e-7
+    log = []
+    sol, numit = AdaProx.adaptive_proxgrad(np.ones(2), f=f, g=g, rule=AdaProx.OurRule(gamma=1.0), log=log)
+    assert fo(sol) < obj_tol and g(sol) == 0
+    assert numit == 4472                                          # oracle / SURVEY section 4 item 1
+    want = [0.025710976884666, 0.026039406387680, 0.036942695125715, 0.057454177251814, 0.069409118354550]
+    assert np.allclose([r["gamma"] for r in log[:5]], want, rtol=1e-12)
+    sol, numit = AdaProx.backtracking_proxgrad(np.ones(2), f=f, g=g, gamma0=1.0, xi=1.1)
+    assert fo(sol) < obj_tol and g(sol) == 0
+    so, no_ = O.backtracking_proxgrad(np.ones(2), f=fo, g=O.Simple2DBox(), gamma0=1.0, xi=1.1)
+    assert numit == no_ and rel(sol, so) < 1e-9
+    sol, numit = AdaProx.backtracking_nesterov(np.ones(2), f=f, g=g, gamma0=1.0)
+    assert fo(sol) < obj_tol and g(sol) == 0
+    so, no_ = O.backtracking_nesterov(np.ones(2), f=fo, g=O.Simple2DBox(), gamma0=1.0)
+    assert numit == no_ and rel(sol, so) < 1e-9
+
+
+def test_counting(AdaProx):
+    f = AdaProx.Counting(AdaProx.Simple2DObjective())
+    g = AdaProx.Counting(AdaProx.Simple2DBox())
+    A = AdaProx.Counting(AdaProx.DeviceMatrix(np.eye(2)))
+    x = np.ones(2)
+    _, pb = AdaProx.eval_with_pullback(f, x)
+    AdaProx.prox(g, x)
+    A @ x
+    assert (f.eval_count, f.grad_count, g.prox_count, A.mul_count, A.amul_count) == (1, 0, 1, 1, 0)
+    pb()
+    assert f.grad_count == 1
+    A.T @ x
+    assert A.amul_count == 1
+    with AdaProx.without_counting():
+        _, pb = AdaProx.eval_with_pullback(f, x)
+        pb()
+        AdaProx.prox(g, x)
+        A @ x
+    assert (f.eval_count, f.grad_count, g.prox_count, A.mul_count, A.amul_count) == (1, 1, 1, 1, 1)
+
+
+def test_nesterov_worst_case(AdaProx):
+    k = n = 100
+    Lc = 100.0
+    f, fo = AdaProx.WorstQuadratic(k, Lc), O.WorstQuadratic(k, Lc)
+    fstar = (Lc / 8) * (1 / (k + 1) - 1)
+    for mk_d, mk_o in [(lambda: AdaProx.OurRule(gamma=1 / Lc), lambda: O.OurRule(gamma=1 / Lc)),
+                       (lambda: AdaProx.MalitskyMishchenkoRule(gamma=1 / Lc), lambda: O.MalitskyMishchenkoRule(gamma=1 / Lc)),
+                       (lambda: AdaProx.FixedStepsize(1 / Lc), lambda: O.FixedStepsize(1 / Lc))]:
+        logd, logo = [], []
+        xd, itd = AdaProx.adaptive_proxgrad(np.zeros(n), f=f, g=AdaProx.Zero(), rule=mk_d(), tol=1e-6, maxit=3000, log=logd)
+        xo, ito = O.adaptive_proxgrad(np.zeros(n), f=fo, g=O.Zero(), rule=mk_o(), tol=1e-6, maxit=3000, log=logo)
+        assert itd == ito == 3000
+        gd = np.array([r["gamma"] for r in logd[:60]]); go = np.array([r["gamma"] for r in logo[:60]])
+        assert np.max(np.abs(gd / go - 1)) < 1e-12
+        assert abs(fo(xd) - fo(xo)) < 1e-8 and fo(xd) > fstar
+    xd, itd = AdaProx.fixed_nesterov(np.zeros(n), f=f, g=AdaProx.Zero(), gamma=1 / Lc, tol=1e-6, maxit=2000)
+    xo, ito = O.fixed_nesterov(np.zeros(n), f=fo, g=O.Zero(), gamma=1 / Lc, tol=1e-6, maxit=2000)
+    assert itd == ito and rel(xd, xo) < 1e-9
+
+
+# ---------------------------------------------------------------- proximal-gradient baselines on the lasso
+def test_pg_baselines_lasso(AdaProx):
+    P = AdaProx.synth.planted_lasso(100, 300, 10, 0)
+    Lf = AdaProx.synth.spectral_norm_sq(P["A"], iters=1000, tol=1e-15)
+    g0 = 1.0 / Lf
+    n = 300
+    def objs():
+        return (AdaProx.Counting(AdaProx.LinearLeastSquares(P["A"], P["b"])), AdaProx.NormL1(1.0),
+                O.Counting(O.LinearLeastSquares(P["A"], P["b"])), O.NormL1(1.0))
+    for xi in (1.0, 1.5, 2.0):
+        fd, gd, fo, go = objs(); ld, lo = [], []
+        xd, itd = AdaProx.backtracking_proxgrad(np.zeros(n), f=fd, g=gd, gamma0=g0, xi=xi, tol=1e-7, maxit=400, log=ld)
+        xo, ito = O.backtracking_proxgrad(np.zeros(n), f=fo, g=go, gamma0=g0, xi=xi, tol=1e-7, maxit=400, log=lo)
+        K = 30
+        assert np.allclose([r["gamma"] for r in ld[:K]], [r["gamma"] for r in lo[:K]], rtol=1e-12)
+        assert [r["f_evals"] for r in ld[:K]] == [r["f_evals"] for r in lo[:K]]
+        assert [r["grad_f_evals"] for r in ld[:K]] == [r["grad_f_evals"] for r in lo[:K]]
+        assert np.allclose([r["objective"] for r in ld[:K]], [r["objective"] for r in lo[:K]], rtol=1e-10)
+        assert abs(itd - ito) <= max(2, 0.03 * ito)
+    fd, gd, fo, go = objs(); ld, lo = [], []
+    xd, itd = AdaProx.backtracking_nesterov(np.zeros(n), f=fd, g=gd, gamma0=g0, tol=1e-7, maxit=400, log=ld)
+    xo, ito = O.backtracking_nesterov(np.zeros(n), f=fo, g=go, gamma0=g0, tol=1e-7, maxit=400, log=lo)
+    assert np.allclose([r["objective"] for r in ld[:30]], [r["objective"] for r in lo[:30]], rtol=1e-10)
+    assert (fd.eval_count, fd.grad_count) == (fo.eval_count, fo.grad_count) or abs(itd - ito) <= 3
+    fd, gd, fo, go = objs(); ld, lo = [], []
+    xd, itd = AdaProx.fixed_nesterov(np.zeros(n), f=fd, g=gd, gamma=g0, tol=1e-7, maxit=400, log=ld)
+    xo, ito = O.fixed_nesterov(np.zeros(n), f=fo, g=go, gamma=g0, tol=1e-7, maxit=400, log=lo)
+    assert np.allclose([r["objective"] for r in ld[:30]], [r["objective"] for r in lo[:30]], rtol=1e-10)
+    assert np.allclose([r["norm_res"] for r in ld[:30]], [r["norm_res"] for r in lo[:30]], rtol=1e-9)
+    assert fd.eval_count == fo.eval_count                          # the logged f(x) is not counted
+    fd, gd, fo, go = objs(); ld, lo = [], []
+    x0 = np.random.default_rng(3).standard_normal(n)
+    xd, itd = AdaProx.agraal(np.zeros(n), f=fd, g=gd, x0=x0, gamma0=g0, tol=1e-7, maxit=400, log=ld)
+    xo, ito = O.agraal(np.zeros(n), f=fo, g=go, x0=x0, gamma0=g0, tol=1e-7, maxit=400, log=lo)
+    assert np.allclose([r["gamma"] for r in ld[:30]], [r["gamma"] for r in lo[:30]], rtol=1e-11)
+    assert np.allclose([r["objective"] for r in ld[:30]], [r["objective"] for r in lo[:30]], rtol=1e-10)
+
+
+# ---------------------------------------------------------------- primal-dual: dual SVM, LAD, square-root lasso
+def _svm(AdaProx, N=300, d=20, seed=0):
+    X, y = AdaProx.synth.dense_classification(N, d, seed)
+    Q = (y[:, None] * X) @ (X.T * y[None, :])
+    return Q, -np.ones(N), y
+
+
+def test_adapdm_dual_svm(AdaProx):
+    Q, q, y = _svm(AdaProx)
+    N = Q.shape[0]
+    Amat = y[None, :].copy()
+    nA = np.linalg.norm(Amat)
+    for t in (0.1, 1.0):
+        fd, fo = AdaProx.Counting(AdaProx.Quadratic(Q, q)), O.Counting(O.Quadratic(Q, q))
+        Ad, Ao = AdaProx.Counting(AdaProx.DeviceMatrix(Amat)), O.Counting(Amat)
+        ld, lo = [], []
+        xd, yd, itd = AdaProx.adaptive_primal_dual(np.zeros(N), np.zeros(1), f=fd, g=AdaProx.IndBox(0.0, 0.1), h=AdaProx.IndZero(),
+                                                   A=Ad, rule=AdaProx.OurRule(t=t, norm_A=nA), tol=1e-5, maxit=5000, log=ld)
+        xo, yo, ito = O.adaptive_primal_dual(np.zeros(N), np.zeros(1), f=fo, g=O.IndBox(0.0, 0.1), h=O.IndZero(),
+                                             A=Ao, rule=O.OurRule(t=t, norm_A=nA), tol=1e-5, maxit=5000, log=lo)
+        K = 40
+        assert np.allclose([r["gamma"] for r in ld[:K]], [r["gamma"] for r in lo[:K]], rtol=1e-12)
+        assert np.allclose([r["sigma"] for r in ld[:K]], [r["sigma"] for r in lo[:K]], rtol=1e-12)
+        assert np.allclose([r["norm_res"] for r in ld[:K]], [r["norm_res"] for r in lo[:K]], rtol=1e-9)
+        assert abs(itd - ito) <= max(3, 0.05 * ito)
+        assert np.all(xd >= 0) and np.all(xd <= 0.1) and abs(y @ xd) < 1e-4
+        assert abs(fo.f(xd) - fo.f(xo)) <= 1e-7 * abs(fo.f(xo))
+        assert (fd.eval_count, fd.grad_count, Ad.mul_count, Ad.amul_count) == (itd + 1, itd + 1, itd + 1, itd if ld[-1]["norm_res"] <= 1e-5 else itd + 1)
+        assert [r["A_evals"] for r in ld[:5]] == [r["A_evals"] for r in lo[:5]]
+        assert [r["At_evals"] for r in ld[:5]] == [r["At_evals"] for r in lo[:5]]
+
+
+def test_condat_vu(AdaProx):
+    Q, q, y = _svm(AdaProx, 120, 10, 1)
+    N = Q.shape[0]
+    Amat = y[None, :].copy()
+    Lf, nA = np.linalg.norm(Q), np.linalg.norm(Amat)
+    ld, lo = [], []
+    xd, yd, itd = AdaProx.condat_vu(np.zeros(N), np.zeros(1), f=AdaProx.Quadratic(Q, q), g=AdaProx.IndBox(0.0, 1.0), h=AdaProx.IndZero(),
+                                    A=AdaProx.DeviceMatrix(Amat), Lf=Lf, norm_A=nA, tol=1e-5, maxit=300, log=ld)
+    xo, yo, ito = O.condat_vu(np.zeros(N), np.zeros(1), f=O.Quadratic(Q, q), g=O.IndBox(0.0, 1.0), h=O.IndZero(),
+                              A=Amat, Lf=Lf, norm_A=nA, tol=1e-5, maxit=300, log=lo)
+    assert itd == ito
+    assert np.allclose([r["norm_res"] for r in ld], [r["norm_res"] for r in lo], rtol=1e-8)
+    assert rel(xd, xo) < 1e-9 and rel(yd, yo) < 1e-9
+
+
+@pytest.mark.parametrize("hname", ["l1", "l2"])
+def test_adapdm_plus_lad_sqrt_lasso(AdaProx, hname):
+    X, yv = AdaProx.synth.dense_regression(200, 10, 0)
+    m = X.shape[0]
+    Amat = np.hstack([X, np.ones((m, 1))])
+    nA = np.linalg.norm(Amat)
+    lam = 0.1
+    hd = AdaProx.Translate(AdaProx.NormL1() if hname == "l1" else AdaProx.NormL2(), -yv)
+    ho = O.Translate(O.NormL1() if hname == "l1" else O.NormL2(), -yv)
+    Ad, Ao = AdaProx.Counting(AdaProx.DeviceMatrix(Amat)), O.Counting(Amat)
+    hdc, hoc = AdaProx.Counting(hd), O.Counting(ho)
+    ld, lo, trials = [], [], []
+    kw = dict(eta=nA, t=1.0, tol=1e-5, maxit=400)
+    xd, yd, itd = AdaProx.adaptive_linesearch_primal_dual(np.zeros(11), np.zeros(m), f=AdaProx.Zero(), g=AdaProx.NormL1(lam), h=hdc, A=Ad, log=ld, **kw)
+    xo, yo, ito = O.adaptive_linesearch_primal_dual(np.zeros(11), np.zeros(m), f=O.Zero(), g=O.NormL1(lam), h=hoc, A=Ao, log=lo, trials=trials, **kw)
+    K = 30
+    assert np.allclose([r["gamma"] for r in ld[:K]], [r["gamma"] for r in lo[:K]], rtol=1e-12)
+    assert np.allclose([r["norm_res"] for r in ld[:K]], [r["norm_res"] for r in lo[:K]], rtol=1e-9)
+    assert np.allclose([r["objective"] for r in ld[:K]], [r["objective"] for r in lo[:K]], rtol=1e-10)
+    assert [r["At_evals"] for r in ld[:K]] == [r["At_evals"] for r in lo[:K]]        # same linesearch trial counts
+    assert [r["prox_h_evals"] for r in ld[:K]] == [r["prox_h_evals"] for r in lo[:K]]
+    assert abs(itd - ito) <= max(3, 0.05 * ito)
+    # the generic loop with the same h
+    ld, lo = [], []
+    xd, yd, itd = AdaProx.adaptive_primal_dual(np.zeros(11), np.zeros(m), f=AdaProx.Zero(), g=AdaProx.NormL1(lam), h=hd, A=AdaProx.DeviceMatrix(Amat),
+                                               rule=AdaProx.OurRule(t=1.0, norm_A=nA), tol=1e-5, maxit=200, log=ld)
+    xo, yo, ito = O.adaptive_primal_dual(np.zeros(11), np.zeros(m), f=O.Zero(), g=O.NormL1(lam), h=ho, A=Amat,
+                                         rule=O.OurRule(t=1.0, norm_A=nA), tol=1e-5, maxit=200, log=lo)
+    assert np.allclose([r["norm_res"] for r in ld[:K]], [r["norm_res"] for r in lo[:K]], rtol=1e-9)
+    assert np.allclose([r["objective"] for r in ld[:K]], [r["objective"] for r in lo[:K]], rtol=1e-10)
+
+
+# ---------------------------------------------------------------- sparse logistic regression (config C2 shape, scaled)
+def test_adapgm_sparse_logreg(AdaProx):
+    import scipy.sparse as sp
+    rp, ci, va, y = AdaProx.synth.sparse_logreg(m=600, n=900, seed=0, nnz_lo=10, nnz_hi=30)
+    X = sp.csr_matrix((va, ci, rp), shape=(600, 900))
+    n = 901
+    X1 = sp.hstack([X, np.ones((600, 1))]).toarray()
+    Lf = np.linalg.norm(X1 @ X1.T) / 4 / 600                       # sparse_logreg/runme.jl:58-59 (Frobenius)
+    ld, lo = [], []
+    xd, itd = AdaProx.adaptive_proxgrad(np.zeros(n), f=AdaProx.Counting(AdaProx.LogisticLoss(X, y)), g=AdaProx.NormL1(0.01),
+                                        rule=AdaProx.OurRule(gamma=1 / Lf), tol=1e-7, maxit=2000, log=ld)
+    xo, ito = O.adaptive_proxgrad(np.zeros(n), f=O.Counting(O.LogisticLoss(X, y)), g=O.NormL1(0.01),
+                                  rule=O.OurRule(gamma=1 / Lf), tol=1e-7, maxit=2000, log=lo)
+    K = 40
+    assert np.allclose([r["gamma"] for r in ld[:K]], [r["gamma"] for r in lo[:K]], rtol=1e-12)
+    assert np.allclose([r["objective"] for r in ld[:K]], [r["objective"] for r in lo[:K]], rtol=1e-10)
+    assert abs(itd - ito) <= max(3, 0.05 * ito)
+    assert abs(ld[-1]["objective"] - lo[-1]["objective"]) <= 1e-9 * abs(lo[-1]["objective"])
+
+
+# ---------------------------------------------------------------- device generator vs host generator
+def test_device_generator_matches_host(AdaProx):
+    m, n = 64, 200
+    Ph = AdaProx.synth.planted_lasso(m, n, 5, 3)
+    Pd = AdaProx.generate_planted_lasso(m, n, 5, 3, power_iters=200)
+    # raw uniforms are bit-identical; derived quantities differ only by summation order
+    e = np.eye(n)
+    cols = [0, 1, 57, n - 1]
+    Ad = np.stack([Pd["A"] @ e[j] for j in cols], axis=1)
+    assert rel(Ad, Ph["A"][:, cols]) < 1e-12
+    assert rel(Pd["b"].download(), Ph["b"]) < 1e-12
+    assert rel(Pd["x_star"], Ph["x_star"]) < 1e-12
+    assert abs(Pd["optimum"] - Ph["optimum"]) < 1e-12 * Ph["optimum"]
+    assert abs(Pd["Lf"] - np.linalg.norm(Ph["A"], 2) ** 2) < 1e-6 * Pd["Lf"]
+    # planted solution is the minimiser: AdaPGM on the device-generated instance reaches the stated optimum
+    f = AdaProx.LinearLeastSquares(Pd["A"], Pd["b"])
+    log = []
+    x, it = AdaProx.adaptive_proxgrad(np.zeros(n), f=f, g=AdaProx.NormL1(1.0), rule=AdaProx.OurRule(gamma=1 / Pd["Lf"]),
+                                      tol=1e-8, maxit=20000, log=log)
+    assert log[-1]["norm_res"] <= 1e-8
+    assert abs(log[-1]["objective"] - Pd["optimum"]) < 1e-10 * Pd["optimum"]
+    assert np.linalg.norm(x - Pd["x_star"]) < 1e-6
+
+
+# ---------------------------------------------------------------- size-independent properties at a larger size
+def test_large_gemv_properties(AdaProx):
+    """Linearity and adjointness <A x, y> = <x, A'y> on a multi-chunk, multi-unit matrix (8192 x 12288)."""
+    P = AdaProx.generate_planted_lasso(8192, 12288, 5, 1, power_iters=0)
+    A = P["A"]
+    rng = np.random.default_rng(0)
+    x1, x2, y = rng.standard_normal(12288), rng.standard_normal(12288), rng.standard_normal(8192)
+    Ax1, Ax2, Axs = A @ x1, A @ x2, A @ (2.0 * x1 - 3.0 * x2)
+    assert rel(Axs, 2.0 * Ax1 - 3.0 * Ax2) < 1e-12
+    assert abs(np.dot(Ax1, y) - np.dot(x1, A.T @ y)) <= 1e-11 * np.linalg.norm(Ax1) * np.linalg.norm(y)
+    A.free()
+
+
+def test_error_behaviour(AdaProx):
+    with pytest.raises(ValueError):
+        AdaProx.OurRule()                                         # src/AdaProx.jl:246
+    with pytest.raises(ValueError):
+        AdaProx.OurRulePlus()                                     # :288
+    with pytest.raises(AssertionError):
+        AdaProx.adaptive_linesearch_primal_dual(np.zeros(2), np.zeros(2), f=AdaProx.Zero(), g=AdaProx.Zero(), h=AdaProx.Zero(),
+                                                A=np.eye(2), eta=-1.0)            # :481
+    class Unknown:
+        pass
+    with pytest.raises(AdaProx.AdaproxError):
+        AdaProx.adaptive_proxgrad(np.zeros(2), f=Unknown(), g=AdaProx.Zero(), rule=AdaProx.OurRule(gamma=1.0))
+    with pytest.raises(AdaProx.AdaproxError):
+        AdaProx.LinearLeastSquares(np.eye(3), np.ones(2))         # b shorter than the rows of A -> status < 0 at solve time
+        AdaProx.adaptive_proxgrad(np.zeros(3), f=AdaProx.LinearLeastSquares(np.eye(3), np.ones(2)), g=AdaProx.Zero(),
+                                  rule=AdaProx.OurRule(gamma=1.0))
