@@ -1,6 +1,7 @@
 // api.cu -- the C ABI of libadaprox_cuda.so (include/adaprox.h).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include "context.hpp"
@@ -53,7 +54,7 @@ static int get_vec(adaprox_ctx* h, adaprox_id id, int64_t min_len, const double*
 
 template <typename K>
 static int coop_launch(adaprox_ctx* h, K kernel, void** args) {
-  cudaError_t e = cudaLaunchCooperativeKernel((const void*)kernel, dim3(h->grid), dim3(kThreads), args, 0, h->stream);
+  cudaError_t e = cudaLaunchCooperativeKernel((const void*)kernel, dim3(h->grid), dim3(kThreads), args, kRingBytes, h->stream);
   if (e != cudaSuccess) return fail(h, ADAPROX_ERR_CUDA, std::string("cooperative launch: ") + cudaGetErrorString(e));
   h->launches++;
   return ADAPROX_OK;
@@ -67,6 +68,8 @@ static void plan_dense(DMat& d, int G) {
   while (rb > 8 && (int64_t)d.nchunks * ((d.m + rb - 1) / rb) < 16LL * G) rb >>= 1;
   d.rb = rb;
   d.nrb = (d.m + rb - 1) / rb;
+  const char* e = std::getenv("ADAPROX_GEMV");       // "ldg": register-staged loads; default: bulk-copy ring
+  d.path = (e && std::strcmp(e, "ldg") == 0) ? 0 : 1;
 }
 
 static int alloc_dense(adaprox_ctx* h, int64_t m, int64_t n, HostMatrix& hm) {
@@ -191,13 +194,17 @@ extern "C" int adaprox_create(adaprox_handle* out, int device) {
   // resident CTAs per SM: the minimum over the persistent kernels
   int per_sm = 2, nb = 0;
   const void* kernels[] = {(const void*)k_primal_dual<false>, (const void*)k_primal_dual<true>, (const void*)k_ops,
-                           (const void*)k_proxgrad_family};
+                           (const void*)k_proxgrad_family, (const void*)k_gemv_pass};
   for (const void* k : kernels) {
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k, kThreads, 0) != cudaSuccess || nb < 1) {
+    if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kRingBytes) != cudaSuccess) {
+      delete h; return ADAPROX_ERR_CUDA;
+    }
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k, kThreads, kRingBytes) != cudaSuccess || nb < 1) {
       delete h; return ADAPROX_ERR_CUDA;
     }
     per_sm = std::min(per_sm, nb);
   }
+  if (comm_setup_kernels() != 0) { delete h; return ADAPROX_ERR_CUDA; }
   h->grid = per_sm * h->sm_count;
   *out = h;
   return ADAPROX_OK;
@@ -582,6 +589,14 @@ extern "C" int adaprox_solve(adaprox_handle h, const adaprox_problem* p, const a
   W.res = reinterpret_cast<DResult*>(ws_doubles(h, (sizeof(DResult) + 7) / 8));
   W.xout = W.aux[2];
   O.max_records = nrec;
+  const bool phase_timing = std::getenv("ADAPROX_PHASE_TIMING") != nullptr;
+  unsigned long long* d_ts = nullptr;
+  const int ts_iters = (int)std::min<int64_t>(O.maxit, 64);
+  if (phase_timing && ts_iters > 0) {
+    AP_CUDA(h, cudaMalloc(&d_ts, (size_t)ts_iters * 8 * sizeof(unsigned long long)));
+    AP_CUDA(h, cudaMemsetAsync(d_ts, 0, (size_t)ts_iters * 8 * sizeof(unsigned long long), h->stream));
+    W.tstamp = d_ts; W.tstamp_iters = ts_iters;
+  }
 
   AP_CUDA(h, cudaMemcpyAsync(W.xb[0], x0, (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
   if (P.md > 0) {
@@ -622,6 +637,26 @@ extern "C" int adaprox_solve(adaprox_handle h, const adaprox_problem* p, const a
   AP_CUDA(h, cudaStreamSynchronize(h->stream));
   if (records && dr.n_records > 0)
     AP_CUDA(h, cudaMemcpy(records, W.rec, (size_t)dr.n_records * sizeof(adaprox_record), cudaMemcpyDeviceToHost));
+  if (d_ts) {     // phase breakdown of the persistent kernel, averaged over the stamped iterations
+    std::vector<unsigned long long> ts((size_t)ts_iters * 8);
+    cudaMemcpy(ts.data(), d_ts, ts.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    cudaFree(d_ts);
+    const int nit = (int)std::min<int64_t>(ts_iters, dr.iters);
+    double sum[8] = {0}; int cnt = 0;
+    for (int i = 0; i < nit; ++i) {
+      const unsigned long long* t = &ts[(size_t)i * 8];
+      if (!t[0] || !t[7]) continue;
+      for (int k = 0; k < 7; ++k) if (t[k + 1] && t[k]) sum[k] += (double)(t[k + 1] - t[k]) * 1e-3;
+      sum[7] += (double)(t[7] - t[0]) * 1e-3;
+      ++cnt;
+    }
+    if (cnt) {
+      const char* names[7] = {"P1 F*x (+A*x)", "P2 rows/residual", "P3 F'*r", "P4 grad+reductions", "P5 stepsize/dual", "P6 record/A'y", "P7 prox step"};
+      std::fprintf(stderr, "[adaprox phase timing] %d iterations, us per iteration:", cnt);
+      for (int k = 0; k < 7; ++k) std::fprintf(stderr, " %s=%.1f", names[k], sum[k] / cnt);
+      std::fprintf(stderr, " total=%.1f\n", sum[7] / cnt);
+    }
+  }
   float ms = 0.f;
   cudaEventElapsedTime(&ms, h->ev0, h->ev1);
   std::memset(res, 0, sizeof(*res));
@@ -650,10 +685,10 @@ extern "C" int adaprox_time_kernel(adaprox_handle h, adaprox_id mat, int which, 
   std::vector<double> ones((size_t)len, 1.0);
   AP_CUDA(h, cudaMemcpyAsync(in, ones.data(), (size_t)len * 8, cudaMemcpyHostToDevice, h->stream));
   double* out = nullptr;
-  k_gemv_pass<<<h->grid, kThreads, 0, h->stream>>>(M, which, in, out);   // warm-up
+  k_gemv_pass<<<h->grid, kThreads, kRingBytes, h->stream>>>(M, which, in, out);   // warm-up
   h->launches++;
   AP_CUDA(h, cudaEventRecord(h->ev0, h->stream));
-  for (int r = 0; r < reps; ++r) { k_gemv_pass<<<h->grid, kThreads, 0, h->stream>>>(M, which, in, out); h->launches++; }
+  for (int r = 0; r < reps; ++r) { k_gemv_pass<<<h->grid, kThreads, kRingBytes, h->stream>>>(M, which, in, out); h->launches++; }
   AP_CUDA(h, cudaEventRecord(h->ev1, h->stream));
   AP_CUDA(h, cudaStreamSynchronize(h->stream));
   AP_CUDA(h, cudaGetLastError());

@@ -7,6 +7,7 @@ namespace adaprox {
 
 int comm_allreduce_sum(adaprox_ctx* h, double* buf_dev, int64_t count);
 void comm_destroy(adaprox_ctx* h);
+int comm_setup_kernels();      // opt the split-phase kernels into the ring's dynamic shared memory
 
 int solve_sharded(adaprox_ctx* h, const adaprox_problem* p, const adaprox_options* o, const DProblem& P, const DOpts& O,
                   HostMatrix* fm, HostMatrix* am, const double* x0, const double* y0, double* x_out, double* y_out,

@@ -94,11 +94,15 @@ __device__ __forceinline__ long long sh_current(const ShArgs& a, bool& done) {
 }
 
 __global__ void __launch_bounds__(kThreads, 2) k_sh_A(ShArgs a) {
-  __shared__ __align__(16) double s_x[kChunk];
+  extern __shared__ __align__(1024) unsigned char dyn_smem[];
   __shared__ double s_scr[kWarps * 8 + kMaxRed];
+  __shared__ double s_part[kPartRows * kWarps];
+  __shared__ unsigned long long s_bars[2 * kStages];
+  Sh sh;
+  sh_init(sh, dyn_smem, s_scr, s_part, s_bars);
   bool done; const long long it = sh_current(a, done);
   if (done) return;
-  f_phase_A(a.P, a.W, a.W.xb[it % 3], s_x, s_scr, blockIdx.x, gridDim.x);
+  f_phase_A(a.P, a.W, a.W.xb[it % 3], sh, s_scr, blockIdx.x, gridDim.x);
 }
 __global__ void __launch_bounds__(kThreads, 2) k_sh_B(ShArgs a) {
   __shared__ double s_scr[kWarps * 8 + kMaxRed];
@@ -107,9 +111,15 @@ __global__ void __launch_bounds__(kThreads, 2) k_sh_B(ShArgs a) {
   f_phase_B(a.P, a.W, a.W.xb[it % 3], s_scr, blockIdx.x, gridDim.x);
 }
 __global__ void __launch_bounds__(kThreads, 2) k_sh_C(ShArgs a) {
+  extern __shared__ __align__(1024) unsigned char dyn_smem[];
+  __shared__ double s_scr[kWarps * 8 + kMaxRed];
+  __shared__ double s_part[kPartRows * kWarps];
+  __shared__ unsigned long long s_bars[2 * kStages];
+  Sh sh;
+  sh_init(sh, dyn_smem, s_scr, s_part, s_bars);
   bool done; sh_current(a, done);
   if (done) return;
-  f_phase_C(a.P, a.W, blockIdx.x, gridDim.x);
+  f_phase_C(a.P, a.W, sh, blockIdx.x, gridDim.x);
 }
 // local partial sums -> the all-reduce buffer
 __global__ void __launch_bounds__(kThreads, 2) k_sh_D(ShArgs a) {
@@ -218,6 +228,12 @@ __global__ void __launch_bounds__(kThreads, 2) k_sh_F(ShArgs a) {
   if (b == 0 && threadIdx.x == 0) a.st[(it + 1) & 1] = nx;
 }
 
+int comm_setup_kernels() {
+  if (cudaFuncSetAttribute((const void*)k_sh_A, cudaFuncAttributeMaxDynamicSharedMemorySize, kRingBytes) != cudaSuccess) return -1;
+  if (cudaFuncSetAttribute((const void*)k_sh_C, cudaFuncAttributeMaxDynamicSharedMemorySize, kRingBytes) != cudaSuccess) return -1;
+  return 0;
+}
+
 int solve_sharded(adaprox_ctx* h, const adaprox_problem* p, const adaprox_options* o, const DProblem& P, const DOpts& Oin,
                   HostMatrix* fm, HostMatrix* am, const double* x0, const double* y0, double* x_out, double* y_out,
                   adaprox_record* records, adaprox_result* res) {
@@ -264,9 +280,9 @@ int solve_sharded(adaprox_ctx* h, const adaprox_problem* p, const adaprox_option
 
   auto one_iteration = [&](int64_t it) -> int {
     a.it = it;
-    k_sh_A<<<G, kThreads, 0, h->stream>>>(a);
+    k_sh_A<<<G, kThreads, kRingBytes, h->stream>>>(a);
     k_sh_B<<<G, kThreads, 0, h->stream>>>(a);
-    k_sh_C<<<G, kThreads, 0, h->stream>>>(a);
+    k_sh_C<<<G, kThreads, kRingBytes, h->stream>>>(a);
     k_sh_D<<<G, kThreads, 0, h->stream>>>(a);
     int r = comm_allreduce_sum(h, a.gbuf, n + 2);
     if (r) return r;

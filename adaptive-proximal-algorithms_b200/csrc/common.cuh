@@ -41,6 +41,7 @@ struct DMat {
   double* zpart;             // [nchunks][m]    A*x partials
   double* gpart;             // [grid][npad]    A'r partials, one row per CTA
   int64_t npad;              // n rounded up to kChunk
+  int path;                  // dense passes: 1 = bulk-copy shared-memory ring (default), 0 = register-staged LDG.128
 };
 
 struct DProx {
@@ -76,6 +77,63 @@ __device__ __forceinline__ double2 ld_stream(const double* p) {
   asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
   return r;
 }
+
+// 16 streaming 128-bit loads issued back to back from ONE asm block, so ptxas
+// cannot interleave the consuming FMAs between them (it does when it is short of
+// registers, which leaves only 4-6 loads in flight per thread and costs ~20 % of
+// the HBM bandwidth -- profiles/r01_notes.md).  `stride_bytes` apart from p.
+__device__ __forceinline__ void ld_stream16_512(const double* p, double2 (&a)[16]) {
+  asm volatile(
+      "ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%32];\n\t"
+      "ld.global.nc.L1::no_allocate.v2.f64 {%2, %3}, [%32+512];\n\t"
+      "ld.global.nc.L1::no_allocate.v2.f64 {%4, %5}, [%32+1024];\n\t"
+      "ld.global.nc.L1::no_allocate.v2.f64 {%6, %7}, [%32+1536];\n\t"
+      "ld.global.nc.L1::no_allocate.v2.f64 {%8, %9}, [%32+2048];\n\t"
+      "ld.global.nc.L1::no_allocate.v2.f64 {%10, %11}, [%32+2560];\n\t"
+      "ld.global.nc.L1::no_allocate.v2.f64 {%12, %13}, [%32+3072];\n\t"
+      "ld.global.nc.L1::no_allocate.v2.f64 {%14, %15}, [%32+3584];\n\t"
+      "ld.global.nc.L1::no_allocate.v2.f64 {%16, %17}, [%32+4096];\n\t"
+      "ld.global.nc.L1::no_allocate.v2.f64 {%18, %19}, [%32+4608];\n\t"
+      "ld.global.nc.L1::no_allocate.v2.f64 {%20, %21}, [%32+5120];\n\t"
+      "ld.global.nc.L1::no_allocate.v2.f64 {%22, %23}, [%32+5632];\n\t"
+      "ld.global.nc.L1::no_allocate.v2.f64 {%24, %25}, [%32+6144];\n\t"
+      "ld.global.nc.L1::no_allocate.v2.f64 {%26, %27}, [%32+6656];\n\t"
+      "ld.global.nc.L1::no_allocate.v2.f64 {%28, %29}, [%32+7168];\n\t"
+      "ld.global.nc.L1::no_allocate.v2.f64 {%30, %31}, [%32+7680];"
+      : "=d"(a[0].x), "=d"(a[0].y), "=d"(a[1].x), "=d"(a[1].y), "=d"(a[2].x), "=d"(a[2].y), "=d"(a[3].x), "=d"(a[3].y),
+        "=d"(a[4].x), "=d"(a[4].y), "=d"(a[5].x), "=d"(a[5].y), "=d"(a[6].x), "=d"(a[6].y), "=d"(a[7].x), "=d"(a[7].y),
+        "=d"(a[8].x), "=d"(a[8].y), "=d"(a[9].x), "=d"(a[9].y), "=d"(a[10].x), "=d"(a[10].y), "=d"(a[11].x), "=d"(a[11].y),
+        "=d"(a[12].x), "=d"(a[12].y), "=d"(a[13].x), "=d"(a[13].y), "=d"(a[14].x), "=d"(a[14].y), "=d"(a[15].x), "=d"(a[15].y)
+      : "l"(p));
+}
+// 4 rows x 4 loads (4096 B apart within a row): the A'r batch of one thread.
+__device__ __forceinline__ void ld_stream4x4_4096(const double* p0, const double* p1, const double* p2, const double* p3,
+                                                  double2 (&a)[4][4]) {
+  asm volatile(
+      "ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%32];\n\t"
+      "ld.global.nc.L1::no_allocate.v2.f64 {%2, %3}, [%32+4096];\n\t"
+      "ld.global.nc.L1::no_allocate.v2.f64 {%4, %5}, [%32+8192];\n\t"
+      "ld.global.nc.L1::no_allocate.v2.f64 {%6, %7}, [%32+12288];\n\t"
+      "ld.global.nc.L1::no_allocate.v2.f64 {%8, %9}, [%33];\n\t"
+      "ld.global.nc.L1::no_allocate.v2.f64 {%10, %11}, [%33+4096];\n\t"
+      "ld.global.nc.L1::no_allocate.v2.f64 {%12, %13}, [%33+8192];\n\t"
+      "ld.global.nc.L1::no_allocate.v2.f64 {%14, %15}, [%33+12288];\n\t"
+      "ld.global.nc.L1::no_allocate.v2.f64 {%16, %17}, [%34];\n\t"
+      "ld.global.nc.L1::no_allocate.v2.f64 {%18, %19}, [%34+4096];\n\t"
+      "ld.global.nc.L1::no_allocate.v2.f64 {%20, %21}, [%34+8192];\n\t"
+      "ld.global.nc.L1::no_allocate.v2.f64 {%22, %23}, [%34+12288];\n\t"
+      "ld.global.nc.L1::no_allocate.v2.f64 {%24, %25}, [%35];\n\t"
+      "ld.global.nc.L1::no_allocate.v2.f64 {%26, %27}, [%35+4096];\n\t"
+      "ld.global.nc.L1::no_allocate.v2.f64 {%28, %29}, [%35+8192];\n\t"
+      "ld.global.nc.L1::no_allocate.v2.f64 {%30, %31}, [%35+12288];"
+      : "=d"(a[0][0].x), "=d"(a[0][0].y), "=d"(a[0][1].x), "=d"(a[0][1].y), "=d"(a[0][2].x), "=d"(a[0][2].y), "=d"(a[0][3].x), "=d"(a[0][3].y),
+        "=d"(a[1][0].x), "=d"(a[1][0].y), "=d"(a[1][1].x), "=d"(a[1][1].y), "=d"(a[1][2].x), "=d"(a[1][2].y), "=d"(a[1][3].x), "=d"(a[1][3].y),
+        "=d"(a[2][0].x), "=d"(a[2][0].y), "=d"(a[2][1].x), "=d"(a[2][1].y), "=d"(a[2][2].x), "=d"(a[2][2].y), "=d"(a[2][3].x), "=d"(a[2][3].y),
+        "=d"(a[3][0].x), "=d"(a[3][0].y), "=d"(a[3][1].x), "=d"(a[3][1].y), "=d"(a[3][2].x), "=d"(a[3][2].y), "=d"(a[3][3].x), "=d"(a[3][3].y)
+      : "l"(p0), "l"(p1), "l"(p2), "l"(p3));
+}
+static_assert(kThreads == 256 && kV == 8 && kRowBatch == 4, "the fused load blocks assume 256 threads x 8 columns, 4-row batches");
+
 // Data produced by other CTAs earlier in the same (persistent) kernel: read
 // through L2 (ld.global.cg) so a stale L1 line can never be observed.
 __device__ __forceinline__ double ldcg(const double* p) { return __ldcg(p); }

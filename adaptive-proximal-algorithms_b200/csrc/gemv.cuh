@@ -16,6 +16,7 @@
 // (no atomics: results are reproducible run to run).
 #pragma once
 #include "common.cuh"
+#include "gemv_ring.cuh"
 
 namespace adaprox {
 
@@ -37,8 +38,7 @@ __device__ __forceinline__ double row_chunk_dot(const double* __restrict__ arow,
   int k = 0;
   for (; k + kU * 32 <= nvec; k += kU * 32) {
     double2 a[kU];
-#pragma unroll
-    for (int u = 0; u < kU; ++u) a[u] = ld_stream(arow + 2 * (k + u * 32 + lane));
+    ld_stream16_512(arow + 2 * (k + lane), a);          // element u: +u*32 double2 = +u*512 B
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
       const double2 xv = *reinterpret_cast<const double2*>(s_x + 2 * (k + u * 32 + lane));
@@ -66,7 +66,7 @@ __device__ __forceinline__ double row_chunk_dot(const double* __restrict__ arow,
   return warp_sum(acc0 + acc1);
 }
 
-__device__ __forceinline__ void gemv_n_dense(const DMat& M, const double* x, double* s_x, int b, int G) {
+__device__ __noinline__ void gemv_n_dense(const DMat& M, const double* x, double* s_x, int b, int G) {
   const int64_t U = (int64_t)M.nchunks * M.nrb;
   const int64_t u0 = unit_begin(U, b, G), u1 = unit_begin(U, b + 1, G);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -95,7 +95,7 @@ __device__ __forceinline__ void gemv_n_dense(const DMat& M, const double* x, dou
 // ---------------------------------------------------------------------------
 // dense A'r partials
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ void gemv_t_dense(const DMat& M, const double* r, int b, int G) {
+__device__ __noinline__ void gemv_t_dense(const DMat& M, const double* r, int b, int G) {
   const int64_t U = (int64_t)M.nchunks * M.nrb;
   const int64_t u0 = unit_begin(U, b, G), u1 = unit_begin(U, b + 1, G);
   constexpr int kH = kV / 2;    // double2 per thread per row
@@ -129,7 +129,24 @@ __device__ __forceinline__ void gemv_t_dense(const DMat& M, const double* r, int
 #pragma unroll
     for (int k = 0; k < kH; ++k) ok[k] = (col0 + 2 * (k * kThreads + threadIdx.x)) < M.ld;
     int64_t row = r0;
-    for (; row + kRowBatch <= r1; row += kRowBatch) {
+    if (ok[kH - 1]) {            // full-width chunk: all 16 loads of a 4-row batch in one block
+      for (; row + kRowBatch <= r1; row += kRowBatch) {
+        double2 a[kRowBatch][kH];
+        double rv[kRowBatch];
+        const double* p = base + row * M.ld;
+        ld_stream4x4_4096(p, p + M.ld, p + 2 * M.ld, p + 3 * M.ld, a);
+#pragma unroll
+        for (int q = 0; q < kRowBatch; ++q) rv[q] = ldcg(r + row + q);
+#pragma unroll
+        for (int q = 0; q < kRowBatch; ++q)
+#pragma unroll
+          for (int k = 0; k < kH; ++k) {
+            acc[k].x = fma(a[q][k].x, rv[q], acc[k].x);
+            acc[k].y = fma(a[q][k].y, rv[q], acc[k].y);
+          }
+      }
+    }
+    for (; row + kRowBatch <= r1; row += kRowBatch) {   // ragged last chunk: predicated loads
       double2 a[kRowBatch][kH];
       double rv[kRowBatch];
 #pragma unroll
@@ -184,13 +201,17 @@ __device__ __forceinline__ void spmv_rows(int64_t nrows, const int64_t* __restri
 // ---------------------------------------------------------------------------
 // phases
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ void gemv_n_phase(const DMat& M, const double* x, double* s_x, int b, int G) {
-  if (M.kind == MAT_DENSE) gemv_n_dense(M, x, s_x, b, G);
-  else if (M.kind == MAT_CSR) spmv_rows(M.m, M.rowptr, M.colind, M.vals, x, M.zpart, b, G);
+__device__ __forceinline__ void gemv_n_phase(const DMat& M, const double* x, Sh& sh, int b, int G) {
+  if (M.kind == MAT_DENSE) {
+    if (M.path == 1) gemv_n_ring(M, x, sh, b, G);
+    else gemv_n_dense(M, x, sh.x, b, G);
+  } else if (M.kind == MAT_CSR) spmv_rows(M.m, M.rowptr, M.colind, M.vals, x, M.zpart, b, G);
 }
-__device__ __forceinline__ void gemv_t_phase(const DMat& M, const double* r, int b, int G) {
-  if (M.kind == MAT_DENSE) gemv_t_dense(M, r, b, G);
-  else if (M.kind == MAT_CSR) spmv_rows(M.n, M.t_rowptr, M.t_colind, M.t_vals, r, M.gpart, b, G);
+__device__ __forceinline__ void gemv_t_phase(const DMat& M, const double* r, Sh& sh, int b, int G) {
+  if (M.kind == MAT_DENSE) {
+    if (M.path == 1) gemv_t_ring(M, r, sh, b, G);
+    else gemv_t_dense(M, r, b, G);
+  } else if (M.kind == MAT_CSR) spmv_rows(M.n, M.t_rowptr, M.t_colind, M.t_vals, r, M.gpart, b, G);
 }
 
 // (A*x)_i from the partials (fixed chunk order)

@@ -24,27 +24,31 @@ struct OpArgs {
 __global__ void __launch_bounds__(kThreads, 2) k_ops(OpArgs a, DWork W) {
   cg::grid_group grid = cg::this_grid();
   const int b = blockIdx.x, G = gridDim.x;
-  __shared__ __align__(16) double s_x[kChunk];
+  extern __shared__ __align__(1024) unsigned char dyn_smem[];
   __shared__ double s_scr[kWarps * 8 + kMaxRed];
+  __shared__ double s_part[kPartRows * kWarps];
+  __shared__ unsigned long long s_bars[2 * kStages];
+  Sh sh;
+  sh_init(sh, dyn_smem, s_scr, s_part, s_bars);
   const int64_t tid = (int64_t)b * kThreads + threadIdx.x, nt = (int64_t)G * kThreads;
 
   if (a.op == OP_MUL) {
-    gemv_n_phase(a.M, a.in, s_x, b, G);
+    gemv_n_phase(a.M, a.in, sh, b, G);
     grid.sync();
     for (int64_t i = tid; i < a.M.m; i += nt) a.out[i] = zsum(a.M, i);
   } else if (a.op == OP_AMUL) {
-    gemv_t_phase(a.M, a.in, b, G);
+    gemv_t_phase(a.M, a.in, sh, b, G);
     grid.sync();
     int64_t j0, j1;
     cta_slice(a.M.n, b, G, j0, j1);
     gsum_slice(a.M, j0, j1, a.out, G);
   } else if (a.op == OP_EVALF) {
     const DProblem& P = a.P;
-    f_phase_A(P, W, a.in, s_x, s_scr, b, G);
+    f_phase_A(P, W, a.in, sh, s_scr, b, G);
     grid.sync();
     f_phase_B(P, W, a.in, s_scr, b, G);
     grid.sync();
-    if (a.want_grad) f_phase_C(P, W, b, G);
+    if (a.want_grad) f_phase_C(P, W, sh, b, G);
     grid.sync();
     double tot[2], xx[1] = {0.0};
     grid_totals<2>(W.red, G, SLOT_F0, tot, s_scr);
@@ -88,9 +92,14 @@ __global__ void __launch_bounds__(kThreads, 2) k_ops(OpArgs a, DWork W) {
 // One pass of a matrix kernel family, for adaprox_time_kernel (roofline measurement).
 __global__ void __launch_bounds__(kThreads, 2) k_gemv_pass(DMat M, int which, const double* in, double* out) {
   const int b = blockIdx.x, G = gridDim.x;
-  __shared__ __align__(16) double s_x[kChunk];
-  if (which == 0) gemv_n_phase(M, in, s_x, b, G);
-  else gemv_t_phase(M, in, b, G);
+  extern __shared__ __align__(1024) unsigned char dyn_smem[];
+  __shared__ double s_scr[kWarps * 8 + kMaxRed];
+  __shared__ double s_part[kPartRows * kWarps];
+  __shared__ unsigned long long s_bars[2 * kStages];
+  Sh sh;
+  sh_init(sh, dyn_smem, s_scr, s_part, s_bars);
+  if (which == 0) gemv_n_phase(M, in, sh, b, G);
+  else gemv_t_phase(M, in, sh, b, G);
 }
 
 // ---------------------------------------------------------------------------

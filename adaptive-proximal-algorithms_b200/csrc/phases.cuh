@@ -57,7 +57,20 @@ struct DWork {
   double* xout; double* yout;
   adaprox_record* rec;
   DResult* res;
+  unsigned long long* tstamp;   // optional [iters][8] globaltimer stamps at phase boundaries (ADAPROX_PHASE_TIMING=1)
+  int tstamp_iters;
 };
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// CTA 0 / thread 0 stamps the time at which it passed phase boundary `k` of iteration `it`
+__device__ __forceinline__ void phase_stamp(const DWork& W, long long it, int k) {
+  if (W.tstamp != nullptr && blockIdx.x == 0 && threadIdx.x == 0 && it >= 1 && it <= W.tstamp_iters)
+    W.tstamp[(it - 1) * 8 + k] = globaltimer_ns();
+}
 
 // ---------------------------------------------------------------------------
 // prox operators (ProximalCore / ProximalOperators bodies)
@@ -193,9 +206,9 @@ __device__ __forceinline__ bool f_has_gemv_n(int k) {
 }
 __device__ __forceinline__ bool f_has_gemv_t(int k) { return k == ADAPROX_F_LEAST_SQUARES || k == ADAPROX_F_LOGISTIC; }
 
-__device__ __forceinline__ void f_phase_A(const DProblem& P, const DWork& W, const double* x, double* s_x, double* s_scr,
+__device__ __forceinline__ void f_phase_A(const DProblem& P, const DWork& W, const double* x, Sh& sh, double* s_scr,
                                           int b, int G) {
-  if (f_has_gemv_n(P.f_kind)) gemv_n_phase(P.F, x, s_x, b, G);
+  if (f_has_gemv_n(P.f_kind)) gemv_n_phase(P.F, x, sh, b, G);
   if (P.f_kind == ADAPROX_F_CUBIC) {
     double acc[1] = {0.0};
     const int64_t tid = (int64_t)b * kThreads + threadIdx.x, nt = (int64_t)G * kThreads;
@@ -281,8 +294,8 @@ __device__ __forceinline__ void f_phase_B(const DProblem& P, const DWork& W, con
   block_reduce_store<2>(acc, W.red, G, SLOT_F0, s_scr);
 }
 
-__device__ __forceinline__ void f_phase_C(const DProblem& P, const DWork& W, int b, int G) {
-  if (f_has_gemv_t(P.f_kind)) gemv_t_phase(P.F, W.r, b, G);
+__device__ __forceinline__ void f_phase_C(const DProblem& P, const DWork& W, Sh& sh, int b, int G) {
+  if (f_has_gemv_t(P.f_kind)) gemv_t_phase(P.F, W.r, sh, b, G);
 }
 
 // f(x) from the two value sums

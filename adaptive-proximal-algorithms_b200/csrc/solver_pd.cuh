@@ -52,8 +52,12 @@ template <bool LINESEARCH>
 __global__ void __launch_bounds__(kThreads, 2) k_primal_dual(DProblem P, DOpts O, DWork W) {
   cg::grid_group grid = cg::this_grid();
   const int b = blockIdx.x, G = gridDim.x;
-  __shared__ __align__(16) double s_x[kChunk];
+  extern __shared__ __align__(1024) unsigned char dyn_smem[];
   __shared__ double s_scr[kWarps * 8 + kMaxRed];
+  __shared__ double s_part[kPartRows * kWarps];
+  __shared__ unsigned long long s_bars[2 * kStages];
+  Sh sh;
+  sh_init(sh, dyn_smem, s_scr, s_part, s_bars);
 
   const bool hasA = (P.A.kind != MAT_NONE);
   const bool h_l2 = hasA && (P.h.kind == ADAPROX_P_NORM_L2);
@@ -79,14 +83,14 @@ __global__ void __launch_bounds__(kThreads, 2) k_primal_dual(DProblem P, DOpts O
   unsigned flags = 0;
 
   // ---- prologue (:327-332) --------------------------------------------------
-  f_phase_A(P, W, x, s_x, s_scr, b, G);
-  if (hasA) gemv_n_phase(P.A, x, s_x, b, G);
+  f_phase_A(P, W, x, sh, s_scr, b, G);
+  if (hasA) gemv_n_phase(P.A, x, sh, b, G);
   grid.sync();
   f_phase_B(P, W, x, s_scr, b, G);
   if (hasA) for (int64_t i = tid; i < P.md; i += nt) W.Axb[axc][i] = zsum(P.A, i);
   grid.sync();
-  f_phase_C(P, W, b, G);
-  if (hasA) gemv_t_phase(P.A, y, b, G);
+  f_phase_C(P, W, sh, b, G);
+  if (hasA) gemv_t_phase(P.A, y, sh, b, G);
   grid.sync();
   {
     double tot[2];
@@ -116,10 +120,12 @@ __global__ void __launch_bounds__(kThreads, 2) k_primal_dual(DProblem P, DOpts O
 
   for (int64_t it = 1; it <= O.maxit; ++it) {
     // ---- P1 ---------------------------------------------------------------
-    f_phase_A(P, W, x, s_x, s_scr, b, G);                                        // :336
-    if (hasA) gemv_n_phase(P.A, x, s_x, b, G);                                   // :335
+    phase_stamp(W, it, 0);
+    f_phase_A(P, W, x, sh, s_scr, b, G);                                        // :336
+    if (hasA) gemv_n_phase(P.A, x, sh, b, G);                                   // :335
     grid.sync();
     // ---- P2 ---------------------------------------------------------------
+    phase_stamp(W, it, 1);
     f_phase_B(P, W, x, s_scr, b, G);
     double* Ax_prev = W.Axb[axc];
     double* Ax = W.Axb[axc ^ 1];
@@ -127,10 +133,12 @@ __global__ void __launch_bounds__(kThreads, 2) k_primal_dual(DProblem P, DOpts O
     n_eval++; n_mul++;
     grid.sync();
     // ---- P3 ---------------------------------------------------------------
-    f_phase_C(P, W, b, G);
+    phase_stamp(W, it, 2);
+    f_phase_C(P, W, sh, b, G);
     n_grad++;
     grid.sync();
     // ---- P4 ---------------------------------------------------------------
+    phase_stamp(W, it, 3);
     double ftot[2];
     grid_totals<2>(W.red, G, SLOT_F0, ftot, s_scr);
     double* grad = W.gb[gc ^ 1];
@@ -151,6 +159,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_primal_dual(DProblem P, DOpts O
     }
     grid.sync();
     // ---- P5: stepsize, dual step ---------------------------------------------
+    phase_stamp(W, it, 4);
     double t5[5];                                   // PR, GG, GX, DXX, GVAL
     {
       double t4[4], tg[1] = {0.0};
@@ -224,7 +233,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_primal_dual(DProblem P, DOpts O
         dual_rows(P, W, w, Ax, ynew, sigma, l2tot[0], want_obj, y, s_scr, b, G, true);   // :525
         n_proxh++;
         grid.sync();
-        gemv_t_phase(P.A, ynew, b, G);                                           // :526
+        gemv_t_phase(P.A, ynew, sh, b, G);                                           // :526
         n_amul++;
         grid.sync();
         gsum_slice(P.A, j0, j1, aty_next, G);
@@ -256,6 +265,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_primal_dual(DProblem P, DOpts O
     }
 
     // ---- P6: residual, record, convergence (:348-356) ----------------------------
+    phase_stamp(W, it, 5);
     norm_res = sqrt(norm_sq_jl(t5[0]) + (hasA ? norm_sq_jl(dr_sum) : 0.0));
     if (!(gamma == gamma) || !(norm_res == norm_res) || isinf(gamma)) flags |= ADAPROX_FLAG_NONFINITE;
     if (b == 0 && threadIdx.x == 0 && W.rec != nullptr && it <= O.max_records) {
@@ -272,12 +282,13 @@ __global__ void __launch_bounds__(kThreads, 2) k_primal_dual(DProblem P, DOpts O
     if (norm_res <= O.tol) { converged = true; it_done = it; break; }            // :354-356
 
     if (hasA && !LINESEARCH) {
-      gemv_t_phase(P.A, y, b, G);                                                // :358
+      gemv_t_phase(P.A, y, sh, b, G);                                                // :358
       n_amul++;
       grid.sync();
       gsum_slice(P.A, j0, j1, W.Aty[atc], G);
     }
     // ---- P7 (:359-361) ---------------------------------------------------------------
+    phase_stamp(W, it, 6);
     {
       double acc[1] = {0.0};
       double* xn = W.xb[(xc + 1) % 3];
@@ -296,6 +307,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_primal_dual(DProblem P, DOpts O
     grad_prev = grad; gc ^= 1;
     if (hasA) axc ^= 1;
     grid.sync();
+    phase_stamp(W, it, 7);
   }
 
   // ---- epilogue: copy out -----------------------------------------------------

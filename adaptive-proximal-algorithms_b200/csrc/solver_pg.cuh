@@ -16,14 +16,14 @@ namespace adaprox {
 // and grid-synced.  Returns with all partials consumed; the caller must
 // grid-sync before anything overwrites W.r / the matrix partials again.
 __device__ __forceinline__ double eval_f_grid(cg::grid_group& grid, const DProblem& P, const DWork& W, const double* x,
-                                              bool want_grad, double* grad_out, int64_t j0, int64_t j1, double* s_x,
+                                              bool want_grad, double* grad_out, int64_t j0, int64_t j1, Sh& sh,
                                               double* s_scr, int b, int G) {
-  f_phase_A(P, W, x, s_x, s_scr, b, G);
+  f_phase_A(P, W, x, sh, s_scr, b, G);
   grid.sync();
   f_phase_B(P, W, x, s_scr, b, G);
   grid.sync();
   if (want_grad) {
-    f_phase_C(P, W, b, G);
+    f_phase_C(P, W, sh, b, G);
     grid.sync();
   }
   double tot[2], xx[1] = {0.0};
@@ -36,8 +36,12 @@ __device__ __forceinline__ double eval_f_grid(cg::grid_group& grid, const DProbl
 __global__ void __launch_bounds__(kThreads, 2) k_proxgrad_family(DProblem P, DOpts O, DWork W) {
   cg::grid_group grid = cg::this_grid();
   const int b = blockIdx.x, G = gridDim.x;
-  __shared__ __align__(16) double s_x[kChunk];
+  extern __shared__ __align__(1024) unsigned char dyn_smem[];
   __shared__ double s_scr[kWarps * 8 + kMaxRed];
+  __shared__ double s_part[kPartRows * kWarps];
+  __shared__ unsigned long long s_bars[2 * kStages];
+  Sh sh;
+  sh_init(sh, dyn_smem, s_scr, s_part, s_bars);
   const int64_t tid = (int64_t)b * kThreads + threadIdx.x, nt = (int64_t)G * kThreads;
   int64_t j0, j1;
   cta_slice(P.n, b, G, j0, j1);
@@ -70,7 +74,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_proxgrad_family(DProblem P, DOp
     double* grad = W.gb[0];
     if (nesterov) for (int64_t j = j0 + threadIdx.x; j < j1; j += kThreads) z_prev[j] = x[j];
     double theta = 1.0;                                                          // :68
-    double f_x = eval_f_grid(grid, P, W, x, true, grad, j0, j1, s_x, s_scr, b, G);   // :52 / :69
+    double f_x = eval_f_grid(grid, P, W, x, true, grad, j0, j1, sh, s_scr, b, G);   // :52 / :69
     n_eval++; n_grad++;
     int64_t trial_no = 0;
     for (int64_t it = 1; it <= O.maxit; ++it) {
@@ -93,7 +97,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_proxgrad_family(DProblem P, DOp
         block_reduce_store<3>(acc, W.red, G, base, s_scr);
         n_proxg++;
         grid.sync();
-        f_z = eval_f_grid(grid, P, W, z, false, nullptr, j0, j1, s_x, s_scr, b, G);   // :37 / :45
+        f_z = eval_f_grid(grid, P, W, z, false, nullptr, j0, j1, sh, s_scr, b, G);   // :37 / :45
         n_eval++;
         double t3[3];
         grid_totals<3>(W.red, G, base, t3, s_scr);
@@ -111,7 +115,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_proxgrad_family(DProblem P, DOp
       if (norm_res <= O.tol) { converged = true; it_done = it; break; }          // :57 / :75
       if (!nesterov) {
         // x, f_x = z, f_z ; grad_x = pb()  (:60-61) -- W.r still holds the residual of z
-        f_phase_C(P, W, b, G);
+        f_phase_C(P, W, sh, b, G);
         grid.sync();
         double tot[2];
         grid_totals<2>(W.red, G, SLOT_F0, tot, s_scr);
@@ -131,7 +135,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_proxgrad_family(DProblem P, DOp
         double* t = z_prev; z_prev = z; z = t;                                   // :71
         result = z_prev;
         grid.sync();
-        f_x = eval_f_grid(grid, P, W, x, true, grad, j0, j1, s_x, s_scr, b, G);  // :81
+        f_x = eval_f_grid(grid, P, W, x, true, grad, j0, j1, sh, s_scr, b, G);  // :81
         n_eval++; n_grad++;
       }
     }
@@ -157,7 +161,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_proxgrad_family(DProblem P, DOp
       }
       for (int64_t j = j0 + threadIdx.x; j < j1; j += kThreads) z[j] = x[j] + beta * (x[j] - x_prev[j]);   // :129
       grid.sync();
-      eval_f_grid(grid, P, W, z, true, grad, j0, j1, s_x, s_scr, b, G);          // :130
+      eval_f_grid(grid, P, W, z, true, grad, j0, j1, sh, s_scr, b, G);          // :130
       n_eval++; n_grad++;
       double acc[2] = {0.0, 0.0};
       for (int64_t j = j0 + threadIdx.x; j < j1; j += kThreads) {               // :131-133 (x_prev <- x, x <- prox)
@@ -178,7 +182,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_proxgrad_family(DProblem P, DOp
       norm_res = sqrt(t2[0]) / gamma;
       double fx = NAN;
       if (want_obj) {                                                            // :134-136, uncounted f(x)
-        fx = eval_f_grid(grid, P, W, x, false, nullptr, j0, j1, s_x, s_scr, b, G);
+        fx = eval_f_grid(grid, P, W, x, false, nullptr, j0, j1, sh, s_scr, b, G);
         grid.sync();
       }
       record(it, fx, prox_value_finish(P.g.kind, P.g.lambda, t2[1]));
@@ -193,9 +197,9 @@ __global__ void __launch_bounds__(kThreads, 2) k_proxgrad_family(DProblem P, DOp
     double* grad_prev = W.gb[1];
     for (int64_t j = j0 + threadIdx.x; j < j1; j += kThreads) { x_prev[j] = W.aux[0][j]; x_bar[j] = x[j]; }   // :165
     grid.sync();
-    eval_f_grid(grid, P, W, x, true, grad, j0, j1, s_x, s_scr, b, G);            // :166
+    eval_f_grid(grid, P, W, x, true, grad, j0, j1, sh, s_scr, b, G);            // :166
     grid.sync();
-    eval_f_grid(grid, P, W, x_prev, true, grad_prev, j0, j1, s_x, s_scr, b, G);  // :167
+    eval_f_grid(grid, P, W, x_prev, true, grad_prev, j0, j1, sh, s_scr, b, G);  // :167
     n_eval = 2; n_grad = 2;
     const double phi = O.phi;
     const double rho = 1.0 / phi + 1.0 / (phi * phi);                            // :172
@@ -238,13 +242,13 @@ __global__ void __launch_bounds__(kThreads, 2) k_proxgrad_family(DProblem P, DOp
       norm_res = sqrt(t3[0]) / gamma;                                            // :182
       double fx = NAN;
       if (want_obj) {
-        fx = eval_f_grid(grid, P, W, x, false, nullptr, j0, j1, s_x, s_scr, b, G);
+        fx = eval_f_grid(grid, P, W, x, false, nullptr, j0, j1, sh, s_scr, b, G);
         grid.sync();
       }
       record(it, fx, prox_value_finish(P.g.kind, P.g.lambda, t3[1]));
       result = x;
       if (norm_res <= O.tol) { converged = true; it_done = it; break; }
-      eval_f_grid(grid, P, W, x, true, grad, j0, j1, s_x, s_scr, b, G);          // :189
+      eval_f_grid(grid, P, W, x, true, grad, j0, j1, sh, s_scr, b, G);          // :189
       n_eval++; n_grad++;
     }
   }
