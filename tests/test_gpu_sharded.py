@@ -1,0 +1,68 @@
+"""Row-sharded AdaPGM over 2 GPUs (one process per GPU, NCCL all-reduce inside the
+library) against the single-GPU solve and the CPU oracle.  Skipped on a 1-GPU box."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), LOCAL_RANK=str(rank))
+    import torch.distributed as dist
+    import adaprox_b200 as AdaProx
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    dev = AdaProx.Device(rank)
+    AdaProx.set_default_device(dev)
+    AdaProx.sharding.attach_communicator(dev, dist)
+    m, n = 400, 1000
+    P = AdaProx.synth.planted_lasso(m, n, 5, 0)
+    Lf = AdaProx.synth.spectral_norm_sq(P["A"], iters=1000, tol=1e-15)
+    row0, rows = AdaProx.sharding.shard_rows(m, world, rank)
+    A = AdaProx.DeviceMatrix(P["A"][row0:row0 + rows], dev=dev)
+    A.set_shard(m, row0)
+    f = AdaProx.Counting(AdaProx.LinearLeastSquares(A, P["b"][row0:row0 + rows]))
+    g = AdaProx.Counting(AdaProx.NormL1(1.0))
+    log = []
+    x, it = AdaProx.adaptive_proxgrad(np.zeros(n), f=f, g=g, rule=AdaProx.OurRule(gamma=1 / Lf), tol=1e-6, maxit=10000, log=log)
+    # device-generated shard of a larger instance: every rank must reach the planted optimum
+    Pd = AdaProx.generate_planted_lasso(512, 4100, 5, 1, power_iters=60, row0=AdaProx.sharding.shard_rows(512, world, rank)[0],
+                                        rows=AdaProx.sharding.shard_rows(512, world, rank)[1], dev=dev)
+    log2 = []
+    x2, it2 = AdaProx.adaptive_proxgrad(np.zeros(4100), f=AdaProx.LinearLeastSquares(Pd["A"], Pd["b"]), g=AdaProx.NormL1(1.0),
+                                        rule=AdaProx.OurRule(gamma=1 / Pd["Lf"]), tol=1e-7, maxit=30000, log=log2)
+    np.savez(out % rank, x=x, it=it, gam=np.array([r["gamma"] for r in log[:40]]), obj=log[-1]["objective"],
+             counts=np.array([f.eval_count, f.grad_count, g.prox_count]), obj2=log2[-1]["objective"], opt2=Pd["optimum"],
+             res2=log2[-1]["norm_res"], x2err=np.linalg.norm(x2 - Pd["x_star"]), launches=AdaProx.last_solve_info()["kernel_launches"])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_adapgm_two_gpus(tmp_path, lasso_small):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    from oracle import adaprox_oracle as O
+    out = str(tmp_path / "rank%d.npz")
+    mp.spawn(_worker, args=(2, 29400 + os.getpid() % 500, out), nprocs=2, join=True)
+    R0, R1 = np.load(out % 0), np.load(out % 1)
+    # replicated state stays in lock step: bit-identical iterates on both ranks
+    assert np.array_equal(R0["x"], R1["x"]) and int(R0["it"]) == int(R1["it"])
+    P = lasso_small
+    logo = []
+    xo, ito = O.adaptive_proxgrad(np.zeros(1000), f=O.LinearLeastSquares(P["A"], P["b"]), g=O.NormL1(1.0),
+                                  rule=O.OurRule(gamma=1 / P["Lf"]), tol=1e-6, maxit=10000, log=logo)
+    go = np.array([r["gamma"] for r in logo[:40]])
+    assert np.max(np.abs(R0["gam"][:15] / go[:15] - 1)) < 1e-12
+    assert np.max(np.abs(R0["gam"] / go - 1)) < 1e-9
+    assert abs(float(R0["obj"]) - logo[-1]["objective"]) <= 1e-10 * abs(logo[-1]["objective"])
+    assert abs(int(R0["it"]) - ito) <= max(2, 0.05 * ito)
+    it = int(R0["it"])
+    assert list(R0["counts"]) == [it + 1, it + 1, it]
+    assert float(R0["res2"]) <= 1e-7 and abs(float(R0["obj2"]) - float(R0["opt2"])) < 1e-9 * float(R0["opt2"])
+    assert float(R0["x2err"]) < 1e-5
