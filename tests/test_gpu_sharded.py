@@ -30,7 +30,7 @@ def _worker(rank, world, port, out):
     log = []
     x, it = AdaProx.adaptive_proxgrad(np.zeros(n), f=f, g=g, rule=AdaProx.OurRule(gamma=1 / Lf), tol=1e-6, maxit=10000, log=log)
     # device-generated shard of a larger instance: every rank must reach the planted optimum
-    Pd = AdaProx.generate_planted_lasso(512, 4100, 5, 1, power_iters=60, row0=AdaProx.sharding.shard_rows(512, world, rank)[0],
+    Pd = AdaProx.generate_planted_lasso(512, 4100, 40, 1, power_iters=60, row0=AdaProx.sharding.shard_rows(512, world, rank)[0],
                                         rows=AdaProx.sharding.shard_rows(512, world, rank)[1], dev=dev)
     log2 = []
     x2, it2 = AdaProx.adaptive_proxgrad(np.zeros(4100), f=AdaProx.LinearLeastSquares(Pd["A"], Pd["b"]), g=AdaProx.NormL1(1.0),
