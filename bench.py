@@ -43,6 +43,16 @@ def b_iter_bytes(m_loc, n):
     return 2 * 8 * m_loc * n + 8 * (3 * m_loc + 8 * n)
 
 
+def ncu_traffic_per_eval(m, n):
+    """DRAM bytes (read + write) per gradient evaluation from the committed `ncu --set full` capture of the
+    persistent kernel at the full size (profiles/r01_ncu_k_primal_dual_ring.json); None for other sizes."""
+    p = os.path.join(ROOT, "profiles", "r01_ncu_k_primal_dual_ring.json")
+    if (m, n) != (M_FULL, N_FULL) or not os.path.exists(p):
+        return None
+    with open(p) as f:
+        return float(json.load(f)["_derived"]["dram_bytes_per_gradient_eval"])
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -252,7 +262,10 @@ def run_b200(args):
     if rank == 0:
         peak, peak_src = peaks()
         bytes_iter_rank = b_iter_bytes(rows, n)
-        achieved = bytes_iter_rank * K / (dev_ms * 1e-3) / 1e9     # per-GPU GB/s
+        # the timed launch(es) perform K iterations plus the solver's prologue (one more A*x / A'r pair, :327-332)
+        bytes_launch = bytes_iter_rank * K + 2 * 8 * rows * n
+        achieved = bytes_launch / (dev_ms * 1e-3) / 1e9            # per-GPU GB/s
+        per_eval = ncu_traffic_per_eval(m, n) if world == 1 else None
         out = {
             "metric": METRIC if (m, n) == (M_FULL, N_FULL) else f"AdaPGM iters/sec on {m}x{n} fp64 lasso",
             "value": K / (dev_ms * 1e-3), "unit": "it/s", "n_gpus": world, "steps": K, "warmup": W,
@@ -264,9 +277,14 @@ def run_b200(args):
                        "l2": "inputs larger than L2 (matrix shard %.1f GB vs 126 MB), no flush needed" % (rows * n * 8 / 1e9),
                        "timing": "library CUDA events on the kernels' stream around one solve of K iterations; max over ranks",
                        "generation_s": round(t_gen, 2), "gamma0": gamma0},
-            "achieved_hbm_gbs_per_gpu": achieved,
+            "achieved_hbm_gbs_per_gpu": bytes_iter_rank * K / (dev_ms * 1e-3) / 1e9,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": (per_eval * (K + 1)) if per_eval else None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": bytes_launch,
+                         "launch": "one persistent launch = K iterations + prologue = K+1 gradient evaluations" if world == 1
+                                   else "K+1 gradient evaluations as 6 launches + 1 all-reduce each",
+                         "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per gradient evaluation x (K+1), "
+                                           "profiles/r01_ncu_k_primal_dual_ring.json" if per_eval else None,
                          "kernel": "k_primal_dual<false> (persistent cooperative kernel: the whole solve is one launch)"
                                    if world == 1 else "k_sh_A + k_sh_C (split-phase GEMV kernels)",
                          "algorithmic_bytes_per_iteration_per_gpu": bytes_iter_rank,
