@@ -768,6 +768,15 @@ def adaptive_linesearch_primal_dual(x, y, *, f, g, h, A, gamma=None, eta=1.0, t=
     return xo, yo, it
 
 
+def malitsky_pock(x, y, *, f, g, h, A, sigma, t=1.0, tol=1e-5, maxit=10_000, name="MP-ls", log=None):
+    """src/AdaProx.jl:581-629."""
+    o = _opts(tol, maxit)
+    o.sigma, o.t = float(sigma), float(t)
+    xo, yo, it, info = _solve(L.S_MALITSKY_POCK, x, y, f=f, g=g, h=h, A=A, opts=o, name=name, log=log, pd=True)
+    _last_info.update(info)
+    return xo, yo, it
+
+
 def backtracking_proxgrad(x0, *, f, g, gamma0, xi=1.0, shrink=0.5, tol=1e-5, maxit=100_000,
                           name="Backtracking PG", log=None):
     """src/AdaProx.jl:50-64."""

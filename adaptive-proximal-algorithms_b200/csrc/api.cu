@@ -8,6 +8,7 @@
 #include "ops.cuh"
 #include "solver_pd.cuh"
 #include "solver_pg.cuh"
+#include "solver_mp.cuh"
 #include "comm.hpp"
 
 using namespace adaprox;
@@ -194,7 +195,7 @@ extern "C" int adaprox_create(adaprox_handle* out, int device) {
   // resident CTAs per SM: the minimum over the persistent kernels
   int per_sm = 2, nb = 0;
   const void* kernels[] = {(const void*)k_primal_dual<false>, (const void*)k_primal_dual<true>, (const void*)k_ops,
-                           (const void*)k_proxgrad_family, (const void*)k_gemv_pass};
+                           (const void*)k_proxgrad_family, (const void*)k_gemv_pass, (const void*)k_malitsky_pock};
   for (const void* k : kernels) {
     if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kRingBytes) != cudaSuccess) {
       delete h; return ADAPROX_ERR_CUDA;
@@ -624,6 +625,9 @@ extern "C" int adaprox_solve(adaprox_handle h, const adaprox_problem* p, const a
     case ADAPROX_S_FIXED_NESTEROV:
     case ADAPROX_S_AGRAAL:
       rc = coop_launch(h, k_proxgrad_family, args);
+      break;
+    case ADAPROX_S_MALITSKY_POCK:
+      rc = coop_launch(h, k_malitsky_pock, args);
       break;
     default:
       return fail(h, ADAPROX_ERR_UNSUPPORTED, "solver has no device kernel yet");

@@ -292,7 +292,7 @@ def test_nesterov_worst_case(AdaProx):
     # (K, final-value tolerance): after 3000 iterations the adaptive trajectories have decorrelated (chaotic stepsizes),
     # only the fixed-step run stays comparable digit for digit
     for K, ftol, mk_d, mk_o in [(35, 2e-3, lambda: AdaProx.OurRule(gamma=1 / Lc), lambda: O.OurRule(gamma=1 / Lc)),
-                                (18, 2e-3, lambda: AdaProx.MalitskyMishchenkoRule(gamma=1 / Lc), lambda: O.MalitskyMishchenkoRule(gamma=1 / Lc)),
+                                (15, 2e-3, lambda: AdaProx.MalitskyMishchenkoRule(gamma=1 / Lc), lambda: O.MalitskyMishchenkoRule(gamma=1 / Lc)),
                                 (35, 1e-10, lambda: AdaProx.FixedStepsize(1 / Lc), lambda: O.FixedStepsize(1 / Lc))]:
         logd, logo = [], []
         xd, itd = AdaProx.adaptive_proxgrad(np.zeros(n), f=f, g=AdaProx.Zero(), rule=mk_d(), tol=1e-6, maxit=3000, log=logd)
@@ -496,3 +496,36 @@ def test_error_behaviour(AdaProx):
         AdaProx.LinearLeastSquares(np.eye(3), np.ones(2))         # b shorter than the rows of A -> status < 0 at solve time
         AdaProx.adaptive_proxgrad(np.zeros(3), f=AdaProx.LinearLeastSquares(np.eye(3), np.ones(2)), g=AdaProx.Zero(),
                                   rule=AdaProx.OurRule(gamma=1.0))
+
+
+# ---------------------------------------------------------------- Malitsky-Pock linesearch (src/AdaProx.jl:555-629)
+def test_malitsky_pock(AdaProx):
+    Q, q, y = _svm(AdaProx, 200, 12, 2)
+    N = Q.shape[0]
+    Amat = y[None, :].copy()
+    nA = np.linalg.norm(Amat)
+    for t in (0.5, 2.0):
+        fd, fo = AdaProx.Counting(AdaProx.Quadratic(Q, q)), O.Counting(O.Quadratic(Q, q))
+        Ad, Ao = AdaProx.Counting(AdaProx.DeviceMatrix(Amat)), O.Counting(Amat)
+        gd, go = AdaProx.Counting(AdaProx.IndBox(0.0, 0.1)), O.Counting(O.IndBox(0.0, 0.1))
+        ld, lo = [], []
+        kw = dict(sigma=1 / nA, t=t, tol=1e-5, maxit=400)
+        xd, yd, itd = AdaProx.malitsky_pock(np.zeros(N), np.zeros(1), f=fd, g=gd, h=AdaProx.IndZero(), A=Ad, log=ld, **kw)
+        xo, yo, ito = O.malitsky_pock(np.zeros(N), np.zeros(1), f=fo, g=go, h=O.IndZero(), A=Ao, log=lo, **kw)
+        K = 40
+        assert np.allclose([r["sigma"] for r in ld[:K]], [r["sigma"] for r in lo[:K]], rtol=1e-12)
+        assert np.allclose([r["gamma"] for r in ld[:K]], [r["gamma"] for r in lo[:K]], rtol=1e-12)
+        assert np.allclose([r["norm_res"] for r in ld[:K]], [r["norm_res"] for r in lo[:K]], rtol=1e-8)
+        for key in ("f_evals", "grad_f_evals", "prox_g_evals", "A_evals", "At_evals"):
+            assert [r[key] for r in ld[:K]] == [r[key] for r in lo[:K]], key
+        assert abs(itd - ito) <= max(3, 0.05 * ito)
+    # LAD-type problem: h = |. - b|_1 through its conjugate, f = Zero
+    X, yv = AdaProx.synth.dense_regression(150, 8, 1)
+    A2 = np.hstack([X, np.ones((150, 1))])
+    ld, lo = [], []
+    kw = dict(sigma=1.0, t=1.0, tol=1e-5, maxit=150)
+    AdaProx.malitsky_pock(np.zeros(9), np.zeros(150), f=AdaProx.Zero(), g=AdaProx.NormL1(0.1), h=AdaProx.Translate(AdaProx.NormL1(), -yv),
+                          A=AdaProx.DeviceMatrix(A2), log=ld, **kw)
+    O.malitsky_pock(np.zeros(9), np.zeros(150), f=O.Zero(), g=O.NormL1(0.1), h=O.Translate(O.NormL1(), -yv), A=A2, log=lo, **kw)
+    assert np.allclose([r["norm_res"] for r in ld[:40]], [r["norm_res"] for r in lo[:40]], rtol=1e-8)
+    assert np.allclose([r["objective"] for r in ld[:40]], [r["objective"] for r in lo[:40]], rtol=1e-10)
