@@ -9,6 +9,7 @@
 #include "solver_pd.cuh"
 #include "solver_pg.cuh"
 #include "solver_mp.cuh"
+#include "solver_fused.cuh"
 #include "comm.hpp"
 
 using namespace adaprox;
@@ -551,6 +552,43 @@ static int validate_options(adaprox_ctx* h, const adaprox_problem* p, const adap
   return ADAPROX_OK;
 }
 
+// Single-pass fused AdaPGM (solver_fused.cuh): cluster + cooperative launch.  Returns 1 if the configuration is not
+// eligible (the caller falls through to the two-pass kernel), < 0 on error.
+static int fused_cluster_size(const DProblem& P) { return (int)((P.F.ld + kFCols - 1) / kFCols); }
+static bool fused_eligible(const adaprox_options* o, const DProblem& P) {
+  const char* e = std::getenv("ADAPROX_FUSED");
+  if (e && std::strcmp(e, "0") == 0) return false;
+  if (o->solver != ADAPROX_S_ADAPTIVE_PROXGRAD || P.f_kind != ADAPROX_F_LEAST_SQUARES || P.F.kind != MAT_DENSE) return false;
+  const bool force = e && std::strcmp(e, "1") == 0;
+  if (!force && P.F.m * P.F.ld < (int64_t)(32 << 20)) return false;        // small problems: the two-pass kernel has more CTAs per column
+  return fused_cluster_size(P) <= kFMaxCluster;
+}
+static int fused_config(adaprox_ctx* h, int C, cudaLaunchConfig_t* cfg, cudaLaunchAttribute* attrs, int* Q) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    AP_CUDA(h, cudaFuncSetAttribute((const void*)k_adapgm_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, kFRingBytes));
+    AP_CUDA(h, cudaFuncSetAttribute((const void*)k_adapgm_fused, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    attr_set = true;
+  }
+  *cfg = cudaLaunchConfig_t{};
+  cfg->gridDim = dim3(C, 1, 1);
+  cfg->blockDim = dim3(kFThreads, 1, 1);
+  cfg->dynamicSmemBytes = kFRingBytes;
+  cfg->stream = h->stream;
+  attrs[0].id = cudaLaunchAttributeClusterDimension;
+  attrs[0].val.clusterDim.x = C; attrs[0].val.clusterDim.y = 1; attrs[0].val.clusterDim.z = 1;
+  attrs[1].id = cudaLaunchAttributeCooperative;
+  attrs[1].val.cooperative = 1;
+  cfg->attrs = attrs;
+  cfg->numAttrs = 2;
+  int q = 0;
+  cudaError_t e = cudaOccupancyMaxActiveClusters(&q, (const void*)k_adapgm_fused, cfg);
+  if (e != cudaSuccess || q < 1) { cudaGetLastError(); return 1; }
+  *Q = q;
+  cfg->gridDim = dim3(C * q, 1, 1);
+  return ADAPROX_OK;
+}
+
 extern "C" int adaprox_solve(adaprox_handle h, const adaprox_problem* p, const adaprox_options* o, const double* x0,
                              const double* y0, double* x_out, double* y_out, adaprox_record* records, adaprox_result* res) {
   if (!h || !p || !o || !x0 || !x_out || !res) return fail(h, ADAPROX_ERR_INVALID, "solve: bad arguments");
@@ -569,8 +607,19 @@ extern "C" int adaprox_solve(adaprox_handle h, const adaprox_problem* p, const a
   const int64_t n = P.n, md = std::max<int64_t>(P.md, 1);
   const int64_t mf = std::max<int64_t>(P.F.kind != MAT_NONE ? P.F.m : 0, n);
   const int64_t nrec = std::min<int64_t>(O.max_records, O.maxit);
-  const int G = h->grid;
-  size_t need = 11 * ws_size_doubles(n) + 6 * ws_size_doubles(md) + ws_size_doubles(mf) +
+  int G = h->grid;
+  bool fused = fused_eligible(o, P);
+  cudaLaunchConfig_t fcfg; cudaLaunchAttribute fattrs[2]; int fQ = 0;
+  FusedArgs fa{};
+  if (fused) {
+    fa.C = fused_cluster_size(P);
+    rc = fused_config(h, fa.C, &fcfg, fattrs, &fQ);
+    if (rc < 0) return rc;
+    if (rc == 1) fused = false;
+    else { fa.npadf = (int64_t)fa.C * kFCols; G = fa.C * fQ; }
+  }
+  size_t need = (fused ? ws_size_doubles((int64_t)fQ * fa.npadf) : 0) +
+                11 * ws_size_doubles(n) + 6 * ws_size_doubles(md) + ws_size_doubles(mf) +
                 ws_size_doubles((int64_t)kMaxRed * G) + ws_size_doubles((nrec * (int64_t)sizeof(adaprox_record) + 7) / 8) +
                 ws_size_doubles((sizeof(DResult) + 7) / 8);
   if ((rc = ws_reset(h, need))) return rc;
@@ -590,6 +639,7 @@ extern "C" int adaprox_solve(adaprox_handle h, const adaprox_problem* p, const a
   W.res = reinterpret_cast<DResult*>(ws_doubles(h, (sizeof(DResult) + 7) / 8));
   W.xout = W.aux[2];
   O.max_records = nrec;
+  if (fused) fa.gpartf = ws_doubles(h, (int64_t)fQ * fa.npadf);
   const bool phase_timing = std::getenv("ADAPROX_PHASE_TIMING") != nullptr;
   unsigned long long* d_ts = nullptr;
   const int ts_iters = (int)std::min<int64_t>(O.maxit, 64);
@@ -612,10 +662,18 @@ extern "C" int adaprox_solve(adaprox_handle h, const adaprox_problem* p, const a
   const int64_t launches0 = h->launches;
   AP_CUDA(h, cudaEventRecord(h->ev0, h->stream));
   void* args[] = {&P, &O, &W};
+  void* fargs[] = {&P, &O, &W, &fa};
   switch (o->solver) {
     case ADAPROX_S_ADAPTIVE_PRIMAL_DUAL:
     case ADAPROX_S_ADAPTIVE_PROXGRAD:
-      rc = coop_launch(h, k_primal_dual<false>, args);
+      if (fused) {
+        cudaError_t e = cudaLaunchKernelExC(&fcfg, (const void*)k_adapgm_fused, fargs);
+        if (e != cudaSuccess) return fail(h, ADAPROX_ERR_CUDA, std::string("fused cluster launch: ") + cudaGetErrorString(e));
+        h->launches++;
+        rc = ADAPROX_OK;
+      } else {
+        rc = coop_launch(h, k_primal_dual<false>, args);
+      }
       break;
     case ADAPROX_S_LINESEARCH_PRIMAL_DUAL:
       rc = coop_launch(h, k_primal_dual<true>, args);
@@ -654,7 +712,12 @@ extern "C" int adaprox_solve(adaprox_handle h, const adaprox_problem* p, const a
       sum[7] += (double)(t[7] - t[0]) * 1e-3;
       ++cnt;
     }
-    if (cnt) {
+    if (cnt && fused) {
+      const unsigned long long* t = &ts[0];
+      std::fprintf(stderr, "[adaprox fused pass, cycles in CTA 0 thread 0, iteration 1] wait_full=%llu dot+send=%llu update+issue=%llu wait_partials=%llu clusters=%d C=%d\n",
+                   t[1], t[2], t[5], t[6], fQ, fa.C);
+    }
+    if (cnt && !fused) {
       const char* names[7] = {"P1 F*x (+A*x)", "P2 rows/residual", "P3 F'*r", "P4 grad+reductions", "P5 stepsize/dual", "P6 record/A'y", "P7 prox step"};
       std::fprintf(stderr, "[adaprox phase timing] %d iterations, us per iteration:", cnt);
       for (int k = 0; k < 7; ++k) std::fprintf(stderr, " %s=%.1f", names[k], sum[k] / cnt);

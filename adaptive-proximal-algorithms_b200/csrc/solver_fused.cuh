@@ -1,0 +1,396 @@
+// solver_fused.cuh -- AdaPGM on a dense least-squares term with ONE pass over A per
+// iteration:  g = A'(A x - b)  (lasso/runme.jl:21-25 value + pullback, fused).
+//
+// The two-pass formulation streams A twice (A*x needs whole rows before A'r can start).
+// Here a thread-block CLUSTER of C = ceil(ld / 8192) <= 16 CTAs owns a block of rows and
+// all n columns (8192 columns per CTA).  For every row i of the block:
+//   1. the bulk-copy engine has put the CTA's 64 KB piece of row i into a 3-slot shared
+//      memory ring (cp.async.bulk + mbarrier, as in gemv_ring.cuh);
+//   2. the CTA computes its partial dot  <A[i, cols], x[cols]>  (x lives in registers),
+//      reduces it over its 16 warps and stores it into every peer's shared memory
+//      (DSMEM, st.shared::cluster), then arrives on the hardware cluster barrier;
+//   3. while that barrier completes, the rank-1 update of the PREVIOUS row,
+//      acc[cols] += A[i-1, cols] * r[i-1], runs from the tile still resident in shared
+//      memory (accumulators live in registers for the whole pass) and the freed slot is
+//      refilled with row i+2;
+//   4. after the barrier every thread sums the C partials in rank order:
+//      r[i] = sum - b[i]  (bit-identical in all CTAs of the cluster), f += r[i]^2.
+// DRAM traffic per iteration is 8 m n instead of 16 m n.  All sums have a fixed order.
+// Correctness of the exchange buffers: partials of row i live in slot i & 1; a CTA writes
+// row i+2 only after passing the cluster barrier of row i+1, which every CTA arrives at
+// only after it has read the partials of row i.
+#pragma once
+#include "phases.cuh"
+
+namespace adaprox {
+
+constexpr int kFThreads = 512;
+constexpr int kFWarps = kFThreads / 32;
+constexpr int kFCols = 8192;                              // columns per CTA
+constexpr int kFH = kFCols / 2 / kFThreads;               // 8 double2 per thread
+constexpr int kFStages = 3;
+constexpr int kFStageBytes = kFCols * 8;                  // 64 KB
+constexpr int kFRingBytes = kFStages * kFStageBytes;      // 192 KB dynamic shared memory
+constexpr int kFMaxCluster = 16;
+
+struct FusedArgs {
+  double* gpartf;      // [nclusters][npadf] per-cluster A'r partials
+  int64_t npadf;       // C * 8192
+  int C;               // cluster size
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_id_x() { uint32_t r; asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t ncluster_id_x() { uint32_t r; asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ void st_peer_f64(uint32_t local_addr, uint32_t peer, double v) {
+  uint32_t raddr;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(local_addr), "r"(peer));
+  asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(raddr), "d"(v) : "memory");
+}
+// sum over the 16 lanes of a half warp; every lane of the half ends with the same bits
+__device__ __forceinline__ double half_warp_sum(double v) {
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+constexpr int kFDepth = 4;                                // exchange-buffer depth (see the header comment)
+
+struct FusedSmem {
+  uint32_t ring, full, empty, cfull, cpart;   // shared-space addresses
+  uint32_t count;                             // rows pushed through the ring / exchange so far (uniform)
+};
+
+// remote 8-byte store that completes `bytes` on the destination CTA's mbarrier (no fence needed on the sender)
+__device__ __forceinline__ void st_async_peer(uint32_t local_data_addr, uint32_t local_mbar_addr, uint32_t peer, double v) {
+  uint32_t rdata, rbar;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rdata) : "r"(local_data_addr), "r"(peer));
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbar) : "r"(local_mbar_addr), "r"(peer));
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];"
+               ::"r"(rdata), "l"(__double_as_longlong(v)), "r"(rbar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t addr, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+  } while (!ok);
+}
+
+// One fused pass: gpartf[cluster][cols] = sum_{rows of the cluster} A[i, cols] * (A[i,:] x - b[i]);
+// this CTA's partial of sum r_i^2 is returned (non-zero in thread 0 of cluster rank 0 only).
+//
+// Exchange protocol (per row, running index g): every warp sends its partial dot to all C peers with
+// st.async into cpart[g % 4][rank][warp], completing 8 bytes on the peer's cfull[g % 4] mbarrier; thread 0 of each
+// CTA arms its own cfull[g % 4] with expect_tx(C * 16 * 8).  A CTA sends row g+4 only after it has waited for row
+// g+2 to complete, which contains every peer's send of row g+2, which every peer issues after it has consumed
+// row g -- so depth 4 can never be overwritten early.
+__device__ __noinline__ double fused_pass(const DMat& M, const double* bvec, const double* x, FusedSmem& fs, const FusedArgs& fa,
+                                           unsigned long long* dbg) {
+  long long c_full = 0, c_send = 0, c_cwait = 0, c_upd = 0, c_t = 0;
+  const bool prof = (dbg != nullptr) && blockIdx.x == 0 && threadIdx.x == 0;
+  const double* const a = M.a;
+  const int64_t ld = M.ld, n = M.n, m = M.m;
+  const uint32_t ring = fs.ring, full = fs.full, empty = fs.empty, cfull = fs.cfull, cpart = fs.cpart;
+  const uint32_t rank = cluster_ctarank(), q = cluster_id_x(), Q = ncluster_id_x();
+  const int C = fa.C;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t r0 = (m * (int64_t)q) / Q, r1 = (m * (int64_t)(q + 1)) / Q;
+  const int64_t col0 = (int64_t)rank * kFCols;
+  int64_t width = ld - col0;
+  width = width < 0 ? 0 : (width > kFCols ? kFCols : width);
+  const uint32_t bytes = (uint32_t)(width * 8);
+  const uint32_t xbytes = (uint32_t)(C * kFWarps * 8);         // exchange bytes per row per CTA
+  const int nval = C * kFWarps;
+  const double* const abase = a + col0;
+
+  double2 xr[kFH], acc[kFH];
+  bool ok[kFH];
+#pragma unroll
+  for (int k = 0; k < kFH; ++k) {
+    const int64_t jl = 2 * (k * kFThreads + threadIdx.x);
+    const int64_t j = col0 + jl;
+    ok[k] = jl < width;
+    xr[k].x = (j < n) ? ldcg(x + j) : 0.0;
+    xr[k].y = (j + 1 < n) ? ldcg(x + j + 1) : 0.0;
+    acc[k] = make_double2(0.0, 0.0);
+  }
+
+  uint32_t g = fs.count;                       // running index of the row being processed
+  auto issue = [&](int64_t row, uint32_t gi) { // thread 0 only
+    const uint32_t s = gi % kFStages, ph = (gi / kFStages) & 1u;
+    mbar_wait(empty + 8 * s, ph ^ 1u);
+    mbar_expect_tx(full + 8 * s, bytes);
+    bulk_g2s(ring + s * kFStageBytes, abase + row * ld, bytes, full + 8 * s);
+  };
+  if (threadIdx.x == 0 && bytes > 0) {
+    if (r0 < r1) issue(r0, g);
+    if (r0 + 1 < r1) issue(r0 + 1, g + 1);
+  }
+
+  // finish row (g_row): wait for all partials, r = sum - b, rank-1 update from the resident tile, free the slot
+  auto finish_row = [&](uint32_t gr, double bval, bool refill, int64_t refill_row) -> double {
+    const uint32_t d = gr % kFDepth, dph = (gr / kFDepth) & 1u;
+    if (prof) c_t = clock64();
+    mbar_wait_cluster(cfull + 8 * d, dph);
+    if (prof) { const long long t = clock64(); c_cwait += t - c_t; c_t = t; }
+    double v = 0.0;
+    for (int i = lane; i < nval; i += 32) v += lds1(cpart + (d * (kFMaxCluster * kFWarps) + i) * 8);
+    v = warp_sum(v);                                            // same order in every warp of every CTA of the cluster
+    const double rs = v - bval;                                 // lasso/runme.jl:22  res = A*w - b
+    if (bytes > 0) {
+      const uint32_t pslot = gr % kFStages;
+      const uint32_t tile = ring + pslot * kFStageBytes + threadIdx.x * 16;
+#pragma unroll
+      for (int k = 0; k < kFH; ++k)
+        if (ok[k]) {
+          const double2 av = lds2(tile + k * kFThreads * 16);
+          acc[k].x = fma(av.x, rs, acc[k].x);
+          acc[k].y = fma(av.y, rs, acc[k].y);
+        }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty + 8 * pslot);
+      if (threadIdx.x == 0 && refill) issue(refill_row, gr + kFStages);
+    }
+    if (prof) { const long long t = clock64(); c_upd += t - c_t; c_t = t; }
+    return rs;
+  };
+
+  double fsum = 0.0;
+  double b_prev = 0.0;
+  for (int64_t s = r0; s < r1; ++s, ++g) {
+    const double b_cur = __ldg(bvec + s);
+    const uint32_t slot = g % kFStages, ph = (g / kFStages) & 1u;
+    const uint32_t d = g % kFDepth;
+    // ---- partial dot of row s, pushed to every peer ----------------------------------------------------
+    if (prof) c_t = clock64();
+    if (threadIdx.x == 0) mbar_expect_tx(cfull + 8 * d, xbytes);
+    double p0 = 0.0, p1 = 0.0;
+    if (bytes > 0) {
+      mbar_wait(full + 8 * slot, ph);
+      if (prof) { const long long t = clock64(); c_full += t - c_t; c_t = t; }
+      const uint32_t tile = ring + slot * kFStageBytes + threadIdx.x * 16;
+#pragma unroll
+      for (int k = 0; k < kFH; ++k)
+        if (ok[k]) {
+          const double2 av = lds2(tile + k * kFThreads * 16);
+          p0 = fma(av.x, xr[k].x, p0);
+          p1 = fma(av.y, xr[k].y, p1);
+        }
+    }
+    const double pw = warp_sum(p0 + p1);
+    if (lane < C)
+      st_async_peer(cpart + (d * (kFMaxCluster * kFWarps) + rank * kFWarps + warp) * 8, cfull + 8 * d, (uint32_t)lane, pw);
+    if (prof) { const long long t = clock64(); c_send += t - c_t; c_t = t; }
+    // ---- finish row s-1 while row s's partials travel ----------------------------------------------------
+    if (s > r0) {
+      const double rs = finish_row(g - 1, b_prev, s + 2 < r1, s + 2);
+      fsum = fma(rs, rs, fsum);
+    } else if (threadIdx.x == 0 && bytes > 0 && s + 2 < r1) {
+      issue(s + 2, g + 2);                                      // first row of the pass: the third slot is free
+    }
+    b_prev = b_cur;
+  }
+  if (r1 > r0) {
+    const double rs = finish_row(g - 1, b_prev, false, 0);
+    fsum = fma(rs, rs, fsum);
+  }
+  fs.count = g;
+  if (prof) { dbg[1] = (unsigned long long)c_full; dbg[2] = (unsigned long long)c_send; dbg[5] = (unsigned long long)c_upd; dbg[6] = (unsigned long long)c_cwait; }
+  double* gout = fa.gpartf + (int64_t)q * fa.npadf + col0;
+#pragma unroll
+  for (int k = 0; k < kFH; ++k)
+    if (ok[k]) *reinterpret_cast<double2*>(gout + 2 * (k * kFThreads + threadIdx.x)) = acc[k];
+  return (rank == 0 && threadIdx.x == 0) ? fsum : 0.0;
+}
+
+// block / grid reductions for a 512-thread CTA (fixed order)
+template <int K>
+__device__ __forceinline__ void f_block_reduce_store(double (&v)[K], double* red, int G, int slot0, uint32_t scr) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const double s = warp_sum(v[k]);
+    if (lane == 0) sts1(scr + (warp * K + k) * 8, s);
+  }
+  __syncthreads();
+  if (threadIdx.x < K) {
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < kFWarps; ++w) s += lds1(scr + (w * K + threadIdx.x) * 8);
+    red[(int64_t)(slot0 + threadIdx.x) * G + blockIdx.x] = s;
+  }
+  __syncthreads();
+}
+template <int K>
+__device__ __forceinline__ void f_grid_totals(const double* red, int G, int slot0, double (&out)[K], uint32_t scr) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int k = warp; k < K; k += kFWarps) {
+    const double* p = red + (int64_t)(slot0 + k) * G;
+    double s = 0.0;
+    for (int b = lane; b < G; b += 32) s += ldcg(p + b);
+    s = warp_sum(s);
+    if (lane == 0) sts1(scr + k * 8, s);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < K; ++k) out[k] = lds1(scr + k * 8);
+  __syncthreads();
+}
+
+// AdaPGM / fixed-step PGM (src/AdaProx.jl:312-364 with A = 0, h = Zero) around the fused pass.
+__global__ void __launch_bounds__(kFThreads, 1) k_adapgm_fused(DProblem P, DOpts O, DWork W, FusedArgs fa) {
+  cg::grid_group grid = cg::this_grid();
+  const int b = blockIdx.x, G = gridDim.x;
+  extern __shared__ __align__(1024) unsigned char dyn_smem[];
+  __shared__ unsigned long long s_bars[2 * kFStages + kFDepth];
+  __shared__ double s_cpart[kFDepth * kFMaxCluster * kFWarps];
+  __shared__ double s_scr[kFWarps * 8 + kMaxRed];
+  FusedSmem fs;
+  fs.ring = smem_u32(dyn_smem);
+  fs.full = smem_u32(s_bars);
+  fs.empty = smem_u32(s_bars + kFStages);
+  fs.cfull = smem_u32(s_bars + 2 * kFStages);
+  fs.cpart = smem_u32(s_cpart);
+  fs.count = 0;
+  const uint32_t scr = smem_u32(s_scr);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kFStages; ++s) { mbar_init(fs.full + 8 * s, 1); mbar_init(fs.empty + 8 * s, kFWarps); }
+    for (int s = 0; s < kFDepth; ++s) mbar_init(fs.cfull + 8 * s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  cluster_arrive();          // every CTA of the cluster has initialised its shared memory before any peer writes into it
+  cluster_wait();
+
+  const int Q = (int)ncluster_id_x();
+  const bool want_obj = O.want_objective != 0;
+  int64_t j0, j1;
+  cta_slice(P.n, b, G, j0, j1);
+
+  double gamma, sigma, s0, s1;
+  rule_init(O, gamma, sigma, s0, s1);
+  int64_t n_eval = 0, n_grad = 0, n_proxg = 0, n_rec = 0;
+  unsigned flags = 0;
+  int xc = 0, gc = 0;
+  double* x = W.xb[0];
+
+  auto gradient_slice = [&](double* out) {     // grad[j] = sum over clusters, fixed order
+    for (int64_t j = j0 + threadIdx.x; j < j1; j += kFThreads) {
+      double s = 0.0;
+      for (int qq = 0; qq < Q; ++qq) s += ldcg(fa.gpartf + (int64_t)qq * fa.npadf + j);
+      out[j] = s;
+    }
+  };
+
+  // ---- prologue (:327-332) ----------------------------------------------------------------------------------
+  {
+    double fv[1] = {fused_pass(P.F, P.fvec, x, fs, fa, nullptr)};
+    f_block_reduce_store<1>(fv, W.red, G, SLOT_F0, scr);
+  }
+  grid.sync();
+  {
+    gradient_slice(W.gb[gc]);
+    double acc[1] = {0.0};
+    double* xn = W.xb[1];
+    for (int64_t j = j0 + threadIdx.x; j < j1; j += kFThreads) {
+      const double vj = x[j] - gamma * W.gb[gc][j];                             // :330
+      W.v[j] = vj;
+      const double xj = prox_elem(P.g, vj, gamma, j, 0.0);                     // :332
+      xn[j] = xj;
+      if (want_obj) acc[0] += prox_value_elem(P.g, xj, j);
+    }
+    f_block_reduce_store<1>(acc, W.red, G, gval_slot(1), scr);
+  }
+  n_eval = 1; n_grad = 1; n_proxg = 1;
+  grid.sync();
+  double* x_prev = W.xb[0];
+  x = W.xb[1]; xc = 1;
+  double* grad_prev = W.gb[0];
+  double norm_res = INFINITY;
+  int64_t it_done = O.maxit;
+  bool converged = false;
+
+  for (int64_t it = 1; it <= O.maxit; ++it) {
+    phase_stamp(W, it, 0);
+    {
+      double fv[1] = {fused_pass(P.F, P.fvec, x, fs, fa, (W.tstamp && it <= W.tstamp_iters) ? W.tstamp + (it - 1) * 8 : nullptr)};   // :336 value + pullback in one pass
+      f_block_reduce_store<1>(fv, W.red, G, SLOT_F0, scr);
+    }
+    n_eval++; n_grad++;
+    grid.sync();
+    phase_stamp(W, it, 3);
+    double* grad = W.gb[gc ^ 1];
+    gradient_slice(grad);
+    {
+      double acc[4] = {0.0, 0.0, 0.0, 0.0};
+      for (int64_t j = j0 + threadIdx.x; j < j1; j += kFThreads) {
+        const double xj = x[j], gj = grad[j];
+        const double pr = (W.v[j] - xj) / gamma + gj;                           // :338
+        const double dg = gj - grad_prev[j], dx = xj - x_prev[j];
+        acc[0] = fma(pr, pr, acc[0]);
+        acc[1] = fma(dg, dg, acc[1]);
+        acc[2] = fma(dg, dx, acc[2]);
+        acc[3] = fma(dx, dx, acc[3]);
+      }
+      f_block_reduce_store<4>(acc, W.red, G, SLOT_PR, scr);
+    }
+    grid.sync();
+    phase_stamp(W, it, 4);
+    double t4[4], tg[1] = {0.0}, tf[1];
+    f_grid_totals<4>(W.red, G, SLOT_PR, t4, scr);
+    f_grid_totals<1>(W.red, G, SLOT_F0, tf, scr);
+    if (want_obj) f_grid_totals<1>(W.red, G, gval_slot(it), tg, scr);
+    rule_step(O, t4[1], t4[2], t4[3], gamma, sigma, s0, s1);                    // :341
+    norm_res = sqrt(norm_sq_jl(t4[0]));                                         // :348 (dual part is identically zero)
+    if (!(gamma == gamma) || !(norm_res == norm_res) || isinf(gamma)) flags |= ADAPROX_FLAG_NONFINITE;
+    if (b == 0 && threadIdx.x == 0 && W.rec != nullptr && it <= O.max_records) {
+      adaprox_record rc;
+      rc.it = it; rc.gamma = gamma; rc.sigma = sigma; rc.norm_res = norm_res;
+      rc.f_x = 0.5 * norm_sq_jl(tf[0]);
+      rc.g_x = want_obj ? prox_value_finish(P.g.kind, P.g.lambda, tg[0]) : NAN;
+      rc.h_Ax = want_obj ? 0.0 : NAN;
+      rc.f_evals = n_eval; rc.grad_f_evals = n_grad; rc.prox_g_evals = n_proxg; rc.prox_h_evals = 0;
+      rc.A_evals = 0; rc.At_evals = 0;
+      W.rec[it - 1] = rc;
+    }
+    if (it <= O.max_records) n_rec = it;
+    if (norm_res <= O.tol) { converged = true; it_done = it; break; }           // :354-356
+    {
+      double acc[1] = {0.0};
+      double* xn = W.xb[(xc + 1) % 3];
+      for (int64_t j = j0 + threadIdx.x; j < j1; j += kFThreads) {
+        const double vj = x[j] - gamma * grad[j];                               // :359
+        W.v[j] = vj;
+        const double xj = prox_elem(P.g, vj, gamma, j, 0.0);                    // :361
+        xn[j] = xj;
+        if (want_obj) acc[0] += prox_value_elem(P.g, xj, j);
+      }
+      f_block_reduce_store<1>(acc, W.red, G, gval_slot(it + 1), scr);
+    }
+    n_proxg++;
+    x_prev = x; xc = (xc + 1) % 3; x = W.xb[xc];
+    grad_prev = grad; gc ^= 1;
+    grid.sync();
+    phase_stamp(W, it, 7);
+  }
+
+  const int64_t tid = (int64_t)b * kFThreads + threadIdx.x, nt = (int64_t)G * kFThreads;
+  for (int64_t j = tid; j < P.n; j += nt) W.xout[j] = x[j];
+  if (b == 0 && threadIdx.x == 0) {
+    DResult r;
+    r.iters = it_done;
+    r.flags = flags | (converged ? ADAPROX_FLAG_CONVERGED : 0u);
+    r.xbuf = 0;
+    r.f_evals = n_eval; r.grad_f_evals = n_grad; r.prox_g_evals = n_proxg; r.prox_h_evals = 0;
+    r.A_evals = 0; r.At_evals = 0; r.n_records = n_rec;
+    r.final_gamma = gamma; r.final_sigma = sigma; r.final_norm_res = norm_res;
+    *W.res = r;
+  }
+  cluster_arrive();          // no CTA exits while a peer could still address its shared memory
+  cluster_wait();
+}
+
+}  // namespace adaprox

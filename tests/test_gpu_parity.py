@@ -529,3 +529,41 @@ def test_malitsky_pock(AdaProx):
     O.malitsky_pock(np.zeros(9), np.zeros(150), f=O.Zero(), g=O.NormL1(0.1), h=O.Translate(O.NormL1(), -yv), A=A2, log=lo, **kw)
     assert np.allclose([r["norm_res"] for r in ld[:40]], [r["norm_res"] for r in lo[:40]], rtol=1e-8)
     assert np.allclose([r["objective"] for r in ld[:40]], [r["objective"] for r in lo[:40]], rtol=1e-10)
+
+
+# ---------------------------------------------------------------- single-pass fused AdaPGM (solver_fused.cuh)
+@pytest.mark.parametrize("m,n,pf", [(400, 1000, 5), (96, 9000, 60), (64, 20000, 200), (40, 131072, 2000)])
+def test_fused_single_pass_matches_two_pass_and_oracle(AdaProx, m, n, pf):
+    """Cluster sizes 1, 2 (ragged second CTA), 3 and 16; forced on with ADAPROX_FUSED=1 (small instances)."""
+    import os
+    P = AdaProx.synth.planted_lasso(m, n, pf, 4)
+    Lf = AdaProx.synth.spectral_norm_sq(P["A"], iters=300)
+    f_raw = AdaProx.LinearLeastSquares(P["A"], P["b"])
+    runs = {}
+    try:
+        for mode in ("0", "1"):
+            os.environ["ADAPROX_FUSED"] = mode
+            f = AdaProx.Counting(f_raw)
+            log = []
+            x, it = AdaProx.adaptive_proxgrad(np.zeros(n), f=f, g=AdaProx.NormL1(1.0), rule=AdaProx.OurRule(gamma=1 / Lf),
+                                              tol=1e-6, maxit=3000, log=log)
+            runs[mode] = (x, it, log, AdaProx.last_solve_info())
+    finally:
+        os.environ.pop("ADAPROX_FUSED", None)
+    logo = []
+    xo, ito = O.adaptive_proxgrad(np.zeros(n), f=O.LinearLeastSquares(P["A"], P["b"]), g=O.NormL1(1.0), rule=O.OurRule(gamma=1 / Lf),
+                                  tol=1e-6, maxit=3000, log=logo)
+    K = 25
+    go = np.array([r["gamma"] for r in logo[:K]])
+    for mode in ("0", "1"):
+        x, it, log, info = runs[mode]
+        gd = np.array([r["gamma"] for r in log[:K]])
+        assert np.max(np.abs(gd[:12] / go[:12] - 1)) < 1e-12, mode
+        assert np.max(np.abs(gd / go - 1)) < 1e-9, mode
+        assert np.allclose([r["objective"] for r in log[:K]], [r["objective"] for r in logo[:K]], rtol=1e-10)
+        # runs that hit maxit before converging are compared loosely (the tail of the trajectory is chaotic)
+        ftol = 1e-10 if (it < 3000 and ito < 3000) else 1e-3
+        assert abs(log[-1]["objective"] - logo[-1]["objective"]) <= ftol * abs(logo[-1]["objective"]), (mode, it, ito)
+        assert abs(it - ito) <= max(3, 0.05 * ito)
+        assert [r["f_evals"] for r in log[:5]] == [2, 3, 4, 5, 6]
+    assert runs["1"][3]["kernel_launches"] == 1
