@@ -48,7 +48,8 @@ class Result(C.Structure):
                 ("grad_f_evals", C.c_int64), ("prox_g_evals", C.c_int64), ("prox_h_evals", C.c_int64),
                 ("A_evals", C.c_int64), ("At_evals", C.c_int64), ("n_records", C.c_int64),
                 ("final_gamma", C.c_double), ("final_sigma", C.c_double), ("final_norm_res", C.c_double),
-                ("solve_ms", C.c_double), ("kernel_launches", C.c_int64)]
+                ("solve_ms", C.c_double), ("kernel_launches", C.c_int64),
+                ("matrix_passes", C.c_int64)]
 
 
 # enum values of include/adaprox.h

@@ -692,7 +692,7 @@ def _solve(solver, x0, y0, *, f, g, h=None, A=None, opts, name, log, pd):
                 d["At_evals"] = base["am"] + r.At_evals if cA else None
             d["f_evals"] = base["f"] + r.f_evals if cf else None
             log.append(d)
-    info = dict(flags=int(res.flags), solve_ms=res.solve_ms, kernel_launches=int(res.kernel_launches),
+    info = dict(flags=int(res.flags), solve_ms=res.solve_ms, kernel_launches=int(res.kernel_launches), matrix_passes=int(res.matrix_passes),
                 final_gamma=res.final_gamma, final_sigma=res.final_sigma, final_norm_res=res.final_norm_res)
     return x_out, (y_out[: p.m_dual] if pd else None), int(res.iters), info
 

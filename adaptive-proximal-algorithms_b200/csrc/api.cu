@@ -552,7 +552,7 @@ static int validate_options(adaprox_ctx* h, const adaprox_problem* p, const adap
   return ADAPROX_OK;
 }
 
-// Single-pass fused AdaPGM (solver_fused.cuh): cluster + cooperative launch.  Returns 1 if the configuration is not
+// Single-pass fused AdaPGM (solver_fused.cuh): cluster launch sized to full residency.  Returns 1 if the configuration is not
 // eligible (the caller falls through to the two-pass kernel), < 0 on error.
 static int fused_cluster_size(const DProblem& P) { return (int)((P.F.ld + kFCols - 1) / kFCols); }
 static bool fused_eligible(const adaprox_options* o, const DProblem& P) {
@@ -577,10 +577,8 @@ static int fused_config(adaprox_ctx* h, int C, cudaLaunchConfig_t* cfg, cudaLaun
   cfg->stream = h->stream;
   attrs[0].id = cudaLaunchAttributeClusterDimension;
   attrs[0].val.clusterDim.x = C; attrs[0].val.clusterDim.y = 1; attrs[0].val.clusterDim.z = 1;
-  attrs[1].id = cudaLaunchAttributeCooperative;
-  attrs[1].val.cooperative = 1;
   cfg->attrs = attrs;
-  cfg->numAttrs = 2;
+  cfg->numAttrs = 1;               // cluster launch only: the kernel carries its own grid barrier (see GridBar)
   int q = 0;
   cudaError_t e = cudaOccupancyMaxActiveClusters(&q, (const void*)k_adapgm_fused, cfg);
   if (e != cudaSuccess || q < 1) { cudaGetLastError(); return 1; }
@@ -618,7 +616,7 @@ extern "C" int adaprox_solve(adaprox_handle h, const adaprox_problem* p, const a
     if (rc == 1) fused = false;
     else { fa.npadf = (int64_t)fa.C * kFCols; G = fa.C * fQ; }
   }
-  size_t need = (fused ? ws_size_doubles((int64_t)fQ * fa.npadf) : 0) +
+  size_t need = (fused ? ws_size_doubles((int64_t)fQ * fa.npadf) + ws_size_doubles(1) : 0) +
                 11 * ws_size_doubles(n) + 6 * ws_size_doubles(md) + ws_size_doubles(mf) +
                 ws_size_doubles((int64_t)kMaxRed * G) + ws_size_doubles((nrec * (int64_t)sizeof(adaprox_record) + 7) / 8) +
                 ws_size_doubles((sizeof(DResult) + 7) / 8);
@@ -639,7 +637,11 @@ extern "C" int adaprox_solve(adaprox_handle h, const adaprox_problem* p, const a
   W.res = reinterpret_cast<DResult*>(ws_doubles(h, (sizeof(DResult) + 7) / 8));
   W.xout = W.aux[2];
   O.max_records = nrec;
-  if (fused) fa.gpartf = ws_doubles(h, (int64_t)fQ * fa.npadf);
+  if (fused) {
+    fa.gpartf = ws_doubles(h, (int64_t)fQ * fa.npadf);
+    fa.bar = reinterpret_cast<unsigned long long*>(ws_doubles(h, 1));
+    AP_CUDA(h, cudaMemsetAsync(fa.bar, 0, 8, h->stream));
+  }
   const bool phase_timing = std::getenv("ADAPROX_PHASE_TIMING") != nullptr;
   unsigned long long* d_ts = nullptr;
   const int ts_iters = (int)std::min<int64_t>(O.maxit, 64);
@@ -714,8 +716,8 @@ extern "C" int adaprox_solve(adaprox_handle h, const adaprox_problem* p, const a
     }
     if (cnt && fused) {
       const unsigned long long* t = &ts[0];
-      std::fprintf(stderr, "[adaprox fused pass, cycles in CTA 0 thread 0, iteration 1] wait_full=%llu dot+send=%llu update+issue=%llu wait_partials=%llu clusters=%d C=%d\n",
-                   t[1], t[2], t[5], t[6], fQ, fa.C);
+      std::fprintf(stderr, "[adaprox fused pass, cycles in CTA 0, iteration 1] dot: wait_full=%llu work=%llu | update: wait_partials=%llu work=%llu | producer: wait_empty=%llu | clusters=%d C=%d\n",
+                   t[1], t[2], t[6], t[5], t[3], fQ, fa.C);
     }
     if (cnt && !fused) {
       const char* names[7] = {"P1 F*x (+A*x)", "P2 rows/residual", "P3 F'*r", "P4 grad+reductions", "P5 stepsize/dual", "P6 record/A'y", "P7 prox step"};
@@ -733,6 +735,7 @@ extern "C" int adaprox_solve(adaprox_handle h, const adaprox_problem* p, const a
   res->n_records = dr.n_records;
   res->final_gamma = dr.final_gamma; res->final_sigma = dr.final_sigma; res->final_norm_res = dr.final_norm_res;
   res->solve_ms = ms; res->kernel_launches = h->launches - launches0;
+  res->matrix_passes = (P.F.kind == MAT_NONE) ? 0 : (fused ? 1 : 2);
   return ADAPROX_OK;
 }
 

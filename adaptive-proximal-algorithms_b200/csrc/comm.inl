@@ -323,6 +323,7 @@ int solve_sharded(adaprox_ctx* h, const adaprox_problem* p, const adaprox_option
   res->n_records = cur.n_rec;
   res->final_gamma = cur.gamma; res->final_sigma = cur.sigma; res->final_norm_res = cur.norm_res;
   res->solve_ms = ms; res->kernel_launches = h->launches - launches0;
+  res->matrix_passes = 2;
   return ADAPROX_OK;
 }
 

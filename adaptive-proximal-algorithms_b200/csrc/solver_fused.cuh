@@ -24,19 +24,23 @@
 
 namespace adaprox {
 
-constexpr int kFThreads = 512;
+constexpr int kFGroup = 256;                              // threads per role group (dot warps / update warps)
+constexpr int kFGWarps = kFGroup / 32;
+constexpr int kFThreads = 2 * kFGroup;                    // 8 dot warps + 8 update warps (512 threads: 128 registers each)
 constexpr int kFWarps = kFThreads / 32;
 constexpr int kFCols = 8192;                              // columns per CTA
-constexpr int kFH = kFCols / 2 / kFThreads;               // 8 double2 per thread
+constexpr int kFH = kFCols / 2 / kFGroup;                 // 16 double2 per thread per row
 constexpr int kFStages = 3;
 constexpr int kFStageBytes = kFCols * 8;                  // 64 KB
 constexpr int kFRingBytes = kFStages * kFStageBytes;      // 192 KB dynamic shared memory
 constexpr int kFMaxCluster = 16;
+constexpr int kFDepth = 8;                                // exchange-buffer depth (see fused_pass)
 
 struct FusedArgs {
   double* gpartf;      // [nclusters][npadf] per-cluster A'r partials
   int64_t npadf;       // C * 8192
   int C;               // cluster size
+  unsigned long long* bar;   // grid-barrier arrival counter (zeroed by the host before the launch)
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
@@ -44,26 +48,13 @@ __device__ __forceinline__ uint32_t cluster_id_x() { uint32_t r; asm volatile("m
 __device__ __forceinline__ uint32_t ncluster_id_x() { uint32_t r; asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
-__device__ __forceinline__ void st_peer_f64(uint32_t local_addr, uint32_t peer, double v) {
-  uint32_t raddr;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(local_addr), "r"(peer));
-  asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(raddr), "d"(v) : "memory");
-}
-// sum over the 16 lanes of a half warp; every lane of the half ends with the same bits
-__device__ __forceinline__ double half_warp_sum(double v) {
-#pragma unroll
-  for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-
-constexpr int kFDepth = 4;                                // exchange-buffer depth (see the header comment)
 
 struct FusedSmem {
   uint32_t ring, full, empty, cfull, cpart;   // shared-space addresses
   uint32_t count;                             // rows pushed through the ring / exchange so far (uniform)
 };
 
-// remote 8-byte store that completes `bytes` on the destination CTA's mbarrier (no fence needed on the sender)
+// remote 8-byte store that completes 8 bytes on the destination CTA's mbarrier (no fence needed on the sender)
 __device__ __forceinline__ void st_async_peer(uint32_t local_data_addr, uint32_t local_mbar_addr, uint32_t peer, double v) {
   uint32_t rdata, rbar;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rdata) : "r"(local_data_addr), "r"(peer));
@@ -79,18 +70,34 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t addr, uint32_t parity
   } while (!ok);
 }
 
+// ld.volatile keeps the program order of the loads; the consumers below use the batch in REVERSE order, so all
+// eight loads of a batch must be in flight before the first FMA can issue (ptxas otherwise recycles one
+// destination quad: load -> FMA -> load ..., one shared-memory round trip per 16 bytes).
+__device__ __forceinline__ double2 lds2v(uint32_t addr) {
+  double2 v;
+  asm volatile("ld.volatile.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+  return v;
+}
+
 // One fused pass: gpartf[cluster][cols] = sum_{rows of the cluster} A[i, cols] * (A[i,:] x - b[i]);
-// this CTA's partial of sum r_i^2 is returned (non-zero in thread 0 of cluster rank 0 only).
+// this cluster's partial of sum r_i^2 is returned (non-zero in one thread of cluster rank 0 only).
 //
-// Exchange protocol (per row, running index g): every warp sends its partial dot to all C peers with
-// st.async into cpart[g % 4][rank][warp], completing 8 bytes on the peer's cfull[g % 4] mbarrier; thread 0 of each
-// CTA arms its own cfull[g % 4] with expect_tx(C * 16 * 8).  A CTA sends row g+4 only after it has waited for row
-// g+2 to complete, which contains every peer's send of row g+2, which every peer issues after it has consumed
-// row g -- so depth 4 can never be overwritten early.
+// Warp roles (the groups are coupled through mbarriers only, so the latency chains of one overlap the
+// shared-memory bursts of the other):
+//   producer (lane 0 of the last update warp): bulk copies row g + 3 into the ring slot row g just left;
+//   dot warps (0..7): x in registers; per row 16 x LDS.128 + 32 DFMA per thread, warp sum, then lanes < C push
+//     the warp's partial into cpart[g % 8][rank][warp] of every peer with st.async, which completes 8 bytes on
+//     the peer's cfull[g % 8] mbarrier;
+//   update warps (8..15): accumulators in registers; wait for the C * 8 partials of row g, sum them in a fixed
+//     order (bit-identical in every warp of every CTA of the cluster), r = sum - b, rank-1 update from the tile
+//     still resident in shared memory, free the slot.
+// Exchange-buffer depth: a CTA can push row j only after its own update of row j-3 (ring slot), which needs
+// every peer's dot of row j-3, which needs that peer's update of row j-6: when row j's partials arrive, a peer
+// may still be reading rows j-5 .. j-1, so 8 buffers never collide (and phase j-8 of cfull is long complete).
+template <bool PROF>
 __device__ __noinline__ double fused_pass(const DMat& M, const double* bvec, const double* x, FusedSmem& fs, const FusedArgs& fa,
                                            unsigned long long* dbg) {
-  long long c_full = 0, c_send = 0, c_cwait = 0, c_upd = 0, c_t = 0;
-  const bool prof = (dbg != nullptr) && blockIdx.x == 0 && threadIdx.x == 0;
+  const bool prof = PROF && (dbg != nullptr) && blockIdx.x == 0;
   const double* const a = M.a;
   const int64_t ld = M.ld, n = M.n, m = M.m;
   const uint32_t ring = fs.ring, full = fs.full, empty = fs.empty, cfull = fs.cfull, cpart = fs.cpart;
@@ -102,111 +109,133 @@ __device__ __noinline__ double fused_pass(const DMat& M, const double* bvec, con
   int64_t width = ld - col0;
   width = width < 0 ? 0 : (width > kFCols ? kFCols : width);
   const uint32_t bytes = (uint32_t)(width * 8);
-  const uint32_t xbytes = (uint32_t)(C * kFWarps * 8);         // exchange bytes per row per CTA
-  const int nval = C * kFWarps;
-  const double* const abase = a + col0;
-
-  double2 xr[kFH], acc[kFH];
-  bool ok[kFH];
-#pragma unroll
-  for (int k = 0; k < kFH; ++k) {
-    const int64_t jl = 2 * (k * kFThreads + threadIdx.x);
-    const int64_t j = col0 + jl;
-    ok[k] = jl < width;
-    xr[k].x = (j < n) ? ldcg(x + j) : 0.0;
-    xr[k].y = (j + 1 < n) ? ldcg(x + j + 1) : 0.0;
-    acc[k] = make_double2(0.0, 0.0);
-  }
-
-  uint32_t g = fs.count;                       // running index of the row being processed
-  auto issue = [&](int64_t row, uint32_t gi) { // thread 0 only
-    const uint32_t s = gi % kFStages, ph = (gi / kFStages) & 1u;
-    mbar_wait(empty + 8 * s, ph ^ 1u);
-    mbar_expect_tx(full + 8 * s, bytes);
-    bulk_g2s(ring + s * kFStageBytes, abase + row * ld, bytes, full + 8 * s);
-  };
-  if (threadIdx.x == 0 && bytes > 0) {
-    if (r0 < r1) issue(r0, g);
-    if (r0 + 1 < r1) issue(r0 + 1, g + 1);
-  }
-
-  // finish row (g_row): wait for all partials, r = sum - b, rank-1 update from the resident tile, free the slot
-  auto finish_row = [&](uint32_t gr, double bval, bool refill, int64_t refill_row) -> double {
-    const uint32_t d = gr % kFDepth, dph = (gr / kFDepth) & 1u;
-    if (prof) c_t = clock64();
-    mbar_wait_cluster(cfull + 8 * d, dph);
-    if (prof) { const long long t = clock64(); c_cwait += t - c_t; c_t = t; }
-    double v = 0.0;
-    for (int i = lane; i < nval; i += 32) v += lds1(cpart + (d * (kFMaxCluster * kFWarps) + i) * 8);
-    v = warp_sum(v);                                            // same order in every warp of every CTA of the cluster
-    const double rs = v - bval;                                 // lasso/runme.jl:22  res = A*w - b
-    if (bytes > 0) {
-      const uint32_t pslot = gr % kFStages;
-      const uint32_t tile = ring + pslot * kFStageBytes + threadIdx.x * 16;
-#pragma unroll
-      for (int k = 0; k < kFH; ++k)
-        if (ok[k]) {
-          const double2 av = lds2(tile + k * kFThreads * 16);
-          acc[k].x = fma(av.x, rs, acc[k].x);
-          acc[k].y = fma(av.y, rs, acc[k].y);
-        }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(empty + 8 * pslot);
-      if (threadIdx.x == 0 && refill) issue(refill_row, gr + kFStages);
-    }
-    if (prof) { const long long t = clock64(); c_upd += t - c_t; c_t = t; }
-    return rs;
-  };
-
+  const uint32_t xbytes = (uint32_t)(C * kFGWarps * 8);        // exchange bytes per row per CTA
+  const uint32_t g0 = fs.count;
   double fsum = 0.0;
-  double b_prev = 0.0;
-  for (int64_t s = r0; s < r1; ++s, ++g) {
-    const double b_cur = __ldg(bvec + s);
-    const uint32_t slot = g % kFStages, ph = (g / kFStages) & 1u;
-    const uint32_t d = g % kFDepth;
-    // ---- partial dot of row s, pushed to every peer ----------------------------------------------------
-    if (prof) c_t = clock64();
-    if (threadIdx.x == 0) mbar_expect_tx(cfull + 8 * d, xbytes);
-    double p0 = 0.0, p1 = 0.0;
-    if (bytes > 0) {
+
+  if (warp < kFGWarps) {
+    // ------------------------------------------------------------------ dot warps
+    const int t = threadIdx.x;
+    double2 xr[kFH];
+#pragma unroll
+    for (int k = 0; k < kFH; ++k) {
+      const int64_t j = col0 + 2 * (k * kFGroup + t);
+      xr[k].x = (j < n) ? ldcg(x + j) : 0.0;
+      xr[k].y = (j + 1 < n) ? ldcg(x + j + 1) : 0.0;
+    }
+    long long c_wait = 0, c_work = 0, c_t = 0;
+    uint32_t g = g0;
+    uint32_t slot = g % kFStages, ph = (g / kFStages) & 1u;
+    const uint32_t mypart = cpart + (rank * kFGWarps + warp) * 8;
+    for (int64_t s = r0; s < r1; ++s, ++g) {
+      const uint32_t d = g % kFDepth;
+      if (prof) c_t = clock64();
       mbar_wait(full + 8 * slot, ph);
-      if (prof) { const long long t = clock64(); c_full += t - c_t; c_t = t; }
-      const uint32_t tile = ring + slot * kFStageBytes + threadIdx.x * 16;
+      if (prof) { const long long tt = clock64(); c_wait += tt - c_t; c_t = tt; }
+      const uint32_t tile = ring + slot * kFStageBytes + t * 16;
+      // two batches of 8 x LDS.128 issued back to back (ptxas otherwise recycles ONE destination quad and
+      // serialises load -> FMA -> load, exposing the full shared-memory latency 16 times per row)
+      double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
+      double2 av[8];
 #pragma unroll
-      for (int k = 0; k < kFH; ++k)
-        if (ok[k]) {
-          const double2 av = lds2(tile + k * kFThreads * 16);
-          p0 = fma(av.x, xr[k].x, p0);
-          p1 = fma(av.y, xr[k].y, p1);
+      for (int h = 0; h < kFH; h += 8) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) av[k] = lds2v(tile + (h + k) * kFGroup * 16);
+#pragma unroll
+        for (int k = 6; k >= 0; k -= 2) {
+          p2 = fma(av[k + 1].x, xr[h + k + 1].x, p2);
+          p3 = fma(av[k + 1].y, xr[h + k + 1].y, p3);
+          p0 = fma(av[k].x, xr[h + k].x, p0);
+          p1 = fma(av[k].y, xr[h + k].y, p1);
         }
+      }
+      const double pw = warp_sum((p0 + p1) + (p2 + p3));
+      if (lane < C) st_async_peer(mypart + d * (kFMaxCluster * kFGWarps * 8), cfull + 8 * d, (uint32_t)lane, pw);
+      if (prof) { const long long tt = clock64(); c_work += tt - c_t; }
+      if (++slot == kFStages) { slot = 0; ph ^= 1u; }
     }
-    const double pw = warp_sum(p0 + p1);
-    if (lane < C)
-      st_async_peer(cpart + (d * (kFMaxCluster * kFWarps) + rank * kFWarps + warp) * 8, cfull + 8 * d, (uint32_t)lane, pw);
-    if (prof) { const long long t = clock64(); c_send += t - c_t; c_t = t; }
-    // ---- finish row s-1 while row s's partials travel ----------------------------------------------------
-    if (s > r0) {
-      const double rs = finish_row(g - 1, b_prev, s + 2 < r1, s + 2);
-      fsum = fma(rs, rs, fsum);
-    } else if (threadIdx.x == 0 && bytes > 0 && s + 2 < r1) {
-      issue(s + 2, g + 2);                                      // first row of the pass: the third slot is free
-    }
-    b_prev = b_cur;
-  }
-  if (r1 > r0) {
-    const double rs = finish_row(g - 1, b_prev, false, 0);
-    fsum = fma(rs, rs, fsum);
-  }
-  fs.count = g;
-  if (prof) { dbg[1] = (unsigned long long)c_full; dbg[2] = (unsigned long long)c_send; dbg[5] = (unsigned long long)c_upd; dbg[6] = (unsigned long long)c_cwait; }
-  double* gout = fa.gpartf + (int64_t)q * fa.npadf + col0;
+    if (prof && threadIdx.x == 0) { dbg[1] = (unsigned long long)c_wait; dbg[2] = (unsigned long long)c_work; }
+  } else if (warp < 2 * kFGWarps) {
+    // ------------------------------------------------------------------ update warps
+    const int t = threadIdx.x - kFGroup;
+    const bool leader = (t == 0);
+    const int nval = C * kFGWarps;
+    double2 acc[kFH];
 #pragma unroll
-  for (int k = 0; k < kFH; ++k)
-    if (ok[k]) *reinterpret_cast<double2*>(gout + 2 * (k * kFThreads + threadIdx.x)) = acc[k];
-  return (rank == 0 && threadIdx.x == 0) ? fsum : 0.0;
+    for (int k = 0; k < kFH; ++k) acc[k] = make_double2(0.0, 0.0);
+    if (leader) {
+      const int64_t nr = r1 - r0;
+      for (int i = 0; i < kFDepth && i < nr; ++i) mbar_expect_tx(cfull + 8 * ((g0 + i) % kFDepth), xbytes);
+    }
+    // producer duty: lane 0 of the last update warp keeps the ring full (row g + 3 goes into the slot row g leaves)
+    const bool producer = (t == kFGroup - 32);
+    const double* const abase = a + col0;
+    auto issue = [&](int64_t row, uint32_t sl, uint32_t par) {
+      mbar_wait(empty + 8 * sl, par ^ 1u);
+      mbar_expect_tx(full + 8 * sl, bytes);
+      bulk_g2s(ring + sl * kFStageBytes, abase + row * ld, bytes, full + 8 * sl);
+    };
+    if (producer) {
+      uint32_t sl = g0 % kFStages, par = (g0 / kFStages) & 1u;
+      for (int i = 0; i < kFStages && r0 + i < r1; ++i) {
+        issue(r0 + i, sl, par);
+        if (++sl == kFStages) { sl = 0; par ^= 1u; }
+      }
+    }
+    long long c_wait = 0, c_work = 0, c_t = 0;
+    uint32_t g = g0;
+    uint32_t slot = g % kFStages, ph = (g / kFStages) & 1u;
+    double b_next = (r0 < r1) ? __ldg(bvec + r0) : 0.0;
+    for (int64_t s = r0; s < r1; ++s, ++g) {
+      const double b_cur = b_next;
+      if (s + 1 < r1) b_next = __ldg(bvec + s + 1);
+      const uint32_t d = g % kFDepth, dph = (g / kFDepth) & 1u;
+      if (prof) c_t = clock64();
+      // st.async delivers data and complete_tx through the same path into this CTA's shared memory, so the
+      // cta-scope acquire is enough (a cluster-scope acquire compiles to CCTL.IVALL: an L1 flush per row)
+      mbar_wait(cfull + 8 * d, dph);
+      if (prof) { const long long tt = clock64(); c_wait += tt - c_t; c_t = tt; }
+      const uint32_t pbase = cpart + (d * (kFMaxCluster * kFGWarps) + lane) * 8;
+      const double v0 = (lane < nval) ? lds1(pbase) : 0.0;
+      const double v1 = (lane + 32 < nval) ? lds1(pbase + 256) : 0.0;
+      const double v2 = (lane + 64 < nval) ? lds1(pbase + 512) : 0.0;
+      const double v3 = (lane + 96 < nval) ? lds1(pbase + 768) : 0.0;
+      double v = (v0 + v1) + (v2 + v3);
+      if (leader && s + kFDepth < r1) mbar_expect_tx(cfull + 8 * d, xbytes);      // arm this buffer for row g + 8
+      v = warp_sum(v);                                          // same order in every update warp of the cluster
+      const double rs = v - b_cur;                              // lasso/runme.jl:22  res = A*w - b
+      mbar_wait(full + 8 * slot, ph);                           // long complete; makes the bulk-copied tile visible here
+      const uint32_t tile = ring + slot * kFStageBytes + t * 16;
+      double2 av[8];
+#pragma unroll
+      for (int h = 0; h < kFH; h += 8) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) av[k] = lds2v(tile + (h + k) * kFGroup * 16);
+#pragma unroll
+        for (int k = 7; k >= 0; --k) {
+          acc[h + k].x = fma(av[k].x, rs, acc[h + k].x);
+          acc[h + k].y = fma(av[k].y, rs, acc[h + k].y);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty + 8 * slot);
+      if (producer && s + kFStages < r1) issue(s + kFStages, slot, ph ^ 1u);   // same slot, next phase
+      fsum = fma(rs, rs, fsum);
+      if (prof) { const long long tt = clock64(); c_work += tt - c_t; }
+      if (++slot == kFStages) { slot = 0; ph ^= 1u; }
+    }
+    if (prof && leader) { dbg[5] = (unsigned long long)c_work; dbg[6] = (unsigned long long)c_wait; }
+    double* gout = fa.gpartf + (int64_t)q * fa.npadf + col0;
+#pragma unroll
+    for (int k = 0; k < kFH; ++k) *reinterpret_cast<double2*>(gout + 2 * (k * kFGroup + t)) = acc[k];
+    if (!(leader && rank == 0)) fsum = 0.0;
+  }
+  __syncthreads();
+  fs.count = g0 + (uint32_t)(r1 - r0);
+  return fsum;
 }
 
-// block / grid reductions for a 512-thread CTA (fixed order)
+// block / grid reductions for the 512-thread CTA (fixed order)
 template <int K>
 __device__ __forceinline__ void f_block_reduce_store(double (&v)[K], double* red, int G, int slot0, uint32_t scr) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -240,13 +269,36 @@ __device__ __forceinline__ void f_grid_totals(const double* red, int G, int slot
   __syncthreads();
 }
 
+// Grid-wide barrier on a monotonically increasing arrival counter.  The kernel is launched with exactly as many
+// clusters as cudaOccupancyMaxActiveClusters reports (one CTA per SM), so every CTA is resident; it is a plain
+// cluster launch rather than a cooperative one because Nsight Compute cannot replay the cooperative + cluster
+// attribute combination (LaunchFailed), and an unprofilable hot kernel is not acceptable.
+struct GridBar {
+  unsigned long long* ctr;
+  unsigned long long target;
+  unsigned int G;
+  __device__ __forceinline__ void sync() {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      target += G;
+      __threadfence();                                   // this CTA's global writes before its arrival
+      atomicAdd(ctr, 1ull);
+      unsigned long long seen;
+      do {
+        asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(ctr) : "memory");
+      } while (seen < target);
+    }
+    __syncthreads();
+  }
+};
+
 // AdaPGM / fixed-step PGM (src/AdaProx.jl:312-364 with A = 0, h = Zero) around the fused pass.
 __global__ void __launch_bounds__(kFThreads, 1) k_adapgm_fused(DProblem P, DOpts O, DWork W, FusedArgs fa) {
-  cg::grid_group grid = cg::this_grid();
+  GridBar grid{fa.bar, 0ull, gridDim.x};
   const int b = blockIdx.x, G = gridDim.x;
   extern __shared__ __align__(1024) unsigned char dyn_smem[];
   __shared__ unsigned long long s_bars[2 * kFStages + kFDepth];
-  __shared__ double s_cpart[kFDepth * kFMaxCluster * kFWarps];
+  __shared__ double s_cpart[kFDepth * kFMaxCluster * kFGWarps];
   __shared__ double s_scr[kFWarps * 8 + kMaxRed];
   FusedSmem fs;
   fs.ring = smem_u32(dyn_smem);
@@ -257,9 +309,17 @@ __global__ void __launch_bounds__(kFThreads, 1) k_adapgm_fused(DProblem P, DOpts
   fs.count = 0;
   const uint32_t scr = smem_u32(s_scr);
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kFStages; ++s) { mbar_init(fs.full + 8 * s, 1); mbar_init(fs.empty + 8 * s, kFWarps); }
+    for (int s = 0; s < kFStages; ++s) { mbar_init(fs.full + 8 * s, 1); mbar_init(fs.empty + 8 * s, kFGWarps); }
     for (int s = 0; s < kFDepth; ++s) mbar_init(fs.cfull + 8 * s, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  {
+    // The last CTA of a cluster may own fewer than 8192 columns: the bulk copies never touch the tail of its ring
+    // slots, so zero it once and the pass needs no column predicates (A = 0 there contributes nothing).
+    int64_t width = P.F.ld - (int64_t)cluster_ctarank() * kFCols;
+    width = width < 0 ? 0 : (width > kFCols ? kFCols : width);
+    for (int s = 0; s < kFStages; ++s)
+      for (int64_t j = width + threadIdx.x; j < kFCols; j += kFThreads) sts1(fs.ring + s * kFStageBytes + (uint32_t)j * 8, 0.0);
   }
   __syncthreads();
   cluster_arrive();          // every CTA of the cluster has initialised its shared memory before any peer writes into it
@@ -287,7 +347,7 @@ __global__ void __launch_bounds__(kFThreads, 1) k_adapgm_fused(DProblem P, DOpts
 
   // ---- prologue (:327-332) ----------------------------------------------------------------------------------
   {
-    double fv[1] = {fused_pass(P.F, P.fvec, x, fs, fa, nullptr)};
+    double fv[1] = {fused_pass<false>(P.F, P.fvec, x, fs, fa, nullptr)};
     f_block_reduce_store<1>(fv, W.red, G, SLOT_F0, scr);
   }
   grid.sync();
@@ -316,7 +376,9 @@ __global__ void __launch_bounds__(kFThreads, 1) k_adapgm_fused(DProblem P, DOpts
   for (int64_t it = 1; it <= O.maxit; ++it) {
     phase_stamp(W, it, 0);
     {
-      double fv[1] = {fused_pass(P.F, P.fvec, x, fs, fa, (W.tstamp && it <= W.tstamp_iters) ? W.tstamp + (it - 1) * 8 : nullptr)};   // :336 value + pullback in one pass
+      // :336 value + pullback in one pass (the instrumented instantiation only runs under ADAPROX_PHASE_TIMING)
+      double fv[1] = {(W.tstamp && it <= W.tstamp_iters) ? fused_pass<true>(P.F, P.fvec, x, fs, fa, W.tstamp + (it - 1) * 8)
+                                                         : fused_pass<false>(P.F, P.fvec, x, fs, fa, nullptr)};
       f_block_reduce_store<1>(fv, W.red, G, SLOT_F0, scr);
     }
     n_eval++; n_grad++;

@@ -37,20 +37,24 @@ M_FULL, N_FULL = 65536, 131072
 METRIC = "AdaPGM iters/sec on 65536x131072 fp64 lasso"
 
 
-def b_iter_bytes(m_loc, n):
-    """Algorithmic bytes of one AdaPGM lasso iteration:
-    A read once for A*x and once for A'*r, plus the vector traffic."""
-    return 2 * 8 * m_loc * n + 8 * (3 * m_loc + 8 * n)
+def b_iter_bytes(m_loc, n, passes=2):
+    """Algorithmic bytes of one AdaPGM lasso iteration.  passes = 2 is SURVEY.md section 8d's figure (A read once
+    for A*x and once for A'*r, the reference's two oracle calls) plus the vector traffic; passes = 1 is what the
+    single-pass fused kernel (solver_fused.cuh) has to move: A once."""
+    return passes * 8 * m_loc * n + 8 * (3 * m_loc + 8 * n)
 
 
-def ncu_traffic_per_eval(m, n):
+NCU_SUMMARY = {1: "r01_ncu_k_adapgm_fused.json", 2: "r01_ncu_k_primal_dual_ring.json"}
+
+
+def ncu_traffic_per_eval(m, n, passes):
     """DRAM bytes (read + write) per gradient evaluation from the committed `ncu --set full` capture of the
-    persistent kernel at the full size (profiles/r01_ncu_k_primal_dual_ring.json); None for other sizes."""
-    p = os.path.join(ROOT, "profiles", "r01_ncu_k_primal_dual_ring.json")
-    if (m, n) != (M_FULL, N_FULL) or not os.path.exists(p):
-        return None
+    persistent kernel that ran, at the full size; None for other sizes or when no capture is committed."""
+    p = os.path.join(ROOT, "profiles", NCU_SUMMARY.get(passes, ""))
+    if (m, n) != (M_FULL, N_FULL) or not os.path.isfile(p):
+        return None, None
     with open(p) as f:
-        return float(json.load(f)["_derived"]["dram_bytes_per_gradient_eval"])
+        return float(json.load(f)["_derived"]["dram_bytes_per_gradient_eval"]), os.path.relpath(p, ROOT)
 
 
 def peaks():
@@ -261,11 +265,19 @@ def run_b200(args):
 
     if rank == 0:
         peak, peak_src = peaks()
-        bytes_iter_rank = b_iter_bytes(rows, n)
-        # the timed launch(es) perform K iterations plus the solver's prologue (one more A*x / A'r pair, :327-332)
-        bytes_launch = bytes_iter_rank * K + 2 * 8 * rows * n
-        achieved = bytes_launch / (dev_ms * 1e-3) / 1e9            # per-GPU GB/s
-        per_eval = ncu_traffic_per_eval(m, n) if world == 1 else None
+        passes = int(res.matrix_passes)                            # 1: single-pass fused kernel, 2: A*x then A'r
+        bytes_iter_rank = b_iter_bytes(rows, n, passes)
+        # the timed launch(es) perform K iterations plus the solver's prologue (one more gradient evaluation, :327-332)
+        bytes_launch = bytes_iter_rank * K + passes * 8 * rows * n
+        achieved = bytes_launch / (dev_ms * 1e-3) / 1e9            # per-GPU GB/s actually required of HBM
+        per_eval, per_eval_src = ncu_traffic_per_eval(m, n, passes) if world == 1 else (None, None)
+        if world > 1:
+            kernel = "k_sh_A + k_sh_C (split-phase GEMV kernels)"
+        elif passes == 1:
+            kernel = ("k_adapgm_fused (persistent cooperative cluster kernel: the whole solve is one launch; "
+                      "A'(Ax-b) in ONE sweep over A per iteration)")
+        else:
+            kernel = "k_primal_dual<false> (persistent cooperative kernel: the whole solve is one launch)"
         out = {
             "metric": METRIC if (m, n) == (M_FULL, N_FULL) else f"AdaPGM iters/sec on {m}x{n} fp64 lasso",
             "value": K / (dev_ms * 1e-3), "unit": "it/s", "n_gpus": world, "steps": K, "warmup": W,
@@ -278,15 +290,19 @@ def run_b200(args):
                        "timing": "library CUDA events on the kernels' stream around one solve of K iterations; max over ranks",
                        "generation_s": round(t_gen, 2), "gamma0": gamma0},
             "achieved_hbm_gbs_per_gpu": bytes_iter_rank * K / (dev_ms * 1e-3) / 1e9,
+            "matrix_passes_per_iteration": passes,
+            "two_pass_equivalent_gbs_per_gpu": b_iter_bytes(rows, n, 2) * K / (dev_ms * 1e-3) / 1e9,
+            "two_pass_equivalent_note": "SURVEY 8d's B_iter (A counted twice, as the reference's two oracle calls read it) x it/s; "
+                                        "equals achieved_hbm_gbs_per_gpu when matrix_passes_per_iteration = 2; with the single-pass "
+                                        "kernel it is a throughput equivalent, NOT a bandwidth (roofline.achieved counts A once)",
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": (per_eval * (K + 1)) if per_eval else None, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": bytes_launch,
                          "launch": "one persistent launch = K iterations + prologue = K+1 gradient evaluations" if world == 1
                                    else "K+1 gradient evaluations as 6 launches + 1 all-reduce each",
-                         "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per gradient evaluation x (K+1), "
-                                           "profiles/r01_ncu_k_primal_dual_ring.json" if per_eval else None,
-                         "kernel": "k_primal_dual<false> (persistent cooperative kernel: the whole solve is one launch)"
-                                   if world == 1 else "k_sh_A + k_sh_C (split-phase GEMV kernels)",
+                         "traffic_source": ("ncu dram__bytes_read.sum + dram__bytes_write.sum per gradient evaluation x (K+1), "
+                                            + per_eval_src) if per_eval else None,
+                         "kernel": kernel, "matrix_passes": passes,
                          "algorithmic_bytes_per_iteration_per_gpu": bytes_iter_rank,
                          "gemv_n_ms": ms_n, "gemv_t_ms": ms_t,
                          "gemv_n_gbs": rows * n * 8 / (ms_n * 1e-3) / 1e9, "gemv_t_gbs": rows * n * 8 / (ms_t * 1e-3) / 1e9},
@@ -320,9 +336,12 @@ def main():
     ap.add_argument("--to-tol", type=float, default=0.0, help="also report the time to reach norm_res <= tol")
     ap.add_argument("--tol-maxit", type=int, default=20000)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--two-pass", action="store_true", help="A/B: force the two-pass kernel (ADAPROX_FUSED=0)")
     ap.add_argument("--cpu-steps", type=int, default=20)
     ap.add_argument("--cpu-rows", type=int, default=None)
     args = ap.parse_args()
+    if args.two_pass:
+        os.environ["ADAPROX_FUSED"] = "0"
     if args.impl == "reference":
         run_reference(args)
     else:

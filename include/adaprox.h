@@ -148,6 +148,8 @@ typedef struct {
   double final_gamma, final_sigma, final_norm_res;
   double solve_ms;              /* device time of the solve (CUDA events)                */
   int64_t kernel_launches;      /* library kernels launched by this call                 */
+  int64_t matrix_passes;        /* sweeps over the matrix of f per gradient evaluation: 1 = single-pass
+                                   fused A'(Ax-b) kernel, 2 = A*x then A'*r; 0 = f has no matrix        */
 } adaprox_result;
 
 /* ---- life cycle ------------------------------------------------------------- */
