@@ -614,7 +614,12 @@ extern "C" int adaprox_solve(adaprox_handle h, const adaprox_problem* p, const a
     rc = fused_config(h, fa.C, &fcfg, fattrs, &fQ);
     if (rc < 0) return rc;
     if (rc == 1) fused = false;
-    else { fa.npadf = (int64_t)fa.C * kFCols; G = fa.C * fQ; }
+    else {
+      fa.npadf = (int64_t)fa.C * kFCols; G = fa.C * fQ;
+      const char* sp = std::getenv("ADAPROX_FUSED_SPLIT");
+      const int spv = sp ? std::atoi(sp) : 1;
+      fa.split = (spv == 2 || spv == 4 || spv == 8) ? spv : 1;
+    }
   }
   size_t need = (fused ? ws_size_doubles((int64_t)fQ * fa.npadf) + ws_size_doubles(1) : 0) +
                 11 * ws_size_doubles(n) + 6 * ws_size_doubles(md) + ws_size_doubles(mf) +

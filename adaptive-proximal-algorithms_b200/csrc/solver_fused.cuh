@@ -41,6 +41,7 @@ struct FusedArgs {
   int64_t npadf;       // C * 8192
   int C;               // cluster size
   unsigned long long* bar;   // grid-barrier arrival counter (zeroed by the host before the launch)
+  int split;           // bulk copies per row piece (1, 2, 4 or 8: 64 KB .. 8 KB each)
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
@@ -49,8 +50,15 @@ __device__ __forceinline__ uint32_t ncluster_id_x() { uint32_t r; asm volatile("
 __device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 
+// Control block in static shared memory: full[3] | empty[3] | cfull[8] mbarriers, then the exchange buffers
+// cpart[8][16 ranks][8 warps].  One base register + compile-time offsets address all of it.
+constexpr uint32_t kOffFull = 0, kOffEmpty = 8 * kFStages, kOffCfull = 16 * kFStages, kOffCpart = 128;
+constexpr uint32_t kPartStride = kFMaxCluster * kFGWarps * 8;                 // bytes per exchange buffer
+constexpr int kCtlBytes = kOffCpart + kFDepth * kPartStride;
+static_assert(16 * kFStages + 8 * kFDepth <= kOffCpart, "control block layout");
+
 struct FusedSmem {
-  uint32_t ring, full, empty, cfull, cpart;   // shared-space addresses
+  uint32_t ring, ctl;                         // shared-space addresses of the tile ring and the control block
   uint32_t count;                             // rows pushed through the ring / exchange so far (uniform)
 };
 
@@ -98,43 +106,46 @@ template <bool PROF>
 __device__ __noinline__ double fused_pass(const DMat& M, const double* bvec, const double* x, FusedSmem& fs, const FusedArgs& fa,
                                            unsigned long long* dbg) {
   const bool prof = PROF && (dbg != nullptr) && blockIdx.x == 0;
-  const double* const a = M.a;
-  const int64_t ld = M.ld, n = M.n, m = M.m;
-  const uint32_t ring = fs.ring, full = fs.full, empty = fs.empty, cfull = fs.cfull, cpart = fs.cpart;
-  const uint32_t rank = cluster_ctarank(), q = cluster_id_x(), Q = ncluster_id_x();
+  const uint32_t ring = fs.ring, ctl = fs.ctl, g0 = fs.count;
+  const uint32_t rank = cluster_ctarank();
   const int C = fa.C;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t r0 = (m * (int64_t)q) / Q, r1 = (m * (int64_t)(q + 1)) / Q;
+  int nrows;
+  int64_t r0;
+  {
+    const int64_t q = cluster_id_x(), Q = ncluster_id_x();
+    r0 = (M.m * q) / Q;
+    nrows = (int)((M.m * (q + 1)) / Q - r0);
+  }
   const int64_t col0 = (int64_t)rank * kFCols;
-  int64_t width = ld - col0;
-  width = width < 0 ? 0 : (width > kFCols ? kFCols : width);
-  const uint32_t bytes = (uint32_t)(width * 8);
-  const uint32_t xbytes = (uint32_t)(C * kFGWarps * 8);        // exchange bytes per row per CTA
-  const uint32_t g0 = fs.count;
   double fsum = 0.0;
 
   if (warp < kFGWarps) {
     // ------------------------------------------------------------------ dot warps
     const int t = threadIdx.x;
     double2 xr[kFH];
+    {
+      const int64_t n = M.n;
 #pragma unroll
-    for (int k = 0; k < kFH; ++k) {
-      const int64_t j = col0 + 2 * (k * kFGroup + t);
-      xr[k].x = (j < n) ? ldcg(x + j) : 0.0;
-      xr[k].y = (j + 1 < n) ? ldcg(x + j + 1) : 0.0;
+      for (int k = 0; k < kFH; ++k) {
+        const int64_t j = col0 + 2 * (k * kFGroup + t);
+        xr[k].x = (j < n) ? ldcg(x + j) : 0.0;
+        xr[k].y = (j + 1 < n) ? ldcg(x + j + 1) : 0.0;
+      }
     }
     long long c_wait = 0, c_work = 0, c_t = 0;
-    uint32_t g = g0;
-    uint32_t slot = g % kFStages, ph = (g / kFStages) & 1u;
-    const uint32_t mypart = cpart + (rank * kFGWarps + warp) * 8;
-    for (int64_t s = r0; s < r1; ++s, ++g) {
-      const uint32_t d = g % kFDepth;
-      if (prof) c_t = clock64();
-      mbar_wait(full + 8 * slot, ph);
-      if (prof) { const long long tt = clock64(); c_wait += tt - c_t; c_t = tt; }
-      const uint32_t tile = ring + slot * kFStageBytes + t * 16;
-      // two batches of 8 x LDS.128 issued back to back (ptxas otherwise recycles ONE destination quad and
-      // serialises load -> FMA -> load, exposing the full shared-memory latency 16 times per row)
+    uint32_t slot = g0 % kFStages, ph = (g0 / kFStages) & 1u, d = g0 % kFDepth;
+    const uint32_t tile0 = ring + t * 16;
+    const uint32_t mypart = ctl + kOffCpart + (rank * kFGWarps + warp) * 8;
+    const bool sender = lane < C;
+    for (int i = 0; i < nrows; ++i) {
+      if (PROF && prof) c_t = clock64();
+      mbar_wait(ctl + kOffFull + 8 * slot, ph);
+      if (PROF && prof) { const long long tt = clock64(); c_wait += tt - c_t; c_t = tt; }
+      const uint32_t tile = tile0 + slot * kFStageBytes;
+      // batches of 8 x LDS.128 issued back to back: ld.volatile keeps their order and the FMA chains consume the
+      // batch in REVERSE, so all eight are in flight before the first FMA (ptxas otherwise recycles ONE destination
+      // quad: load -> FMA -> load ..., a full shared-memory round trip per 16 bytes)
       double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
       double2 av[8];
 #pragma unroll
@@ -150,67 +161,82 @@ __device__ __noinline__ double fused_pass(const DMat& M, const double* bvec, con
         }
       }
       const double pw = warp_sum((p0 + p1) + (p2 + p3));
-      if (lane < C) st_async_peer(mypart + d * (kFMaxCluster * kFGWarps * 8), cfull + 8 * d, (uint32_t)lane, pw);
-      if (prof) { const long long tt = clock64(); c_work += tt - c_t; }
+      if (sender) st_async_peer(mypart + d * kPartStride, ctl + kOffCfull + 8 * d, (uint32_t)lane, pw);
+      if (PROF && prof) { const long long tt = clock64(); c_work += tt - c_t; }
       if (++slot == kFStages) { slot = 0; ph ^= 1u; }
+      d = (d + 1) % kFDepth;
     }
-    if (prof && threadIdx.x == 0) { dbg[1] = (unsigned long long)c_wait; dbg[2] = (unsigned long long)c_work; }
-  } else if (warp < 2 * kFGWarps) {
+    if (PROF && prof && threadIdx.x == 0) { dbg[1] = (unsigned long long)c_wait; dbg[2] = (unsigned long long)c_work; }
+  } else {
     // ------------------------------------------------------------------ update warps
     const int t = threadIdx.x - kFGroup;
     const bool leader = (t == 0);
-    const int nval = C * kFGWarps;
+    const bool producer = (t == kFGroup - 32);       // lane 0 of the last update warp keeps the ring full
+    const uint32_t xbytes = (uint32_t)(C * kFGWarps * 8);        // exchange bytes per row per CTA
+    uint32_t bytes;
+    {
+      int64_t width = M.ld - col0;
+      width = width < 0 ? 0 : (width > kFCols ? kFCols : width);
+      bytes = (uint32_t)(width * 8);
+    }
+    const int64_t ldb = M.ld;
+    const uint32_t piece = (uint32_t)kFStageBytes / (uint32_t)fa.split;
+    const double* src = M.a + col0 + r0 * ldb;       // next row to copy (producer)
     double2 acc[kFH];
 #pragma unroll
     for (int k = 0; k < kFH; ++k) acc[k] = make_double2(0.0, 0.0);
-    if (leader) {
-      const int64_t nr = r1 - r0;
-      for (int i = 0; i < kFDepth && i < nr; ++i) mbar_expect_tx(cfull + 8 * ((g0 + i) % kFDepth), xbytes);
-    }
-    // producer duty: lane 0 of the last update warp keeps the ring full (row g + 3 goes into the slot row g leaves)
-    const bool producer = (t == kFGroup - 32);
-    const double* const abase = a + col0;
-    auto issue = [&](int64_t row, uint32_t sl, uint32_t par) {
-      mbar_wait(empty + 8 * sl, par ^ 1u);
-      mbar_expect_tx(full + 8 * sl, bytes);
-      bulk_g2s(ring + sl * kFStageBytes, abase + row * ld, bytes, full + 8 * sl);
+    if (leader)
+      for (int i = 0; i < kFDepth && i < nrows; ++i) mbar_expect_tx(ctl + kOffCfull + 8 * ((g0 + i) % kFDepth), xbytes);
+    uint32_t slot = g0 % kFStages, ph = (g0 / kFStages) & 1u, d = g0 % kFDepth, dph = (g0 / kFDepth) & 1u;
+    auto issue = [&](uint32_t sl, uint32_t par) {    // wait until the update warps left slot sl, then refill it
+      mbar_wait(ctl + kOffEmpty + 8 * sl, par ^ 1u);
+      mbar_expect_tx(ctl + kOffFull + 8 * sl, bytes);
+      for (uint32_t off = 0; off < bytes; off += piece) {
+        const uint32_t nb = (bytes - off < piece) ? (bytes - off) : piece;
+        bulk_g2s(ring + sl * kFStageBytes + off, reinterpret_cast<const char*>(src) + off, nb, ctl + kOffFull + 8 * sl);
+      }
+      src += ldb;
     };
     if (producer) {
-      uint32_t sl = g0 % kFStages, par = (g0 / kFStages) & 1u;
-      for (int i = 0; i < kFStages && r0 + i < r1; ++i) {
-        issue(r0 + i, sl, par);
+      uint32_t sl = slot, par = ph;
+      for (int i = 0; i < kFStages && i < nrows; ++i) {
+        issue(sl, par);
         if (++sl == kFStages) { sl = 0; par ^= 1u; }
       }
     }
+    // predicates of the four partial loads of this lane (C * 8 <= 128 partials per row)
+    const int nval = C * kFGWarps;
+    const bool q0 = lane < nval, q1 = lane + 32 < nval, q2 = lane + 64 < nval, q3 = lane + 96 < nval;
+    const uint32_t tile0 = ring + t * 16;
+    const uint32_t part0 = ctl + kOffCpart + lane * 8;
+    const double* bp = bvec + r0;
     long long c_wait = 0, c_work = 0, c_t = 0;
-    uint32_t g = g0;
-    uint32_t slot = g % kFStages, ph = (g / kFStages) & 1u;
-    double b_next = (r0 < r1) ? __ldg(bvec + r0) : 0.0;
-    for (int64_t s = r0; s < r1; ++s, ++g) {
+    double b_next = (nrows > 0) ? __ldg(bp) : 0.0;
+    for (int i = 0; i < nrows; ++i) {
       const double b_cur = b_next;
-      if (s + 1 < r1) b_next = __ldg(bvec + s + 1);
-      const uint32_t d = g % kFDepth, dph = (g / kFDepth) & 1u;
-      if (prof) c_t = clock64();
+      if (i + 1 < nrows) b_next = __ldg(bp + i + 1);
+      if (PROF && prof) c_t = clock64();
       // st.async delivers data and complete_tx through the same path into this CTA's shared memory, so the
       // cta-scope acquire is enough (a cluster-scope acquire compiles to CCTL.IVALL: an L1 flush per row)
-      mbar_wait(cfull + 8 * d, dph);
-      if (prof) { const long long tt = clock64(); c_wait += tt - c_t; c_t = tt; }
-      const uint32_t pbase = cpart + (d * (kFMaxCluster * kFGWarps) + lane) * 8;
-      const double v0 = (lane < nval) ? lds1(pbase) : 0.0;
-      const double v1 = (lane + 32 < nval) ? lds1(pbase + 256) : 0.0;
-      const double v2 = (lane + 64 < nval) ? lds1(pbase + 512) : 0.0;
-      const double v3 = (lane + 96 < nval) ? lds1(pbase + 768) : 0.0;
-      double v = (v0 + v1) + (v2 + v3);
-      if (leader && s + kFDepth < r1) mbar_expect_tx(cfull + 8 * d, xbytes);      // arm this buffer for row g + 8
-      v = warp_sum(v);                                          // same order in every update warp of the cluster
-      const double rs = v - b_cur;                              // lasso/runme.jl:22  res = A*w - b
-      mbar_wait(full + 8 * slot, ph);                           // long complete; makes the bulk-copied tile visible here
-      const uint32_t tile = ring + slot * kFStageBytes + t * 16;
+      mbar_wait(ctl + kOffCfull + 8 * d, dph);
+      if (PROF && prof) { const long long tt = clock64(); c_wait += tt - c_t; c_t = tt; }
+      const uint32_t pb = part0 + d * kPartStride;
+      const double v0 = q0 ? lds1(pb) : 0.0;
+      const double v1 = q1 ? lds1(pb + 256) : 0.0;
+      const double v2 = q2 ? lds1(pb + 512) : 0.0;
+      const double v3 = q3 ? lds1(pb + 768) : 0.0;
+      if (leader && i + kFDepth < nrows) mbar_expect_tx(ctl + kOffCfull + 8 * d, xbytes);    // arm this buffer for row g + 8
+      const double rs = warp_sum((v0 + v1) + (v2 + v3)) - b_cur;   // same order in every update warp of the cluster;
+                                                                   // lasso/runme.jl:22  res = A*w - b
+      mbar_wait(ctl + kOffFull + 8 * slot, ph);                 // long complete; makes the bulk-copied tile visible here
+      const uint32_t tile = tile0 + slot * kFStageBytes;
       double2 av[8];
 #pragma unroll
       for (int h = 0; h < kFH; h += 8) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) av[k] = lds2v(tile + (h + k) * kFGroup * 16);
+        __syncwarp();                                           // scheduling fence: the independent FMAs below must not be
+                                                                // hoisted between the loads (one load in flight otherwise)
 #pragma unroll
         for (int k = 7; k >= 0; --k) {
           acc[h + k].x = fma(av[k].x, rs, acc[h + k].x);
@@ -218,20 +244,21 @@ __device__ __noinline__ double fused_pass(const DMat& M, const double* bvec, con
         }
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(empty + 8 * slot);
-      if (producer && s + kFStages < r1) issue(s + kFStages, slot, ph ^ 1u);   // same slot, next phase
+      if (lane == 0) mbar_arrive(ctl + kOffEmpty + 8 * slot);
+      if (producer && i + kFStages < nrows) issue(slot, ph ^ 1u);   // same slot, next phase: row g + 3
       fsum = fma(rs, rs, fsum);
-      if (prof) { const long long tt = clock64(); c_work += tt - c_t; }
+      if (PROF && prof) { const long long tt = clock64(); c_work += tt - c_t; }
       if (++slot == kFStages) { slot = 0; ph ^= 1u; }
+      if (++d == kFDepth) { d = 0; dph ^= 1u; }
     }
-    if (prof && leader) { dbg[5] = (unsigned long long)c_work; dbg[6] = (unsigned long long)c_wait; }
-    double* gout = fa.gpartf + (int64_t)q * fa.npadf + col0;
+    if (PROF && prof && leader) { dbg[5] = (unsigned long long)c_work; dbg[6] = (unsigned long long)c_wait; }
+    double* gout = fa.gpartf + (int64_t)cluster_id_x() * fa.npadf + col0;
 #pragma unroll
     for (int k = 0; k < kFH; ++k) *reinterpret_cast<double2*>(gout + 2 * (k * kFGroup + t)) = acc[k];
     if (!(leader && rank == 0)) fsum = 0.0;
   }
   __syncthreads();
-  fs.count = g0 + (uint32_t)(r1 - r0);
+  fs.count = g0 + (uint32_t)nrows;
   return fsum;
 }
 
@@ -297,20 +324,16 @@ __global__ void __launch_bounds__(kFThreads, 1) k_adapgm_fused(DProblem P, DOpts
   GridBar grid{fa.bar, 0ull, gridDim.x};
   const int b = blockIdx.x, G = gridDim.x;
   extern __shared__ __align__(1024) unsigned char dyn_smem[];
-  __shared__ unsigned long long s_bars[2 * kFStages + kFDepth];
-  __shared__ double s_cpart[kFDepth * kFMaxCluster * kFGWarps];
+  __shared__ __align__(16) unsigned char s_ctl[kCtlBytes];
   __shared__ double s_scr[kFWarps * 8 + kMaxRed];
   FusedSmem fs;
   fs.ring = smem_u32(dyn_smem);
-  fs.full = smem_u32(s_bars);
-  fs.empty = smem_u32(s_bars + kFStages);
-  fs.cfull = smem_u32(s_bars + 2 * kFStages);
-  fs.cpart = smem_u32(s_cpart);
+  fs.ctl = smem_u32(s_ctl);
   fs.count = 0;
   const uint32_t scr = smem_u32(s_scr);
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kFStages; ++s) { mbar_init(fs.full + 8 * s, 1); mbar_init(fs.empty + 8 * s, kFGWarps); }
-    for (int s = 0; s < kFDepth; ++s) mbar_init(fs.cfull + 8 * s, 1);
+    for (int s = 0; s < kFStages; ++s) { mbar_init(fs.ctl + kOffFull + 8 * s, 1); mbar_init(fs.ctl + kOffEmpty + 8 * s, kFGWarps); }
+    for (int s = 0; s < kFDepth; ++s) mbar_init(fs.ctl + kOffCfull + 8 * s, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   {
