@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libadaprox_cuda.so")
+LIB_PATH = os.environ.get("ADAPROX_LIB") or os.path.join(_HERE, "libadaprox_cuda.so")   # ADAPROX_LIB: A/B builds
 
 c_id = C.c_int64
 c_dp = C.POINTER(C.c_double)

@@ -563,13 +563,9 @@ static bool fused_eligible(const adaprox_options* o, const DProblem& P) {
   if (!force && P.F.m * P.F.ld < (int64_t)(32 << 20)) return false;        // small problems: the two-pass kernel has more CTAs per column
   return fused_cluster_size(P) <= kFMaxCluster;
 }
-static int fused_config(adaprox_ctx* h, int C, cudaLaunchConfig_t* cfg, cudaLaunchAttribute* attrs, int* Q) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    AP_CUDA(h, cudaFuncSetAttribute((const void*)k_adapgm_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, kFRingBytes));
-    AP_CUDA(h, cudaFuncSetAttribute((const void*)k_adapgm_fused, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    attr_set = true;
-  }
+static int fused_config(adaprox_ctx* h, const void* kernel, int C, cudaLaunchConfig_t* cfg, cudaLaunchAttribute* attrs, int* Q) {
+  AP_CUDA(h, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFRingBytes));
+  AP_CUDA(h, cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   *cfg = cudaLaunchConfig_t{};
   cfg->gridDim = dim3(C, 1, 1);
   cfg->blockDim = dim3(kFThreads, 1, 1);
@@ -580,11 +576,68 @@ static int fused_config(adaprox_ctx* h, int C, cudaLaunchConfig_t* cfg, cudaLaun
   cfg->attrs = attrs;
   cfg->numAttrs = 1;               // cluster launch only: the kernel carries its own grid barrier (see GridBar)
   int q = 0;
-  cudaError_t e = cudaOccupancyMaxActiveClusters(&q, (const void*)k_adapgm_fused, cfg);
+  cudaError_t e = cudaOccupancyMaxActiveClusters(&q, kernel, cfg);
   if (e != cudaSuccess || q < 1) { cudaGetLastError(); return 1; }
   *Q = q;
   cfg->gridDim = dim3(C * q, 1, 1);
   return ADAPROX_OK;
+}
+
+// Plan of one fused solve: launch configuration, chunk size of the dynamic schedule, workspace.
+struct FusedPlan {
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attrs[2];
+  int Q = 0;                 // resident clusters
+  int G = 0;                 // CTAs = C * Q
+  FusedArgs fa{};
+};
+// returns 0 = ok, 1 = not possible on this device (fall back to the two-pass kernels), < 0 = error
+static int fused_plan(adaprox_ctx* h, const void* kernel, const DProblem& P, FusedPlan* pl) {
+  pl->fa = FusedArgs{};
+  pl->fa.C = fused_cluster_size(P);
+  int rc = fused_config(h, kernel, pl->fa.C, &pl->cfg, pl->attrs, &pl->Q);
+  if (rc) return rc;
+  pl->G = pl->fa.C * pl->Q;
+  pl->fa.npadf = (int64_t)pl->fa.C * kFCols;
+  // chunk size: about 8 chunks per cluster (a chunk boundary costs a cluster barrier, an atomic and a refill of the
+  // 3-slot ring, ~10 us: ~2 % at this granularity, while a cluster that is 2x slower than the rest -- seen on
+  // some parts -- only delays the sweep by ~8 % instead of 100 %)
+  int64_t pw = P.F.m / ((int64_t)pl->Q * 8);
+  pw = ((pw + 7) / 8) * 8;
+  pw = pw < 32 ? 32 : (pw > 4096 ? 4096 : pw);
+  if (const char* e = std::getenv("ADAPROX_FUSED_CHUNK")) { const int v = std::atoi(e); if (v >= 1) pw = v; }
+  pl->fa.chunk_rows = (int)pw;
+  pl->fa.nchunks = (int)((P.F.m + pw - 1) / pw);
+  return 0;
+}
+static size_t fused_ws_bytes(const FusedPlan& pl) {
+  return ws_size_doubles((int64_t)pl.fa.nchunks * pl.fa.npadf) + ws_size_doubles(pl.fa.nchunks) + 2 * ws_size_doubles(1) +
+         ws_size_doubles(4 * 256);
+}
+static int fused_ws_alloc(adaprox_ctx* h, FusedPlan* pl) {
+  FusedArgs& fa = pl->fa;
+  fa.gpartf = ws_doubles(h, (int64_t)fa.nchunks * fa.npadf);
+  fa.fpart = ws_doubles(h, fa.nchunks);
+  fa.bar = reinterpret_cast<unsigned long long*>(ws_doubles(h, 1));
+  fa.next = reinterpret_cast<unsigned long long*>(ws_doubles(h, 1));
+  AP_CUDA(h, cudaMemsetAsync(fa.bar, 0, 8, h->stream));
+  AP_CUDA(h, cudaMemsetAsync(fa.next, 0, 8, h->stream));
+  unsigned long long* lat = reinterpret_cast<unsigned long long*>(ws_doubles(h, 4 * 256));
+  if (std::getenv("ADAPROX_FUSED_LAT")) {
+    fa.lat = lat;
+    AP_CUDA(h, cudaMemsetAsync(fa.lat, 0, 4 * 256 * 8, h->stream));
+  }
+  return ADAPROX_OK;
+}
+static void fused_print_probe(const FusedPlan& pl, const char* what) {
+  if (!pl.fa.lat) return;
+  unsigned long long L4[4 * 256];
+  cudaMemcpy(L4, pl.fa.lat, sizeof(L4), cudaMemcpyDeviceToHost);
+  std::fprintf(stderr, "[adaprox %s: chunk_rows=%d nchunks=%d; per cluster: chunks taken (all sweeps) / last sweep us @ first smid]", what,
+               pl.fa.chunk_rows, pl.fa.nchunks);
+  for (int i = 0; i < pl.G; i += pl.fa.C)
+    std::fprintf(stderr, " %llu/%.0f@%llu", L4[4 * i], (double)L4[4 * i + 1] * 1e-3, L4[4 * i + 3]);
+  std::fprintf(stderr, "\n");
 }
 
 extern "C" int adaprox_solve(adaprox_handle h, const adaprox_problem* p, const adaprox_options* o, const double* x0,
@@ -599,7 +652,7 @@ extern "C" int adaprox_solve(adaprox_handle h, const adaprox_problem* p, const a
   DOpts O{};
   fill_opts(o, &O);
   if (!records) O.max_records = 0;
-  const bool sharded = (fm && fm->sharded) || (am && am->sharded);
+  const bool sharded = ((fm && fm->sharded) || (am && am->sharded)) && !std::getenv("ADAPROX_DEBUG_IGNORE_SHARD");
   if (sharded) return solve_sharded(h, p, o, P, O, fm, am, x0, y0, x_out, y_out, records, res);
 
   const int64_t n = P.n, md = std::max<int64_t>(P.md, 1);
@@ -607,21 +660,15 @@ extern "C" int adaprox_solve(adaprox_handle h, const adaprox_problem* p, const a
   const int64_t nrec = std::min<int64_t>(O.max_records, O.maxit);
   int G = h->grid;
   bool fused = fused_eligible(o, P);
-  cudaLaunchConfig_t fcfg; cudaLaunchAttribute fattrs[2]; int fQ = 0;
-  FusedArgs fa{};
+  FusedPlan fpl;
   if (fused) {
-    fa.C = fused_cluster_size(P);
-    rc = fused_config(h, fa.C, &fcfg, fattrs, &fQ);
+    rc = fused_plan(h, (const void*)k_adapgm_fused, P, &fpl);
     if (rc < 0) return rc;
-    if (rc == 1) fused = false;
-    else {
-      fa.npadf = (int64_t)fa.C * kFCols; G = fa.C * fQ;
-      const char* sp = std::getenv("ADAPROX_FUSED_SPLIT");
-      const int spv = sp ? std::atoi(sp) : 1;
-      fa.split = (spv == 2 || spv == 4 || spv == 8) ? spv : 1;
-    }
+    if (rc == 1) fused = false; else G = fpl.G;
   }
-  size_t need = (fused ? ws_size_doubles((int64_t)fQ * fa.npadf) + ws_size_doubles(1) : 0) +
+  FusedArgs& fa = fpl.fa;
+  const int fQ = fpl.Q;
+  size_t need = (fused ? fused_ws_bytes(fpl) : 0) +
                 11 * ws_size_doubles(n) + 6 * ws_size_doubles(md) + ws_size_doubles(mf) +
                 ws_size_doubles((int64_t)kMaxRed * G) + ws_size_doubles((nrec * (int64_t)sizeof(adaprox_record) + 7) / 8) +
                 ws_size_doubles((sizeof(DResult) + 7) / 8);
@@ -642,11 +689,7 @@ extern "C" int adaprox_solve(adaprox_handle h, const adaprox_problem* p, const a
   W.res = reinterpret_cast<DResult*>(ws_doubles(h, (sizeof(DResult) + 7) / 8));
   W.xout = W.aux[2];
   O.max_records = nrec;
-  if (fused) {
-    fa.gpartf = ws_doubles(h, (int64_t)fQ * fa.npadf);
-    fa.bar = reinterpret_cast<unsigned long long*>(ws_doubles(h, 1));
-    AP_CUDA(h, cudaMemsetAsync(fa.bar, 0, 8, h->stream));
-  }
+  if (fused && (rc = fused_ws_alloc(h, &fpl))) return rc;
   const bool phase_timing = std::getenv("ADAPROX_PHASE_TIMING") != nullptr;
   unsigned long long* d_ts = nullptr;
   const int ts_iters = (int)std::min<int64_t>(O.maxit, 64);
@@ -674,7 +717,7 @@ extern "C" int adaprox_solve(adaprox_handle h, const adaprox_problem* p, const a
     case ADAPROX_S_ADAPTIVE_PRIMAL_DUAL:
     case ADAPROX_S_ADAPTIVE_PROXGRAD:
       if (fused) {
-        cudaError_t e = cudaLaunchKernelExC(&fcfg, (const void*)k_adapgm_fused, fargs);
+        cudaError_t e = cudaLaunchKernelExC(&fpl.cfg, (const void*)k_adapgm_fused, fargs);
         if (e != cudaSuccess) return fail(h, ADAPROX_ERR_CUDA, std::string("fused cluster launch: ") + cudaGetErrorString(e));
         h->launches++;
         rc = ADAPROX_OK;
@@ -704,6 +747,7 @@ extern "C" int adaprox_solve(adaprox_handle h, const adaprox_problem* p, const a
   AP_CUDA(h, cudaMemcpyAsync(x_out, W.xout, (size_t)n * 8, cudaMemcpyDeviceToHost, h->stream));
   if (y_out && P.md > 0) AP_CUDA(h, cudaMemcpyAsync(y_out, W.yout, (size_t)P.md * 8, cudaMemcpyDeviceToHost, h->stream));
   AP_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (fused) fused_print_probe(fpl, "fused");
   if (records && dr.n_records > 0)
     AP_CUDA(h, cudaMemcpy(records, W.rec, (size_t)dr.n_records * sizeof(adaprox_record), cudaMemcpyDeviceToHost));
   if (d_ts) {     // phase breakdown of the persistent kernel, averaged over the stamped iterations
@@ -719,10 +763,15 @@ extern "C" int adaprox_solve(adaprox_handle h, const adaprox_problem* p, const a
       sum[7] += (double)(t[7] - t[0]) * 1e-3;
       ++cnt;
     }
-    if (cnt && fused) {
-      const unsigned long long* t = &ts[0];
-      std::fprintf(stderr, "[adaprox fused pass, cycles in CTA 0, iteration 1] dot: wait_full=%llu work=%llu | update: wait_partials=%llu work=%llu | producer: wait_empty=%llu | clusters=%d C=%d\n",
-                   t[1], t[2], t[6], t[5], t[3], fQ, fa.C);
+    if (fused) {
+      std::fprintf(stderr, "[adaprox fused, us per iteration (pass | rest), CTA 0, clusters=%d C=%d]", fQ, fa.C);
+      std::fprintf(stderr, " prologue pass %.0f;", (double)(ts[2] - ts[1]) * 1e-3);
+      for (int64_t it = 0; it < ts_iters && it < 12; ++it) {
+        const unsigned long long* t = &ts[(size_t)it * 8];
+        if (!t[0] || !t[7]) break;
+        std::fprintf(stderr, " %.0f|%.0f", (double)(t[3] - t[0]) * 1e-3, (double)(t[7] - t[3]) * 1e-3);
+      }
+      std::fprintf(stderr, "\n");
     }
     if (cnt && !fused) {
       const char* names[7] = {"P1 F*x (+A*x)", "P2 rows/residual", "P3 F'*r", "P4 grad+reductions", "P5 stepsize/dual", "P6 record/A'y", "P7 prox step"};

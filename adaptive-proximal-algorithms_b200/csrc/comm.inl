@@ -7,9 +7,11 @@
 // A'r partials with the value sums.  NCCL delivers bit-identical sums on every
 // rank, so the replicated prox / stepsize arithmetic stays in lock step with no
 // second collective.  A persistent kernel cannot call NCCL, so the iteration is
-// split at the all-reduce into ordinary launches on one stream; convergence is
-// a device flag polled by the host once per batch of iterations, so there is
-// still no host round trip per iteration.
+// split at the all-reduce into ordinary launches on one stream (six per
+// iteration on the two-pass path, ONE per iteration with the single-pass fused
+// kernel in sweep-only mode on dense least squares); convergence is a device flag
+// polled by the host once per batch of iterations, so there is still no host
+// round trip per iteration.
 #include <dlfcn.h>
 #include <nccl.h>
 
@@ -135,11 +137,17 @@ __global__ void __launch_bounds__(kThreads, 2) k_sh_D(ShArgs a) {
   grid_totals<2>(a.W.red, G, SLOT_F0, tot, s_scr);
   if (b == 0 && threadIdx.x == 0) { a.gbuf[a.P.n] = tot[0]; a.gbuf[a.P.n + 1] = tot[1]; }
 }
+// Block/grid reduction policy of the split-phase kernels (256-thread CTAs).
+struct Red256 {
+  static constexpr int NT = kThreads;
+  double* scr;
+  template <int K> __device__ __forceinline__ void store(double (&v)[K], double* red, int G, int slot0) { block_reduce_store<K>(v, red, G, slot0, scr); }
+  template <int K> __device__ __forceinline__ void totals(const double* red, int G, int slot0, double (&out)[K]) { grid_totals<K>(red, G, slot0, out, scr); }
+};
+
 // after the all-reduce: gradient, primal residual, stepsize reductions (P4)
-__global__ void __launch_bounds__(kThreads, 2) k_sh_E(ShArgs a) {
-  __shared__ double s_scr[kWarps * 8 + kMaxRed];
-  bool done; const long long it = sh_current(a, done);
-  if (done) return;
+template <class R>
+__device__ __forceinline__ void sh_phase_E(const ShArgs& a, long long it, R red) {
   const DProblem& P = a.P;
   const int b = blockIdx.x, G = gridDim.x;
   const ShState& st = sh_state(a, it);
@@ -151,7 +159,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_sh_E(ShArgs a) {
   const double* x_prev = a.W.xb[(it + 2) % 3];
   const double f1 = a.gbuf[P.n + 1];
   double acc[4] = {0.0, 0.0, 0.0, 0.0};
-  for (int64_t j = j0 + threadIdx.x; j < j1; j += kThreads) {
+  for (int64_t j = j0 + threadIdx.x; j < j1; j += R::NT) {
     double gj = a.gbuf[j];
     if (P.f_kind == ADAPROX_F_LOGISTIC) gj = (j == P.n - 1) ? f1 / P.f_N : gj / P.f_N;
     grad[j] = gj;
@@ -165,16 +173,11 @@ __global__ void __launch_bounds__(kThreads, 2) k_sh_E(ShArgs a) {
       acc[3] = fma(dx, dx, acc[3]);
     }
   }
-  block_reduce_store<4>(acc, a.W.red, G, SLOT_PR, s_scr);
+  red.template store<4>(acc, a.W.red, G, SLOT_PR);
 }
 // stepsize, residual, record, convergence, prox step (P5 + P7); advances the state
-__global__ void __launch_bounds__(kThreads, 2) k_sh_F(ShArgs a) {
-  __shared__ double s_scr[kWarps * 8 + kMaxRed];
-  bool done; const long long it = sh_current(a, done);
-  if (done) {          // keep the final state alive in both slots
-    if (blockIdx.x == 0 && threadIdx.x == 0) a.st[(it + 1) & 1] = a.st[it & 1];
-    return;
-  }
+template <class R>
+__device__ __forceinline__ void sh_phase_F(const ShArgs& a, long long it, R red) {
   const DProblem& P = a.P;
   const DOpts& O = a.O;
   const int b = blockIdx.x, G = gridDim.x;
@@ -186,8 +189,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_sh_F(ShArgs a) {
   bool stop = false;
   if (it > 0) {
     double t4[4], tg[1] = {0.0};
-    grid_totals<4>(a.W.red, G, SLOT_PR, t4, s_scr);
-    if (O.want_objective) grid_totals<1>(a.W.red, G, gval_slot(it), tg, s_scr);
+    red.template totals<4>(a.W.red, G, SLOT_PR, t4);
+    if (O.want_objective) red.template totals<1>(a.W.red, G, gval_slot(it), tg);
     rule_step(O, t4[1], t4[2], t4[3], gamma, sigma, s0, s1);
     const double norm_res = sqrt(norm_sq_jl(t4[0]));
     nx.norm_res = norm_res;
@@ -211,14 +214,14 @@ __global__ void __launch_bounds__(kThreads, 2) k_sh_F(ShArgs a) {
     const double* grad = a.W.gb[it & 1];
     double* xn = a.W.xb[(it + 1) % 3];
     double acc[1] = {0.0};
-    for (int64_t j = j0 + threadIdx.x; j < j1; j += kThreads) {
+    for (int64_t j = j0 + threadIdx.x; j < j1; j += R::NT) {
       const double vj = x[j] - gamma * grad[j];
       a.W.v[j] = vj;
       const double xj = prox_elem(P.g, vj, gamma, j, 0.0);
       xn[j] = xj;
       if (O.want_objective) acc[0] += prox_value_elem(P.g, xj, j);
     }
-    block_reduce_store<1>(acc, a.W.red, G, gval_slot(it + 1), s_scr);
+    red.template store<1>(acc, a.W.red, G, gval_slot(it + 1));
     nx.n_proxg = st.n_proxg + 1;
     if (it >= O.maxit) { nx.done = 1; nx.it = it; }           // maxit reached: x is the last prox, xb[(it + 1) % 3]
     else { nx.n_eval = st.n_eval + 1; nx.n_grad = st.n_grad + 1; }
@@ -227,6 +230,25 @@ __global__ void __launch_bounds__(kThreads, 2) k_sh_F(ShArgs a) {
   }
   if (b == 0 && threadIdx.x == 0) a.st[(it + 1) & 1] = nx;
 }
+__global__ void __launch_bounds__(kThreads, 2) k_sh_E(ShArgs a) {
+  __shared__ double s_scr[kWarps * 8 + kMaxRed];
+  bool done; const long long it = sh_current(a, done);
+  if (done) return;
+  sh_phase_E(a, it, Red256{s_scr});
+}
+__global__ void __launch_bounds__(kThreads, 2) k_sh_F(ShArgs a) {
+  __shared__ double s_scr[kWarps * 8 + kMaxRed];
+  bool done; const long long it = sh_current(a, done);
+  if (done) {          // keep the final state alive in both slots
+    if (blockIdx.x == 0 && threadIdx.x == 0) a.st[(it + 1) & 1] = a.st[it & 1];
+    return;
+  }
+  sh_phase_F(a, it, Red256{s_scr});
+}
+
+// Row-sharded AdaPGM on a dense least-squares term: the four launches k_sh_A .. k_sh_D are replaced by ONE launch
+// of k_adapgm_fused in sweep-only mode (solver_fused.cuh), which sweeps this rank's row shard once for x_it and
+// leaves the shard's A'r partial and value sum in gbuf for the all-reduce; k_sh_E / k_sh_F finish the iteration.
 
 int comm_setup_kernels() {
   if (cudaFuncSetAttribute((const void*)k_sh_A, cudaFuncAttributeMaxDynamicSharedMemorySize, kRingBytes) != cudaSuccess) return -1;
@@ -248,8 +270,18 @@ int solve_sharded(adaprox_ctx* h, const adaprox_problem* p, const adaprox_option
   const int64_t n = P.n, mf = P.F.m;
   const int64_t nrec = std::min<int64_t>(O.max_records, O.maxit);
   O.max_records = nrec;
-  const int G = h->grid;
-  size_t need = 7 * ws_size_doubles(n) + ws_size_doubles(n + 2) + ws_size_doubles(mf) + ws_size_doubles((int64_t)kMaxRed * G) +
+  int G = h->grid;
+  // dense least squares: the single-pass fused kernel in sweep-only mode replaces k_sh_A .. k_sh_D
+  bool fused = fused_eligible(o, P);
+  FusedPlan fpl;
+  if (fused) {
+    int frc = fused_plan(h, (const void*)k_adapgm_fused, P, &fpl);
+    if (frc < 0) return frc;
+    if (frc == 1) fused = false; else G = fpl.G;
+  }
+  FusedArgs& fa = fpl.fa;
+  const int Gred = std::max(G, h->grid);             // k_sh_E / k_sh_F always run on the regular grid
+  size_t need = (fused ? fused_ws_bytes(fpl) : 0) + 7 * ws_size_doubles(n) + ws_size_doubles(n + 2) + ws_size_doubles(mf) + ws_size_doubles((int64_t)kMaxRed * Gred) +
                 ws_size_doubles((nrec * (int64_t)sizeof(adaprox_record) + 7) / 8) + ws_size_doubles(2 * (sizeof(ShState) + 7) / 8);
   int rc;
   if ((rc = ws_reset(h, need))) return rc;
@@ -262,9 +294,10 @@ int solve_sharded(adaprox_ctx* h, const adaprox_problem* p, const adaprox_option
   W.xout = ws_doubles(h, n);
   a.gbuf = ws_doubles(h, n + 2);
   W.r = ws_doubles(h, mf);
-  W.red = ws_doubles(h, (int64_t)kMaxRed * G);
+  W.red = ws_doubles(h, (int64_t)kMaxRed * Gred);
   W.rec = nrec > 0 ? reinterpret_cast<adaprox_record*>(ws_doubles(h, (nrec * (int64_t)sizeof(adaprox_record) + 7) / 8)) : nullptr;
   a.st = reinterpret_cast<ShState*>(ws_doubles(h, 2 * (sizeof(ShState) + 7) / 8));
+  if (fused && (rc = fused_ws_alloc(h, &fpl))) return rc;
 
   ShState init[2];
   std::memset(init, 0, sizeof(init));
@@ -273,7 +306,7 @@ int solve_sharded(adaprox_ctx* h, const adaprox_problem* p, const adaprox_option
   init[1] = init[0];
   AP_CUDA(h, cudaMemcpyAsync(a.st, init, sizeof(init), cudaMemcpyHostToDevice, h->stream));
   AP_CUDA(h, cudaMemcpyAsync(W.xb[0], x0, (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
-  AP_CUDA(h, cudaMemsetAsync(W.red, 0, (size_t)kMaxRed * G * 8, h->stream));
+  AP_CUDA(h, cudaMemsetAsync(W.red, 0, (size_t)kMaxRed * Gred * 8, h->stream));
   AP_CUDA(h, cudaMemsetAsync(a.gbuf, 0, (size_t)(n + 2) * 8, h->stream));
   const int64_t launches0 = h->launches;
   AP_CUDA(h, cudaEventRecord(h->ev0, h->stream));
@@ -292,21 +325,46 @@ int solve_sharded(adaprox_ctx* h, const adaprox_problem* p, const adaprox_option
     return ADAPROX_OK;
   };
 
+  // fused path: launch L = finish iteration L-1 + sweep for x_L; launches 0 .. maxit+1 (the last one only finishes)
+  // fused path: one sweep kernel instead of k_sh_A .. k_sh_D
+  auto one_iteration_fused = [&](int64_t it) -> int {
+    a.it = it;
+    fa.bar_base = (unsigned long long)G * (unsigned long long)it;
+    fa.next_base = (unsigned long long)(fa.nchunks + fpl.Q) * (unsigned long long)it;
+    fa.sweep_only = 1;
+    fa.sh_x = a.W.xb[it % 3];
+    fa.sh_gbuf = a.gbuf;
+    fa.sh_done = &a.st[it & 1].done;
+    void* fargs[] = {&a.P, &a.O, &a.W, &fa};
+    cudaError_t e = cudaLaunchKernelExC(&fpl.cfg, (const void*)k_adapgm_fused, fargs);
+    if (e != cudaSuccess) return fail(h, ADAPROX_ERR_CUDA, std::string("fused cluster launch (sharded): ") + cudaGetErrorString(e));
+    static const int dbg_skip = std::getenv("ADAPROX_DEBUG_SKIP") ? std::atoi(std::getenv("ADAPROX_DEBUG_SKIP")) : 0;
+    if (!(dbg_skip & 1)) { int r = comm_allreduce_sum(h, a.gbuf, n + 2); if (r) return r; }
+    if (!(dbg_skip & 2)) {
+      k_sh_E<<<h->grid, kThreads, 0, h->stream>>>(a);
+      k_sh_F<<<h->grid, kThreads, 0, h->stream>>>(a);
+    }
+    h->launches += 3;
+    return ADAPROX_OK;
+  };
+
   ShState live[2];
   int64_t enqueued = 0;               // gradient evaluations enqueued (prologue + iterations)
   const int64_t total = O.maxit + 1;
   bool finished = false;
   while (!finished) {
     const int64_t batch = std::min<int64_t>(32, total - enqueued);
-    for (int64_t k = 0; k < batch; ++k) if ((rc = one_iteration(enqueued + k))) return rc;
+    for (int64_t k = 0; k < batch; ++k) if ((rc = fused ? one_iteration_fused(enqueued + k) : one_iteration(enqueued + k))) return rc;
     enqueued += batch;
     AP_CUDA(h, cudaMemcpyAsync(live, a.st, sizeof(live), cudaMemcpyDeviceToHost, h->stream));
     AP_CUDA(h, cudaStreamSynchronize(h->stream));
     AP_CUDA(h, cudaGetLastError());
     if (live[enqueued & 1].done || enqueued >= total) finished = true;
   }
+  const int cur_idx = (int)(enqueued & 1);          // written by the last k_sh_F
   AP_CUDA(h, cudaEventRecord(h->ev1, h->stream));
-  const ShState& cur = live[enqueued & 1];          // written by the last k_sh_F
+  if (fused) fused_print_probe(fpl, "sharded fused");
+  const ShState& cur = live[cur_idx];
   const bool converged = (cur.flags & ADAPROX_FLAG_CONVERGED) != 0;
   // converged at iteration k: x is xb[k % 3]; maxit: the last prox, xb[(maxit + 1) % 3]
   const int64_t it_final = converged ? cur.it : O.maxit;
@@ -323,7 +381,7 @@ int solve_sharded(adaprox_ctx* h, const adaprox_problem* p, const adaprox_option
   res->n_records = cur.n_rec;
   res->final_gamma = cur.gamma; res->final_sigma = cur.sigma; res->final_norm_res = cur.norm_res;
   res->solve_ms = ms; res->kernel_launches = h->launches - launches0;
-  res->matrix_passes = 2;
+  res->matrix_passes = fused ? 1 : 2;
   return ADAPROX_OK;
 }
 

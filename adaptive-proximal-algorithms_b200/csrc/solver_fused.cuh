@@ -37,11 +37,22 @@ constexpr int kFMaxCluster = 16;
 constexpr int kFDepth = 8;                                // exchange-buffer depth (see fused_pass)
 
 struct FusedArgs {
-  double* gpartf;      // [nclusters][npadf] per-cluster A'r partials
+  double* gpartf;      // [nchunks][npadf] per-chunk A'r partials
+  double* fpart;       // [nchunks] per-chunk sums of r_i^2
   int64_t npadf;       // C * 8192
   int C;               // cluster size
-  unsigned long long* bar;   // grid-barrier arrival counter (zeroed by the host before the launch)
-  int split;           // bulk copies per row piece (1, 2, 4 or 8: 64 KB .. 8 KB each)
+  int chunk_rows;      // rows per chunk (unit of the dynamic schedule)
+  int nchunks;         // ceil(m / chunk_rows)
+  unsigned long long* bar;       // grid-barrier arrival counter (zeroed by the host before the launch)
+  unsigned long long bar_base;   // arrivals already counted on `bar` by earlier launches (row-sharded solve)
+  unsigned long long* next;      // chunk dispenser (monotonic; zeroed by the host before the launch)
+  unsigned long long next_base;  // dispenser value at the start of this launch's first sweep
+  // sweep-only mode (row-sharded solve, comm.inl): one sweep for sh_x, shard partials into sh_gbuf[n + 2], exit
+  int sweep_only;
+  const double* sh_x;
+  double* sh_gbuf;
+  const int* sh_done;            // the solve has stopped: do nothing
+  unsigned long long* lat;       // optional [grid][4] probe (ADAPROX_FUSED_LAT): chunks taken, sweep ns, -, smid
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
@@ -52,10 +63,10 @@ __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.w
 
 // Control block in static shared memory: full[3] | empty[3] | cfull[8] mbarriers, then the exchange buffers
 // cpart[8][16 ranks][8 warps].  One base register + compile-time offsets address all of it.
-constexpr uint32_t kOffFull = 0, kOffEmpty = 8 * kFStages, kOffCfull = 16 * kFStages, kOffCpart = 128;
+constexpr uint32_t kOffFull = 0, kOffEmpty = 8 * kFStages, kOffCfull = 16 * kFStages, kOffChunk = 16 * kFStages + 8 * kFDepth, kOffCpart = 128;
 constexpr uint32_t kPartStride = kFMaxCluster * kFGWarps * 8;                 // bytes per exchange buffer
 constexpr int kCtlBytes = kOffCpart + kFDepth * kPartStride;
-static_assert(16 * kFStages + 8 * kFDepth <= kOffCpart, "control block layout");
+static_assert(kOffChunk + 8 <= kOffCpart, "control block layout");
 
 struct FusedSmem {
   uint32_t ring, ctl;                         // shared-space addresses of the tile ring and the control block
@@ -78,6 +89,24 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t addr, uint32_t parity
   } while (!ok);
 }
 
+// Waits of the fused pass POLL (mbarrier.test_wait in a loop) instead of using the suspending try_wait.  Measured on
+// the same B200, same build otherwise, 65536 x 131072: 11.99 ms per sweep with polling, 27.98 ms with try_wait.  A
+// warp that try_wait suspended is resumed late; in this pipeline every late consumer delays the refill of its ring
+// slot, which makes the next wait block as well -- once a cluster drops into that regime it stays there (all warps
+// on the long scoreboard, DRAM at 37 %).  With only 16 warps per SM the issue slots the polling costs are free.
+// ADAPROX_FUSED_TRYWAIT (build flag) restores the suspending wait for A/B measurements.
+#ifndef ADAPROX_FUSED_TRYWAIT
+__device__ __forceinline__ void fmbar_wait(uint32_t addr, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+  } while (!ok);
+}
+#else
+__device__ __forceinline__ void fmbar_wait(uint32_t addr, uint32_t parity) { mbar_wait(addr, parity); }
+#endif
+
 // ld.volatile keeps the program order of the loads; the consumers below use the batch in REVERSE order, so all
 // eight loads of a batch must be in flight before the first FMA can issue (ptxas otherwise recycles one
 // destination quad: load -> FMA -> load ..., one shared-memory round trip per 16 bytes).
@@ -87,8 +116,8 @@ __device__ __forceinline__ double2 lds2v(uint32_t addr) {
   return v;
 }
 
-// One fused pass: gpartf[cluster][cols] = sum_{rows of the cluster} A[i, cols] * (A[i,:] x - b[i]);
-// this cluster's partial of sum r_i^2 is returned (non-zero in one thread of cluster rank 0 only).
+// fused_pass: rows [r0, r0 + nrows) of the matrix.  gout_row[cols] = sum_i A[i, cols] * (A[i,:] x - b[i]);
+// returns sum r_i^2 (non-zero in one thread of cluster rank 0 only).
 //
 // Warp roles (the groups are coupled through mbarriers only, so the latency chains of one overlap the
 // shared-memory bursts of the other):
@@ -102,21 +131,15 @@ __device__ __forceinline__ double2 lds2v(uint32_t addr) {
 // Exchange-buffer depth: a CTA can push row j only after its own update of row j-3 (ring slot), which needs
 // every peer's dot of row j-3, which needs that peer's update of row j-6: when row j's partials arrive, a peer
 // may still be reading rows j-5 .. j-1, so 8 buffers never collide (and phase j-8 of cfull is long complete).
-template <bool PROF>
-__device__ __noinline__ double fused_pass(const DMat& M, const double* bvec, const double* x, FusedSmem& fs, const FusedArgs& fa,
-                                           unsigned long long* dbg) {
-  const bool prof = PROF && (dbg != nullptr) && blockIdx.x == 0;
+// Register budget: 512 threads leave 128 registers per thread, so the loop state is kept minimal: x or the
+// accumulators (64 registers), one batch of tile data (16), a handful of 32-bit addresses and counters.
+constexpr int kFB = 4;                                    // LDS.128 per batch (16 registers of tile data per thread)
+
+__device__ __noinline__ double fused_pass(const DMat& M, const double* bvec, const double* x, FusedSmem& fs, int C,
+                                           int64_t r0, int nrows, double* gout_row) {
   const uint32_t ring = fs.ring, ctl = fs.ctl, g0 = fs.count;
   const uint32_t rank = cluster_ctarank();
-  const int C = fa.C;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  int nrows;
-  int64_t r0;
-  {
-    const int64_t q = cluster_id_x(), Q = ncluster_id_x();
-    r0 = (M.m * q) / Q;
-    nrows = (int)((M.m * (q + 1)) / Q - r0);
-  }
   const int64_t col0 = (int64_t)rank * kFCols;
   double fsum = 0.0;
 
@@ -133,27 +156,24 @@ __device__ __noinline__ double fused_pass(const DMat& M, const double* bvec, con
         xr[k].y = (j + 1 < n) ? ldcg(x + j + 1) : 0.0;
       }
     }
-    long long c_wait = 0, c_work = 0, c_t = 0;
     uint32_t slot = g0 % kFStages, ph = (g0 / kFStages) & 1u, d = g0 % kFDepth;
     const uint32_t tile0 = ring + t * 16;
     const uint32_t mypart = ctl + kOffCpart + (rank * kFGWarps + warp) * 8;
     const bool sender = lane < C;
     for (int i = 0; i < nrows; ++i) {
-      if (PROF && prof) c_t = clock64();
-      mbar_wait(ctl + kOffFull + 8 * slot, ph);
-      if (PROF && prof) { const long long tt = clock64(); c_wait += tt - c_t; c_t = tt; }
+      fmbar_wait(ctl + kOffFull + 8 * slot, ph);
       const uint32_t tile = tile0 + slot * kFStageBytes;
-      // batches of 8 x LDS.128 issued back to back: ld.volatile keeps their order and the FMA chains consume the
-      // batch in REVERSE, so all eight are in flight before the first FMA (ptxas otherwise recycles ONE destination
-      // quad: load -> FMA -> load ..., a full shared-memory round trip per 16 bytes)
+      // batches of kFB x LDS.128 issued back to back: ld.volatile keeps their order and the FMA chains consume the
+      // batch in REVERSE, so the whole batch is in flight before the first FMA (ptxas otherwise recycles ONE
+      // destination quad: load -> FMA -> load ..., a full shared-memory round trip per 16 bytes)
       double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
-      double2 av[8];
+      double2 av[kFB];
 #pragma unroll
-      for (int h = 0; h < kFH; h += 8) {
+      for (int h = 0; h < kFH; h += kFB) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) av[k] = lds2v(tile + (h + k) * kFGroup * 16);
+        for (int k = 0; k < kFB; ++k) av[k] = lds2v(tile + (h + k) * kFGroup * 16);
 #pragma unroll
-        for (int k = 6; k >= 0; k -= 2) {
+        for (int k = kFB - 2; k >= 0; k -= 2) {
           p2 = fma(av[k + 1].x, xr[h + k + 1].x, p2);
           p3 = fma(av[k + 1].y, xr[h + k + 1].y, p3);
           p0 = fma(av[k].x, xr[h + k].x, p0);
@@ -162,26 +182,24 @@ __device__ __noinline__ double fused_pass(const DMat& M, const double* bvec, con
       }
       const double pw = warp_sum((p0 + p1) + (p2 + p3));
       if (sender) st_async_peer(mypart + d * kPartStride, ctl + kOffCfull + 8 * d, (uint32_t)lane, pw);
-      if (PROF && prof) { const long long tt = clock64(); c_work += tt - c_t; }
       if (++slot == kFStages) { slot = 0; ph ^= 1u; }
       d = (d + 1) % kFDepth;
     }
-    if (PROF && prof && threadIdx.x == 0) { dbg[1] = (unsigned long long)c_wait; dbg[2] = (unsigned long long)c_work; }
   } else {
     // ------------------------------------------------------------------ update warps
     const int t = threadIdx.x - kFGroup;
     const bool leader = (t == 0);
     const bool producer = (t == kFGroup - 32);       // lane 0 of the last update warp keeps the ring full
-    const uint32_t xbytes = (uint32_t)(C * kFGWarps * 8);        // exchange bytes per row per CTA
+    const int nval = C * kFGWarps;                   // partials per row (<= 128)
+    const uint32_t xbytes = (uint32_t)nval * 8;      // exchange bytes per row per CTA
     uint32_t bytes;
     {
       int64_t width = M.ld - col0;
       width = width < 0 ? 0 : (width > kFCols ? kFCols : width);
       bytes = (uint32_t)(width * 8);
     }
-    const int64_t ldb = M.ld;
-    const uint32_t piece = (uint32_t)kFStageBytes / (uint32_t)fa.split;
-    const double* src = M.a + col0 + r0 * ldb;       // next row to copy (producer)
+    const int64_t ldb = M.ld * 8;
+    const char* src = reinterpret_cast<const char*>(M.a + col0 + r0 * M.ld);     // next row to copy (producer)
     double2 acc[kFH];
 #pragma unroll
     for (int k = 0; k < kFH; ++k) acc[k] = make_double2(0.0, 0.0);
@@ -189,12 +207,9 @@ __device__ __noinline__ double fused_pass(const DMat& M, const double* bvec, con
       for (int i = 0; i < kFDepth && i < nrows; ++i) mbar_expect_tx(ctl + kOffCfull + 8 * ((g0 + i) % kFDepth), xbytes);
     uint32_t slot = g0 % kFStages, ph = (g0 / kFStages) & 1u, d = g0 % kFDepth, dph = (g0 / kFDepth) & 1u;
     auto issue = [&](uint32_t sl, uint32_t par) {    // wait until the update warps left slot sl, then refill it
-      mbar_wait(ctl + kOffEmpty + 8 * sl, par ^ 1u);
+      fmbar_wait(ctl + kOffEmpty + 8 * sl, par ^ 1u);
       mbar_expect_tx(ctl + kOffFull + 8 * sl, bytes);
-      for (uint32_t off = 0; off < bytes; off += piece) {
-        const uint32_t nb = (bytes - off < piece) ? (bytes - off) : piece;
-        bulk_g2s(ring + sl * kFStageBytes + off, reinterpret_cast<const char*>(src) + off, nb, ctl + kOffFull + 8 * sl);
-      }
+      bulk_g2s(ring + sl * kFStageBytes, src, bytes, ctl + kOffFull + 8 * sl);
       src += ldb;
     };
     if (producer) {
@@ -204,55 +219,47 @@ __device__ __noinline__ double fused_pass(const DMat& M, const double* bvec, con
         if (++sl == kFStages) { sl = 0; par ^= 1u; }
       }
     }
-    // predicates of the four partial loads of this lane (C * 8 <= 128 partials per row)
-    const int nval = C * kFGWarps;
-    const bool q0 = lane < nval, q1 = lane + 32 < nval, q2 = lane + 64 < nval, q3 = lane + 96 < nval;
     const uint32_t tile0 = ring + t * 16;
     const uint32_t part0 = ctl + kOffCpart + lane * 8;
     const double* bp = bvec + r0;
-    long long c_wait = 0, c_work = 0, c_t = 0;
-    double b_next = (nrows > 0) ? __ldg(bp) : 0.0;
+    double bblk = 0.0;                               // lane l holds b[r0 + 32 * (i / 32) + l]
     for (int i = 0; i < nrows; ++i) {
-      const double b_cur = b_next;
-      if (i + 1 < nrows) b_next = __ldg(bp + i + 1);
-      if (PROF && prof) c_t = clock64();
+      if ((i & 31) == 0) bblk = (i + lane < nrows) ? __ldg(bp + i + lane) : 0.0;
+      const double b_cur = __shfl_sync(0xffffffffu, bblk, i & 31);
       // st.async delivers data and complete_tx through the same path into this CTA's shared memory, so the
       // cta-scope acquire is enough (a cluster-scope acquire compiles to CCTL.IVALL: an L1 flush per row)
-      mbar_wait(ctl + kOffCfull + 8 * d, dph);
-      if (PROF && prof) { const long long tt = clock64(); c_wait += tt - c_t; c_t = tt; }
+      fmbar_wait(ctl + kOffCfull + 8 * d, dph);
       const uint32_t pb = part0 + d * kPartStride;
-      const double v0 = q0 ? lds1(pb) : 0.0;
-      const double v1 = q1 ? lds1(pb + 256) : 0.0;
-      const double v2 = q2 ? lds1(pb + 512) : 0.0;
-      const double v3 = q3 ? lds1(pb + 768) : 0.0;
+      const double v0 = (lane < nval) ? lds1(pb) : 0.0;
+      const double v1 = (lane + 32 < nval) ? lds1(pb + 256) : 0.0;
+      const double v2 = (lane + 64 < nval) ? lds1(pb + 512) : 0.0;
+      const double v3 = (lane + 96 < nval) ? lds1(pb + 768) : 0.0;
       if (leader && i + kFDepth < nrows) mbar_expect_tx(ctl + kOffCfull + 8 * d, xbytes);    // arm this buffer for row g + 8
       const double rs = warp_sum((v0 + v1) + (v2 + v3)) - b_cur;   // same order in every update warp of the cluster;
                                                                    // lasso/runme.jl:22  res = A*w - b
-      mbar_wait(ctl + kOffFull + 8 * slot, ph);                 // long complete; makes the bulk-copied tile visible here
+      fmbar_wait(ctl + kOffFull + 8 * slot, ph);                 // long complete; makes the bulk-copied tile visible here
       const uint32_t tile = tile0 + slot * kFStageBytes;
-      double2 av[8];
+      double2 av[kFB];
 #pragma unroll
-      for (int h = 0; h < kFH; h += 8) {
+      for (int h = 0; h < kFH; h += kFB) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) av[k] = lds2v(tile + (h + k) * kFGroup * 16);
+        for (int k = 0; k < kFB; ++k) av[k] = lds2v(tile + (h + k) * kFGroup * 16);
         __syncwarp();                                           // scheduling fence: the independent FMAs below must not be
                                                                 // hoisted between the loads (one load in flight otherwise)
 #pragma unroll
-        for (int k = 7; k >= 0; --k) {
+        for (int k = kFB - 1; k >= 0; --k) {
           acc[h + k].x = fma(av[k].x, rs, acc[h + k].x);
           acc[h + k].y = fma(av[k].y, rs, acc[h + k].y);
         }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(ctl + kOffEmpty + 8 * slot);
-      if (producer && i + kFStages < nrows) issue(slot, ph ^ 1u);   // same slot, next phase: row g + 3
+      if (producer && i + kFStages < nrows) issue(slot, ph ^ 1u);   // row i + 3 into the slot row i just left
       fsum = fma(rs, rs, fsum);
-      if (PROF && prof) { const long long tt = clock64(); c_work += tt - c_t; }
       if (++slot == kFStages) { slot = 0; ph ^= 1u; }
       if (++d == kFDepth) { d = 0; dph ^= 1u; }
     }
-    if (PROF && prof && leader) { dbg[5] = (unsigned long long)c_work; dbg[6] = (unsigned long long)c_wait; }
-    double* gout = fa.gpartf + (int64_t)cluster_id_x() * fa.npadf + col0;
+    double* gout = gout_row + col0;
 #pragma unroll
     for (int k = 0; k < kFH; ++k) *reinterpret_cast<double2*>(gout + 2 * (k * kFGroup + t)) = acc[k];
     if (!(leader && rank == 0)) fsum = 0.0;
@@ -260,6 +267,77 @@ __device__ __noinline__ double fused_pass(const DMat& M, const double* bvec, con
   __syncthreads();
   fs.count = g0 + (uint32_t)nrows;
   return fsum;
+}
+
+// One sweep over the matrix: g = A'(A x - b) as per-chunk partials gpartf[c][cols], fpart[c] = sum of r_i^2 over
+// the rows of chunk c.  Chunks of fa.chunk_rows rows are handed to the clusters DYNAMICALLY (one atomicAdd per
+// chunk by the cluster's rank-0 CTA, the index mailed to every peer through DSMEM): the 16 CTAs of a cluster run
+// in lock step, so a single SM with a slower path to L2 slows its whole cluster down, and with a static row split
+// the slowest of the 7 clusters (often 1.6-2x behind on this part) set the time of the sweep.  The OUTPUT does
+// not depend on who processed what: partials are stored per chunk and reduced in chunk order afterwards, so
+// results stay bit-reproducible.  `sweep` = number of sweeps this launch has done before (dispenser base).
+__device__ __forceinline__ void fused_sweep(const DMat& M, const double* bvec, const double* x, FusedSmem& fs, const FusedArgs& fa,
+                                            unsigned long long sweep) {
+  const uint32_t rank = cluster_ctarank();
+  const unsigned long long base = fa.next_base + sweep * (unsigned long long)(fa.nchunks + (int)ncluster_id_x());
+  const uint32_t mailbox = fs.ctl + kOffChunk;
+  int taken = 0;
+  for (;;) {
+    if (rank == 0 && threadIdx.x == 0) {
+      const long long c = (long long)(atomicAdd(fa.next, 1ull) - base);
+      for (int p = 0; p < fa.C; ++p) {
+        uint32_t raddr;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(mailbox), "r"(p));
+        asm volatile("st.shared::cluster.s64 [%0], %1;" ::"r"(raddr), "l"(c) : "memory");
+      }
+    }
+    cluster_arrive();          // release: the mailbox stores; acquire: every thread of every CTA sees its mailbox
+    cluster_wait();
+    long long c;
+    asm volatile("ld.volatile.shared.s64 %0, [%1];" : "=l"(c) : "r"(mailbox));
+    if (c >= fa.nchunks) break;
+    const int64_t r0 = c * (int64_t)fa.chunk_rows;
+    const int64_t left = M.m - r0;
+    const int nrows = (int)(left < fa.chunk_rows ? left : fa.chunk_rows);
+    const double fv = fused_pass(M, bvec, x, fs, fa.C, r0, nrows, fa.gpartf + c * fa.npadf);
+    if (rank == 0 && threadIdx.x == kFGroup) fa.fpart[c] = fv;       // the leader thread of the update warps holds the sum
+    ++taken;
+    // the next mailbox store happens after this CTA's rank-0 peer finished the chunk, which needs every CTA's
+    // last partial dot, which every CTA sends after it has read the mailbox above: no overwrite race
+  }
+  if (fa.lat && threadIdx.x == 0) fa.lat[4 * blockIdx.x] += (unsigned long long)taken;
+}
+
+// grad[j] = sum over chunks in chunk order (fixed), for j in [j0, j1)
+__device__ __forceinline__ void fused_gradient_slice(const FusedArgs& fa, int64_t j0, int64_t j1, double* out) {
+  for (int64_t j = j0 + threadIdx.x; j < j1; j += kFThreads) {
+    const double* p = fa.gpartf + j;
+    double s = 0.0;
+    int c = 0;
+    for (; c + 8 <= fa.nchunks; c += 8) {
+      double v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = ldcg(p + (int64_t)(c + k) * fa.npadf);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s += v[k];
+    }
+    for (; c < fa.nchunks; ++c) s += ldcg(p + (int64_t)c * fa.npadf);
+    out[j] = s;
+  }
+}
+// sum_c fpart[c], same bits in every thread of every CTA (lane-strided partial sums, xor butterfly, fixed order)
+__device__ __forceinline__ double fused_fsum(const FusedArgs& fa, uint32_t scr) {
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x < 32) {
+    double s = 0.0;
+    for (int c = lane; c < fa.nchunks; c += 32) s += ldcg(fa.fpart + c);
+    s = warp_sum(s);
+    if (lane == 0) sts1(scr, s);
+  }
+  __syncthreads();
+  const double r = lds1(scr);
+  __syncthreads();
+  return r;
 }
 
 // block / grid reductions for the 512-thread CTA (fixed order)
@@ -319,18 +397,11 @@ struct GridBar {
   }
 };
 
-// AdaPGM / fixed-step PGM (src/AdaProx.jl:312-364 with A = 0, h = Zero) around the fused pass.
-__global__ void __launch_bounds__(kFThreads, 1) k_adapgm_fused(DProblem P, DOpts O, DWork W, FusedArgs fa) {
-  GridBar grid{fa.bar, 0ull, gridDim.x};
-  const int b = blockIdx.x, G = gridDim.x;
-  extern __shared__ __align__(1024) unsigned char dyn_smem[];
-  __shared__ __align__(16) unsigned char s_ctl[kCtlBytes];
-  __shared__ double s_scr[kFWarps * 8 + kMaxRed];
-  FusedSmem fs;
+// once per kernel, by all threads of every CTA: mbarriers, ragged-tail zero fill, cluster handshake
+__device__ __forceinline__ void fused_smem_init(FusedSmem& fs, unsigned char* dyn_smem, unsigned char* s_ctl, int64_t ld) {
   fs.ring = smem_u32(dyn_smem);
   fs.ctl = smem_u32(s_ctl);
   fs.count = 0;
-  const uint32_t scr = smem_u32(s_scr);
   if (threadIdx.x == 0) {
     for (int s = 0; s < kFStages; ++s) { mbar_init(fs.ctl + kOffFull + 8 * s, 1); mbar_init(fs.ctl + kOffEmpty + 8 * s, kFGWarps); }
     for (int s = 0; s < kFDepth; ++s) mbar_init(fs.ctl + kOffCfull + 8 * s, 1);
@@ -339,7 +410,7 @@ __global__ void __launch_bounds__(kFThreads, 1) k_adapgm_fused(DProblem P, DOpts
   {
     // The last CTA of a cluster may own fewer than 8192 columns: the bulk copies never touch the tail of its ring
     // slots, so zero it once and the pass needs no column predicates (A = 0 there contributes nothing).
-    int64_t width = P.F.ld - (int64_t)cluster_ctarank() * kFCols;
+    int64_t width = ld - (int64_t)cluster_ctarank() * kFCols;
     width = width < 0 ? 0 : (width > kFCols ? kFCols : width);
     for (int s = 0; s < kFStages; ++s)
       for (int64_t j = width + threadIdx.x; j < kFCols; j += kFThreads) sts1(fs.ring + s * kFStageBytes + (uint32_t)j * 8, 0.0);
@@ -347,11 +418,47 @@ __global__ void __launch_bounds__(kFThreads, 1) k_adapgm_fused(DProblem P, DOpts
   __syncthreads();
   cluster_arrive();          // every CTA of the cluster has initialised its shared memory before any peer writes into it
   cluster_wait();
+}
 
-  const int Q = (int)ncluster_id_x();
+// AdaPGM / fixed-step PGM (src/AdaProx.jl:312-364 with A = 0, h = Zero) around the fused pass.
+__global__ void __launch_bounds__(kFThreads, 1) k_adapgm_fused(DProblem P, DOpts O, DWork W, FusedArgs fa) {
+  GridBar grid{fa.bar, 0ull, gridDim.x};
+  const int b = blockIdx.x, G = gridDim.x;
+  extern __shared__ __align__(1024) unsigned char dyn_smem[];
+  __shared__ __align__(16) unsigned char s_ctl[kCtlBytes];
+  __shared__ double s_scr[kFWarps * 8 + kMaxRed];
+  FusedSmem fs;
+  fused_smem_init(fs, dyn_smem, s_ctl, P.F.ld);
+  const uint32_t scr = smem_u32(s_scr);
+
   const bool want_obj = O.want_objective != 0;
   int64_t j0, j1;
   cta_slice(P.n, b, G, j0, j1);
+  unsigned long long sweep = 0;
+
+  if (fa.sweep_only) {
+    // Row-sharded solve: this launch only produces the shard's A'(Ax - b) partial and value sum for the all-reduce.
+    // (A separate __global__ entry with the same body runs the sweep 1.7x slower for reasons not understood --
+    // same SASS loops, same CTA placement, same data; see profiles/r01_notes.md -- so the sharded path shares
+    // this entry point.)
+    grid.target = fa.bar_base;
+    const bool done = __ldcg(fa.sh_done) != 0;
+    if (!done) {
+      unsigned long long tq0 = 0;
+      if (fa.lat && threadIdx.x == 0) tq0 = globaltimer_ns();
+      fused_sweep(P.F, P.fvec, fa.sh_x, fs, fa, 0ull);
+      if (fa.lat && threadIdx.x == 0) { fa.lat[4 * b + 1] = globaltimer_ns() - tq0; unsigned sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); fa.lat[4 * b + 3] = sm; }
+    }
+    grid.sync();
+    if (!done) {
+      fused_gradient_slice(fa, j0, j1, fa.sh_gbuf);
+      const double f0 = fused_fsum(fa, scr);
+      if (b == 0 && threadIdx.x == 0) { fa.sh_gbuf[P.n] = f0; fa.sh_gbuf[P.n + 1] = 0.0; }
+    }
+    cluster_arrive();          // no CTA exits while a peer could still address its shared memory
+    cluster_wait();
+    return;
+  }
 
   double gamma, sigma, s0, s1;
   rule_init(O, gamma, sigma, s0, s1);
@@ -360,22 +467,15 @@ __global__ void __launch_bounds__(kFThreads, 1) k_adapgm_fused(DProblem P, DOpts
   int xc = 0, gc = 0;
   double* x = W.xb[0];
 
-  auto gradient_slice = [&](double* out) {     // grad[j] = sum over clusters, fixed order
-    for (int64_t j = j0 + threadIdx.x; j < j1; j += kFThreads) {
-      double s = 0.0;
-      for (int qq = 0; qq < Q; ++qq) s += ldcg(fa.gpartf + (int64_t)qq * fa.npadf + j);
-      out[j] = s;
-    }
-  };
-
   // ---- prologue (:327-332) ----------------------------------------------------------------------------------
   {
-    double fv[1] = {fused_pass<false>(P.F, P.fvec, x, fs, fa, nullptr)};
-    f_block_reduce_store<1>(fv, W.red, G, SLOT_F0, scr);
+    phase_stamp(W, 1, 1);
+    fused_sweep(P.F, P.fvec, x, fs, fa, sweep++);
   }
   grid.sync();
+  phase_stamp(W, 1, 2);
   {
-    gradient_slice(W.gb[gc]);
+    fused_gradient_slice(fa, j0, j1, W.gb[gc]);
     double acc[1] = {0.0};
     double* xn = W.xb[1];
     for (int64_t j = j0 + threadIdx.x; j < j1; j += kFThreads) {
@@ -399,16 +499,17 @@ __global__ void __launch_bounds__(kFThreads, 1) k_adapgm_fused(DProblem P, DOpts
   for (int64_t it = 1; it <= O.maxit; ++it) {
     phase_stamp(W, it, 0);
     {
-      // :336 value + pullback in one pass (the instrumented instantiation only runs under ADAPROX_PHASE_TIMING)
-      double fv[1] = {(W.tstamp && it <= W.tstamp_iters) ? fused_pass<true>(P.F, P.fvec, x, fs, fa, W.tstamp + (it - 1) * 8)
-                                                         : fused_pass<false>(P.F, P.fvec, x, fs, fa, nullptr)};
-      f_block_reduce_store<1>(fv, W.red, G, SLOT_F0, scr);
+      // :336 value + pullback in one sweep
+      unsigned long long tq0 = 0;
+      if (fa.lat && threadIdx.x == 0) tq0 = globaltimer_ns();
+      fused_sweep(P.F, P.fvec, x, fs, fa, sweep++);
+      if (fa.lat && threadIdx.x == 0) { fa.lat[4 * b + 1] = globaltimer_ns() - tq0; unsigned sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); fa.lat[4 * b + 3] = sm; }
     }
     n_eval++; n_grad++;
     grid.sync();
     phase_stamp(W, it, 3);
     double* grad = W.gb[gc ^ 1];
-    gradient_slice(grad);
+    fused_gradient_slice(fa, j0, j1, grad);
     {
       double acc[4] = {0.0, 0.0, 0.0, 0.0};
       for (int64_t j = j0 + threadIdx.x; j < j1; j += kFThreads) {
@@ -426,7 +527,7 @@ __global__ void __launch_bounds__(kFThreads, 1) k_adapgm_fused(DProblem P, DOpts
     phase_stamp(W, it, 4);
     double t4[4], tg[1] = {0.0}, tf[1];
     f_grid_totals<4>(W.red, G, SLOT_PR, t4, scr);
-    f_grid_totals<1>(W.red, G, SLOT_F0, tf, scr);
+    tf[0] = fused_fsum(fa, scr);
     if (want_obj) f_grid_totals<1>(W.red, G, gval_slot(it), tg, scr);
     rule_step(O, t4[1], t4[2], t4[3], gamma, sigma, s0, s1);                    // :341
     norm_res = sqrt(norm_sq_jl(t4[0]));                                         // :348 (dual part is identically zero)

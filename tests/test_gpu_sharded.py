@@ -10,9 +10,10 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, fused):
     sys.path.insert(0, ROOT)
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), LOCAL_RANK=str(rank))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), LOCAL_RANK=str(rank), ADAPROX_FUSED=fused)
+    m2, n2, pf2 = (512, 4100, 40) if fused == "0" else (256, 20000, 200)     # fused: clusters of 3 CTAs
     import torch.distributed as dist
     import adaprox_b200 as AdaProx
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -30,26 +31,39 @@ def _worker(rank, world, port, out):
     log = []
     x, it = AdaProx.adaptive_proxgrad(np.zeros(n), f=f, g=g, rule=AdaProx.OurRule(gamma=1 / Lf), tol=1e-6, maxit=10000, log=log)
     # device-generated shard of a larger instance: every rank must reach the planted optimum
-    Pd = AdaProx.generate_planted_lasso(512, 4100, 40, 1, power_iters=60, row0=AdaProx.sharding.shard_rows(512, world, rank)[0],
-                                        rows=AdaProx.sharding.shard_rows(512, world, rank)[1], dev=dev)
+    Pd = AdaProx.generate_planted_lasso(m2, n2, pf2, 1, power_iters=60, row0=AdaProx.sharding.shard_rows(m2, world, rank)[0],
+                                        rows=AdaProx.sharding.shard_rows(m2, world, rank)[1], dev=dev)
     log2 = []
-    x2, it2 = AdaProx.adaptive_proxgrad(np.zeros(4100), f=AdaProx.LinearLeastSquares(Pd["A"], Pd["b"]), g=AdaProx.NormL1(1.0),
-                                        rule=AdaProx.OurRule(gamma=1 / Pd["Lf"]), tol=1e-7, maxit=30000, log=log2)
+    tol2, maxit2 = (1e-7, 30000) if fused == "0" else (0.0, 150)
+    x2, it2 = AdaProx.adaptive_proxgrad(np.zeros(n2), f=AdaProx.LinearLeastSquares(Pd["A"], Pd["b"]), g=AdaProx.NormL1(1.0),
+                                        rule=AdaProx.OurRule(gamma=1 / Pd["Lf"]), tol=tol2, maxit=maxit2, log=log2)
+    info2 = AdaProx.last_solve_info()
+    # the same instance unsharded on this GPU (same kernel family): the trajectories must agree to rounding
+    Pf = AdaProx.generate_planted_lasso(m2, n2, pf2, 1, power_iters=60, dev=dev)
+    log3 = []
+    AdaProx.adaptive_proxgrad(np.zeros(n2), f=AdaProx.LinearLeastSquares(Pf["A"], Pf["b"]), g=AdaProx.NormL1(1.0),
+                              rule=AdaProx.OurRule(gamma=1 / Pd["Lf"]), tol=0.0, maxit=100, log=log3)
+    obj_sh = np.array([r["objective"] for r in log2[:100]]); obj_1 = np.array([r["objective"] for r in log3[:100]])
+    gam_sh = np.array([r["gamma"] for r in log2[:100]]); gam_1 = np.array([r["gamma"] for r in log3[:100]])
     np.savez(out % rank, x=x, it=it, gam=np.array([r["gamma"] for r in log[:40]]), obj=log[-1]["objective"],
              counts=np.array([f.eval_count, f.grad_count, g.prox_count]), obj2=log2[-1]["objective"], opt2=Pd["optimum"],
-             res2=log2[-1]["norm_res"], x2err=np.linalg.norm(x2 - Pd["x_star"]), launches=AdaProx.last_solve_info()["kernel_launches"])
+             res2=log2[-1]["norm_res"], x2err=np.linalg.norm(x2 - Pd["x_star"]), launches=info2["kernel_launches"], passes=info2["matrix_passes"], it2=it2,
+             obj_sh=obj_sh, obj_1=obj_1, gam_sh=gam_sh, gam_1=gam_1)
     dist.barrier()
     dist.destroy_process_group()
 
 
-def test_sharded_adapgm_two_gpus(tmp_path, lasso_small):
+@pytest.mark.parametrize("fused", ["0", "1"])
+def test_sharded_adapgm_two_gpus(tmp_path, lasso_small, fused):
+    """fused = "0": six split-phase launches per iteration (two sweeps over the shard); fused = "1": the single-pass
+    cluster kernel k_sh_fused, one launch per iteration."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
     from oracle import adaprox_oracle as O
     out = str(tmp_path / "rank%d.npz")
-    mp.spawn(_worker, args=(2, 29400 + os.getpid() % 500, out), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, 29400 + os.getpid() % 500 + 500 * int(fused), out, fused), nprocs=2, join=True)
     R0, R1 = np.load(out % 0), np.load(out % 1)
     # replicated state stays in lock step: bit-identical iterates on both ranks
     assert np.array_equal(R0["x"], R1["x"]) and int(R0["it"]) == int(R1["it"])
@@ -64,5 +78,11 @@ def test_sharded_adapgm_two_gpus(tmp_path, lasso_small):
     assert abs(int(R0["it"]) - ito) <= max(2, 0.05 * ito)
     it = int(R0["it"])
     assert list(R0["counts"]) == [it + 1, it + 1, it]
-    assert float(R0["res2"]) <= 1e-7 and abs(float(R0["obj2"]) - float(R0["opt2"])) < 1e-9 * float(R0["opt2"])
-    assert float(R0["x2err"]) < 1e-5
+    if fused == "0":
+        assert float(R0["res2"]) <= 1e-7 and abs(float(R0["obj2"]) - float(R0["opt2"])) < 1e-9 * float(R0["opt2"])
+        assert float(R0["x2err"]) < 1e-5
+    assert np.allclose(R0["obj_sh"], R0["obj_1"], rtol=1e-9) and np.allclose(R0["gam_sh"][:20], R0["gam_1"][:20], rtol=1e-11)
+    assert np.array_equal(R0["obj_sh"], R1["obj_sh"])
+    assert int(R0["passes"]) == (1 if fused == "1" else 2)
+    if fused == "1":
+        assert int(R0["launches"]) == 3 * (int(R0["it2"]) + 1)      # sweep kernel + E + F per gradient evaluation
