@@ -66,14 +66,36 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    """SM clock and throttle reasons DURING the timed region: NVML polled every 5 ms from a thread (the timed region
+    of a multi-GPU run lasts only tens of milliseconds), nvidia-smi at 100 ms as the fallback."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index, self.lines, self.proc = index, [], None
+        self.nv, self.samples, self.stop_flag, self.t = None, [], threading.Event(), None
+
+    def _nvml_loop(self):
+        nv, hd = self.nv, self.handle
+        while not self.stop_flag.is_set():
+            try:
+                self.samples.append((nv.nvmlDeviceGetClockInfo(hd, nv.NVML_CLOCK_SM), nv.nvmlDeviceGetCurrentClocksEventReasons(hd)))
+            except Exception:
+                break
+            time.sleep(0.005)
 
     def start(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            self.handle = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(self.handle, nv.NVML_CLOCK_SM)
+            self.nv = nv
+            self.t = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nv = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -84,6 +106,16 @@ class ClockSampler:
             self.proc = None
 
     def stop(self):
+        if self.nv is not None:
+            self.stop_flag.set()
+            self.t.join(timeout=2)
+            nv = self.nv
+            names = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                     "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+            sm = [s[0] for s in self.samples]
+            reasons = sorted(k for k, bit in names.items() if any(s[1] & bit for s in self.samples))
+            return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.max_mhz, "samples": len(sm),
+                    "reasons": reasons, "source": "NVML, 5 ms period"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -106,7 +138,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi, 100 ms period"}
 
 
 # ----------------------------------------------------------------------------------------------
