@@ -4,7 +4,8 @@
 (src/AdaProx.jl) backed by libadaprox_cuda.so; see INTEGRATION.md for the Julia
 ``ccall`` shim that binds the same C ABI.
 """
-from . import synth, sharding                                    # noqa: F401  (numpy only; no GPU needed)
+from . import synth, sharding, records                           # noqa: F401  (numpy only; no GPU needed)
+from .records import JsonlSink, read_jsonl, find_best, is_logstep, load_libsvm_dataset   # noqa: F401
 from ._lib import AdaproxError, LIB_PATH, SYMBOLS, load          # noqa: F401
 from .core import (                                               # noqa: F401
     Device, DeviceMatrix, DeviceVector, default_device, set_default_device,

@@ -567,3 +567,47 @@ def test_fused_single_pass_matches_two_pass_and_oracle(AdaProx, m, n, pf):
         assert abs(it - ito) <= max(3, 0.05 * ito)
         assert [r["f_evals"] for r in log[:5]] == [2, 3, 4, 5, 6]
     assert runs["1"][3]["kernel_launches"] == 1
+
+
+# ---------------------------------------------------------------- LIBSVM file -> CSR upload -> solve -> JSONL records
+def test_libsvm_file_to_jsonl_records(AdaProx, tmp_path):
+    import json
+    import scipy.sparse as sp
+    rp, ci, va, y = AdaProx.synth.sparse_logreg(m=300, n=500, seed=1, nnz_lo=5, nnz_hi=20)
+    X = sp.csr_matrix((va, ci, rp), shape=(300, 500))
+    path = str(tmp_path / "toy.libsvm")
+    with open(path, "w") as fh:
+        for i in range(300):
+            feats = " ".join(f"{j + 1}:{v!r}" for j, v in zip(X.indices[X.indptr[i]:X.indptr[i + 1]], X.data[X.indptr[i]:X.indptr[i + 1]]))
+            fh.write(f"{'+1' if y[i] > 0.5 else '-1'} {feats}\n")
+    Xl, yl = AdaProx.load_libsvm_dataset(path, labels=(0.0, 1.0))                 # sparse_logreg/runme.jl maps labels to {0, 1}
+    assert Xl.shape[0] == 300 and np.array_equal(yl, y)
+    Xl = sp.csr_matrix((Xl.data, Xl.indices, Xl.indptr), shape=(300, 500))        # trailing all-zero columns are not in the file
+    assert abs(Xl - X).max() == 0.0
+    n = 501
+    X1 = sp.hstack([Xl, np.ones((300, 1))]).toarray()
+    Lf = np.linalg.norm(X1 @ X1.T) / 4 / 300
+    jl = str(tmp_path / "run.jsonl")
+    lo = []
+    with AdaProx.JsonlSink(jl, mode="w") as sink:
+        xd, itd = AdaProx.adaptive_proxgrad(np.zeros(n), f=AdaProx.Counting(AdaProx.LogisticLoss(Xl, yl)), g=AdaProx.NormL1(0.01),
+                                            rule=AdaProx.OurRule(gamma=1 / Lf), tol=1e-6, maxit=500, name="AdaPGM (1/Lf)", log=sink)
+        AdaProx.fixed_proxgrad(np.zeros(n), f=AdaProx.Counting(AdaProx.LogisticLoss(Xl, yl)), g=AdaProx.NormL1(0.01), gamma=1 / Lf,
+                               tol=1e-6, maxit=500, name="PGM (1/Lf)", log=sink)
+    xo, ito = O.adaptive_proxgrad(np.zeros(n), f=O.Counting(O.LogisticLoss(Xl, yl)), g=O.NormL1(0.01), rule=O.OurRule(gamma=1 / Lf),
+                                  tol=1e-6, maxit=500, log=lo)
+    gb = AdaProx.read_jsonl(jl)
+    assert list(gb) == ["AdaPGM (1/Lf)", "PGM (1/Lf)"]
+    recs = gb["AdaPGM (1/Lf)"]
+    assert len(recs) == itd and [r["it"] for r in recs] == list(range(1, itd + 1))
+    assert list(recs[0]) == ["method", "it", "gamma", "sigma", "norm_res", "objective", "grad_f_evals", "prox_g_evals", "prox_h_evals",
+                             "A_evals", "At_evals", "f_evals"]
+    K = min(30, len(lo), len(recs))
+    assert np.allclose([r["gamma"] for r in recs[:K]], [r["gamma"] for r in lo[:K]], rtol=1e-12)
+    assert np.allclose([r["objective"] for r in recs[:K]], [r["objective"] for r in lo[:K]], rtol=1e-10)
+    assert [r["grad_f_evals"] for r in recs[:5]] == [r["grad_f_evals"] for r in lo[:5]]
+    # both reach the tolerance or not; the selection helper of logging.jl picks by gradient evaluations
+    best = AdaProx.find_best(gb, list(gb), "norm_res", 1e-6, "grad_f_evals")
+    assert best in gb
+    with open(jl) as fh:
+        json.loads(fh.readline())
