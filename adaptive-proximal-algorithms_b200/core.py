@@ -161,6 +161,12 @@ class DeviceMatrix:
     def T(self):
         return _Adjoint(self)
 
+    def time_path_gemm(self, L_cols, which, reps=5):
+        """mean device ms of one DMMA contraction of the lambda-path solver (0: R = A X - b, 1: G = A' R) on L_cols columns"""
+        ms = C.c_double()
+        self.dev.check(self.dev.lib.adaprox_time_path_gemm(self.dev.h, self.id, int(L_cols), int(which), int(reps), C.byref(ms)))
+        return ms.value
+
     def time_kernel(self, which, reps=5):
         ms = C.c_double()
         self.dev.check(self.dev.lib.adaprox_time_kernel(self.dev.h, self.id, int(which), int(reps), C.byref(ms)))
@@ -746,6 +752,55 @@ def adaptive_proxgrad(x, *, f, g, rule, tol=1e-5, maxit=100_000, name="AdaPGM", 
     xo, _, it, info = _solve(L.S_ADAPTIVE_PROXGRAD, x, None, f=f, g=g, opts=o, name=name, log=log, pd=False)
     _last_info.update(info)
     return xo, it
+
+
+def adaptive_proxgrad_path(X0=None, *, f, lambdas, rule, gamma0=None, tol=1e-5, maxit=100_000, history=0):
+    """Batched multi-lambda lasso path (BASELINE config 5; include/adaprox.h: adaprox_solve_lambda_path): column j of the
+    result is what ``adaptive_proxgrad(X0[:, j], f=f, g=NormL1(lambdas[j]), rule=rule_j, tol=tol, maxit=maxit)`` returns,
+    where rule_j is ``rule`` with ``gamma = gamma0[j]`` when ``gamma0`` is given.  ``f`` must be a dense
+    ``LinearLeastSquares``.  Returns ``(X, its, info)`` with X of shape (n, L), ``its`` the per-column iteration counts
+    and ``info`` holding per-column ``norm_res``, ``gamma``, ``f_x`` and, with ``history = H > 0``, the arrays
+    ``gamma_hist``, ``res_hist``, ``obj_hist`` of shape (min(H, maxit), L) (NaN after a column stopped)."""
+    ff, _ = _unwrap(f)
+    if not isinstance(ff, LinearLeastSquares):
+        raise L.AdaproxError(-3, "adaptive_proxgrad_path: f must be a LinearLeastSquares term (no CPU fallback)")
+    lam = np.ascontiguousarray(np.asarray(lambdas, dtype=F64).ravel())
+    Lc = lam.shape[0]
+    n = ff.n if getattr(ff, "n", None) is not None else ff.A.shape[1]
+    dev = ff._dev()
+    p = ff._problem(n)
+    p.g = NormL1(1.0)._desc()
+    o = _opts(tol, maxit)
+    rule._fill(o)
+    o.solver = L.S_ADAPTIVE_PROXGRAD
+    x0T = None
+    if X0 is not None:
+        X0 = np.asarray(X0, dtype=F64)
+        if X0.shape != (n, Lc):
+            raise ValueError(f"X0 has shape {X0.shape}, expected {(n, Lc)}")
+        x0T = np.ascontiguousarray(X0.T)
+    g0 = None
+    if gamma0 is not None:
+        g0 = np.ascontiguousarray(np.asarray(gamma0, dtype=F64).ravel())
+        if g0.shape[0] != Lc:
+            raise ValueError("gamma0 must have one entry per lambda")
+    xoT = np.empty((Lc, n), dtype=F64)
+    its = np.zeros(Lc, dtype=np.int64)
+    nres, gout, fout = np.empty(Lc, dtype=F64), np.empty(Lc, dtype=F64), np.empty(Lc, dtype=F64)
+    H = int(min(history, maxit)) if history else 0
+    hist = np.empty((3, max(H, 1), Lc), dtype=F64) if H > 0 else None
+    res = L.Result()
+    dev.check(dev.lib.adaprox_solve_lambda_path(dev.h, C.byref(p), C.byref(o), Lc, _dp(lam), _dp(g0) if g0 is not None else None,
+                                                _dp(x0T) if x0T is not None else None, _dp(xoT),
+                                                its.ctypes.data_as(C.POINTER(C.c_int64)), _dp(nres), _dp(gout), _dp(fout),
+                                                _dp(hist) if hist is not None else None, H, C.byref(res)))
+    dev.launches += res.kernel_launches
+    info = dict(norm_res=nres, gamma=gout, f_x=fout, flags=int(res.flags), solve_ms=res.solve_ms, kernel_launches=int(res.kernel_launches),
+                batched_evals=int(res.f_evals), iters_max=int(res.iters))
+    if hist is not None:
+        info.update(gamma_hist=hist[0], res_hist=hist[1], obj_hist=hist[2])
+    _last_info.update(dict(flags=info["flags"], solve_ms=res.solve_ms, kernel_launches=int(res.kernel_launches), matrix_passes=2))
+    return np.ascontiguousarray(xoT.T), its, info
 
 
 def fixed_proxgrad(x, *, f, g, gamma, tol=1e-5, maxit=100_000, name="Fixed stepsize PGM", log=None):

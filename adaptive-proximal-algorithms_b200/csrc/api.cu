@@ -824,3 +824,4 @@ extern "C" int adaprox_time_kernel(adaprox_handle h, adaprox_id mat, int which, 
 
 #include "comm.inl"
 #include "generate.inl"
+#include "path.inl"

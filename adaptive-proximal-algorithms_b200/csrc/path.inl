@@ -1,0 +1,169 @@
+// path.inl -- included at the end of api.cu: host side of the batched multi-lambda lasso path (path_gemm.cuh).
+#include "path_gemm.cuh"
+
+namespace adaprox {
+
+static int path_setup_kernels(adaprox_ctx* h) {
+  static bool done = false;
+  if (done) return ADAPROX_OK;
+  AP_CUDA(h, cudaFuncSetAttribute((const void*)k_path_gemm<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGSmemBytes));
+  AP_CUDA(h, cudaFuncSetAttribute((const void*)k_path_gemm<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGSmemBytes));
+  done = true;
+  return ADAPROX_OK;
+}
+
+static void path_launch_gemm(adaprox_ctx* h, int mode, const PathGemmArgs& g) {
+  if (mode == 1) {
+    dim3 grid((unsigned)((g.m + kGBM - 1) / kGBM), (unsigned)((g.L + kGBN - 1) / kGBN));
+    k_path_gemm<1><<<grid, kGT, kGSmemBytes, h->stream>>>(g);
+  } else {
+    dim3 grid((unsigned)((g.L + kGBM - 1) / kGBM), (unsigned)((g.n + kGBN - 1) / kGBN));
+    k_path_gemm<2><<<grid, kGT, kGSmemBytes, h->stream>>>(g);
+  }
+  h->launches++;
+}
+
+}  // namespace adaprox
+
+using namespace adaprox;
+
+extern "C" int adaprox_solve_lambda_path(adaprox_handle h, const adaprox_problem* p, const adaprox_options* o, int64_t L,
+                                         const double* lambdas, const double* gamma0, const double* x0T, double* x_outT,
+                                         int64_t* iters, double* norm_res, double* gamma_out, double* f_out,
+                                         double* hist, int64_t hist_rows, adaprox_result* res) {
+  if (!h || !p || !o || !lambdas || !x_outT || !res || L < 1) return fail(h, ADAPROX_ERR_INVALID, "solve_lambda_path: bad arguments");
+  AP_CUDA(h, cudaSetDevice(h->device));
+  int rc;
+  if (o->solver != ADAPROX_S_ADAPTIVE_PROXGRAD)
+    return fail(h, ADAPROX_ERR_UNSUPPORTED, "solve_lambda_path: adaptive_proxgrad / fixed_proxgrad only");
+  if ((rc = validate_options(h, p, o))) return rc;
+  DProblem P;
+  HostMatrix *fm, *am;
+  if ((rc = fill_problem(h, p, &P, &fm, &am))) return rc;
+  if (P.f_kind != ADAPROX_F_LEAST_SQUARES || P.F.kind != MAT_DENSE)
+    return fail(h, ADAPROX_ERR_UNSUPPORTED, "solve_lambda_path: the smooth term must be a dense least-squares term");
+  if (fm && fm->sharded) return fail(h, ADAPROX_ERR_UNSUPPORTED, "solve_lambda_path: split the lambdas over the ranks, not the rows");
+  for (int64_t j = 0; j < L; ++j)
+    if (!(lambdas[j] >= 0.0)) return fail(h, ADAPROX_ERR_INVALID, "solve_lambda_path: lambdas must be >= 0");
+  if ((rc = path_setup_kernels(h))) return rc;
+  DOpts O{};
+  fill_opts(o, &O);
+  const int64_t nrec = hist ? std::min<int64_t>(hist_rows, O.maxit) : 0;
+  O.max_records = nrec;
+  const int64_t n = P.n, m = P.F.m;
+  const int64_t ldx = round_up(n, 16), ldr = round_up(m, 16);
+  const int64_t mtiles = (m + kGBM - 1) / kGBM;
+  size_t need = 7 * ws_size_doubles(L * ldx) + ws_size_doubles(L * ldr) + ws_size_doubles(mtiles * L) +
+                ws_size_doubles((L * (int64_t)sizeof(PathCol) + 7) / 8) + 3 * ws_size_doubles(std::max<int64_t>(nrec, 1) * L) + ws_size_doubles(1);
+  if ((rc = ws_reset(h, need))) return rc;
+  PathStepArgs sa{};
+  sa.n = n; sa.ldx = ldx; sa.L = L; sa.mtiles = mtiles; sa.O = O;
+  for (int k = 0; k < 3; ++k) sa.XT[k] = ws_doubles(h, L * ldx);
+  for (int k = 0; k < 2; ++k) sa.GT[k] = ws_doubles(h, L * ldx);
+  sa.VT = ws_doubles(h, L * ldx);
+  sa.XoutT = ws_doubles(h, L * ldx);
+  double* RT = ws_doubles(h, L * ldr);
+  double* fpart = ws_doubles(h, mtiles * L);
+  sa.fpart = fpart;
+  sa.col = reinterpret_cast<PathCol*>(ws_doubles(h, (L * (int64_t)sizeof(PathCol) + 7) / 8));
+  double* histd = ws_doubles(h, 3 * std::max<int64_t>(nrec, 1) * L);
+  if (nrec > 0) { sa.gamma_hist = histd; sa.res_hist = histd + nrec * L; sa.obj_hist = histd + 2 * nrec * L; }
+  sa.n_active = reinterpret_cast<int*>(ws_doubles(h, 1));
+
+  // zero everything once: the padding of XT / RT is read by the tile loads and must stay zero
+  AP_CUDA(h, cudaMemsetAsync(sa.XT[0], 0, (size_t)(7 * ws_size_doubles(L * ldx) + ws_size_doubles(L * ldr)), h->stream));
+  if (nrec > 0) {
+    std::vector<double> nanv((size_t)(3 * nrec * L), std::numeric_limits<double>::quiet_NaN());
+    AP_CUDA(h, cudaMemcpyAsync(histd, nanv.data(), nanv.size() * 8, cudaMemcpyHostToDevice, h->stream));
+    AP_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
+  if (x0T) AP_CUDA(h, cudaMemcpy2DAsync(sa.XT[0], (size_t)ldx * 8, x0T, (size_t)n * 8, (size_t)n * 8, (size_t)L, cudaMemcpyHostToDevice, h->stream));
+  std::vector<PathCol> cols((size_t)L);
+  for (int64_t j = 0; j < L; ++j) {
+    PathCol& c = cols[(size_t)j];
+    std::memset(&c, 0, sizeof(c));
+    DOpts Oj = O;
+    if (gamma0) Oj.gamma = gamma0[j];
+    rule_init(Oj, c.gamma, c.sigma, c.s0, c.s1);                       // stepsize(rule) per column (:324)
+    c.norm_res = INFINITY; c.lambda = lambdas[j];
+  }
+  AP_CUDA(h, cudaMemcpyAsync(sa.col, cols.data(), cols.size() * sizeof(PathCol), cudaMemcpyHostToDevice, h->stream));
+
+  PathGemmArgs g{};
+  g.A = P.F.a; g.m = m; g.n = n; g.lda = P.F.ld; g.b = P.fvec; g.L = L; g.ldx = ldx; g.RT = RT; g.ldr = ldr; g.fpart = fpart;
+  const int64_t launches0 = h->launches;
+  AP_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+  int64_t evals = 0;
+  int active = (int)L;
+  for (int64_t it = 0; it <= O.maxit && active > 0; ++it) {
+    g.XT = sa.XT[it % 3];
+    g.GT = sa.GT[it & 1];
+    path_launch_gemm(h, 1, g);                                         // R = A X - b, per-tile sums of r^2   (:336 value)
+    path_launch_gemm(h, 2, g);                                         // G = A' R                            (:336 pullback)
+    ++evals;
+    AP_CUDA(h, cudaMemsetAsync(sa.n_active, 0, sizeof(int), h->stream));
+    sa.it = it;
+    k_path_step<<<(unsigned)L, kPT, 0, h->stream>>>(sa);
+    h->launches++;
+    AP_CUDA(h, cudaMemcpyAsync(&active, sa.n_active, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    AP_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
+  AP_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+  AP_CUDA(h, cudaGetLastError());
+  AP_CUDA(h, cudaMemcpy2DAsync(x_outT, (size_t)n * 8, sa.XoutT, (size_t)ldx * 8, (size_t)n * 8, (size_t)L, cudaMemcpyDeviceToHost, h->stream));
+  AP_CUDA(h, cudaMemcpyAsync(cols.data(), sa.col, cols.size() * sizeof(PathCol), cudaMemcpyDeviceToHost, h->stream));
+  if (nrec > 0) AP_CUDA(h, cudaMemcpyAsync(hist, histd, (size_t)(3 * nrec * L) * 8, cudaMemcpyDeviceToHost, h->stream));
+  AP_CUDA(h, cudaStreamSynchronize(h->stream));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+  std::memset(res, 0, sizeof(*res));
+  int64_t itmax = 0;
+  unsigned all_conv = ADAPROX_FLAG_CONVERGED;
+  for (int64_t j = 0; j < L; ++j) {
+    const PathCol& c = cols[(size_t)j];
+    if (iters) iters[j] = c.it_done;
+    if (norm_res) norm_res[j] = c.norm_res;
+    if (gamma_out) gamma_out[j] = c.gamma;
+    if (f_out) f_out[j] = c.f_x;
+    itmax = std::max<int64_t>(itmax, c.it_done);
+    if (!(c.flags & ADAPROX_FLAG_CONVERGED)) all_conv = 0;
+  }
+  res->iters = itmax; res->flags = all_conv;
+  res->f_evals = evals; res->grad_f_evals = evals; res->prox_g_evals = evals;      // batched oracle calls (each covers L columns)
+  res->n_records = nrec;
+  res->solve_ms = ms; res->kernel_launches = h->launches - launches0;
+  res->matrix_passes = 2;
+  return ADAPROX_OK;
+}
+
+extern "C" int adaprox_time_path_gemm(adaprox_handle h, adaprox_id mat, int64_t L, int which, int reps, double* ms_per_launch) {
+  if (!h || !ms_per_launch || reps <= 0 || L < 1 || (which != 0 && which != 1)) return fail(h, ADAPROX_ERR_INVALID, "time_path_gemm: bad arguments");
+  HostMatrix* hm;
+  int rc = get_mat(h, mat, &hm);
+  if (rc) return rc;
+  if (hm->d.kind != MAT_DENSE) return fail(h, ADAPROX_ERR_UNSUPPORTED, "time_path_gemm: dense matrices only");
+  AP_CUDA(h, cudaSetDevice(h->device));
+  if ((rc = path_setup_kernels(h))) return rc;
+  const DMat& M = hm->d;
+  const int64_t ldx = round_up(M.n, 16), ldr = round_up(M.m, 16), mtiles = (M.m + kGBM - 1) / kGBM;
+  size_t need = 2 * ws_size_doubles(L * ldx) + ws_size_doubles(L * ldr) + ws_size_doubles(mtiles * L) + ws_size_doubles(M.m);
+  if ((rc = ws_reset(h, need))) return rc;
+  PathGemmArgs g{};
+  double* XT = ws_doubles(h, L * ldx);
+  g.GT = ws_doubles(h, L * ldx);
+  g.RT = ws_doubles(h, L * ldr);
+  g.fpart = ws_doubles(h, mtiles * L);
+  double* bz = ws_doubles(h, M.m);
+  AP_CUDA(h, cudaMemsetAsync(XT, 0, need, h->stream));
+  g.A = M.a; g.m = M.m; g.n = M.n; g.lda = M.ld; g.b = bz; g.L = L; g.XT = XT; g.ldx = ldx; g.ldr = ldr;
+  path_launch_gemm(h, which + 1, g);                                   // warm-up
+  AP_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+  for (int r = 0; r < reps; ++r) path_launch_gemm(h, which + 1, g);
+  AP_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+  AP_CUDA(h, cudaStreamSynchronize(h->stream));
+  AP_CUDA(h, cudaGetLastError());
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+  *ms_per_launch = (double)ms / reps;
+  return ADAPROX_OK;
+}

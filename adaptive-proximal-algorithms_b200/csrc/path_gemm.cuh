@@ -1,0 +1,343 @@
+// path_gemm.cuh -- the batched multi-lambda lasso path (BASELINE config 5): AdaPGM on L problems
+//     min_x 1/2 |A x - b|^2 + lambda_j |x|_1,   j = 0 .. L-1,
+// that share A and b.  The L iterates are the columns of X, so the two oracle calls of the loop
+// (lasso/runme.jl:22-23) become dense fp64 contractions
+//     R = A X - b 1'   (m x L, K = n)        G = A' R   (n x L, K = m)
+// with ~L/4 flop per byte of A: compute bound, the one place of this library where tensor cores apply.
+// fp64 has no tcgen05 kind; the fp64 tensor-core path of sm_100a is mma.sync (SASS: DMMA).
+//
+// Layout: every column of X, R, G is CONTIGUOUS (XT[L][ldx], RT[L][ldr], GT[L][ldx]; ld = length rounded up
+// to 16 doubles, zero padded), which is the natural layout for the per-column vector work and makes both mma
+// operands of R = A X k-contiguous.
+//
+// Tile engine: 128 x 128 output tile per CTA, 16 warps as 4 x 4, 32 x 32 per warp = 4 x 4 DMMA m8n8k4 tiles
+// (32 accumulator doubles per thread); BK = 16 per stage, 4-stage cp.async (LDGSTS) ring.  Shared-memory rows are
+// padded by 4 doubles (row stride = 32 bytes mod 128), so the fragment loads -- lane l reads element
+// [8 r + l / 4][k + l % 4] -- are bank-conflict free.
+//   mode 1 (R = A X - b):  M index = row i of A, N index = column j; A-operand A[i][k], B-operand XT[j][k].
+//   mode 2 (G = A' R):     M index = column j,   N index = column c of A; A-operand RT[j][i], B-operand A[i][c]
+//                          (the B tile is staged [k][n]: A is row-major, so c is the contiguous index).
+#pragma once
+#include "phases.cuh"
+
+namespace adaprox {
+
+constexpr int kGT = 512;                 // threads per CTA of the GEMM kernels
+constexpr int kGBM = 128, kGBN = 128, kGBK = 16, kGStages = 4;
+constexpr int kGPadK = kGBK + 4;         // 20 doubles: row stride of the k-contiguous tiles
+constexpr int kGPadN = kGBN + 4;         // 132 doubles: row stride of the [k][n] tile of mode 2
+constexpr int kGATile = kGBM * kGPadK;                                   // doubles
+constexpr int kGBTile1 = kGBN * kGPadK;
+constexpr int kGBTile2 = kGBK * kGPadN;
+constexpr int kGStage = kGATile + (kGBTile1 > kGBTile2 ? kGBTile1 : kGBTile2);
+constexpr int kGSmemBytes = kGStages * kGStage * 8;                      // 163 840 B
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
+  // 16-byte global -> shared copy; bytes beyond src_bytes (0 or 16) are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+struct PathGemmArgs {
+  const double* A; int64_t m, n, lda;       // row-major m x n
+  const double* b;                          // [m]
+  int64_t L;
+  const double* XT; int64_t ldx;            // [L][ldx]   (mode 1: B operand)
+  double* RT; int64_t ldr;                  // [L][ldr]   (mode 1: output, mode 2: A operand)
+  double* GT;                               // [L][ldx]   (mode 2: output)
+  double* fpart;                            // [m tiles][L]  per-tile sums of r^2 (mode 1), reduced in tile order later
+};
+
+// MODE 1: RT[j][i] = sum_k A[i][k] XT[j][k] - b[i]  (+ fpart);   MODE 2: GT[j][c] = sum_i RT[j][i] A[i][c]
+template <int MODE>
+__global__ void __launch_bounds__(kGT, 1) k_path_gemm(PathGemmArgs g) {
+  extern __shared__ __align__(16) double gsm[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp >> 2, wn = warp & 3;
+  const int64_t Mdim = (MODE == 1) ? g.m : g.L;
+  const int64_t Ndim = (MODE == 1) ? g.L : g.n;
+  const int64_t Kdim = (MODE == 1) ? g.n : g.m;
+  const int64_t m0 = (int64_t)blockIdx.x * kGBM, n0 = (int64_t)blockIdx.y * kGBN;
+  // operand descriptors
+  const double* Aop = (MODE == 1) ? g.A : g.RT;          // rows = M index, k contiguous
+  const int64_t lda = (MODE == 1) ? g.lda : g.ldr;
+  const int64_t a_kmax = (MODE == 1) ? g.lda : g.ldr;    // padded (zero-filled) extent that may be read
+  const double* Bop = (MODE == 1) ? g.XT : g.A;
+  const int64_t ldb = (MODE == 1) ? g.ldx : g.lda;
+  const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(gsm);
+
+  auto load_stage = [&](int stage, int64_t k0) {
+    const uint32_t sa = smem0 + (uint32_t)(stage * kGStage) * 8;
+    const uint32_t sb = sa + kGATile * 8;
+    // A tile: 128 rows x 16 doubles = 128 x 8 chunks of 16 B
+#pragma unroll
+    for (int q = 0; q < (kGBM * kGBK / 2) / kGT; ++q) {
+      const int ch = tid + q * kGT;
+      const int r = ch >> 3, kc = (ch & 7) * 2;
+      const int64_t row = m0 + r, k = k0 + kc;
+      const bool ok = (row < Mdim) && (k + 2 <= a_kmax);
+      const double* src = Aop + (ok ? row * lda + k : 0);
+      cp_async16(sa + (uint32_t)(r * kGPadK + kc) * 8, src, ok ? 16 : 0);
+    }
+    if (MODE == 1) {
+      // B tile: 128 rows (columns j of X) x 16 doubles, k contiguous
+#pragma unroll
+      for (int q = 0; q < (kGBN * kGBK / 2) / kGT; ++q) {
+        const int ch = tid + q * kGT;
+        const int r = ch >> 3, kc = (ch & 7) * 2;
+        const int64_t col = n0 + r, k = k0 + kc;
+        const bool ok = (col < Ndim) && (k + 2 <= ldb);
+        const double* src = Bop + (ok ? col * ldb + k : 0);
+        cp_async16(sb + (uint32_t)(r * kGPadK + kc) * 8, src, ok ? 16 : 0);
+      }
+    } else {
+      // B tile: 16 rows (k = row i of A) x 128 columns c, c contiguous
+#pragma unroll
+      for (int q = 0; q < (kGBK * kGBN / 2) / kGT; ++q) {
+        const int ch = tid + q * kGT;
+        const int r = ch >> 6, cc = (ch & 63) * 2;
+        const int64_t krow = k0 + r, col = n0 + cc;
+        const bool ok = (krow < Kdim) && (col + 2 <= ldb);
+        const double* src = Bop + (ok ? krow * ldb + col : 0);
+        cp_async16(sb + (uint32_t)(r * kGPadN + cc) * 8, src, ok ? 16 : 0);
+      }
+    }
+  };
+
+  double acc[4][4][2];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[r][c][0] = acc[r][c][1] = 0.0;
+
+  const int64_t nk = (Kdim + kGBK - 1) / kGBK;
+#pragma unroll
+  for (int s = 0; s < kGStages - 1; ++s) {
+    if (s < nk) load_stage(s, (int64_t)s * kGBK);
+    cp_async_commit();
+  }
+  const int lr = lane >> 2, lk = lane & 3;
+  for (int64_t kt = 0; kt < nk; ++kt) {
+    cp_async_wait<kGStages - 2>();
+    __syncthreads();                                    // stage kt landed for every thread; stage kt-1 is free
+    {
+      const int64_t kn = kt + kGStages - 1;
+      if (kn < nk) load_stage((int)(kn % kGStages), kn * kGBK);
+      cp_async_commit();
+    }
+    const double* sa = gsm + (size_t)(kt % kGStages) * kGStage;
+    const double* sb = sa + kGATile;
+#pragma unroll
+    for (int kk = 0; kk < kGBK; kk += 4) {
+      double a[4], b[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) a[r] = sa[(wm * 32 + r * 8 + lr) * kGPadK + kk + lk];
+      if (MODE == 1) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) b[c] = sb[(wn * 32 + c * 8 + lr) * kGPadK + kk + lk];
+      } else {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) b[c] = sb[(kk + lk) * kGPadN + wn * 32 + c * 8 + lr];
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) dmma_m8n8k4(acc[r][c][0], acc[r][c][1], a[r], b[c]);
+    }
+  }
+  cp_async_wait<0>();
+
+  // epilogue.  Accumulator fragment: row = lane / 4 (M index within the 8 x 8 tile), cols = 2 (lane % 4) + {0, 1}.
+  if (MODE == 1) {
+    __shared__ double s_f[4][kGBN];                     // [wm][column within the CTA tile]
+    double fs[4][2];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) fs[c][0] = fs[c][1] = 0.0;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int64_t i = m0 + wm * 32 + r * 8 + lr;
+      const double bi = (i < g.m) ? __ldg(g.b + i) : 0.0;
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int64_t j = n0 + wn * 32 + c * 8 + 2 * lk + e;
+          if (i < g.m && j < g.L) {
+            const double rv = acc[r][c][e] - bi;        // lasso/runme.jl:22
+            g.RT[j * g.ldr + i] = rv;
+            fs[c][e] = fma(rv, rv, fs[c][e]);
+          }
+        }
+    }
+    // sum over the 8 row-lanes (lane / 4) with a fixed xor tree, then over the 4 warps along M in fixed order
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        double v = fs[c][e];
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 16);
+        if (lr == 0) s_f[wm][wn * 32 + c * 8 + 2 * lk + e] = v;
+      }
+    __syncthreads();
+    if (tid < kGBN) {
+      const int64_t j = n0 + tid;
+      if (j < g.L) g.fpart[(int64_t)blockIdx.x * g.L + j] = ((s_f[0][tid] + s_f[1][tid]) + s_f[2][tid]) + s_f[3][tid];
+    }
+  } else {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int64_t j = m0 + wm * 32 + r * 8 + lr;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int64_t col = n0 + wn * 32 + c * 8 + 2 * lk;
+        if (j < g.L && col < g.n) {
+          if (col + 1 < g.n) *reinterpret_cast<double2*>(g.GT + j * g.ldx + col) = make_double2(acc[r][c][0], acc[r][c][1]);
+          else g.GT[j * g.ldx + col] = acc[r][c][0];
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// per-column step of the loop (src/AdaProx.jl:334-362 with A = 0, h = Zero): one CTA per column
+// ---------------------------------------------------------------------------
+struct PathCol {           // per-column solver state
+  double gamma, sigma, s0, s1, norm_res, f_x, lambda;
+  long long it_done;       // iteration at which the column stopped (0 = still running)
+  unsigned flags;
+  int pad;
+};
+
+struct PathStepArgs {
+  int64_t n, ldx, L, mtiles;
+  DOpts O;
+  double* XT[3];           // iterate ring [L][ldx]
+  double* GT[2];           // gradient ring
+  double* VT;              // v = x - gamma g
+  double* XoutT;           // result columns (frozen at convergence)
+  const double* fpart;     // [mtiles][L]
+  PathCol* col;
+  double* gamma_hist; double* res_hist; double* obj_hist;   // optional [max_records][L]
+  long long it;            // iteration being finished (0 = prologue)
+  int* n_active;           // columns still running after this step (device counter)
+};
+
+constexpr int kPT = 256;
+
+__global__ void __launch_bounds__(kPT, 2) k_path_step(PathStepArgs a) {
+  __shared__ double s_scr[kPT / 32 * 4 + 8];
+  __shared__ double s_bc[4];
+  const int64_t j = blockIdx.x;
+  const long long it = a.it;
+  PathCol st = a.col[j];
+  const double* x = a.XT[it % 3] + j * a.ldx;
+  const double* x_prev = a.XT[(it + 2) % 3] + j * a.ldx;
+  double* xn = a.XT[(it + 1) % 3] + j * a.ldx;
+  const double* grad = a.GT[it & 1] + j * a.ldx;
+  const double* grad_prev = a.GT[(it + 1) & 1] + j * a.ldx;
+  double* v = a.VT + j * a.ldx;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool frozen = st.it_done != 0;
+
+  // value of f (fixed order over the row tiles)
+  double f_x;
+  {
+    double s = 0.0;
+    for (int64_t t = 0; t < a.mtiles; ++t) s += a.fpart[t * a.L + j];
+    f_x = 0.5 * norm_sq_jl(s);
+  }
+  double gamma = st.gamma, sigma = st.sigma, s0 = st.s0, s1 = st.s1;
+  bool stop = false;
+  double norm_res = st.norm_res;
+  if (it > 0 && !frozen) {
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int64_t q = threadIdx.x; q < a.n; q += kPT) {
+      const double xj = x[q], gj = grad[q];
+      const double pr = (v[q] - xj) / gamma + gj;                       // :338 (old gamma)
+      const double dg = gj - grad_prev[q], dx = xj - x_prev[q];
+      acc[0] = fma(pr, pr, acc[0]);
+      acc[1] = fma(dg, dg, acc[1]);
+      acc[2] = fma(dg, dx, acc[2]);
+      acc[3] = fma(dx, dx, acc[3]);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const double s = warp_sum(acc[k]);
+      if (lane == 0) s_scr[warp * 4 + k] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+      double s = 0.0;
+#pragma unroll
+      for (int w = 0; w < kPT / 32; ++w) s += s_scr[w * 4 + threadIdx.x];
+      s_bc[threadIdx.x] = s;
+    }
+    __syncthreads();
+    rule_step(a.O, s_bc[1], s_bc[2], s_bc[3], gamma, sigma, s0, s1);     // :341
+    norm_res = sqrt(norm_sq_jl(s_bc[0]));                                // :348
+    if (norm_res <= a.O.tol) stop = true;                                // :354
+  }
+  // objective of the record: f(x) + lambda |x|_1
+  const bool want_hist = a.gamma_hist != nullptr && it >= 1 && it <= a.O.max_records && !frozen;
+  if (want_hist) {
+    double l1 = 0.0;
+    for (int64_t q = threadIdx.x; q < a.n; q += kPT) l1 += fabs(x[q]);
+    l1 = warp_sum(l1);
+    __syncthreads();
+    if (lane == 0) s_scr[warp] = l1;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double s = 0.0;
+      for (int w = 0; w < kPT / 32; ++w) s += s_scr[w];
+      a.gamma_hist[(it - 1) * a.L + j] = gamma;
+      a.res_hist[(it - 1) * a.L + j] = norm_res;
+      a.obj_hist[(it - 1) * a.L + j] = f_x + st.lambda * s;
+    }
+  }
+  if (frozen) return;
+  if (stop || (it >= a.O.maxit && it > 0)) {
+    // converged: the result is x_it (:355); maxit: the reference returns x after the last prox (:361-363)
+    const bool conv = stop;
+    if (conv) {
+      for (int64_t q = threadIdx.x; q < a.n; q += kPT) a.XoutT[j * a.ldx + q] = x[q];
+    } else {
+      for (int64_t q = threadIdx.x; q < a.n; q += kPT) {
+        const double vj = x[q] - gamma * grad[q];
+        const double gl = gamma * st.lambda;
+        a.XoutT[j * a.ldx + q] = vj + (vj <= -gl ? gl : (vj >= gl ? -gl : -vj));
+      }
+    }
+    if (threadIdx.x == 0) {
+      st.gamma = gamma; st.sigma = sigma; st.s0 = s0; st.s1 = s1; st.norm_res = norm_res; st.f_x = f_x;
+      st.it_done = it; st.flags = conv ? ADAPROX_FLAG_CONVERGED : 0u;
+      a.col[j] = st;
+    }
+    // keep the ring defined for the (ignored) later iterations of this column
+    for (int64_t q = threadIdx.x; q < a.n; q += kPT) xn[q] = x[q];
+    return;
+  }
+  // v = x - gamma grad ; x+ = prox_{gamma lambda |.|_1}(v)   (:359-361; NormL1 in ProximalOperators' form, Appendix A)
+  const double gl = gamma * st.lambda;
+  for (int64_t q = threadIdx.x; q < a.n; q += kPT) {
+    const double vj = x[q] - gamma * grad[q];
+    v[q] = vj;
+    xn[q] = vj + (vj <= -gl ? gl : (vj >= gl ? -gl : -vj));
+  }
+  if (threadIdx.x == 0) {
+    st.gamma = gamma; st.sigma = sigma; st.s0 = s0; st.s1 = s1; st.norm_res = norm_res; st.f_x = f_x;
+    a.col[j] = st;
+    atomicAdd(a.n_active, 1);
+  }
+}
+
+}  // namespace adaprox

@@ -205,6 +205,27 @@ int adaprox_stepsize(const adaprox_options* o, double gamma1, double gamma0_or_r
 int adaprox_solve(adaprox_handle h, const adaprox_problem* p, const adaprox_options* o, const double* x0,
                   const double* y0, double* x_out, double* y_out, adaprox_record* records, adaprox_result* res);
 
+/* ---- batched multi-lambda lasso path (BASELINE config 5) --------------------- */
+/* AdaPGM (src/AdaProx.jl:418-421 -> :312-364 with A = 0, h = Zero) on the L problems
+ *     min_x 1/2 |A x - b|^2 + lambdas[j] |x|_1 ,  j = 0 .. L-1
+ * that share the dense least-squares term of `p` (lasso/runme.jl:16-27; p->g is ignored).  The reference has no batched
+ * entry point: running adaptive_proxgrad once per lambda is the behaviour this call reproduces column by column -- every
+ * column has its own stepsize state, residual and stopping iteration and is frozen when it converges (its result is the
+ * iterate the single-lambda call returns).  The L iterates advance together so that A*X and A'*R are fp64 tensor-core
+ * contractions (mma.sync DMMA) instead of 2 L matrix-vector products.
+ *   gamma0  : L initial stepsizes, or NULL to use o->gamma for every column
+ *   x0T     : [L][n] (column j contiguous), or NULL for zeros
+ *   x_outT  : [L][n];  iters / norm_res / gamma_out / f_out : [L] (each may be NULL)
+ *   hist    : optional 3 * hist_rows * L doubles: gamma, norm_res, objective per (iteration - 1, column); NaN where a
+ *             column had already stopped.  res->iters = largest per-column iteration count. */
+int adaprox_solve_lambda_path(adaprox_handle h, const adaprox_problem* p, const adaprox_options* o, int64_t L,
+                              const double* lambdas, const double* gamma0, const double* x0T, double* x_outT,
+                              int64_t* iters, double* norm_res, double* gamma_out, double* f_out,
+                              double* hist, int64_t hist_rows, adaprox_result* res);
+/* which: 0 = R = A X - b (K = n), 1 = G = A' R (K = m); mean device ms per launch over `reps` launches on an L-column
+ * batch of zeros (measurement hook of tools/bench_configs.py) */
+int adaprox_time_path_gemm(adaprox_handle h, adaprox_id mat, int64_t L, int which, int reps, double* ms_per_launch);
+
 /* ---- row-sharded multi-GPU (one process per GPU) ---------------------------- */
 /* NCCL bootstrap: rank 0 calls unique_id, the host side broadcasts the 128
  * bytes, every rank calls comm_init.  After that, solves on matrices flagged as

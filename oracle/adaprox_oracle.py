@@ -857,6 +857,26 @@ def auto_adaptive_proxgrad(x, *, f, g, gamma=None, tol=1e-5, maxit=100_000, name
     return adaptive_proxgrad(x_prev, f=f, g=g, rule=rule, tol=tol, maxit=maxit, name=name, log=log)
 
 
+def adaptive_proxgrad_path(X0, *, f, lambdas, rule_of, tol=1e-5, maxit=100_000, history=0):
+    """Checker for the batched multi-lambda path (include/adaprox.h: adaprox_solve_lambda_path): the reference has no
+    batched entry point, so this is literally one ``adaptive_proxgrad`` call (src/AdaProx.jl:418-421) per lambda.
+    ``rule_of(j)`` returns the rule of column j.  Returns (X, its, gamma_hist, res_hist, obj_hist)."""
+    lambdas = np.asarray(lambdas, dtype=float)
+    n, Lc = X0.shape
+    X = np.empty((n, Lc))
+    its = np.zeros(Lc, dtype=np.int64)
+    H = int(min(history, maxit)) if history else 0
+    gh = np.full((H, Lc), np.nan); rh = np.full((H, Lc), np.nan); oh = np.full((H, Lc), np.nan)
+    for j in range(Lc):
+        log = []
+        x, it = adaptive_proxgrad(X0[:, j].copy(), f=f, g=NormL1(float(lambdas[j])), rule=rule_of(j), tol=tol, maxit=maxit, log=log)
+        X[:, j] = x
+        its[j] = it
+        for r in log[:H]:
+            gh[r["it"] - 1, j] = r["gamma"]; rh[r["it"] - 1, j] = r["norm_res"]; oh[r["it"] - 1, j] = r["objective"]
+    return X, its, gh, rh, oh
+
+
 def fixed_proxgrad(x, *, f, g, gamma, tol=1e-5, maxit=100_000, name="Fixed stepsize PGM", log=None):
     """src/AdaProx.jl:457-459."""
     return adaptive_proxgrad(x, f=f, g=g, rule=FixedStepsize(gamma, 1.0), tol=tol, maxit=maxit,

@@ -578,7 +578,7 @@ def test_libsvm_file_to_jsonl_records(AdaProx, tmp_path):
     path = str(tmp_path / "toy.libsvm")
     with open(path, "w") as fh:
         for i in range(300):
-            feats = " ".join(f"{j + 1}:{v!r}" for j, v in zip(X.indices[X.indptr[i]:X.indptr[i + 1]], X.data[X.indptr[i]:X.indptr[i + 1]]))
+            feats = " ".join(f"{j + 1}:{float(v)!r}" for j, v in zip(X.indices[X.indptr[i]:X.indptr[i + 1]], X.data[X.indptr[i]:X.indptr[i + 1]]))
             fh.write(f"{'+1' if y[i] > 0.5 else '-1'} {feats}\n")
     Xl, yl = AdaProx.load_libsvm_dataset(path, labels=(0.0, 1.0))                 # sparse_logreg/runme.jl maps labels to {0, 1}
     assert Xl.shape[0] == 300 and np.array_equal(yl, y)
@@ -611,3 +611,63 @@ def test_libsvm_file_to_jsonl_records(AdaProx, tmp_path):
     assert best in gb
     with open(jl) as fh:
         json.loads(fh.readline())
+
+
+# ---------------------------------------------------------------- batched multi-lambda lasso path (FP64 DMMA contractions)
+@pytest.mark.parametrize("m,n,Lc", [(400, 1000, 7), (130, 300, 33), (257, 2050, 130)])
+def test_lambda_path_matches_per_lambda_solves(AdaProx, m, n, Lc):
+    """Column j of the batched solve == adaptive_proxgrad with NormL1(lambdas[j]) (the oracle runs them one by one).
+    Shapes exercise ragged tiles in every dimension (rows, columns, lambdas not multiples of 128 / 16)."""
+    P = AdaProx.synth.planted_lasso(m, n, 5, 2)
+    Lf = AdaProx.synth.spectral_norm_sq(P["A"], iters=500)
+    lam_max = float(np.max(np.abs(P["A"].T @ P["b"])))
+    lambdas = lam_max * (1e-2) ** (np.arange(Lc) / max(Lc - 1, 1)) * 0.5
+    f = AdaProx.LinearLeastSquares(P["A"], P["b"])
+    H = 60
+    X, its, info = AdaProx.adaptive_proxgrad_path(None, f=f, lambdas=lambdas, rule=AdaProx.OurRule(gamma=1 / Lf), tol=1e-6, maxit=400, history=H)
+    Xo, itso, gh, rh, oh = O.adaptive_proxgrad_path(np.zeros((n, Lc)), f=O.LinearLeastSquares(P["A"], P["b"]), lambdas=lambdas,
+                                                   rule_of=lambda j: O.OurRule(gamma=1 / Lf), tol=1e-6, maxit=400, history=H)
+    K = 25
+    gd, go = info["gamma_hist"][:K], gh[:K]
+    live = ~np.isnan(go) & ~np.isnan(gd)
+    assert np.array_equal(np.isnan(go[:12]), np.isnan(gd[:12]))                    # the same columns stop at the same early iterations
+    assert np.max(np.abs(gd[live] / go[live] - 1)) < 1e-9
+    assert np.max(np.abs(gd[:10][live[:10]] / go[:10][live[:10]] - 1)) < 5e-12        # 1.6e-12 measured on the widest case
+    od, oo = info["obj_hist"][:K], oh[:K]
+    assert np.allclose(od[live], oo[live], rtol=1e-10)
+    # stopping iterations agree within the oracle's own rounding sensitivity
+    assert np.all(np.abs(its - itso) <= np.maximum(3, 0.05 * itso)), (its, itso)
+    # columns that converged on both sides: the minimiser to O(tol), the objective to 1e-9; columns cut off at maxit are
+    # compared through the objective only (their trajectories are chaotic w.r.t. rounding, SURVEY 0.7)
+    conv = (its < 400) & (itso < 400)
+    assert conv.sum() >= 1
+    scale = np.maximum(np.linalg.norm(Xo, axis=0), 1e-12)
+    assert np.max((np.linalg.norm(X - Xo, axis=0) / scale)[conv]) < 1e-4
+    fo = np.array([0.5 * np.linalg.norm(P["A"] @ Xo[:, j] - P["b"]) ** 2 + lambdas[j] * np.abs(Xo[:, j]).sum() for j in range(Lc)])
+    fd = np.array([0.5 * np.linalg.norm(P["A"] @ X[:, j] - P["b"]) ** 2 + lambdas[j] * np.abs(X[:, j]).sum() for j in range(Lc)])
+    assert np.max((np.abs(fd - fo) / np.abs(fo))[conv]) < 1e-9
+    assert np.max(np.abs(fd - fo) / np.abs(fo)) < 1e-3
+    # larger lambda => sparser solution (a property of the path itself)
+    nnz = (np.abs(X) > 0).sum(axis=0)
+    assert nnz[0] <= nnz[-1]
+
+
+def test_lambda_path_equals_single_solves_on_device(AdaProx):
+    """Same device, same arithmetic family: the batched columns against adaptive_proxgrad called per lambda through the C ABI
+    (two-pass GEMV kernel); also per-column gamma0 and a non-zero X0."""
+    m, n, Lc = 200, 520, 9
+    P = AdaProx.synth.planted_lasso(m, n, 5, 5)
+    Lf = AdaProx.synth.spectral_norm_sq(P["A"], iters=500)
+    rng = np.random.default_rng(0)
+    lambdas = np.linspace(0.2, 2.0, Lc)
+    gam0 = (1 / Lf) * np.linspace(0.5, 1.0, Lc)
+    X0 = 0.01 * rng.standard_normal((n, Lc))
+    f = AdaProx.LinearLeastSquares(P["A"], P["b"])
+    X, its, info = AdaProx.adaptive_proxgrad_path(X0, f=f, lambdas=lambdas, rule=AdaProx.OurRule(gamma=1 / Lf), gamma0=gam0, tol=1e-7, maxit=3000)
+    for j in range(Lc):
+        xj, itj = AdaProx.adaptive_proxgrad(X0[:, j], f=f, g=AdaProx.NormL1(lambdas[j]), rule=AdaProx.OurRule(gamma=gam0[j]), tol=1e-7, maxit=3000)
+        assert abs(int(its[j]) - itj) <= max(3, 0.05 * itj)
+        assert np.linalg.norm(X[:, j] - xj) <= 5e-4 * max(np.linalg.norm(xj), 1e-9)          # both stopped at norm_res <= 1e-7
+    assert np.all(info["norm_res"] <= 1e-7)
+    with pytest.raises(Exception):
+        AdaProx.adaptive_proxgrad_path(None, f=f, lambdas=[-1.0], rule=AdaProx.OurRule(gamma=1 / Lf))

@@ -2,6 +2,7 @@
 C3 LAD / sqrt-lasso 50000x2001 with AdaPDM+, dual SVM with AdaPDM).  Prints one JSON line per config.
 These are parity-test cases, not the headline bench; numbers go to profiles/."""
 import json
+import os
 import sys
 import time
 
@@ -18,7 +19,7 @@ def timed(fn):
 
 
 def main():
-    which = sys.argv[1:] or ["c1", "c2", "lad", "sqrtlasso", "svm"]
+    which = sys.argv[1:] or ["c1", "c2", "lad", "sqrtlasso", "svm", "c5"]
     AdaProx.default_device()
     if "c1" in which:
         P = AdaProx.synth.planted_lasso(400, 1000, 5, 0)
@@ -86,6 +87,29 @@ def main():
             print(json.dumps(dict(config=f"C3 dual SVM N={N} dense Q AdaPDM t={t}", iterations=it, device_ms=info["solve_ms"],
                                   us_per_iteration=1e3 * info["solve_ms"] / it, hbm_gbs=it * N * N * 8 / (info["solve_ms"] * 1e-3) / 1e9,
                                   final_norm_res=info["final_norm_res"], gen_s=tg + tq)), flush=True)
+    if "c5" in which:
+        # BASELINE configs[4]: batched multi-lambda lasso path, 256 lambdas, A 16384 x 8192, FP64 DMMA contractions.
+        # Multi-GPU: the lambdas are split over the ranks (no collective), see tools/bench_path_multi.py.
+        m, n, Lc = 16384, 8192, int(os.environ.get("C5_LAMBDAS", "256"))
+        P, tg = timed(lambda: AdaProx.generate_planted_lasso(m, n, pfactor=5, seed=0, power_iters=30))
+        f = AdaProx.LinearLeastSquares(P["A"], P["b"])
+        lam_max = float(np.max(np.abs(P["A"].T @ P["b"].download())))
+        lambdas = lam_max * (1e-3) ** (np.arange(Lc) / max(Lc - 1, 1))
+        flop_iter = 4.0 * m * n * Lc                                     # two contractions of 2 m n L
+        ms_r = P["A"].time_path_gemm(Lc, 0, reps=5)
+        ms_g = P["A"].time_path_gemm(Lc, 1, reps=5)
+        for maxit in (20, 300):
+            (res, wall) = timed(lambda: AdaProx.adaptive_proxgrad_path(None, f=f, lambdas=lambdas, rule=AdaProx.OurRule(gamma=1 / P["Lf"]),
+                                                                       tol=1e-6, maxit=maxit))
+            X, its, info = res
+            evals = info["batched_evals"]
+            print(json.dumps(dict(config=f"C5 lambda path {m}x{n} L={Lc} AdaPGM OurRule (DMMA m8n8k4)", maxit=maxit, batched_evals=evals,
+                                  device_ms=info["solve_ms"], ms_per_iteration=info["solve_ms"] / evals,
+                                  tflops=flop_iter * evals / (info["solve_ms"] * 1e-3) / 1e12,
+                                  gemm_AX_ms=ms_r, gemm_AtR_ms=ms_g, gemm_AX_tflops=2.0 * m * n * Lc / (ms_r * 1e-3) / 1e12,
+                                  gemm_AtR_tflops=2.0 * m * n * Lc / (ms_g * 1e-3) / 1e12,
+                                  converged_columns=int((info["norm_res"] <= 1e-6).sum()), iters_min=int(its.min()), iters_max=int(its.max()),
+                                  nnz_first_last=[int((X[:, 0] != 0).sum()), int((X[:, -1] != 0).sum())], e2e_ms=wall * 1e3, gen_s=tg)), flush=True)
 
 
 if __name__ == "__main__":
