@@ -6,19 +6,38 @@ namespace adaprox {
 static int path_setup_kernels(adaprox_ctx* h) {
   static bool done = false;
   if (done) return ADAPROX_OK;
-  AP_CUDA(h, cudaFuncSetAttribute((const void*)k_path_gemm<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGSmemBytes));
-  AP_CUDA(h, cudaFuncSetAttribute((const void*)k_path_gemm<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGSmemBytes));
+  AP_CUDA(h, cudaFuncSetAttribute((const void*)k_path_gemm<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<4>::SmemBytes));
+  AP_CUDA(h, cudaFuncSetAttribute((const void*)k_path_gemm<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<4>::SmemBytes));
+  AP_CUDA(h, cudaFuncSetAttribute((const void*)k_path_gemm<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<1>::SmemBytes));
+  AP_CUDA(h, cudaFuncSetAttribute((const void*)k_path_gemm<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<1>::SmemBytes));
   done = true;
   return ADAPROX_OK;
 }
 
+// G = A' R has only ceil(n / 128) * ceil(L / BN) output tiles; when that leaves most SMs idle (narrow batches) K = m is cut
+// into slabs written to separate buffers and summed in slab order by k_path_step.
+static int path_ksplit(adaprox_ctx* h, int64_t n, int64_t m, int64_t L) {
+  const int bn = (L <= 64) ? GemmCfg<1>::BN : GemmCfg<4>::BN;
+  const int64_t ctas = ((n + kGBM - 1) / kGBM) * ((L + bn - 1) / bn);
+  int ks = (int)(h->sm_count / std::max<int64_t>(ctas, 1));
+  ks = std::max(1, std::min(ks, 4));
+  while (ks > 1 && m / ks < 8 * kGBK) --ks;
+  return ks;
+}
+
+// The batch is the N dimension of both contractions; narrow batches (L <= 64: e.g. 32 lambdas per rank when the path is
+// split over 8 GPUs) use the 128 x 32 tile.
 static void path_launch_gemm(adaprox_ctx* h, int mode, const PathGemmArgs& g) {
+  const bool narrow = g.L <= 64;
+  const int bn = narrow ? GemmCfg<1>::BN : GemmCfg<4>::BN;
+  const int64_t Mdim = (mode == 1) ? g.m : g.n;
+  dim3 grid((unsigned)((Mdim + kGBM - 1) / kGBM), (unsigned)((g.L + bn - 1) / bn), (unsigned)((mode == 2 && g.ksplit > 1) ? g.ksplit : 1));
   if (mode == 1) {
-    dim3 grid((unsigned)((g.m + kGBM - 1) / kGBM), (unsigned)((g.L + kGBN - 1) / kGBN));
-    k_path_gemm<1><<<grid, kGT, kGSmemBytes, h->stream>>>(g);
+    if (narrow) k_path_gemm<1, 1><<<grid, kGT, GemmCfg<1>::SmemBytes, h->stream>>>(g);
+    else k_path_gemm<1, 4><<<grid, kGT, GemmCfg<4>::SmemBytes, h->stream>>>(g);
   } else {
-    dim3 grid((unsigned)((g.L + kGBM - 1) / kGBM), (unsigned)((g.n + kGBN - 1) / kGBN));
-    k_path_gemm<2><<<grid, kGT, kGSmemBytes, h->stream>>>(g);
+    if (narrow) k_path_gemm<2, 1><<<grid, kGT, GemmCfg<1>::SmemBytes, h->stream>>>(g);
+    else k_path_gemm<2, 4><<<grid, kGT, GemmCfg<4>::SmemBytes, h->stream>>>(g);
   }
   h->launches++;
 }
@@ -53,7 +72,8 @@ extern "C" int adaprox_solve_lambda_path(adaprox_handle h, const adaprox_problem
   const int64_t n = P.n, m = P.F.m;
   const int64_t ldx = round_up(n, 16), ldr = round_up(m, 16);
   const int64_t mtiles = (m + kGBM - 1) / kGBM;
-  size_t need = 7 * ws_size_doubles(L * ldx) + ws_size_doubles(L * ldr) + ws_size_doubles(mtiles * L) +
+  const int ksplit = path_ksplit(h, n, m, L);
+  size_t need = 7 * ws_size_doubles(L * ldx) + ws_size_doubles(L * ldr) + ws_size_doubles(mtiles * L) + ws_size_doubles((int64_t)ksplit * L * ldx) +
                 ws_size_doubles((L * (int64_t)sizeof(PathCol) + 7) / 8) + 3 * ws_size_doubles(std::max<int64_t>(nrec, 1) * L) + ws_size_doubles(1);
   if ((rc = ws_reset(h, need))) return rc;
   PathStepArgs sa{};
@@ -65,6 +85,7 @@ extern "C" int adaprox_solve_lambda_path(adaprox_handle h, const adaprox_problem
   double* RT = ws_doubles(h, L * ldr);
   double* fpart = ws_doubles(h, mtiles * L);
   sa.fpart = fpart;
+  double* gslab = ws_doubles(h, (int64_t)ksplit * L * ldx);
   sa.col = reinterpret_cast<PathCol*>(ws_doubles(h, (L * (int64_t)sizeof(PathCol) + 7) / 8));
   double* histd = ws_doubles(h, 3 * std::max<int64_t>(nrec, 1) * L);
   if (nrec > 0) { sa.gamma_hist = histd; sa.res_hist = histd + nrec * L; sa.obj_hist = histd + 2 * nrec * L; }
@@ -91,13 +112,15 @@ extern "C" int adaprox_solve_lambda_path(adaprox_handle h, const adaprox_problem
 
   PathGemmArgs g{};
   g.A = P.F.a; g.m = m; g.n = n; g.lda = P.F.ld; g.b = P.fvec; g.L = L; g.ldx = ldx; g.RT = RT; g.ldr = ldr; g.fpart = fpart;
+  g.ksplit = ksplit; g.gstride = L * ldx;
+  sa.ksplit = ksplit; sa.gstride = L * ldx; sa.Gslab = gslab;
   const int64_t launches0 = h->launches;
   AP_CUDA(h, cudaEventRecord(h->ev0, h->stream));
   int64_t evals = 0;
   int active = (int)L;
   for (int64_t it = 0; it <= O.maxit && active > 0; ++it) {
     g.XT = sa.XT[it % 3];
-    g.GT = sa.GT[it & 1];
+    g.GT = ksplit > 1 ? gslab : sa.GT[it & 1];
     path_launch_gemm(h, 1, g);                                         // R = A X - b, per-tile sums of r^2   (:336 value)
     path_launch_gemm(h, 2, g);                                         // G = A' R                            (:336 pullback)
     ++evals;
@@ -146,16 +169,18 @@ extern "C" int adaprox_time_path_gemm(adaprox_handle h, adaprox_id mat, int64_t 
   if ((rc = path_setup_kernels(h))) return rc;
   const DMat& M = hm->d;
   const int64_t ldx = round_up(M.n, 16), ldr = round_up(M.m, 16), mtiles = (M.m + kGBM - 1) / kGBM;
-  size_t need = 2 * ws_size_doubles(L * ldx) + ws_size_doubles(L * ldr) + ws_size_doubles(mtiles * L) + ws_size_doubles(M.m);
+  const int ksplit = path_ksplit(h, M.n, M.m, L);
+  size_t need = ws_size_doubles(L * ldx) + ws_size_doubles((int64_t)ksplit * L * ldx) + ws_size_doubles(L * ldr) + ws_size_doubles(mtiles * L) + ws_size_doubles(M.m);
   if ((rc = ws_reset(h, need))) return rc;
   PathGemmArgs g{};
   double* XT = ws_doubles(h, L * ldx);
-  g.GT = ws_doubles(h, L * ldx);
+  g.GT = ws_doubles(h, (int64_t)ksplit * L * ldx);
   g.RT = ws_doubles(h, L * ldr);
   g.fpart = ws_doubles(h, mtiles * L);
   double* bz = ws_doubles(h, M.m);
   AP_CUDA(h, cudaMemsetAsync(XT, 0, need, h->stream));
   g.A = M.a; g.m = M.m; g.n = M.n; g.lda = M.ld; g.b = bz; g.L = L; g.XT = XT; g.ldx = ldx; g.ldr = ldr;
+  g.ksplit = ksplit; g.gstride = L * ldx;
   path_launch_gemm(h, which + 1, g);                                   // warm-up
   AP_CUDA(h, cudaEventRecord(h->ev0, h->stream));
   for (int r = 0; r < reps; ++r) path_launch_gemm(h, which + 1, g);

@@ -15,22 +15,26 @@
 // padded by 4 doubles (row stride = 32 bytes mod 128), so the fragment loads -- lane l reads element
 // [8 r + l / 4][k + l % 4] -- are bank-conflict free.
 //   mode 1 (R = A X - b):  M index = row i of A, N index = column j; A-operand A[i][k], B-operand XT[j][k].
-//   mode 2 (G = A' R):     M index = column j,   N index = column c of A; A-operand RT[j][i], B-operand A[i][c]
-//                          (the B tile is staged [k][n]: A is row-major, so c is the contiguous index).
+//   mode 2 (G = A' R):     M index = column c of A, N index = column j; A-operand A[i][c] staged [k][m], B-operand RT[j][i]
+//                          (A is row-major, so c is the contiguous index of the A tile).
 #pragma once
 #include "phases.cuh"
 
 namespace adaprox {
 
 constexpr int kGT = 512;                 // threads per CTA of the GEMM kernels
-constexpr int kGBM = 128, kGBN = 128, kGBK = 16, kGStages = 4;
+constexpr int kGBM = 128, kGBK = 16, kGStages = 4;
 constexpr int kGPadK = kGBK + 4;         // 20 doubles: row stride of the k-contiguous tiles
-constexpr int kGPadN = kGBN + 4;         // 132 doubles: row stride of the [k][n] tile of mode 2
-constexpr int kGATile = kGBM * kGPadK;                                   // doubles
-constexpr int kGBTile1 = kGBN * kGPadK;
-constexpr int kGBTile2 = kGBK * kGPadN;
-constexpr int kGStage = kGATile + (kGBTile1 > kGBTile2 ? kGBTile1 : kGBTile2);
-constexpr int kGSmemBytes = kGStages * kGStage * 8;                      // 163 840 B
+constexpr int kGPadM = kGBM + 4;         // 132 doubles: row stride of the [k][m] tile of mode 2 (32 B mod 128)
+// NT = 8-column DMMA tiles per warp along N: NT = 4 -> 128 x 128 CTA tile, NT = 1 -> 128 x 32 (narrow batches:
+// the lambdas of one rank when the path is split over 8 GPUs)
+template <int NT> struct GemmCfg {
+  static constexpr int BN = 32 * NT;
+  static constexpr int ATile = (kGBM * kGPadK > kGBK * kGPadM) ? kGBM * kGPadK : kGBK * kGPadM;   // doubles
+  static constexpr int BTile = BN * kGPadK;
+  static constexpr int Stage = ATile + BTile;
+  static constexpr int SmemBytes = kGStages * Stage * 8;                 // NT = 4: 163 840 B
+};
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
   // 16-byte global -> shared copy; bytes beyond src_bytes (0 or 16) are zero-filled
@@ -53,74 +57,88 @@ struct PathGemmArgs {
   double* RT; int64_t ldr;                  // [L][ldr]   (mode 1: output, mode 2: A operand)
   double* GT;                               // [L][ldx]   (mode 2: output)
   double* fpart;                            // [m tiles][L]  per-tile sums of r^2 (mode 1), reduced in tile order later
+  int ksplit;                               // mode 2: K = m is cut into ksplit slabs (blockIdx.z); slab z writes GT + z * gstride
+  int64_t gstride;                          //         (the slabs are summed in slab order by k_path_step: deterministic)
 };
 
-// MODE 1: RT[j][i] = sum_k A[i][k] XT[j][k] - b[i]  (+ fpart);   MODE 2: GT[j][c] = sum_i RT[j][i] A[i][c]
-template <int MODE>
+// MODE 1: RT[j][i] = sum_k A[i][k] XT[j][k] - b[i]  (+ fpart): M index = row i of A, N index = column j, K = n.
+//         A-operand A[i][k] and B-operand XT[j][k] are both k-contiguous.
+// MODE 2: GT[j][c] = sum_i A[i][c] RT[j][i]: M index = column c of A, N index = column j, K = m.
+//         A-operand A[i][c] is staged [k][m] (A is row-major, so c is the contiguous index), B-operand RT[j][i] is
+//         k-contiguous.  In both modes the batch is the N dimension, so a narrow batch only needs a narrow N tile.
+template <int MODE, int NT>
 __global__ void __launch_bounds__(kGT, 1) k_path_gemm(PathGemmArgs g) {
+  constexpr int kGBN = GemmCfg<NT>::BN, kGStage = GemmCfg<NT>::Stage;
   extern __shared__ __align__(16) double gsm[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = warp >> 2, wn = warp & 3;
-  const int64_t Mdim = (MODE == 1) ? g.m : g.L;
-  const int64_t Ndim = (MODE == 1) ? g.L : g.n;
+  const int64_t Mdim = (MODE == 1) ? g.m : g.n;
+  const int64_t Ndim = g.L;
   const int64_t Kdim = (MODE == 1) ? g.n : g.m;
   const int64_t m0 = (int64_t)blockIdx.x * kGBM, n0 = (int64_t)blockIdx.y * kGBN;
-  // operand descriptors
-  const double* Aop = (MODE == 1) ? g.A : g.RT;          // rows = M index, k contiguous
-  const int64_t lda = (MODE == 1) ? g.lda : g.ldr;
-  const int64_t a_kmax = (MODE == 1) ? g.lda : g.ldr;    // padded (zero-filled) extent that may be read
-  const double* Bop = (MODE == 1) ? g.XT : g.A;
-  const int64_t ldb = (MODE == 1) ? g.ldx : g.lda;
+  const double* Bop = (MODE == 1) ? g.XT : g.RT;         // rows = column j, k contiguous
+  const int64_t ldb = (MODE == 1) ? g.ldx : g.ldr;
   const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(gsm);
+  // k range of this CTA (mode 2 may split K over blockIdx.z; slabs are multiples of BK)
+  int64_t kbeg = 0, kend = Kdim;
+  if (MODE == 2 && g.ksplit > 1) {
+    const int64_t tiles = (Kdim + kGBK - 1) / kGBK;
+    const int64_t per = (tiles + g.ksplit - 1) / g.ksplit;
+    kbeg = (int64_t)blockIdx.z * per * kGBK;
+    kend = kbeg + per * kGBK;
+    if (kend > Kdim) kend = Kdim;
+    if (kbeg > kend) kbeg = kend;
+  }
 
   auto load_stage = [&](int stage, int64_t k0) {
     const uint32_t sa = smem0 + (uint32_t)(stage * kGStage) * 8;
-    const uint32_t sb = sa + kGATile * 8;
-    // A tile: 128 rows x 16 doubles = 128 x 8 chunks of 16 B
-#pragma unroll
-    for (int q = 0; q < (kGBM * kGBK / 2) / kGT; ++q) {
-      const int ch = tid + q * kGT;
-      const int r = ch >> 3, kc = (ch & 7) * 2;
-      const int64_t row = m0 + r, k = k0 + kc;
-      const bool ok = (row < Mdim) && (k + 2 <= a_kmax);
-      const double* src = Aop + (ok ? row * lda + k : 0);
-      cp_async16(sa + (uint32_t)(r * kGPadK + kc) * 8, src, ok ? 16 : 0);
-    }
+    const uint32_t sb = sa + GemmCfg<NT>::ATile * 8;
     if (MODE == 1) {
-      // B tile: 128 rows (columns j of X) x 16 doubles, k contiguous
+      // A tile: 128 rows i x 16 doubles (k contiguous) = 128 x 8 chunks of 16 B
 #pragma unroll
-      for (int q = 0; q < (kGBN * kGBK / 2) / kGT; ++q) {
+      for (int q = 0; q < (kGBM * kGBK / 2) / kGT; ++q) {
         const int ch = tid + q * kGT;
         const int r = ch >> 3, kc = (ch & 7) * 2;
-        const int64_t col = n0 + r, k = k0 + kc;
-        const bool ok = (col < Ndim) && (k + 2 <= ldb);
-        const double* src = Bop + (ok ? col * ldb + k : 0);
-        cp_async16(sb + (uint32_t)(r * kGPadK + kc) * 8, src, ok ? 16 : 0);
+        const int64_t row = m0 + r, k = k0 + kc;
+        const bool ok = (row < Mdim) && (k + 2 <= g.lda);               // the zero padding up to lda may be read
+        const double* src = g.A + (ok ? row * g.lda + k : 0);
+        cp_async16(sa + (uint32_t)(r * kGPadK + kc) * 8, src, ok ? 16 : 0);
       }
     } else {
-      // B tile: 16 rows (k = row i of A) x 128 columns c, c contiguous
+      // A tile: 16 rows (k = row i of A) x 128 columns c (c contiguous) = 16 x 64 chunks
 #pragma unroll
-      for (int q = 0; q < (kGBK * kGBN / 2) / kGT; ++q) {
+      for (int q = 0; q < (kGBK * kGBM / 2) / kGT; ++q) {
         const int ch = tid + q * kGT;
         const int r = ch >> 6, cc = (ch & 63) * 2;
-        const int64_t krow = k0 + r, col = n0 + cc;
-        const bool ok = (krow < Kdim) && (col + 2 <= ldb);
-        const double* src = Bop + (ok ? krow * ldb + col : 0);
-        cp_async16(sb + (uint32_t)(r * kGPadN + cc) * 8, src, ok ? 16 : 0);
+        const int64_t krow = k0 + r, col = m0 + cc;
+        const bool ok = (krow < kend) && (col + 2 <= g.lda);
+        const double* src = g.A + (ok ? krow * g.lda + col : 0);
+        cp_async16(sa + (uint32_t)(r * kGPadM + cc) * 8, src, ok ? 16 : 0);
       }
+    }
+    // B tile: BN rows (columns j of the batch) x 16 doubles, k contiguous
+#pragma unroll
+    for (int q = 0; q < (kGBN * kGBK / 2 + kGT - 1) / kGT; ++q) {
+      const int ch = tid + q * kGT;
+      if (ch >= kGBN * kGBK / 2) break;
+      const int r = ch >> 3, kc = (ch & 7) * 2;
+      const int64_t col = n0 + r, k = k0 + kc;
+      const bool ok = (col < Ndim) && (k + 2 <= ldb) && (MODE == 1 || k < kend);   // slabs end on even k (BK multiples or m padded)
+      const double* src = Bop + (ok ? col * ldb + k : 0);
+      cp_async16(sb + (uint32_t)(r * kGPadK + kc) * 8, src, ok ? 16 : 0);
     }
   };
 
-  double acc[4][4][2];
+  double acc[4][NT][2];
 #pragma unroll
   for (int r = 0; r < 4; ++r)
 #pragma unroll
-    for (int c = 0; c < 4; ++c) acc[r][c][0] = acc[r][c][1] = 0.0;
+    for (int c = 0; c < NT; ++c) acc[r][c][0] = acc[r][c][1] = 0.0;
 
-  const int64_t nk = (Kdim + kGBK - 1) / kGBK;
+  const int64_t nk = (kend - kbeg + kGBK - 1) / kGBK;
 #pragma unroll
   for (int s = 0; s < kGStages - 1; ++s) {
-    if (s < nk) load_stage(s, (int64_t)s * kGBK);
+    if (s < nk) load_stage(s, kbeg + (int64_t)s * kGBK);
     cp_async_commit();
   }
   const int lr = lane >> 2, lk = lane & 3;
@@ -129,27 +147,27 @@ __global__ void __launch_bounds__(kGT, 1) k_path_gemm(PathGemmArgs g) {
     __syncthreads();                                    // stage kt landed for every thread; stage kt-1 is free
     {
       const int64_t kn = kt + kGStages - 1;
-      if (kn < nk) load_stage((int)(kn % kGStages), kn * kGBK);
+      if (kn < nk) load_stage((int)(kn % kGStages), kbeg + kn * kGBK);
       cp_async_commit();
     }
     const double* sa = gsm + (size_t)(kt % kGStages) * kGStage;
-    const double* sb = sa + kGATile;
+    const double* sb = sa + GemmCfg<NT>::ATile;
 #pragma unroll
     for (int kk = 0; kk < kGBK; kk += 4) {
-      double a[4], b[4];
-#pragma unroll
-      for (int r = 0; r < 4; ++r) a[r] = sa[(wm * 32 + r * 8 + lr) * kGPadK + kk + lk];
+      double a[4], b[NT];
       if (MODE == 1) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) b[c] = sb[(wn * 32 + c * 8 + lr) * kGPadK + kk + lk];
+        for (int r = 0; r < 4; ++r) a[r] = sa[(wm * 32 + r * 8 + lr) * kGPadK + kk + lk];
       } else {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) b[c] = sb[(kk + lk) * kGPadN + wn * 32 + c * 8 + lr];
+        for (int r = 0; r < 4; ++r) a[r] = sa[(kk + lk) * kGPadM + wm * 32 + r * 8 + lr];
       }
+#pragma unroll
+      for (int c = 0; c < NT; ++c) b[c] = sb[(wn * 8 * NT + c * 8 + lr) * kGPadK + kk + lk];
 #pragma unroll
       for (int r = 0; r < 4; ++r)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) dmma_m8n8k4(acc[r][c][0], acc[r][c][1], a[r], b[c]);
+        for (int c = 0; c < NT; ++c) dmma_m8n8k4(acc[r][c][0], acc[r][c][1], a[r], b[c]);
     }
   }
   cp_async_wait<0>();
@@ -157,18 +175,18 @@ __global__ void __launch_bounds__(kGT, 1) k_path_gemm(PathGemmArgs g) {
   // epilogue.  Accumulator fragment: row = lane / 4 (M index within the 8 x 8 tile), cols = 2 (lane % 4) + {0, 1}.
   if (MODE == 1) {
     __shared__ double s_f[4][kGBN];                     // [wm][column within the CTA tile]
-    double fs[4][2];
+    double fs[NT][2];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) fs[c][0] = fs[c][1] = 0.0;
+    for (int c = 0; c < NT; ++c) fs[c][0] = fs[c][1] = 0.0;
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
       const int64_t i = m0 + wm * 32 + r * 8 + lr;
       const double bi = (i < g.m) ? __ldg(g.b + i) : 0.0;
 #pragma unroll
-      for (int c = 0; c < 4; ++c)
+      for (int c = 0; c < NT; ++c)
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-          const int64_t j = n0 + wn * 32 + c * 8 + 2 * lk + e;
+          const int64_t j = n0 + wn * 8 * NT + c * 8 + 2 * lk + e;
           if (i < g.m && j < g.L) {
             const double rv = acc[r][c][e] - bi;        // lasso/runme.jl:22
             g.RT[j * g.ldr + i] = rv;
@@ -178,14 +196,14 @@ __global__ void __launch_bounds__(kGT, 1) k_path_gemm(PathGemmArgs g) {
     }
     // sum over the 8 row-lanes (lane / 4) with a fixed xor tree, then over the 4 warps along M in fixed order
 #pragma unroll
-    for (int c = 0; c < 4; ++c)
+    for (int c = 0; c < NT; ++c)
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         double v = fs[c][e];
         v += __shfl_xor_sync(0xffffffffu, v, 4);
         v += __shfl_xor_sync(0xffffffffu, v, 8);
         v += __shfl_xor_sync(0xffffffffu, v, 16);
-        if (lr == 0) s_f[wm][wn * 32 + c * 8 + 2 * lk + e] = v;
+        if (lr == 0) s_f[wm][wn * 8 * NT + c * 8 + 2 * lk + e] = v;
       }
     __syncthreads();
     if (tid < kGBN) {
@@ -195,15 +213,14 @@ __global__ void __launch_bounds__(kGT, 1) k_path_gemm(PathGemmArgs g) {
   } else {
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-      const int64_t j = m0 + wm * 32 + r * 8 + lr;
+      const int64_t col = m0 + wm * 32 + r * 8 + lr;                     // column c of A = row of the accumulator tile
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const int64_t col = n0 + wn * 32 + c * 8 + 2 * lk;
-        if (j < g.L && col < g.n) {
-          if (col + 1 < g.n) *reinterpret_cast<double2*>(g.GT + j * g.ldx + col) = make_double2(acc[r][c][0], acc[r][c][1]);
-          else g.GT[j * g.ldx + col] = acc[r][c][0];
+      for (int c = 0; c < NT; ++c)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int64_t j = n0 + wn * 8 * NT + c * 8 + 2 * lk + e;
+          if (col < g.n && j < g.L) g.GT[(int64_t)blockIdx.z * g.gstride + j * g.ldx + col] = acc[r][c][e];   // lasso/runme.jl:23
         }
-      }
     }
   }
 }
@@ -223,6 +240,8 @@ struct PathStepArgs {
   DOpts O;
   double* XT[3];           // iterate ring [L][ldx]
   double* GT[2];           // gradient ring
+  const double* Gslab;     // mode-2 K slabs [ksplit][L][ldx] (ksplit > 1), summed in slab order into GT[it & 1]
+  int ksplit; int64_t gstride;
   double* VT;              // v = x - gamma g
   double* XoutT;           // result columns (frozen at convergence)
   const double* fpart;     // [mtiles][L]
@@ -243,6 +262,15 @@ __global__ void __launch_bounds__(kPT, 2) k_path_step(PathStepArgs a) {
   const double* x = a.XT[it % 3] + j * a.ldx;
   const double* x_prev = a.XT[(it + 2) % 3] + j * a.ldx;
   double* xn = a.XT[(it + 1) % 3] + j * a.ldx;
+  if (a.ksplit > 1) {
+    double* gw = a.GT[it & 1] + j * a.ldx;
+    for (int64_t q = threadIdx.x; q < a.n; q += kPT) {
+      double s = 0.0;
+      for (int z = 0; z < a.ksplit; ++z) s += a.Gslab[(int64_t)z * a.gstride + j * a.ldx + q];
+      gw[q] = s;
+    }
+    __syncthreads();
+  }
   const double* grad = a.GT[it & 1] + j * a.ldx;
   const double* grad_prev = a.GT[(it + 1) & 1] + j * a.ldx;
   double* v = a.VT + j * a.ldx;
