@@ -49,7 +49,7 @@ class Result(C.Structure):
                 ("A_evals", C.c_int64), ("At_evals", C.c_int64), ("n_records", C.c_int64),
                 ("final_gamma", C.c_double), ("final_sigma", C.c_double), ("final_norm_res", C.c_double),
                 ("solve_ms", C.c_double), ("kernel_launches", C.c_int64),
-                ("matrix_passes", C.c_int64)]
+                ("matrix_passes", C.c_int64), ("collective", C.c_int64)]
 
 
 # enum values of include/adaprox.h
@@ -94,6 +94,8 @@ SYMBOLS = {
     "adaprox_comm_unique_id": (C.c_int, [C.c_void_p]),
     "adaprox_comm_init": (C.c_int, [_h, C.c_int, C.c_int, C.c_void_p]),
     "adaprox_comm_info": (C.c_int, [_h, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "adaprox_p2p_export": (C.c_int, [_h, C.c_int64, C.c_void_p]),
+    "adaprox_p2p_attach": (C.c_int, [_h, C.c_int, C.c_int, C.c_void_p]),
     "adaprox_matrix_set_shard": (C.c_int, [_h, c_id, C.c_int64, C.c_int64]),
     "adaprox_time_kernel": (C.c_int, [_h, c_id, C.c_int, C.c_int, c_dp]),
 }

@@ -70,6 +70,16 @@ class Device:
         buf = C.create_string_buffer(unique_id, 128)
         self.check(self.lib.adaprox_comm_init(self.h, int(nranks), int(rank), buf))
 
+    def p2p_export(self, n_max) -> bytes:
+        """allocate this rank's peer-visible exchange block (vectors up to n_max) and return its 64-byte CUDA IPC handle"""
+        buf = C.create_string_buffer(64)
+        self.check(self.lib.adaprox_p2p_export(self.h, int(n_max), buf))
+        return buf.raw
+
+    def p2p_attach(self, nranks, rank, handles: bytes):
+        buf = C.create_string_buffer(handles, 64 * int(nranks))
+        self.check(self.lib.adaprox_p2p_attach(self.h, int(nranks), int(rank), buf))
+
     def close(self):
         if getattr(self, "h", None):
             self.lib.adaprox_destroy(self.h)
@@ -698,7 +708,7 @@ def _solve(solver, x0, y0, *, f, g, h=None, A=None, opts, name, log, pd):
                 d["At_evals"] = base["am"] + r.At_evals if cA else None
             d["f_evals"] = base["f"] + r.f_evals if cf else None
             log.append(d)
-    info = dict(flags=int(res.flags), solve_ms=res.solve_ms, kernel_launches=int(res.kernel_launches), matrix_passes=int(res.matrix_passes),
+    info = dict(flags=int(res.flags), solve_ms=res.solve_ms, kernel_launches=int(res.kernel_launches), matrix_passes=int(res.matrix_passes), collective=int(res.collective),
                 final_gamma=res.final_gamma, final_sigma=res.final_sigma, final_norm_res=res.final_norm_res)
     return x_out, (y_out[: p.m_dual] if pd else None), int(res.iters), info
 

@@ -790,6 +790,7 @@ extern "C" int adaprox_solve(adaprox_handle h, const adaprox_problem* p, const a
   res->final_gamma = dr.final_gamma; res->final_sigma = dr.final_sigma; res->final_norm_res = dr.final_norm_res;
   res->solve_ms = ms; res->kernel_launches = h->launches - launches0;
   res->matrix_passes = (P.F.kind == MAT_NONE) ? 0 : (fused ? 1 : 2);
+  res->collective = 0;
   return ADAPROX_OK;
 }
 

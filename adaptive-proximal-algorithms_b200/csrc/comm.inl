@@ -49,10 +49,26 @@ static NcclApi* nccl_api() {
   return &api;
 }
 
+// Peer-mapped exchange block of the in-kernel all-reduce (solver_fused.cuh, sweep-only mode):
+//   [ flags: kP2PMaxRanks x u64, padded to 1 KB ][ buffer 0: cap doubles ][ buffer 1: cap doubles ]
+// allocated with cudaMalloc by every rank, exported with cudaIpcGetMemHandle and opened by the peers.
+struct P2P {
+  bool attached = false;
+  int nranks = 1, rank = 0;
+  int64_t cap = 0;                               // doubles per buffer
+  char* local = nullptr;                         // this rank's block
+  char* peer[kP2PMaxRanks] = {};                 // every rank's block as mapped here (peer[rank] == local)
+  int* err = nullptr;                            // device flag: a peer did not show up
+};
+
 struct Comm {
   ncclComm_t comm = nullptr;
   int nranks = 1, rank = 0;
+  P2P p2p;
 };
+
+static constexpr size_t kP2PFlagBytes = 1024;
+static double* p2p_buf(char* block, int64_t cap, int which) { return reinterpret_cast<double*>(block + kP2PFlagBytes + (size_t)which * (size_t)cap * 8); }
 
 int comm_allreduce_sum(adaprox_ctx* h, double* buf_dev, int64_t count) {
   if (!h->comm) return fail(h, ADAPROX_ERR_COMM, "no communicator attached");
@@ -64,6 +80,12 @@ int comm_allreduce_sum(adaprox_ctx* h, double* buf_dev, int64_t count) {
 
 void comm_destroy(adaprox_ctx* h) {
   if (h->comm) {
+    P2P& pp = h->comm->p2p;
+    for (int q = 0; q < kP2PMaxRanks; ++q)
+      if (pp.peer[q] && pp.peer[q] != pp.local) cudaIpcCloseMemHandle(pp.peer[q]);
+    if (pp.local) cudaFree(pp.local);
+    if (pp.err) cudaFree(pp.err);
+    pp = P2P{};
     NcclApi* api = nccl_api();
     if (api->lib && h->comm->comm) api->CommDestroy(h->comm->comm);
     delete h->comm;
@@ -326,24 +348,35 @@ int solve_sharded(adaprox_ctx* h, const adaprox_problem* p, const adaprox_option
   };
 
   // fused path: launch L = finish iteration L-1 + sweep for x_L; launches 0 .. maxit+1 (the last one only finishes)
+  // in-kernel all-reduce over NVLink peer memory when the exchange blocks are attached and large enough.  Flags carry a
+  // monotonically increasing iteration number across solves (p2p_epoch): every rank performs the same solves in the same order.
+  const bool use_p2p = fused && h->comm->p2p.attached && h->comm->p2p.cap >= n + 2 && !std::getenv("ADAPROX_NO_P2P");
+  static long long p2p_epoch_next = 0;
+  const long long p2p_epoch = p2p_epoch_next;
+  if (use_p2p) p2p_epoch_next += O.maxit + 2;
   // fused path: one sweep kernel instead of k_sh_A .. k_sh_D
   auto one_iteration_fused = [&](int64_t it) -> int {
     a.it = it;
-    fa.bar_base = (unsigned long long)G * (unsigned long long)it;
+    fa.bar_base = (unsigned long long)(use_p2p ? 3 : 1) * (unsigned long long)G * (unsigned long long)it;   // grid barriers per launch
     fa.next_base = (unsigned long long)(fa.nchunks + fpl.Q) * (unsigned long long)it;
     fa.sweep_only = 1;
     fa.sh_x = a.W.xb[it % 3];
     fa.sh_gbuf = a.gbuf;
     fa.sh_done = &a.st[it & 1].done;
+    if (use_p2p) {
+      const P2P& pp = h->comm->p2p;
+      fa.p2p_n = pp.nranks; fa.p2p_rank = pp.rank; fa.p2p_it = p2p_epoch + it; fa.p2p_err = pp.err;
+      for (int q = 0; q < pp.nranks; ++q) {
+        fa.p2p_gloc[q] = p2p_buf(pp.peer[q], pp.cap, (int)((p2p_epoch + it) & 1));
+        fa.p2p_flags[q] = reinterpret_cast<unsigned long long*>(pp.peer[q]);
+      }
+    }
     void* fargs[] = {&a.P, &a.O, &a.W, &fa};
     cudaError_t e = cudaLaunchKernelExC(&fpl.cfg, (const void*)k_adapgm_fused, fargs);
     if (e != cudaSuccess) return fail(h, ADAPROX_ERR_CUDA, std::string("fused cluster launch (sharded): ") + cudaGetErrorString(e));
-    static const int dbg_skip = std::getenv("ADAPROX_DEBUG_SKIP") ? std::atoi(std::getenv("ADAPROX_DEBUG_SKIP")) : 0;
-    if (!(dbg_skip & 1)) { int r = comm_allreduce_sum(h, a.gbuf, n + 2); if (r) return r; }
-    if (!(dbg_skip & 2)) {
-      k_sh_E<<<h->grid, kThreads, 0, h->stream>>>(a);
-      k_sh_F<<<h->grid, kThreads, 0, h->stream>>>(a);
-    }
+    if (!use_p2p) { int r = comm_allreduce_sum(h, a.gbuf, n + 2); if (r) return r; }    // else: reduced inside the kernel
+    k_sh_E<<<h->grid, kThreads, 0, h->stream>>>(a);
+    k_sh_F<<<h->grid, kThreads, 0, h->stream>>>(a);
     h->launches += 3;
     return ADAPROX_OK;
   };
@@ -363,6 +396,11 @@ int solve_sharded(adaprox_ctx* h, const adaprox_problem* p, const adaprox_option
   }
   const int cur_idx = (int)(enqueued & 1);          // written by the last k_sh_F
   AP_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+  if (use_p2p) {
+    int perr = 0;
+    AP_CUDA(h, cudaMemcpy(&perr, h->comm->p2p.err, sizeof(int), cudaMemcpyDeviceToHost));
+    if (perr) return fail(h, ADAPROX_ERR_COMM, "in-kernel all-reduce: a peer rank did not arrive within 5 s");
+  }
   if (fused) fused_print_probe(fpl, "sharded fused");
   const ShState& cur = live[cur_idx];
   const bool converged = (cur.flags & ADAPROX_FLAG_CONVERGED) != 0;
@@ -382,6 +420,7 @@ int solve_sharded(adaprox_ctx* h, const adaprox_problem* p, const adaprox_option
   res->final_gamma = cur.gamma; res->final_sigma = cur.sigma; res->final_norm_res = cur.norm_res;
   res->solve_ms = ms; res->kernel_launches = h->launches - launches0;
   res->matrix_passes = fused ? 1 : 2;
+  res->collective = use_p2p ? 2 : 1;
   return ADAPROX_OK;
 }
 
@@ -411,6 +450,44 @@ extern "C" int adaprox_comm_init(adaprox_handle h, int nranks, int rank, const v
   ncclResult_t r = api->CommInitRank(&c->comm, nranks, id, rank);
   if (r != ncclSuccess) { delete c; return adaprox::fail(h, ADAPROX_ERR_COMM, std::string("ncclCommInitRank: ") + api->GetErrorString(r)); }
   h->comm = c;
+  return ADAPROX_OK;
+}
+
+extern "C" int adaprox_p2p_export(adaprox_handle h, int64_t n_max, void* ipc_handle64) {
+  if (!h || !ipc_handle64 || n_max < 1) return adaprox::fail(h, ADAPROX_ERR_INVALID, "p2p_export: bad arguments");
+  if (!h->comm) return adaprox::fail(h, ADAPROX_ERR_COMM, "p2p_export: call adaprox_comm_init first");
+  AP_CUDA(h, cudaSetDevice(h->device));
+  adaprox::P2P& pp = h->comm->p2p;
+  if (pp.local) return adaprox::fail(h, ADAPROX_ERR_INVALID, "p2p_export: already exported on this handle");
+  pp.cap = (n_max + 2 + 15) / 16 * 16;
+  const size_t bytes = adaprox::kP2PFlagBytes + 2 * (size_t)pp.cap * 8;
+  AP_CUDA(h, cudaMalloc(&pp.local, bytes));
+  AP_CUDA(h, cudaMemset(pp.local, 0, bytes));
+  AP_CUDA(h, cudaMalloc(&pp.err, sizeof(int)));
+  AP_CUDA(h, cudaMemset(pp.err, 0, sizeof(int)));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  cudaIpcMemHandle_t hd;
+  AP_CUDA(h, cudaIpcGetMemHandle(&hd, pp.local));
+  std::memcpy(ipc_handle64, &hd, 64);
+  return ADAPROX_OK;
+}
+
+extern "C" int adaprox_p2p_attach(adaprox_handle h, int nranks, int rank, const void* ipc_handles) {
+  if (!h || !ipc_handles || nranks < 1 || nranks > adaprox::kP2PMaxRanks || rank < 0 || rank >= nranks)
+    return adaprox::fail(h, ADAPROX_ERR_INVALID, "p2p_attach: bad arguments (at most 8 ranks)");
+  if (!h->comm || !h->comm->p2p.local) return adaprox::fail(h, ADAPROX_ERR_COMM, "p2p_attach: call adaprox_p2p_export first");
+  if (h->comm->nranks != nranks || h->comm->rank != rank) return adaprox::fail(h, ADAPROX_ERR_INVALID, "p2p_attach: ranks differ from adaprox_comm_init");
+  AP_CUDA(h, cudaSetDevice(h->device));
+  adaprox::P2P& pp = h->comm->p2p;
+  for (int q = 0; q < nranks; ++q) {
+    if (q == rank) { pp.peer[q] = pp.local; continue; }
+    cudaIpcMemHandle_t hd;
+    std::memcpy(&hd, static_cast<const char*>(ipc_handles) + 64 * q, 64);
+    void* p = nullptr;
+    AP_CUDA(h, cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess));
+    pp.peer[q] = static_cast<char*>(p);
+  }
+  pp.nranks = nranks; pp.rank = rank; pp.attached = true;
   return ADAPROX_OK;
 }
 

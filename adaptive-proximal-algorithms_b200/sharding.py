@@ -38,3 +38,18 @@ def attach_communicator(dev, dist=None):
     dist.broadcast_object_list(box, src=0)
     dev.comm_init(world, rank, box[0])
     return world, rank
+
+
+def attach_p2p(dev, n_max, dist=None):
+    """Enable the in-kernel all-reduce over NVLink peer memory (include/adaprox.h: adaprox_p2p_*): every rank exports its
+    exchange block, the 64-byte IPC handles are all-gathered through ``torch.distributed`` and every rank maps its
+    peers' blocks.  Call after ``attach_communicator``; at most 8 ranks on one node."""
+    if dist is None:
+        import torch.distributed as dist
+    rank, world = dist.get_rank(), dist.get_world_size()
+    mine = dev.p2p_export(n_max)
+    handles = [None] * world
+    dist.all_gather_object(handles, mine)
+    dev.p2p_attach(world, rank, b"".join(handles))
+    dist.barrier()
+    return world, rank

@@ -220,6 +220,8 @@ def run_b200(args):
     AdaProx.set_default_device(dev)
     if world > 1:
         AdaProx.sharding.attach_communicator(dev, dist)
+        if not args.nccl:
+            AdaProx.sharding.attach_p2p(dev, args.n, dist)       # all-reduce inside the sweep kernel over NVLink peer memory
 
     m, n = args.m, args.n
     row0, rows = AdaProx.sharding.shard_rows(m, world, rank)
@@ -303,7 +305,9 @@ def run_b200(args):
         bytes_launch = bytes_iter_rank * K + passes * 8 * rows * n
         achieved = bytes_launch / (dev_ms * 1e-3) / 1e9            # per-GPU GB/s actually required of HBM
         per_eval, per_eval_src = ncu_traffic_per_eval(m, n, passes) if world == 1 else (None, None)
-        if world > 1:
+        if world > 1 and passes == 1:
+            kernel = "k_adapgm_fused in sweep-only mode (one sweep of the row shard per iteration)"
+        elif world > 1:
             kernel = "k_sh_A + k_sh_C (split-phase GEMV kernels)"
         elif passes == 1:
             kernel = ("k_adapgm_fused (persistent cooperative cluster kernel: the whole solve is one launch; "
@@ -331,7 +335,8 @@ def run_b200(args):
                          "traffic": (per_eval * (K + 1)) if per_eval else None, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": bytes_launch,
                          "launch": "one persistent launch = K iterations + prologue = K+1 gradient evaluations" if world == 1
-                                   else "K+1 gradient evaluations as 6 launches + 1 all-reduce each",
+                                   else ("K+1 gradient evaluations as 3 launches each (fused sweep + all-reduce, 2 small kernels)" if passes == 1
+                                         else "K+1 gradient evaluations as 6 launches + 1 all-reduce each"),
                          "traffic_source": ("ncu dram__bytes_read.sum + dram__bytes_write.sum per gradient evaluation x (K+1), "
                                             + per_eval_src) if per_eval else None,
                          "kernel": kernel, "matrix_passes": passes,
@@ -342,6 +347,8 @@ def run_b200(args):
                     "d2h_bytes_per_step": (n * 8 + K * C.sizeof(L.Record) + C.sizeof(L.Result)) / K,
                     "call": "one blocking adaprox_solve (C ABI) of K iterations: x0 from pinned host memory, x and K records copied back"},
             "gpu_launches": launches,
+            "collective": {0: "none", 1: "ncclAllReduce of n+2 doubles per iteration",
+                           2: "all-reduce inside the sweep kernel over NVLink peer memory (no NCCL on the data path)"}[int(res.collective)],
             "clocks": clocks,
             "final_record": {"it": int(last.it), "gamma": last.gamma, "norm_res": last.norm_res,
                              "objective": last.f_x + last.g_x, "optimum": P["optimum"]},
@@ -369,6 +376,7 @@ def main():
     ap.add_argument("--tol-maxit", type=int, default=20000)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--two-pass", action="store_true", help="A/B: force the two-pass kernel (ADAPROX_FUSED=0)")
+    ap.add_argument("--nccl", action="store_true", help="A/B (N > 1): ncclAllReduce per iteration instead of the in-kernel all-reduce")
     ap.add_argument("--cpu-steps", type=int, default=20)
     ap.add_argument("--cpu-rows", type=int, default=None)
     args = ap.parse_args()

@@ -150,6 +150,8 @@ typedef struct {
   int64_t kernel_launches;      /* library kernels launched by this call                 */
   int64_t matrix_passes;        /* sweeps over the matrix of f per gradient evaluation: 1 = single-pass
                                    fused A'(Ax-b) kernel, 2 = A*x then A'*r; 0 = f has no matrix        */
+  int64_t collective;           /* row-sharded solves: 1 = ncclAllReduce per iteration, 2 = all-reduce inside the sweep
+                                   kernel over NVLink peer memory; 0 = single GPU                       */
 } adaprox_result;
 
 /* ---- life cycle ------------------------------------------------------------- */
@@ -234,6 +236,12 @@ int adaprox_time_path_gemm(adaprox_handle h, adaprox_id mat, int64_t L, int whic
 int adaprox_comm_unique_id(void* id128);
 int adaprox_comm_init(adaprox_handle h, int nranks, int rank, const void* id128);
 int adaprox_comm_info(adaprox_handle h, int* nranks, int* rank);
+/* Optional: in-kernel all-reduce over NVLink peer memory for row-sharded dense least squares (replaces the NCCL call
+ * of every iteration).  After comm_init every rank calls p2p_export (allocates its exchange block for vectors of up to
+ * n_max entries and returns a 64-byte CUDA IPC handle), the host side all-gathers the handles (rank order), every rank
+ * calls p2p_attach.  All ranks must then issue the same sharded solves in the same order. */
+int adaprox_p2p_export(adaprox_handle h, int64_t n_max, void* ipc_handle64);
+int adaprox_p2p_attach(adaprox_handle h, int nranks, int rank, const void* ipc_handles);
 /* mark a matrix as the local row block [row0, row0+rows) of an m_global-row matrix */
 int adaprox_matrix_set_shard(adaprox_handle h, adaprox_id mat, int64_t m_global, int64_t row0);
 

@@ -51,7 +51,7 @@ mutable struct CResult
     iters::Int64; flags::UInt32; reserved::Int32
     f_evals::Int64; grad_f_evals::Int64; prox_g_evals::Int64; prox_h_evals::Int64; A_evals::Int64; At_evals::Int64
     n_records::Int64
-    final_gamma::Float64; final_sigma::Float64; final_norm_res::Float64; solve_ms::Float64; kernel_launches::Int64; matrix_passes::Int64
+    final_gamma::Float64; final_sigma::Float64; final_norm_res::Float64; solve_ms::Float64; kernel_launches::Int64; matrix_passes::Int64; collective::Int64
     CResult() = new(0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0.0, 0.0, 0.0, 0.0, 0)
 end
 

@@ -12,6 +12,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def _worker(rank, world, port, out, fused):
     sys.path.insert(0, ROOT)
+    p2p = fused == "p2p"
+    fused = "1" if p2p else fused
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), LOCAL_RANK=str(rank), ADAPROX_FUSED=fused)
     m2, n2, pf2 = (512, 4100, 40) if fused == "0" else (256, 20000, 200)     # fused: clusters of 3 CTAs
     import torch.distributed as dist
@@ -20,6 +22,8 @@ def _worker(rank, world, port, out, fused):
     dev = AdaProx.Device(rank)
     AdaProx.set_default_device(dev)
     AdaProx.sharding.attach_communicator(dev, dist)
+    if p2p:
+        AdaProx.sharding.attach_p2p(dev, 20000, dist)          # in-kernel all-reduce over peer memory instead of NCCL
     m, n = 400, 1000
     P = AdaProx.synth.planted_lasso(m, n, 5, 0)
     Lf = AdaProx.synth.spectral_norm_sq(P["A"], iters=1000, tol=1e-15)
@@ -47,23 +51,24 @@ def _worker(rank, world, port, out, fused):
     gam_sh = np.array([r["gamma"] for r in log2[:100]]); gam_1 = np.array([r["gamma"] for r in log3[:100]])
     np.savez(out % rank, x=x, it=it, gam=np.array([r["gamma"] for r in log[:40]]), obj=log[-1]["objective"],
              counts=np.array([f.eval_count, f.grad_count, g.prox_count]), obj2=log2[-1]["objective"], opt2=Pd["optimum"],
-             res2=log2[-1]["norm_res"], x2err=np.linalg.norm(x2 - Pd["x_star"]), launches=info2["kernel_launches"], passes=info2["matrix_passes"], it2=it2,
+             res2=log2[-1]["norm_res"], x2err=np.linalg.norm(x2 - Pd["x_star"]), launches=info2["kernel_launches"], passes=info2["matrix_passes"], it2=it2, collective=info2["collective"],
              obj_sh=obj_sh, obj_1=obj_1, gam_sh=gam_sh, gam_1=gam_1)
     dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("fused", ["0", "1"])
+@pytest.mark.parametrize("fused", ["0", "1", "p2p"])
 def test_sharded_adapgm_two_gpus(tmp_path, lasso_small, fused):
-    """fused = "0": six split-phase launches per iteration (two sweeps over the shard); fused = "1": the single-pass
-    cluster kernel k_sh_fused, one launch per iteration."""
+    """fused = "0": six split-phase launches per iteration (two sweeps over the shard) + ncclAllReduce; "1": the single-sweep
+    cluster kernel in sweep-only mode + ncclAllReduce; "p2p": the same kernel with the all-reduce done inside it over NVLink
+    peer memory (CUDA IPC mapped exchange buffers, system-scope flags)."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
     from oracle import adaprox_oracle as O
     out = str(tmp_path / "rank%d.npz")
-    mp.spawn(_worker, args=(2, 29400 + os.getpid() % 500 + 500 * int(fused), out, fused), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, 29400 + os.getpid() % 500 + 500 * ["0", "1", "p2p"].index(fused), out, fused), nprocs=2, join=True)
     R0, R1 = np.load(out % 0), np.load(out % 1)
     # replicated state stays in lock step: bit-identical iterates on both ranks
     assert np.array_equal(R0["x"], R1["x"]) and int(R0["it"]) == int(R1["it"])
@@ -83,6 +88,7 @@ def test_sharded_adapgm_two_gpus(tmp_path, lasso_small, fused):
         assert float(R0["x2err"]) < 1e-5
     assert np.allclose(R0["obj_sh"], R0["obj_1"], rtol=1e-9) and np.allclose(R0["gam_sh"][:20], R0["gam_1"][:20], rtol=1e-11)
     assert np.array_equal(R0["obj_sh"], R1["obj_sh"])
-    assert int(R0["passes"]) == (1 if fused == "1" else 2)
-    if fused == "1":
+    assert int(R0["passes"]) == (2 if fused == "0" else 1)
+    assert int(R0["collective"]) == (2 if fused == "p2p" else 1)
+    if fused != "0":
         assert int(R0["launches"]) == 3 * (int(R0["it2"]) + 1)      # sweep kernel + E + F per gradient evaluation

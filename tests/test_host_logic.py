@@ -39,7 +39,7 @@ def test_struct_layouts_match_the_header():
     assert C.sizeof(L.Prox) == 4 + 4 + 8 * 3 + 8 * 3 == 56
     assert C.sizeof(L.Problem) == 4 + 4 + 8 + 8 + 8 + 56 + 56 + 8 + 8 + 8 == 168
     assert C.sizeof(L.Record) == 8 + 8 * 6 + 8 * 6 == 104
-    assert C.sizeof(L.Result) == 8 + 4 + 4 + 8 * 6 + 8 + 8 * 3 + 8 + 8 + 8 == 120
+    assert C.sizeof(L.Result) == 8 + 4 + 4 + 8 * 6 + 8 + 8 * 3 + 8 + 8 + 8 + 8 == 128
     assert C.sizeof(L.Options) == 4 + 4 + 8 * 18 + 8 + 4 * 5 + 4 + 8 == 192
 
 
