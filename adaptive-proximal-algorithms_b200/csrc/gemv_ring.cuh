@@ -47,8 +47,13 @@ __device__ __forceinline__ void mbar_arrive(uint32_t addr) {
 __device__ __forceinline__ void mbar_wait(uint32_t addr, uint32_t parity) {
   uint32_t ok;
   do {
+#ifdef ADAPROX_RING_POLL
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+#else
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                  : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+#endif
   } while (!ok);
 }
 // global -> shared bulk copy completing on an mbarrier (bytes: multiple of 16; both addresses 16-byte aligned)

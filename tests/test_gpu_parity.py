@@ -671,3 +671,69 @@ def test_lambda_path_equals_single_solves_on_device(AdaProx):
     assert np.all(info["norm_res"][its < 6000] <= 1e-5) and (its < 6000).sum() >= Lc // 2
     with pytest.raises(Exception):
         AdaProx.adaptive_proxgrad_path(None, f=f, lambdas=[-1.0], rule=AdaProx.OurRule(gamma=1 / Lf))
+
+
+# ---------------------------------------------------------------- edge cases of the fused sweep and the lambda path
+def test_fused_edge_cases(AdaProx):
+    """Fewer rows than clusters, a single row, maxit = 1, chunk size 1 (every row its own chunk), and the fallback to the
+    two-pass kernel when the row does not fit a 16-CTA cluster (n > 131072)."""
+    import os
+    rng = np.random.default_rng(3)
+
+    def both(A, b, lam, gamma, maxit, env=None):
+        res = {}
+        for mode in ("0", "1"):
+            os.environ["ADAPROX_FUSED"] = mode
+            for k, v in (env or {}).items():
+                os.environ[k] = v
+            try:
+                log = []
+                x, it = AdaProx.adaptive_proxgrad(np.zeros(A.shape[1]), f=AdaProx.LinearLeastSquares(A, b), g=AdaProx.NormL1(lam),
+                                                  rule=AdaProx.OurRule(gamma=gamma), tol=1e-9, maxit=maxit, log=log)
+                res[mode] = (x, it, [r["gamma"] for r in log], [r["objective"] for r in log], AdaProx.last_solve_info()["matrix_passes"])
+            finally:
+                os.environ.pop("ADAPROX_FUSED", None)
+                for k in (env or {}):
+                    os.environ.pop(k, None)
+        return res
+
+    for (m, n, maxit, env) in [(3, 700, 40, None), (1, 64, 25, None), (50, 9000, 1, None), (37, 1200, 30, {"ADAPROX_FUSED_CHUNK": "1"}),
+                               (64, 300, 30, {"ADAPROX_FUSED_CHUNK": "1000000"})]:
+        A = rng.standard_normal((m, n)) / np.sqrt(n)
+        b = rng.standard_normal(m)
+        gam = 0.5 / np.linalg.norm(A, 2) ** 2
+        R = both(A, b, 0.05, gam, maxit, env)
+        assert R["0"][4] == 2 and R["1"][4] == 1
+        assert R["0"][1] == R["1"][1]
+        assert np.allclose(R["0"][2], R["1"][2], rtol=1e-10) and np.allclose(R["0"][3], R["1"][3], rtol=1e-11)
+        assert np.allclose(R["0"][0], R["1"][0], rtol=1e-8, atol=1e-12)
+        lo = []
+        O.adaptive_proxgrad(np.zeros(n), f=O.LinearLeastSquares(A, b), g=O.NormL1(0.05), rule=O.OurRule(gamma=gam), tol=1e-9, maxit=maxit, log=lo)
+        assert np.allclose(R["1"][2], [r["gamma"] for r in lo], rtol=1e-9)
+    # n > 16 * 8192: not eligible, silently the two-pass kernel (same results)
+    n = 131072 + 16
+    A = np.zeros((2, n)); A[0, 0] = 1.0; A[1, n - 1] = 2.0; A[0, 5] = 0.5
+    R = both(A, np.array([1.0, -1.0]), 0.01, 0.1, 20)
+    assert R["1"][4] == 2 and np.array_equal(R["0"][0], R["1"][0])
+
+
+def test_lambda_path_edge_cases(AdaProx):
+    """One lambda, one row, lambda = 0, sizes far from the tile sizes, maxit = 1; 65 lambdas (first width above the narrow tile)."""
+    rng = np.random.default_rng(4)
+    for (m, n, Lc, maxit) in [(1, 40, 1, 30), (33, 17, 3, 50), (70, 260, 65, 40), (129, 131, 2, 1)]:
+        A = rng.standard_normal((m, n)) / np.sqrt(max(n, 1))
+        b = rng.standard_normal(m)
+        gam = 0.5 / max(np.linalg.norm(A, 2) ** 2, 1e-12)
+        lambdas = np.linspace(0.0, 0.3, Lc)
+        f = AdaProx.LinearLeastSquares(A, b)
+        X, its, info = AdaProx.adaptive_proxgrad_path(None, f=f, lambdas=lambdas, rule=AdaProx.OurRule(gamma=gam), tol=1e-8, maxit=maxit, history=maxit)
+        Xo, itso, gh, rh, oh = O.adaptive_proxgrad_path(np.zeros((n, Lc)), f=O.LinearLeastSquares(A, b), lambdas=lambdas,
+                                                       rule_of=lambda j: O.OurRule(gamma=gam), tol=1e-8, maxit=maxit, history=maxit)
+        K = min(maxit, 20)
+        live = ~np.isnan(gh[:K]) & ~np.isnan(info["gamma_hist"][:K])
+        assert live.any()
+        assert np.allclose(info["gamma_hist"][:K][live], gh[:K][live], rtol=1e-9)
+        assert np.allclose(info["obj_hist"][:K][live], oh[:K][live], rtol=1e-9, atol=1e-13)
+        assert np.all(np.abs(its - itso) <= np.maximum(2, 0.1 * itso))
+        ok = its == itso
+        assert np.allclose(X[:, ok], Xo[:, ok], rtol=1e-6, atol=1e-9)
