@@ -70,6 +70,27 @@ struct Comm {
 static constexpr size_t kP2PFlagBytes = 1024;
 static double* p2p_buf(char* block, int64_t cap, int which) { return reinterpret_cast<double*>(block + kP2PFlagBytes + (size_t)which * (size_t)cap * 8); }
 
+// kernel-side view of the exchange blocks (p2p.cuh)
+void p2p_fill(adaprox_ctx* h, P2PArgs* pa) {
+  *pa = P2PArgs{};
+  if (!h->comm || !h->comm->p2p.attached) return;
+  const P2P& pp = h->comm->p2p;
+  pa->n = pp.nranks; pa->rank = pp.rank; pa->cap = pp.cap; pa->err = pp.err;
+  for (int q = 0; q < pp.nranks; ++q) {
+    pa->buf[q][0] = p2p_buf(pp.peer[q], pp.cap, 0);
+    pa->buf[q][1] = p2p_buf(pp.peer[q], pp.cap, 1);
+    pa->flags[q] = reinterpret_cast<unsigned long long*>(pp.peer[q]);
+  }
+}
+bool p2p_ready(adaprox_ctx* h, int64_t count) { return h->comm && h->comm->p2p.attached && h->comm->p2p.cap >= count; }
+int p2p_check(adaprox_ctx* h) {
+  if (!h->comm || !h->comm->p2p.err) return ADAPROX_OK;
+  int perr = 0;
+  AP_CUDA(h, cudaMemcpy(&perr, h->comm->p2p.err, sizeof(int), cudaMemcpyDeviceToHost));
+  if (perr) return fail(h, ADAPROX_ERR_COMM, "in-kernel all-reduce: a peer rank did not arrive within 5 s");
+  return ADAPROX_OK;
+}
+
 int comm_allreduce_sum(adaprox_ctx* h, double* buf_dev, int64_t count) {
   if (!h->comm) return fail(h, ADAPROX_ERR_COMM, "no communicator attached");
   NcclApi* api = nccl_api();
@@ -348,29 +369,18 @@ int solve_sharded(adaprox_ctx* h, const adaprox_problem* p, const adaprox_option
   };
 
   // fused path: launch L = finish iteration L-1 + sweep for x_L; launches 0 .. maxit+1 (the last one only finishes)
-  // in-kernel all-reduce over NVLink peer memory when the exchange blocks are attached and large enough.  Flags carry a
-  // monotonically increasing iteration number across solves (p2p_epoch): every rank performs the same solves in the same order.
+  // in-kernel all-reduce over NVLink peer memory when the exchange blocks are attached and large enough (p2p.cuh)
   const bool use_p2p = fused && h->comm->p2p.attached && h->comm->p2p.cap >= n + 2 && !std::getenv("ADAPROX_NO_P2P");
-  static long long p2p_epoch_next = 0;
-  const long long p2p_epoch = p2p_epoch_next;
-  if (use_p2p) p2p_epoch_next += O.maxit + 2;
   // fused path: one sweep kernel instead of k_sh_A .. k_sh_D
   auto one_iteration_fused = [&](int64_t it) -> int {
     a.it = it;
-    fa.bar_base = (unsigned long long)(use_p2p ? 3 : 1) * (unsigned long long)G * (unsigned long long)it;   // grid barriers per launch
+    fa.bar_base = (unsigned long long)(use_p2p ? 4 : 1) * (unsigned long long)G * (unsigned long long)it;   // grid barriers per launch
     fa.next_base = (unsigned long long)(fa.nchunks + fpl.Q) * (unsigned long long)it;
     fa.sweep_only = 1;
     fa.sh_x = a.W.xb[it % 3];
     fa.sh_gbuf = a.gbuf;
     fa.sh_done = &a.st[it & 1].done;
-    if (use_p2p) {
-      const P2P& pp = h->comm->p2p;
-      fa.p2p_n = pp.nranks; fa.p2p_rank = pp.rank; fa.p2p_it = p2p_epoch + it; fa.p2p_err = pp.err;
-      for (int q = 0; q < pp.nranks; ++q) {
-        fa.p2p_gloc[q] = p2p_buf(pp.peer[q], pp.cap, (int)((p2p_epoch + it) & 1));
-        fa.p2p_flags[q] = reinterpret_cast<unsigned long long*>(pp.peer[q]);
-      }
-    }
+    if (use_p2p) p2p_fill(h, &fa.p2p);
     void* fargs[] = {&a.P, &a.O, &a.W, &fa};
     cudaError_t e = cudaLaunchKernelExC(&fpl.cfg, (const void*)k_adapgm_fused, fargs);
     if (e != cudaSuccess) return fail(h, ADAPROX_ERR_CUDA, std::string("fused cluster launch (sharded): ") + cudaGetErrorString(e));
@@ -396,11 +406,7 @@ int solve_sharded(adaprox_ctx* h, const adaprox_problem* p, const adaprox_option
   }
   const int cur_idx = (int)(enqueued & 1);          // written by the last k_sh_F
   AP_CUDA(h, cudaEventRecord(h->ev1, h->stream));
-  if (use_p2p) {
-    int perr = 0;
-    AP_CUDA(h, cudaMemcpy(&perr, h->comm->p2p.err, sizeof(int), cudaMemcpyDeviceToHost));
-    if (perr) return fail(h, ADAPROX_ERR_COMM, "in-kernel all-reduce: a peer rank did not arrive within 5 s");
-  }
+  if (use_p2p && (rc = p2p_check(h))) return rc;
   if (fused) fused_print_probe(fpl, "sharded fused");
   const ShState& cur = live[cur_idx];
   const bool converged = (cur.flags & ADAPROX_FLAG_CONVERGED) != 0;

@@ -21,6 +21,7 @@
 // only after it has read the partials of row i.
 #pragma once
 #include "phases.cuh"
+#include "p2p.cuh"
 
 namespace adaprox {
 
@@ -35,8 +36,6 @@ constexpr int kFStageBytes = kFCols * 8;                  // 64 KB
 constexpr int kFRingBytes = kFStages * kFStageBytes;      // 192 KB dynamic shared memory
 constexpr int kFMaxCluster = 16;
 constexpr int kFDepth = 8;                                // exchange-buffer depth (see fused_pass)
-
-constexpr int kP2PMaxRanks = 8;
 
 struct FusedArgs {
   double* gpartf;      // [nchunks][npadf] per-chunk A'r partials
@@ -54,12 +53,7 @@ struct FusedArgs {
   const double* sh_x;
   double* sh_gbuf;
   const int* sh_done;            // the solve has stopped: do nothing
-  // in-kernel all-reduce over peer-mapped buffers (NVLink), replaces ncclAllReduce when attached (p2p_n > 1):
-  int p2p_n, p2p_rank;
-  long long p2p_it;              // iteration number of this launch (flags carry it + 1)
-  double* p2p_gloc[kP2PMaxRanks];              // rank q's exchange buffer of THIS iteration's parity (own rank: local pointer)
-  unsigned long long* p2p_flags[kP2PMaxRanks]; // rank q's flag array [kP2PMaxRanks] (own rank: local pointer)
-  int* p2p_err;                  // set when a peer did not show up within the timeout
+  P2PArgs p2p;                   // in-kernel all-reduce over peer-mapped buffers (p2p.cuh); p2p.n <= 1: ncclAllReduce by the host
   unsigned long long* lat;       // optional [grid][4] probe (ADAPROX_FUSED_LAT): chunks taken, sweep ns, -, smid
 };
 
@@ -458,79 +452,26 @@ __global__ void __launch_bounds__(kFThreads, 1) k_adapgm_fused(DProblem P, DOpts
       if (fa.lat && threadIdx.x == 0) { fa.lat[4 * b + 1] = globaltimer_ns() - tq0; unsigned sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); fa.lat[4 * b + 3] = sm; }
     }
     grid.sync();
-    if (fa.p2p_n <= 1) {
+    if (fa.p2p.n <= 1) {
       if (!done) {
         fused_gradient_slice(fa, j0, j1, fa.sh_gbuf);
         const double f0 = fused_fsum(fa, scr);
         if (b == 0 && threadIdx.x == 0) { fa.sh_gbuf[P.n] = f0; fa.sh_gbuf[P.n + 1] = 0.0; }
       }
     } else {
-      // ---- all-reduce inside the kernel, over NVLink peer memory (every rank runs this with identical `done`) ----
-      // NOTE: this branch performs exactly two more grid barriers whether or not the solve has stopped (the host
-      // computes fa.bar_base from a fixed number of barriers per launch).
-      // Flag words in every rank's block: [q] = "rank q has published iteration T" (value T + 1), [8 + q] = "rank q has
-      // finished READING iteration T", [16] = T + 1 of this rank's last exchange.  Bounded spins; one poller per peer.
-      const unsigned long long want = (unsigned long long)(fa.p2p_it + 1);
-      unsigned long long* myflags = fa.p2p_flags[fa.p2p_rank];
-      auto wait_ge = [&](const unsigned long long* src, unsigned long long v) {
-        const unsigned long long t0 = globaltimer_ns();
-        unsigned long long seen;
-        for (unsigned spin = 0;; ++spin) {
-          asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(src) : "memory");
-          if (seen >= v) break;
-          if ((spin & 1023u) == 1023u && globaltimer_ns() - t0 > 5000000000ull) { *fa.p2p_err = 1; break; }
-        }
-      };
-      // 0. the buffer about to be overwritten was last read by the peers during this rank's previous exchange (possibly
-      //    in an earlier solve): wait until all of them have reported that they finished reading it
-      if (!done && threadIdx.x < fa.p2p_n) {
-        unsigned long long last;
-        asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(last) : "l"(myflags + 16) : "memory");
-        wait_ge(myflags + 8 + threadIdx.x, last);
-      }
-      __syncthreads();
-      // 1. this rank's partial gradient and value sum -> its exchange buffer
+      // All-reduce inside the kernel over NVLink peer memory (p2p.cuh).  Every rank holds the same `done`, and this
+      // branch performs exactly three more grid barriers whether or not the solve has stopped (the host computes
+      // fa.bar_base from a fixed number of barriers per launch).
+      P2PState ps;
+      p2p_begin(fa.p2p, ps);
       if (!done) {
-        double* mine = fa.p2p_gloc[fa.p2p_rank];
-        fused_gradient_slice(fa, j0, j1, mine);
+        fused_gradient_slice(fa, j0, j1, fa.sh_gbuf);          // this rank's partial gradient (each CTA its own slice)
         const double f0 = fused_fsum(fa, scr);
-        if (b == 0 && threadIdx.x == 0) { mine[P.n] = f0; mine[P.n + 1] = 0.0; }
+        if (b == 0 && threadIdx.x == 0) { fa.sh_gbuf[P.n] = f0; fa.sh_gbuf[P.n + 1] = 0.0; }
       }
-      grid.sync();                                             // every CTA's part of the buffer is written
-      // 2. tell every peer: flags_q[my rank] = T + 1 (one thread per peer; system-scope release)
-      if (!done && b == 0 && threadIdx.x < fa.p2p_n) {
-        __threadfence_system();
-        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(fa.p2p_flags[threadIdx.x] + fa.p2p_rank), "l"(want) : "memory");
-      }
-      // 3. wait until every rank has published (the flags live in OUR memory)
-      if (!done && threadIdx.x < fa.p2p_n) wait_ge(myflags + threadIdx.x, want);
-      __syncthreads();
-      // 4. sum the ranks' buffers in rank order: the same bits on every rank
-      for (int64_t j = j0 + threadIdx.x; !done && j < j1; j += kFThreads) {
-        double s = 0.0;
-        for (int q = 0; q < fa.p2p_n; ++q) {
-          double v;
-          asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(fa.p2p_gloc[q] + j));
-          s += v;
-        }
-        fa.sh_gbuf[j] = s;
-      }
-      if (!done && b == 0 && threadIdx.x < 2) {
-        double s = 0.0;
-        for (int q = 0; q < fa.p2p_n; ++q) {
-          double v;
-          asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(fa.p2p_gloc[q] + P.n + threadIdx.x));
-          s += v;
-        }
-        fa.sh_gbuf[P.n + threadIdx.x] = s;
-      }
-      // 5. every CTA of this rank has finished reading: report it to the peers and remember this exchange
-      grid.sync();
-      if (!done && b == 0 && threadIdx.x < fa.p2p_n) {
-        __threadfence_system();
-        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(fa.p2p_flags[threadIdx.x] + 8 + fa.p2p_rank), "l"(want) : "memory");
-        if (threadIdx.x == 0) asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(myflags + 16), "l"(want) : "memory");
-      }
+      grid.sync();                                             // the two value sums were written by CTA 0 only
+      if (!done) p2p_allreduce<kFThreads>(fa.p2p, ps, grid, fa.sh_gbuf, fa.sh_gbuf, P.n + 2);
+      else { grid.sync(); grid.sync(); }
     }
     cluster_arrive();          // no CTA exits while a peer could still address its shared memory
     cluster_wait();
