@@ -653,7 +653,16 @@ extern "C" int adaprox_solve(adaprox_handle h, const adaprox_problem* p, const a
   fill_opts(o, &O);
   if (!records) O.max_records = 0;
   const bool sharded = ((fm && fm->sharded) || (am && am->sharded)) && !std::getenv("ADAPROX_DEBUG_IGNORE_SHARD");
-  if (sharded) return solve_sharded(h, p, o, P, O, fm, am, x0, y0, x_out, y_out, records, res);
+  // Row-sharded linear map A of the primal-dual loop (AdaPDM / Condat-Vu; f without a sharded matrix): the persistent
+  // kernel itself all-reduces A'y and the dual sums over NVLink peer memory -- needs the exchange blocks (adaprox_p2p_*).
+  const bool sharded_pd = sharded && am && am->sharded && !(fm && fm->sharded) && o->solver == ADAPROX_S_ADAPTIVE_PRIMAL_DUAL;
+  if (sharded_pd) {
+    if (!p2p_ready(h, std::max<int64_t>(P.n, 8)))
+      return fail(h, ADAPROX_ERR_COMM, "row-sharded primal-dual solve: attach the peer exchange blocks first (adaprox_p2p_export / adaprox_p2p_attach)");
+    p2p_fill(h, &P.p2p);
+  } else if (sharded) {
+    return solve_sharded(h, p, o, P, O, fm, am, x0, y0, x_out, y_out, records, res);
+  }
 
   const int64_t n = P.n, md = std::max<int64_t>(P.md, 1);
   const int64_t mf = std::max<int64_t>(P.F.kind != MAT_NONE ? P.F.m : 0, n);
@@ -790,7 +799,8 @@ extern "C" int adaprox_solve(adaprox_handle h, const adaprox_problem* p, const a
   res->final_gamma = dr.final_gamma; res->final_sigma = dr.final_sigma; res->final_norm_res = dr.final_norm_res;
   res->solve_ms = ms; res->kernel_launches = h->launches - launches0;
   res->matrix_passes = (P.F.kind == MAT_NONE) ? 0 : (fused ? 1 : 2);
-  res->collective = 0;
+  res->collective = sharded_pd ? 2 : 0;
+  if (sharded_pd && (rc = p2p_check(h))) return rc;
   return ADAPROX_OK;
 }
 

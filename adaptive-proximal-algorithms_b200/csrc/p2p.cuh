@@ -11,19 +11,9 @@
 // finished reading exchange T - 1 (hence T - 2).  Spins are bounded (5 s): on timeout *err is set and the caller's
 // results are garbage -- the host checks the flag.
 #pragma once
-#include "phases.cuh"
+#include "phases.cuh"      // pulls in p2p_args.cuh
 
 namespace adaprox {
-
-constexpr int kP2PMaxRanks = 8;
-
-struct P2PArgs {
-  int n, rank;                                   // n <= 1: not sharded / not attached
-  int64_t cap;
-  double* buf[kP2PMaxRanks][2];                  // rank q's two exchange buffers as mapped here
-  unsigned long long* flags[kP2PMaxRanks];       // rank q's flag words as mapped here
-  int* err;
-};
 
 struct P2PState { unsigned long long T; };
 

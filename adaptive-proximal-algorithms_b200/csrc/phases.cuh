@@ -7,6 +7,7 @@
 // on every scalar without a single-thread bottleneck or a host round trip.
 #pragma once
 #include "gemv.cuh"
+#include "p2p_args.cuh"
 #include "../../include/adaprox.h"
 
 namespace adaprox {
@@ -30,7 +31,8 @@ struct DProblem {
   double f_N;              // logistic: global number of samples
   DProx g, h;
   DMat A;                  // linear map of the primal-dual solvers (MAT_NONE: `A = 0`)
-  int64_t n, md;           // primal / dual dimension
+  int64_t n, md;           // primal / dual dimension (md: LOCAL rows of A when A is a row shard)
+  P2PArgs p2p;             // row-sharded primal-dual solves: in-kernel all-reduce over peer memory (p2p.n <= 1: single GPU)
 };
 
 struct DOpts {

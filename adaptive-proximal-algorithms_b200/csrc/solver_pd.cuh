@@ -18,6 +18,7 @@
 //   P6  norm_res, record, convergence; A'*y+ partials            :348-358
 //   P7  slice: A'y, v, x+ = prox_{gamma g}(v)                    :359-361
 #pragma once
+#include "p2p.cuh"
 #include "phases.cuh"
 
 namespace adaprox {
@@ -61,6 +62,12 @@ __global__ void __launch_bounds__(kThreads, 2) k_primal_dual(DProblem P, DOpts O
 
   const bool hasA = (P.A.kind != MAT_NONE);
   const bool h_l2 = hasA && (P.h.kind == ADAPROX_P_NORM_L2);
+  // Row-sharded A: this rank holds md = local rows of A, the dual iterate y and A*x are row-local, x and every
+  // n-vector are replicated.  A'y and the dual-side sums are combined across the ranks INSIDE this kernel (p2p.cuh); every
+  // rank then holds identical bits and the replicated control flow stays in lock step.
+  const bool shardedA = hasA && P.p2p.n > 1;
+  P2PState ps;
+  p2p_begin(P.p2p, ps);
   const bool want_obj = O.want_objective != 0;
   const int64_t tid = (int64_t)b * kThreads + threadIdx.x, nt = (int64_t)G * kThreads;
   int64_t j0, j1;
@@ -97,6 +104,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_primal_dual(DProblem P, DOpts O
     grid_totals<2>(W.red, G, SLOT_F0, tot, s_scr);
     grad_slice(P, W, j0, j1, W.gb[gc], tot[1], G);
     if (hasA) gsum_slice(P.A, j0, j1, W.Aty[atc], G);
+    if (shardedA) p2p_allreduce<kThreads>(P.p2p, ps, grid, W.Aty[atc], W.Aty[atc], P.n);     // A'y over all row blocks
     double acc[1] = {0.0};
     double* xn = W.xb[1];
     for (int64_t j = j0 + threadIdx.x; j < j1; j += kThreads) {
@@ -192,6 +200,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_primal_dual(DProblem P, DOpts O
           block_reduce_store<1>(l2acc, W.red, G, SLOT_L2, s_scr);
           grid.sync();
           grid_totals<1>(W.red, G, SLOT_L2, l2tot, s_scr);
+          if (shardedA) p2p_allreduce_scalars<1>(P.p2p, ps, grid, l2tot);                      // |w/sigma + shift|^2 over all rows
         }
         // each thread re-reads only the w[i] it wrote itself (same stride) -> no sync needed
         dual_rows(P, W, w, Ax, ynew, sigma, l2tot[0], want_obj, y, s_scr, b, G, false);
@@ -199,6 +208,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_primal_dual(DProblem P, DOpts O
         grid.sync();
         double t2[2];
         grid_totals<2>(W.red, G, SLOT_DR, t2, s_scr);
+        if (shardedA) p2p_allreduce_scalars<2>(P.p2p, ps, grid, t2);                          // |dual_res|^2, h value
         dr_sum = t2[0]; h_sum = t2[1];
       }
     } else {
@@ -286,6 +296,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_primal_dual(DProblem P, DOpts O
       n_amul++;
       grid.sync();
       gsum_slice(P.A, j0, j1, W.Aty[atc], G);
+      if (shardedA) p2p_allreduce<kThreads>(P.p2p, ps, grid, W.Aty[atc], W.Aty[atc], P.n);
     }
     // ---- P7 (:359-361) ---------------------------------------------------------------
     phase_stamp(W, it, 6);
