@@ -653,9 +653,10 @@ extern "C" int adaprox_solve(adaprox_handle h, const adaprox_problem* p, const a
   fill_opts(o, &O);
   if (!records) O.max_records = 0;
   const bool sharded = ((fm && fm->sharded) || (am && am->sharded)) && !std::getenv("ADAPROX_DEBUG_IGNORE_SHARD");
-  // Row-sharded linear map A of the primal-dual loop (AdaPDM / Condat-Vu; f without a sharded matrix): the persistent
+  // Row-sharded linear map A of the primal-dual loops (AdaPDM / Condat-Vu / AdaPDM+; f without a sharded matrix): the persistent
   // kernel itself all-reduces A'y and the dual sums over NVLink peer memory -- needs the exchange blocks (adaprox_p2p_*).
-  const bool sharded_pd = sharded && am && am->sharded && !(fm && fm->sharded) && o->solver == ADAPROX_S_ADAPTIVE_PRIMAL_DUAL;
+  const bool sharded_pd = sharded && am && am->sharded && !(fm && fm->sharded) &&
+                          (o->solver == ADAPROX_S_ADAPTIVE_PRIMAL_DUAL || o->solver == ADAPROX_S_LINESEARCH_PRIMAL_DUAL);
   if (sharded_pd) {
     if (!p2p_ready(h, std::max<int64_t>(P.n, 8)))
       return fail(h, ADAPROX_ERR_COMM, "row-sharded primal-dual solve: attach the peer exchange blocks first (adaprox_p2p_export / adaprox_p2p_attach)");

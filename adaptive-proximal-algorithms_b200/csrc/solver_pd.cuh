@@ -239,6 +239,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_primal_dual(DProblem P, DOpts O
           block_reduce_store<1>(l2acc, W.red, G, SLOT_L2, s_scr);
           grid.sync();
           grid_totals<1>(W.red, G, SLOT_L2, l2tot, s_scr);
+          if (shardedA) p2p_allreduce_scalars<1>(P.p2p, ps, grid, l2tot);
         }
         dual_rows(P, W, w, Ax, ynew, sigma, l2tot[0], want_obj, y, s_scr, b, G, true);   // :525
         n_proxh++;
@@ -247,6 +248,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_primal_dual(DProblem P, DOpts O
         n_amul++;
         grid.sync();
         gsum_slice(P.A, j0, j1, aty_next, G);
+        if (shardedA) p2p_allreduce<kThreads>(P.p2p, ps, grid, aty_next, aty_next, P.n);      // A'y_next over all row blocks
         {
           double acc[1] = {0.0};
           const double* aty = W.Aty[atc];
@@ -259,6 +261,11 @@ __global__ void __launch_bounds__(kThreads, 2) k_primal_dual(DProblem P, DOpts O
         grid.sync();
         double tl[2];                               // DY, DATY
         grid_totals<2>(W.red, G, SLOT_DY, tl, s_scr);
+        if (shardedA) {                             // |y_next - y|^2 is a sum over rows; |A'y_next - A'y|^2 is already global
+          double dy[1] = {tl[0]};
+          p2p_allreduce_scalars<1>(P.p2p, ps, grid, dy);
+          tl[0] = dy[0];
+        }
         const bool accept = eta >= sqrt(tl[1]) / sqrt(tl[0]);                    // :527
         if (accept || trial >= 200) {
           if (!accept) flags |= ADAPROX_FLAG_LS_CAP;
@@ -270,6 +277,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_primal_dual(DProblem P, DOpts O
       }
       double t2[2];
       grid_totals<2>(W.red, G, SLOT_DR, t2, s_scr);
+      if (shardedA) p2p_allreduce_scalars<2>(P.p2p, ps, grid, t2);
       dr_sum = t2[0]; h_sum = t2[1];
       atc ^= 1;                                                                  // :529  At_y = At_y_next
     }

@@ -124,6 +124,15 @@ def _worker_pd(rank, world, port, out):
         res[hname + "_gam"] = np.array([r["gamma"] for r in log]); res[hname + "_res"] = np.array([r["norm_res"] for r in log])
         res[hname + "_obj"] = np.array([r["objective"] for r in log]); res[hname + "_coll"] = info["collective"]
         res[hname + "_At"] = np.array([r["At_evals"] for r in log])
+        # AdaPDM+ (linesearch on the estimate of |A|, src/AdaProx.jl:463-550) on the same shard
+        A2 = AdaProx.DeviceMatrix(Amat[row0:row0 + rows].copy(), dev=dev)
+        A2.set_shard(m, row0)
+        log = []
+        x, y, it = AdaProx.adaptive_linesearch_primal_dual(np.zeros(11), np.zeros(rows), f=AdaProx.Zero(), g=AdaProx.NormL1(0.1), h=AdaProx.Counting(h),
+                                                           A=AdaProx.Counting(A2), eta=nA, t=1.0, tol=1e-6, maxit=300, log=log)
+        res[hname + "_ls_x"] = x; res[hname + "_ls_it"] = it
+        res[hname + "_ls_gam"] = np.array([r["gamma"] for r in log]); res[hname + "_ls_res"] = np.array([r["norm_res"] for r in log])
+        res[hname + "_ls_At"] = np.array([r["At_evals"] for r in log]); res[hname + "_ls_ph"] = np.array([r["prox_h_evals"] for r in log])
     np.savez(out % rank, row0=row0, rows=rows, **res)
     dist.barrier()
     dist.destroy_process_group()
@@ -158,6 +167,16 @@ def test_sharded_adapdm_two_gpus(tmp_path):
         assert np.allclose(R0[hname + "_obj"][:K], [r["objective"] for r in lo[:K]], rtol=1e-10)
         assert list(R0[hname + "_At"][:K]) == [r["At_evals"] for r in lo[:K]]
         assert abs(int(R0[hname + "_it"]) - ito) <= max(3, 0.05 * ito)
+        lo2 = []
+        xo2, yo2, ito2 = O.adaptive_linesearch_primal_dual(np.zeros(11), np.zeros(m), f=O.Zero(), g=O.NormL1(0.1), h=O.Counting(ho), A=O.Counting(Amat),
+                                                           eta=nA, t=1.0, tol=1e-6, maxit=300, log=lo2)
+        assert np.array_equal(R0[hname + "_ls_x"], R1[hname + "_ls_x"])
+        K2 = min(40, len(lo2), len(R0[hname + "_ls_gam"]))
+        assert np.allclose(R0[hname + "_ls_gam"][:K2], [r["gamma"] for r in lo2[:K2]], rtol=1e-11)
+        assert np.allclose(R0[hname + "_ls_res"][:K2], [r["norm_res"] for r in lo2[:K2]], rtol=1e-9)
+        assert list(R0[hname + "_ls_At"][:K2]) == [r["At_evals"] for r in lo2[:K2]]          # same number of linesearch trials
+        assert list(R0[hname + "_ls_ph"][:K2]) == [r["prox_h_evals"] for r in lo2[:K2]]
+        assert abs(int(R0[hname + "_ls_it"]) - ito2) <= max(3, 0.05 * ito2)
         y = np.concatenate([R0[hname + "_y"], R1[hname + "_y"]])
         if int(R0[hname + "_it"]) == ito:
             assert np.allclose(R0[hname + "_x"], xo, rtol=1e-6, atol=1e-9) and np.allclose(y, yo, rtol=1e-6, atol=1e-9)
