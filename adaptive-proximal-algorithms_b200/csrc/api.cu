@@ -652,7 +652,7 @@ extern "C" int adaprox_solve(adaprox_handle h, const adaprox_problem* p, const a
   DOpts O{};
   fill_opts(o, &O);
   if (!records) O.max_records = 0;
-  const bool sharded = ((fm && fm->sharded) || (am && am->sharded)) && !std::getenv("ADAPROX_DEBUG_IGNORE_SHARD");
+  const bool sharded = (fm && fm->sharded) || (am && am->sharded);
   // Row-sharded linear map A of the primal-dual loops (AdaPDM / Condat-Vu / AdaPDM+; f without a sharded matrix): the persistent
   // kernel itself all-reduces A'y and the dual sums over NVLink peer memory -- needs the exchange blocks (adaprox_p2p_*).
   const bool sharded_pd = sharded && am && am->sharded && !(fm && fm->sharded) &&
