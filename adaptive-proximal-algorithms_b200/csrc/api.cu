@@ -599,12 +599,13 @@ static int fused_plan(adaprox_ctx* h, const void* kernel, const DProblem& P, Fus
   if (rc) return rc;
   pl->G = pl->fa.C * pl->Q;
   pl->fa.npadf = (int64_t)pl->fa.C * kFCols;
-  // chunk size: about 8 chunks per cluster (a chunk boundary costs a cluster barrier, an atomic and a refill of the
-  // 3-slot ring, ~10 us: ~2 % at this granularity, while a cluster that is 2x slower than the rest -- seen on
-  // some parts -- only delays the sweep by ~8 % instead of 100 %)
-  int64_t pw = P.F.m / ((int64_t)pl->Q * 8);
-  pw = ((pw + 7) / 8) * 8;
-  pw = pw < 32 ? 32 : (pw > 4096 ? 4096 : pw);
+  // chunk size: k chunks per cluster, k = 8 for long sweeps and 4 for short ones (row shards at N = 8).  A chunk boundary costs a
+  // cluster barrier, an atomic, the reload of x and a refill of the 3-slot ring (~10 us); chunks of ceil(m / (Q k)) rows make the
+  // number of chunks a multiple of the cluster count, so equally fast clusters finish together, while a cluster that is 2x slower
+  // than the rest -- seen on some parts -- only delays the sweep by 12 % (k = 8) / 25 % (k = 4) instead of 100 %.
+  const int kper = (P.F.m / std::max(pl->Q, 1) >= 4096) ? 8 : 4;
+  int64_t pw = (P.F.m + (int64_t)pl->Q * kper - 1) / ((int64_t)pl->Q * kper);
+  pw = pw < 16 ? 16 : pw;
   if (const char* e = std::getenv("ADAPROX_FUSED_CHUNK")) { const int v = std::atoi(e); if (v >= 1) pw = v; }
   pl->fa.chunk_rows = (int)pw;
   pl->fa.nchunks = (int)((P.F.m + pw - 1) / pw);

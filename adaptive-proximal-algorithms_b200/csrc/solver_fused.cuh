@@ -100,13 +100,30 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t addr, uint32_t parity
 #ifndef ADAPROX_FUSED_TRYWAIT
 __device__ __forceinline__ void fmbar_wait(uint32_t addr, uint32_t parity) {
   uint32_t ok;
-  do {
+  for (;;) {
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                  : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
-  } while (!ok);
+    if (ok) break;
+#ifdef ADAPROX_FUSED_POLL_SLEEP_NS
+    __nanosleep(ADAPROX_FUSED_POLL_SLEEP_NS);
+#endif
+  }
 }
 #else
 __device__ __forceinline__ void fmbar_wait(uint32_t addr, uint32_t parity) { mbar_wait(addr, parity); }
+#endif
+
+// One warp of a role group polls, the other seven park on a hardware named barrier (bar.sync id, 256): parked warps issue
+// nothing (unlike 16 polling warps, which keep the issue slots and the power budget busy) and are released within a few
+// cycles of the poller's arrival (unlike warps suspended by try_wait).  Build flag ADAPROX_FUSED_ALLPOLL restores "every warp polls".
+__device__ __forceinline__ void group_bar(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(kFGroup) : "memory"); }
+#ifndef ADAPROX_FUSED_ALLPOLL
+__device__ __forceinline__ void group_wait(bool poller, int id, uint32_t addr, uint32_t parity) {
+  if (poller) fmbar_wait(addr, parity);
+  group_bar(id);
+}
+#else
+__device__ __forceinline__ void group_wait(bool, int, uint32_t addr, uint32_t parity) { fmbar_wait(addr, parity); }
 #endif
 
 // ld.volatile keeps the program order of the loads; the consumers below use the batch in REVERSE order, so all
@@ -163,7 +180,7 @@ __device__ __noinline__ double fused_pass(const DMat& M, const double* bvec, con
     const uint32_t mypart = ctl + kOffCpart + (rank * kFGWarps + warp) * 8;
     const bool sender = lane < C;
     for (int i = 0; i < nrows; ++i) {
-      fmbar_wait(ctl + kOffFull + 8 * slot, ph);
+      group_wait(warp == 0, 1, ctl + kOffFull + 8 * slot, ph);
       const uint32_t tile = tile0 + slot * kFStageBytes;
       // batches of kFB x LDS.128 issued back to back: ld.volatile keeps their order and the FMA chains consume the
       // batch in REVERSE, so the whole batch is in flight before the first FMA (ptxas otherwise recycles ONE
@@ -230,7 +247,7 @@ __device__ __noinline__ double fused_pass(const DMat& M, const double* bvec, con
       const double b_cur = __shfl_sync(0xffffffffu, bblk, i & 31);
       // st.async delivers data and complete_tx through the same path into this CTA's shared memory, so the
       // cta-scope acquire is enough (a cluster-scope acquire compiles to CCTL.IVALL: an L1 flush per row)
-      fmbar_wait(ctl + kOffCfull + 8 * d, dph);
+      group_wait(warp == kFGWarps, 2, ctl + kOffCfull + 8 * d, dph);
       const uint32_t pb = part0 + d * kPartStride;
       const double v0 = (lane < nval) ? lds1(pb) : 0.0;
       const double v1 = (lane + 32 < nval) ? lds1(pb + 256) : 0.0;
@@ -239,7 +256,11 @@ __device__ __noinline__ double fused_pass(const DMat& M, const double* bvec, con
       if (leader && i + kFDepth < nrows) mbar_expect_tx(ctl + kOffCfull + 8 * d, xbytes);    // arm this buffer for row g + 8
       const double rs = warp_sum((v0 + v1) + (v2 + v3)) - b_cur;   // same order in every update warp of the cluster;
                                                                    // lasso/runme.jl:22  res = A*w - b
+#ifdef ADAPROX_FUSED_ALLPOLL
       fmbar_wait(ctl + kOffFull + 8 * slot, ph);                 // long complete; makes the bulk-copied tile visible here
+#endif
+      // (default build: the tile was observed complete by the dot warps' poller, whose partial sum is part of the
+      //  exchange this warp was just released on -- mbarrier completion -> named barrier is a causality chain)
       const uint32_t tile = tile0 + slot * kFStageBytes;
       double2 av[kFB];
 #pragma unroll
