@@ -1,24 +1,26 @@
-// solver_fused.cuh -- AdaPGM on a dense least-squares term with ONE pass over A per
+// solver_fused.cuh -- AdaPGM on a dense least-squares term with ONE sweep over A per
 // iteration:  g = A'(A x - b)  (lasso/runme.jl:21-25 value + pullback, fused).
 //
 // The two-pass formulation streams A twice (A*x needs whole rows before A'r can start).
-// Here a thread-block CLUSTER of C = ceil(ld / 8192) <= 16 CTAs owns a block of rows and
-// all n columns (8192 columns per CTA).  For every row i of the block:
-//   1. the bulk-copy engine has put the CTA's 64 KB piece of row i into a 3-slot shared
-//      memory ring (cp.async.bulk + mbarrier, as in gemv_ring.cuh);
-//   2. the CTA computes its partial dot  <A[i, cols], x[cols]>  (x lives in registers),
-//      reduces it over its 16 warps and stores it into every peer's shared memory
-//      (DSMEM, st.shared::cluster), then arrives on the hardware cluster barrier;
-//   3. while that barrier completes, the rank-1 update of the PREVIOUS row,
-//      acc[cols] += A[i-1, cols] * r[i-1], runs from the tile still resident in shared
-//      memory (accumulators live in registers for the whole pass) and the freed slot is
-//      refilled with row i+2;
-//   4. after the barrier every thread sums the C partials in rank order:
-//      r[i] = sum - b[i]  (bit-identical in all CTAs of the cluster), f += r[i]^2.
-// DRAM traffic per iteration is 8 m n instead of 16 m n.  All sums have a fixed order.
-// Correctness of the exchange buffers: partials of row i live in slot i & 1; a CTA writes
-// row i+2 only after passing the cluster barrier of row i+1, which every CTA arrives at
-// only after it has read the partials of row i.
+// Here a thread-block CLUSTER of C = ceil(ld / 8192) <= 16 CTAs owns whole rows
+// (8192 columns per CTA).  For every row i:
+//   1. one lane per CTA (the producer) has bulk-copied the CTA's 64 KB piece of row i into a
+//      3-slot shared-memory ring (cp.async.bulk + mbarrier);
+//   2. the 8 DOT warps (x in registers) form the partial dot <A[i, cols], x[cols]> from shared
+//      memory and push one partial per warp into every peer's shared memory with
+//      st.async ... mbarrier::complete_tx (DSMEM), 8-deep exchange buffers;
+//   3. the 8 UPDATE warps (column accumulators in registers) wait for the C * 8 partials of the
+//      row, sum them in a fixed order (same bits in every warp of every CTA of the cluster),
+//      r[i] = sum - b[i], f += r[i]^2, and apply acc[cols] += A[i, cols] * r[i] from the tile
+//      that is still resident; the freed slot is refilled with row i + 3.
+//   Waits: one warp per role group polls the mbarrier, the other seven park on a named
+//   barrier (sleeping waiters -- try_wait, nanosleep -- halve the speed of the sweep).
+// Rows are handed to the clusters in chunks, dynamically; every chunk stores its own partial
+// (gpartf[chunk][n], fpart[chunk]) and the chunks are reduced in chunk order, so results do not
+// depend on the schedule and reruns are bit-identical.  DRAM traffic per iteration is 8 m n
+// instead of 16 m n.  Kernels: k_adapgm_fused = the whole single-GPU solve as one cluster
+// launch with an own grid barrier; its sweep-only mode serves the row-sharded solve
+// (comm.inl), optionally with the all-reduce inside the kernel (p2p.cuh).
 #pragma once
 #include "phases.cuh"
 #include "p2p.cuh"

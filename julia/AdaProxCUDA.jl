@@ -52,7 +52,7 @@ mutable struct CResult
     f_evals::Int64; grad_f_evals::Int64; prox_g_evals::Int64; prox_h_evals::Int64; A_evals::Int64; At_evals::Int64
     n_records::Int64
     final_gamma::Float64; final_sigma::Float64; final_norm_res::Float64; solve_ms::Float64; kernel_launches::Int64; matrix_passes::Int64; collective::Int64
-    CResult() = new(0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0.0, 0.0, 0.0, 0.0, 0)
+    CResult() = new(0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0.0, 0.0, 0.0, 0.0, 0, 0, 0)
 end
 
 # ---- handle -------------------------------------------------------------------
@@ -200,6 +200,39 @@ function backtracking_nesterov(x0; f, g, gamma0, shrink = 0.5, tol = 1e-5, maxit
                 counting = cflags(f, g, nothing, nothing))
     xs, _, it = solve(4, x0, nothing; f, g, opts = o, name, pd = false)
     return xs, it
+end
+
+
+# ---- batched multi-lambda lasso path (include/adaprox.h: adaprox_solve_lambda_path) ---------------------------
+# Column j of the result is what `adaptive_proxgrad(X0[:, j]; f, g = NormL1(lambdas[j]), rule, tol, maxit)` returns; the L
+# columns advance together so that A*X and A'*R are FP64 tensor-core contractions.  NOT EXECUTED (no Julia in the build image).
+function adaptive_proxgrad_path(X0::Union{Nothing,Matrix{Float64}}; f, lambdas::Vector{Float64}, rule, gamma0 = nothing,
+                                tol = 1e-5, maxit = 100_000)
+    L = length(lambdas)
+    prob = problem(f, NormL1(1.0), nothing, nothing)          # same CProblem as adaptive_proxgrad; g is ignored by the library
+    n = Int(prob.n)
+    o = options(1; rule = rule_fields(rule), tol, maxit, want = Int32(0), counting = cflags(f, nothing, nothing, nothing))
+    X = Matrix{Float64}(undef, n, L)                          # column-major: column j contiguous = the library's [L][n] layout
+    its = zeros(Int64, L); nres = zeros(L); gam = zeros(L); fx = zeros(L)
+    res = CResult()
+    x0ptr = X0 === nothing ? Ptr{Float64}(C_NULL) : pointer(X0)
+    g0ptr = gamma0 === nothing ? Ptr{Float64}(C_NULL) : pointer(gamma0)
+    GC.@preserve X0 gamma0 lambdas X its nres gam fx begin
+        check(ccall((:adaprox_solve_lambda_path, lib), Cint,
+                    (Handle, Ref{CProblem}, Ref{COptions}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+                     Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64, Ref{CResult}),
+                    handle(), prob, o, L, lambdas, g0ptr, x0ptr, X, its, nres, gam, fx, C_NULL, 0, res))
+    end
+    return X, its, (norm_res = nres, gamma = gam, f_x = fx, solve_ms = res.solve_ms)
+end
+
+# ---- multi-GPU: peer exchange blocks for the all-reduce inside the kernels (adaprox_p2p_*) -----------------------
+# `allgather` is supplied by the caller (e.g. MPI.Allgather on the 64-byte handles); rank order.  NOT EXECUTED.
+function attach_p2p(n_max::Integer, nranks::Integer, rank::Integer, allgather::Function)
+    mine = zeros(UInt8, 64)
+    check(ccall((:adaprox_p2p_export, lib), Cint, (Handle, Int64, Ptr{UInt8}), handle(), n_max, mine))
+    all = allgather(mine)::Vector{UInt8}                      # 64 * nranks bytes
+    check(ccall((:adaprox_p2p_attach, lib), Cint, (Handle, Cint, Cint, Ptr{UInt8}), handle(), nranks, rank, all))
 end
 
 end # module
