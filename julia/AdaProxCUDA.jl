@@ -99,7 +99,7 @@ unwrap(c::AdaProx.Counting) = c.f
 iscounting(f) = f isa AdaProx.Counting
 device_oracle(f) = error("eval_with_pullback not defined on the device for type $(typeof(f)) (no CPU fallback)")
 device_oracle(::ProximalCore.Zero) = (kind = 0, ipar = 0, mat = 0, vec = 0, c = 0.0)
-least_squares(A, b) = (kind = 1, ipar = 0, mat = upload(A), vec = upload(b), c = 0.0)   # lasso/runme.jl:16-27
+least_squares(A, b) = (kind = 1, ipar = 0, mat = upload(A), vec = upload(b), c = 0.0, n = size(A, 2))   # lasso/runme.jl:16-27
 logistic(X, y) = (kind = 2, ipar = 0, mat = upload(X), vec = upload(y), c = 0.0)        # sparse_logreg/runme.jl:18-39
 quadratic(Q, q) = (kind = 3, ipar = 0, mat = upload(Q), vec = upload(q), c = 0.0)       # dual_svm/runme.jl:19-28
 cubic(Q, q, c) = (kind = 4, ipar = 0, mat = upload(Q), vec = upload(q), c = Float64(c)) # cubic_sparse_logreg/runme.jl:20-32
@@ -209,8 +209,9 @@ end
 function adaptive_proxgrad_path(X0::Union{Nothing,Matrix{Float64}}; f, lambdas::Vector{Float64}, rule, gamma0 = nothing,
                                 tol = 1e-5, maxit = 100_000)
     L = length(lambdas)
-    prob = problem(f, NormL1(1.0), nothing, nothing)          # same CProblem as adaptive_proxgrad; g is ignored by the library
-    n = Int(prob.n)
+    fo = device_oracle(unwrap(f))                              # same CProblem as solve(); g is ignored by the library
+    n = X0 === nothing ? fo.n : size(X0, 1)                    # least_squares(A, b) records n = size(A, 2)
+    prob = CProblem(fo.kind, fo.ipar, fo.mat, fo.vec, fo.c, device_prox(NormL1(1.0)), noprox(), 0, n, 0)
     o = options(1; rule = rule_fields(rule), tol, maxit, want = Int32(0), counting = cflags(f, nothing, nothing, nothing))
     X = Matrix{Float64}(undef, n, L)                          # column-major: column j contiguous = the library's [L][n] layout
     its = zeros(Int64, L); nres = zeros(L); gam = zeros(L); fx = zeros(L)
