@@ -40,16 +40,39 @@ def attach_communicator(dev, dist=None):
     return world, rank
 
 
-def attach_p2p(dev, n_max, dist=None):
-    """Enable the in-kernel all-reduce over NVLink peer memory (include/adaprox.h: adaprox_p2p_*): every rank exports its
-    exchange block, the 64-byte IPC handles are all-gathered through ``torch.distributed`` and every rank maps its
-    peers' blocks.  Call after ``attach_communicator``; at most 8 ranks on one node."""
+def attach_p2p(dev, n_max, dist=None) -> bool:
+    """Enable the all-reduce inside the kernels over NVLink peer memory (include/adaprox.h: adaprox_p2p_*): every rank
+    exports its exchange block, the 64-byte CUDA IPC handles are all-gathered through ``torch.distributed`` and every rank
+    maps its peers' blocks.  Call after ``attach_communicator``; at most 8 ranks on one node.
+
+    Collective and failure-safe: every rank takes part in both gathers whatever happens locally, and the function
+    returns True only if EVERY rank attached; otherwise it returns False on every rank and sets ``ADAPROX_NO_P2P=1`` so
+    that the library keeps using ``ncclAllReduce`` (row-sharded primal-dual solves then raise, they need the blocks)."""
+    import os
     if dist is None:
         import torch.distributed as dist
     rank, world = dist.get_rank(), dist.get_world_size()
-    mine = dev.p2p_export(n_max)
+    mine = None
+    try:
+        mine = dev.p2p_export(n_max)
+    except Exception as e:                                          # noqa: BLE001 - reported to every rank below
+        mine = None
+        err = repr(e)
     handles = [None] * world
     dist.all_gather_object(handles, mine)
-    dev.p2p_attach(world, rank, b"".join(handles))
-    dist.barrier()
-    return world, rank
+    ok = all(h is not None for h in handles)
+    if ok:
+        try:
+            dev.p2p_attach(world, rank, b"".join(handles))
+        except Exception as e:                                      # noqa: BLE001
+            ok = False
+            err = repr(e)
+    oks = [None] * world
+    dist.all_gather_object(oks, ok)
+    if not all(oks):
+        os.environ["ADAPROX_NO_P2P"] = "1"
+        if rank == 0:
+            import sys
+            print("[adaprox] peer exchange blocks not available on every rank; falling back to ncclAllReduce", file=sys.stderr)
+        return False
+    return True

@@ -23,7 +23,7 @@ def _worker(rank, world, port, out, fused):
     AdaProx.set_default_device(dev)
     AdaProx.sharding.attach_communicator(dev, dist)
     if p2p:
-        AdaProx.sharding.attach_p2p(dev, 20000, dist)          # in-kernel all-reduce over peer memory instead of NCCL
+        assert AdaProx.sharding.attach_p2p(dev, 20000, dist)   # in-kernel all-reduce over peer memory instead of NCCL
     m, n = 400, 1000
     P = AdaProx.synth.planted_lasso(m, n, 5, 0)
     Lf = AdaProx.synth.spectral_norm_sq(P["A"], iters=1000, tol=1e-15)
@@ -104,7 +104,7 @@ def _worker_pd(rank, world, port, out):
     dev = AdaProx.Device(rank)
     AdaProx.set_default_device(dev)
     AdaProx.sharding.attach_communicator(dev, dist)
-    AdaProx.sharding.attach_p2p(dev, 4096, dist)
+    assert AdaProx.sharding.attach_p2p(dev, 4096, dist)
     X, yv = AdaProx.synth.dense_regression(203, 10, 0)
     m = X.shape[0]
     Amat = np.hstack([X, np.ones((m, 1))])

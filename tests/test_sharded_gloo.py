@@ -85,3 +85,56 @@ def test_row_sharded_adapgm_world_size_2(tmp_path):
     assert abs(float(R["obj"]) - log[-1]["objective"]) < 1e-10 * abs(log[-1]["objective"])
     assert int(R["n_allreduce"]) == int(R["it"]) + 1                # one all-reduce per gradient evaluation, no other collective
     assert abs(float(R["obj"]) - P["optimum"]) < 1e-9 * P["optimum"]
+
+
+# ---------------------------------------------------------------- attach_p2p: collective and failure-safe on every rank
+class _FakeDev:
+    """Stands in for adaprox_b200.Device: the export / attach calls of the peer exchange blocks, with scripted failures."""
+
+    def __init__(self, rank, fail_export_on=None, fail_attach_on=None):
+        self.rank, self.fail_export_on, self.fail_attach_on = rank, fail_export_on, fail_attach_on
+        self.attached = None
+
+    def p2p_export(self, n_max):
+        if self.rank == self.fail_export_on:
+            raise RuntimeError("cudaIpcGetMemHandle failed (scripted)")
+        return bytes([self.rank]) * 64
+
+    def p2p_attach(self, nranks, rank, handles):
+        if self.rank == self.fail_attach_on:
+            raise RuntimeError("cudaIpcOpenMemHandle failed (scripted)")
+        assert len(handles) == 64 * nranks and handles[64 * rank] == rank
+        self.attached = (nranks, rank)
+
+
+def _worker_p2p(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    os.environ.pop("ADAPROX_NO_P2P", None)
+    import adaprox_b200 as AdaProx
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    results = []
+    for fe, fa in [(None, None), (1, None), (None, 0)]:
+        os.environ.pop("ADAPROX_NO_P2P", None)
+        dev = _FakeDev(rank, fe, fa)
+        ok = AdaProx.sharding.attach_p2p(dev, 1000, dist)
+        results.append((bool(ok), os.environ.get("ADAPROX_NO_P2P"), dev.attached))
+    with open(out % rank, "w") as fh:
+        fh.write(repr(results))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_attach_p2p_is_collective_and_falls_back(tmp_path):
+    """A failure on ONE rank (export or attach) must not hang the others: every rank returns False and switches the
+    library to ncclAllReduce (ADAPROX_NO_P2P=1); with no failure every rank attaches."""
+    import torch.multiprocessing as mp
+    out = str(tmp_path / "p2p_rank%d.txt")
+    mp.spawn(_worker_p2p, args=(2, 30200 + os.getpid() % 500, out), nprocs=2, join=True)
+    r0, r1 = eval(open(out % 0).read()), eval(open(out % 1).read())
+    assert r0[0] == (True, None, (2, 0)) and r1[0] == (True, None, (2, 1))
+    # export failed on rank 1: nobody attaches
+    assert r0[1][:2] == (False, "1") and r1[1][:2] == (False, "1") and r0[1][2] is None and r1[1][2] is None
+    # attach failed on rank 0: rank 1 did attach locally, but both report failure and fall back
+    assert r0[2][:2] == (False, "1") and r1[2][:2] == (False, "1")
