@@ -16,13 +16,22 @@ static int path_setup_kernels(adaprox_ctx* h) {
 
 // G = A' R has only ceil(n / 128) * ceil(L / BN) output tiles; when that leaves most SMs idle (narrow batches) K = m is cut
 // into slabs written to separate buffers and summed in slab order by k_path_step.
-static int path_ksplit(adaprox_ctx* h, int64_t n, int64_t m, int64_t L) {
+// mdim = rows of the output tile grid (n for G = A' R, m for R = A X), kdim = the contracted dimension
+static int path_ksplit(adaprox_ctx* h, int64_t mdim, int64_t kdim, int64_t L) {
   const int bn = (L <= 64) ? GemmCfg<1>::BN : GemmCfg<4>::BN;
-  const int64_t ctas = ((n + kGBM - 1) / kGBM) * ((L + bn - 1) / bn);
-  int ks = (int)(h->sm_count / std::max<int64_t>(ctas, 1));
-  ks = std::max(1, std::min(ks, 4));
-  while (ks > 1 && m / ks < 8 * kGBK) --ks;
-  return ks;
+  const int64_t ctas = ((mdim + kGBM - 1) / kGBM) * ((L + bn - 1) / bn);
+  const int64_t m = kdim;
+  // makespan of ctas * ks equal work items on sm_count SMs, in units of one unsplit tile: ceil(ctas ks / SMs) / ks.
+  // E.g. 128 tiles on 148 SMs: ks = 1 .. 7 all give 1.0 (20 SMs idle), ks = 8 gives 7/8.  Each slab costs one extra
+  // L x n buffer that k_path_step reads, so only a clear gain (> 8 %) justifies splitting.
+  int best = 1;
+  double best_span = (double)((ctas + h->sm_count - 1) / h->sm_count);
+  for (int ks = 2; ks <= 8; ++ks) {
+    if (m / ks < 8 * kGBK) break;
+    const double span = (double)((ctas * ks + h->sm_count - 1) / h->sm_count) / ks;
+    if (span < 0.92 * best_span) { best = ks; best_span = span; }
+  }
+  return best;
 }
 
 // The batch is the N dimension of both contractions; narrow batches (L <= 64: e.g. 32 lambdas per rank when the path is
@@ -31,7 +40,8 @@ static void path_launch_gemm(adaprox_ctx* h, int mode, const PathGemmArgs& g) {
   const bool narrow = g.L <= 64;
   const int bn = narrow ? GemmCfg<1>::BN : GemmCfg<4>::BN;
   const int64_t Mdim = (mode == 1) ? g.m : g.n;
-  dim3 grid((unsigned)((Mdim + kGBM - 1) / kGBM), (unsigned)((g.L + bn - 1) / bn), (unsigned)((mode == 2 && g.ksplit > 1) ? g.ksplit : 1));
+  const int ksp = (mode == 2) ? g.ksplit : g.ksplit1;
+  dim3 grid((unsigned)((Mdim + kGBM - 1) / kGBM), (unsigned)((g.L + bn - 1) / bn), (unsigned)(ksp > 1 ? ksp : 1));
   if (mode == 1) {
     if (narrow) k_path_gemm<1, 1><<<grid, kGT, GemmCfg<1>::SmemBytes, h->stream>>>(g);
     else k_path_gemm<1, 4><<<grid, kGT, GemmCfg<4>::SmemBytes, h->stream>>>(g);
@@ -40,6 +50,21 @@ static void path_launch_gemm(adaprox_ctx* h, int mode, const PathGemmArgs& g) {
     else k_path_gemm<2, 4><<<grid, kGT, GemmCfg<4>::SmemBytes, h->stream>>>(g);
   }
   h->launches++;
+}
+
+// R = A X - b (+ fpart): one launch, or K-split partial products followed by the fix-up kernel
+static void path_launch_r(adaprox_ctx* h, PathGemmArgs& g, double* RT, double* rslab) {
+  if (g.ksplit1 > 1) {
+    g.RT = rslab;
+    path_launch_gemm(h, 1, g);
+    g.RT = RT;
+    dim3 grid((unsigned)((g.m + kRFixRows - 1) / kRFixRows), (unsigned)g.L);
+    k_path_rfix<<<grid, 256, 0, h->stream>>>(g, rslab);
+    h->launches++;
+  } else {
+    g.RT = RT;
+    path_launch_gemm(h, 1, g);
+  }
 }
 
 }  // namespace adaprox
@@ -71,9 +96,11 @@ extern "C" int adaprox_solve_lambda_path(adaprox_handle h, const adaprox_problem
   O.max_records = nrec;
   const int64_t n = P.n, m = P.F.m;
   const int64_t ldx = round_up(n, 16), ldr = round_up(m, 16);
-  const int64_t mtiles = (m + kGBM - 1) / kGBM;
-  const int ksplit = path_ksplit(h, n, m, L);
+  const int ksplit = path_ksplit(h, n, m, L);             // G = A' R: tiles over n, contraction over m
+  const int ksplit1 = path_ksplit(h, m, n, L);            // R = A X:  tiles over m, contraction over n
+  const int64_t mtiles = ksplit1 > 1 ? (m + kRFixRows - 1) / kRFixRows : (m + kGBM - 1) / kGBM;
   size_t need = 7 * ws_size_doubles(L * ldx) + ws_size_doubles(L * ldr) + ws_size_doubles(mtiles * L) + ws_size_doubles((int64_t)ksplit * L * ldx) +
+                (ksplit1 > 1 ? ws_size_doubles((int64_t)ksplit1 * L * ldr) : 0) +
                 ws_size_doubles((L * (int64_t)sizeof(PathCol) + 7) / 8) + 3 * ws_size_doubles(std::max<int64_t>(nrec, 1) * L) + ws_size_doubles(1);
   if ((rc = ws_reset(h, need))) return rc;
   PathStepArgs sa{};
@@ -86,6 +113,7 @@ extern "C" int adaprox_solve_lambda_path(adaprox_handle h, const adaprox_problem
   double* fpart = ws_doubles(h, mtiles * L);
   sa.fpart = fpart;
   double* gslab = ws_doubles(h, (int64_t)ksplit * L * ldx);
+  double* rslab = ksplit1 > 1 ? ws_doubles(h, (int64_t)ksplit1 * L * ldr) : nullptr;
   sa.col = reinterpret_cast<PathCol*>(ws_doubles(h, (L * (int64_t)sizeof(PathCol) + 7) / 8));
   double* histd = ws_doubles(h, 3 * std::max<int64_t>(nrec, 1) * L);
   if (nrec > 0) { sa.gamma_hist = histd; sa.res_hist = histd + nrec * L; sa.obj_hist = histd + 2 * nrec * L; }
@@ -113,6 +141,7 @@ extern "C" int adaprox_solve_lambda_path(adaprox_handle h, const adaprox_problem
   PathGemmArgs g{};
   g.A = P.F.a; g.m = m; g.n = n; g.lda = P.F.ld; g.b = P.fvec; g.L = L; g.ldx = ldx; g.RT = RT; g.ldr = ldr; g.fpart = fpart;
   g.ksplit = ksplit; g.gstride = L * ldx;
+  g.ksplit1 = ksplit1; g.rstride = L * ldr;
   sa.ksplit = ksplit; sa.gstride = L * ldx; sa.Gslab = gslab;
   const int64_t launches0 = h->launches;
   AP_CUDA(h, cudaEventRecord(h->ev0, h->stream));
@@ -121,7 +150,8 @@ extern "C" int adaprox_solve_lambda_path(adaprox_handle h, const adaprox_problem
   for (int64_t it = 0; it <= O.maxit && active > 0; ++it) {
     g.XT = sa.XT[it % 3];
     g.GT = ksplit > 1 ? gslab : sa.GT[it & 1];
-    path_launch_gemm(h, 1, g);                                         // R = A X - b, per-tile sums of r^2   (:336 value)
+    path_launch_r(h, g, RT, rslab);                                    // R = A X - b, per-tile sums of r^2   (:336 value)
+    g.RT = RT;
     path_launch_gemm(h, 2, g);                                         // G = A' R                            (:336 pullback)
     ++evals;
     AP_CUDA(h, cudaMemsetAsync(sa.n_active, 0, sizeof(int), h->stream));
@@ -168,22 +198,27 @@ extern "C" int adaprox_time_path_gemm(adaprox_handle h, adaprox_id mat, int64_t 
   AP_CUDA(h, cudaSetDevice(h->device));
   if ((rc = path_setup_kernels(h))) return rc;
   const DMat& M = hm->d;
-  const int64_t ldx = round_up(M.n, 16), ldr = round_up(M.m, 16), mtiles = (M.m + kGBM - 1) / kGBM;
-  const int ksplit = path_ksplit(h, M.n, M.m, L);
-  size_t need = ws_size_doubles(L * ldx) + ws_size_doubles((int64_t)ksplit * L * ldx) + ws_size_doubles(L * ldr) + ws_size_doubles(mtiles * L) + ws_size_doubles(M.m);
+  const int64_t ldx = round_up(M.n, 16), ldr = round_up(M.m, 16);
+  const int ksplit = path_ksplit(h, M.n, M.m, L), ksplit1 = path_ksplit(h, M.m, M.n, L);
+  const int64_t mtiles = ksplit1 > 1 ? (M.m + kRFixRows - 1) / kRFixRows : (M.m + kGBM - 1) / kGBM;
+  size_t need = ws_size_doubles(L * ldx) + ws_size_doubles((int64_t)ksplit * L * ldx) + ws_size_doubles(L * ldr) + ws_size_doubles(mtiles * L) +
+                ws_size_doubles(M.m) + (ksplit1 > 1 ? ws_size_doubles((int64_t)ksplit1 * L * ldr) : 0);
   if ((rc = ws_reset(h, need))) return rc;
   PathGemmArgs g{};
   double* XT = ws_doubles(h, L * ldx);
   g.GT = ws_doubles(h, (int64_t)ksplit * L * ldx);
-  g.RT = ws_doubles(h, L * ldr);
+  double* RT = ws_doubles(h, L * ldr);
+  g.RT = RT;
   g.fpart = ws_doubles(h, mtiles * L);
   double* bz = ws_doubles(h, M.m);
+  double* rslab = ksplit1 > 1 ? ws_doubles(h, (int64_t)ksplit1 * L * ldr) : nullptr;
   AP_CUDA(h, cudaMemsetAsync(XT, 0, need, h->stream));
   g.A = M.a; g.m = M.m; g.n = M.n; g.lda = M.ld; g.b = bz; g.L = L; g.XT = XT; g.ldx = ldx; g.ldr = ldr;
-  g.ksplit = ksplit; g.gstride = L * ldx;
-  path_launch_gemm(h, which + 1, g);                                   // warm-up
+  g.ksplit = ksplit; g.gstride = L * ldx; g.ksplit1 = ksplit1; g.rstride = L * ldr;
+  auto launch = [&]() { if (which == 0) path_launch_r(h, g, RT, rslab); else { g.RT = RT; path_launch_gemm(h, 2, g); } };
+  launch();                                                            // warm-up
   AP_CUDA(h, cudaEventRecord(h->ev0, h->stream));
-  for (int r = 0; r < reps; ++r) path_launch_gemm(h, which + 1, g);
+  for (int r = 0; r < reps; ++r) launch();
   AP_CUDA(h, cudaEventRecord(h->ev1, h->stream));
   AP_CUDA(h, cudaStreamSynchronize(h->stream));
   AP_CUDA(h, cudaGetLastError());

@@ -59,6 +59,8 @@ struct PathGemmArgs {
   double* fpart;                            // [m tiles][L]  per-tile sums of r^2 (mode 1), reduced in tile order later
   int ksplit;                               // mode 2: K = m is cut into ksplit slabs (blockIdx.z); slab z writes GT + z * gstride
   int64_t gstride;                          //         (the slabs are summed in slab order by k_path_step: deterministic)
+  int ksplit1;                              // mode 1: K = n cut into ksplit1 slabs; slab z writes the RAW partial product to
+  int64_t rstride;                          //         RT + z * rstride; k_path_rfix sums the slabs in order, subtracts b, forms fpart
 };
 
 // MODE 1: RT[j][i] = sum_k A[i][k] XT[j][k] - b[i]  (+ fpart): M index = row i of A, N index = column j, K = n.
@@ -81,9 +83,10 @@ __global__ void __launch_bounds__(kGT, 1) k_path_gemm(PathGemmArgs g) {
   const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(gsm);
   // k range of this CTA (mode 2 may split K over blockIdx.z; slabs are multiples of BK)
   int64_t kbeg = 0, kend = Kdim;
-  if (MODE == 2 && g.ksplit > 1) {
+  const int ksp = (MODE == 2) ? g.ksplit : g.ksplit1;
+  if (ksp > 1) {
     const int64_t tiles = (Kdim + kGBK - 1) / kGBK;
-    const int64_t per = (tiles + g.ksplit - 1) / g.ksplit;
+    const int64_t per = (tiles + ksp - 1) / ksp;
     kbeg = (int64_t)blockIdx.z * per * kGBK;
     kend = kbeg + per * kGBK;
     if (kend > Kdim) kend = Kdim;
@@ -100,7 +103,7 @@ __global__ void __launch_bounds__(kGT, 1) k_path_gemm(PathGemmArgs g) {
         const int ch = tid + q * kGT;
         const int r = ch >> 3, kc = (ch & 7) * 2;
         const int64_t row = m0 + r, k = k0 + kc;
-        const bool ok = (row < Mdim) && (k + 2 <= g.lda);               // the zero padding up to lda may be read
+        const bool ok = (row < Mdim) && (k + 2 <= g.lda) && (k < kend);   // the zero padding up to lda may be read
         const double* src = g.A + (ok ? row * g.lda + k : 0);
         cp_async16(sa + (uint32_t)(r * kGPadK + kc) * 8, src, ok ? 16 : 0);
       }
@@ -123,7 +126,7 @@ __global__ void __launch_bounds__(kGT, 1) k_path_gemm(PathGemmArgs g) {
       if (ch >= kGBN * kGBK / 2) break;
       const int r = ch >> 3, kc = (ch & 7) * 2;
       const int64_t col = n0 + r, k = k0 + kc;
-      const bool ok = (col < Ndim) && (k + 2 <= ldb) && (MODE == 1 || k < kend);   // slabs end on even k (BK multiples or m padded)
+      const bool ok = (col < Ndim) && (k + 2 <= ldb) && (k < kend);   // slabs end on even k (multiples of BK, or the padded end)
       const double* src = Bop + (ok ? col * ldb + k : 0);
       cp_async16(sb + (uint32_t)(r * kGPadK + kc) * 8, src, ok ? 16 : 0);
     }
@@ -173,7 +176,20 @@ __global__ void __launch_bounds__(kGT, 1) k_path_gemm(PathGemmArgs g) {
   cp_async_wait<0>();
 
   // epilogue.  Accumulator fragment: row = lane / 4 (M index within the 8 x 8 tile), cols = 2 (lane % 4) + {0, 1}.
-  if (MODE == 1) {
+  if (MODE == 1 && g.ksplit1 > 1) {
+    double* out = g.RT + (int64_t)blockIdx.z * g.rstride;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int64_t i = m0 + wm * 32 + r * 8 + lr;
+#pragma unroll
+      for (int c = 0; c < NT; ++c)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int64_t j = n0 + wn * 8 * NT + c * 8 + 2 * lk + e;
+          if (i < g.m && j < g.L) out[j * g.ldr + i] = acc[r][c][e];
+        }
+    }
+  } else if (MODE == 1) {
     __shared__ double s_f[4][kGBN];                     // [wm][column within the CTA tile]
     double fs[NT][2];
 #pragma unroll
@@ -222,6 +238,30 @@ __global__ void __launch_bounds__(kGT, 1) k_path_gemm(PathGemmArgs g) {
           if (col < g.n && j < g.L) g.GT[(int64_t)blockIdx.z * g.gstride + j * g.ldx + col] = acc[r][c][e];   // lasso/runme.jl:23
         }
     }
+  }
+}
+
+// R = sum of the K slabs of A X (slab order) - b, and the per-(row chunk, column) sums of r^2.  One CTA per (1024-row chunk,
+// column); fpart[chunk][j] is reduced over the chunks in order by k_path_step.
+constexpr int kRFixRows = 1024;
+__global__ void __launch_bounds__(256, 4) k_path_rfix(PathGemmArgs g, const double* slabs) {
+  __shared__ double s_w[8];
+  const int64_t j = blockIdx.y, i0 = (int64_t)blockIdx.x * kRFixRows;
+  double fs = 0.0;
+  for (int64_t i = i0 + threadIdx.x; i < i0 + kRFixRows && i < g.m; i += 256) {
+    double s = 0.0;
+    for (int z = 0; z < g.ksplit1; ++z) s += slabs[(int64_t)z * g.rstride + j * g.ldr + i];
+    const double rv = s - __ldg(g.b + i);                  // lasso/runme.jl:22
+    g.RT[j * g.ldr + i] = rv;
+    fs = fma(rv, rv, fs);
+  }
+  fs = warp_sum(fs);
+  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = fs;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < 8; ++w) s += s_w[w];
+    g.fpart[(int64_t)blockIdx.x * g.L + j] = s;
   }
 }
 
