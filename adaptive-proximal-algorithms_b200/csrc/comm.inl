@@ -2,16 +2,18 @@
 //
 // Row-sharded AdaPGM: rows of A (and b / labels) are split
 // in contiguous blocks over the ranks, x / grad / stepsize state are replicated.
-// Per iteration every rank streams its shard twice (A*x is purely local, A'r
-// yields a partial n-vector) and ONE all-reduce of n+2 doubles combines the
-// A'r partials with the value sums.  NCCL delivers bit-identical sums on every
-// rank, so the replicated prox / stepsize arithmetic stays in lock step with no
-// second collective.  A persistent kernel cannot call NCCL, so the iteration is
-// split at the all-reduce into ordinary launches on one stream (six per
-// iteration on the two-pass path, ONE per iteration with the single-pass fused
-// kernel in sweep-only mode on dense least squares); convergence is a device flag
-// polled by the host once per batch of iterations, so there is still no host
-// round trip per iteration.
+// Per iteration every rank sweeps its shard (once with the fused kernel on dense
+// least squares, twice -- A*x, then A'r -- otherwise) and ONE all-reduce of n+2
+// doubles combines the A'r partials with the value sums.  Every rank obtains
+// bit-identical sums, so the replicated prox / stepsize arithmetic stays in lock
+// step with no second collective.  The all-reduce is either ncclAllReduce between
+// ordinary launches on one stream (three launches per iteration with the fused
+// sweep, six on the two-pass path) or, when the peer exchange blocks are attached
+// (adaprox_p2p_*), done INSIDE the sweep kernel over NVLink peer memory (p2p.cuh).
+// Convergence is a device flag polled by the host once per batch of iterations, so
+// there is no host round trip per iteration.  This file also owns the NCCL loader,
+// the CUDA-IPC exchange blocks and their C entry points; the row-sharded
+// primal-dual solves run in the persistent kernel of solver_pd.cuh.
 #include <dlfcn.h>
 #include <nccl.h>
 

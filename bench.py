@@ -4,13 +4,19 @@
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
     python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host cores
 
-A step is ONE AdaPGM iteration (src/AdaProx.jl:334-362: A*x, A'*r, the stepsize
-rule, the prox step) on the planted lasso of lasso/runme.jl:40-77 generated on
-the device.  N = 1 runs configs[3] at its full size, 65536 x 131072 fp64
-(68.7 GB, far larger than the 126 MB L2, so no L2 flush is needed between
-iterations).  N > 1 row-shards the same instance (strong scaling): per
-iteration each rank streams its shard twice and one NCCL all-reduce of n + 2
-doubles combines the A'r partials.
+A step is ONE AdaPGM iteration (src/AdaProx.jl:334-362: value and gradient of
+the least-squares term, the stepsize rule, the prox step) on the planted lasso
+of lasso/runme.jl:40-77 generated on the device.  N = 1 runs configs[3] at its
+full size, 65536 x 131072 fp64 (68.7 GB, far larger than the 126 MB L2, so no
+L2 flush is needed between iterations).  N > 1 row-shards the same instance
+(strong scaling): per iteration each rank sweeps its shard and the A'r partials
+(n + 2 doubles) are all-reduced -- inside the sweep kernel over NVLink peer
+memory by default, with ncclAllReduce under --nccl.
+
+The default kernel is the single-sweep fused kernel (A is read ONCE per
+iteration: g = A'(Ax - b) per row block while the rows are in shared memory);
+--two-pass times the two-sweep persistent kernel (A*x, then A'r) for the A/B.
+`roofline.achieved` counts the bytes the kernel that ran has to move.
 
 `value` comes from CUDA events recorded by the library on the stream its kernels
 run on, around a solve of exactly K iterations with everything resident in HBM
