@@ -737,3 +737,35 @@ def test_lambda_path_edge_cases(AdaProx):
         assert np.all(np.abs(its - itso) <= np.maximum(2, 0.1 * itso))
         ok = its == itso
         assert np.allclose(X[:, ok], Xo[:, ok], rtol=1e-6, atol=1e-9)
+
+
+def test_fused_full_width_large_instance(AdaProx):
+    """16384 x 131072 (17 GB, the full row width of BASELINE configs[3]: clusters of 16 CTAs, dynamic chunk schedule over
+    7 clusters) generated on the device: the single-sweep kernel against the two-pass kernels on the same matrix, the planted
+    optimum as the size-independent anchor, and run-to-run bit reproducibility of the dynamically scheduled sweep."""
+    import os
+    m, n = 16384, 131072
+    dev = AdaProx.default_device()
+    if dev.info()["free_bytes"] < 40e9:
+        pytest.skip("needs ~20 GB of device memory")
+    P = AdaProx.generate_planted_lasso(m, n, pfactor=5, seed=1, power_iters=20)
+    f, g = AdaProx.LinearLeastSquares(P["A"], P["b"]), AdaProx.NormL1(1.0)
+    runs = {}
+    try:
+        for mode in ("0", "1", "1"):
+            os.environ["ADAPROX_FUSED"] = mode
+            log = []
+            x, it = AdaProx.adaptive_proxgrad(np.zeros(n), f=f, g=g, rule=AdaProx.OurRule(gamma=1 / P["Lf"]), tol=0.0, maxit=12, log=log)
+            runs.setdefault(mode, []).append((x, log, AdaProx.last_solve_info()["matrix_passes"]))
+    finally:
+        os.environ.pop("ADAPROX_FUSED", None)
+    (x2, l2, p2), (x1, l1, p1), (x1b, l1b, _) = runs["0"][0], runs["1"][0], runs["1"][1]
+    assert p2 == 2 and p1 == 1
+    assert np.allclose([r["gamma"] for r in l1], [r["gamma"] for r in l2], rtol=1e-9)
+    assert np.allclose([r["objective"] for r in l1], [r["objective"] for r in l2], rtol=1e-11)
+    assert np.allclose([r["norm_res"] for r in l1], [r["norm_res"] for r in l2], rtol=1e-9)
+    assert np.linalg.norm(x1 - x2) <= 1e-9 * np.linalg.norm(x2)
+    assert np.array_equal(x1, x1b) and [r["gamma"] for r in l1] == [r["gamma"] for r in l1b]      # dynamic schedule, same bits
+    # the objective decreases towards the planted optimum and never undershoots it
+    obj = np.array([r["objective"] for r in l1])
+    assert np.all(obj >= P["optimum"] * (1 - 1e-12)) and obj[-1] < obj[0]
