@@ -290,7 +290,9 @@ __device__ __noinline__ double fused_pass(const DMat& M, const double* bvec, con
     if (!(leader && rank == 0)) fsum = 0.0;
   }
   __syncthreads();
-  fs.count = g0 + (uint32_t)nrows;
+  // slot = g % 3, ring phase = (g / 3) & 1, exchange buffer = g % 8, its phase = (g / 8) & 1: everything is periodic in g with
+  // period lcm(6, 16) = 48, so the running row index is kept modulo 48 (a 32-bit count would wrap after 4e9 rows)
+  fs.count = (uint32_t)(((uint64_t)g0 + (uint64_t)nrows) % 48u);
   return fsum;
 }
 
