@@ -143,8 +143,10 @@ static int fill_problem(adaprox_ctx* h, const adaprox_problem* p, DProblem* out,
       P.F = (*fmat)->d;
       const int64_t ncols = (p->f_kind == ADAPROX_F_LOGISTIC) ? p->n - 1 : p->n;
       if (P.F.n != ncols) return fail(h, ADAPROX_ERR_INVALID, "f matrix has " + std::to_string(P.F.n) + " columns, expected " + std::to_string(ncols));
-      if ((p->f_kind == ADAPROX_F_QUADRATIC || p->f_kind == ADAPROX_F_CUBIC) && P.F.m != p->n)
+      if ((p->f_kind == ADAPROX_F_QUADRATIC || p->f_kind == ADAPROX_F_CUBIC) && (*fmat)->m_global != p->n)
         return fail(h, ADAPROX_ERR_INVALID, "Q must be square");
+      if (p->f_kind == ADAPROX_F_CUBIC && (*fmat)->sharded) return fail(h, ADAPROX_ERR_UNSUPPORTED, "Cubic: a row-sharded Q is not supported");
+      if (p->f_kind == ADAPROX_F_QUADRATIC) P.f_row0 = (*fmat)->sharded ? (*fmat)->row0 : 0;
       vec_len = (p->f_kind == ADAPROX_F_QUADRATIC || p->f_kind == ADAPROX_F_CUBIC) ? p->n : P.F.m;
       P.f_N = (double)((*fmat)->m_global);
       if (p->f_vec == 0) return fail(h, ADAPROX_ERR_INVALID, "f_vec (b / y / q) is required");
@@ -656,12 +658,18 @@ extern "C" int adaprox_solve(adaprox_handle h, const adaprox_problem* p, const a
   const bool sharded = (fm && fm->sharded) || (am && am->sharded);
   // Row-sharded linear map A of the primal-dual loops (AdaPDM / Condat-Vu / AdaPDM+; f without a sharded matrix): the persistent
   // kernel itself all-reduces A'y and the dual sums over NVLink peer memory -- needs the exchange blocks (adaprox_p2p_*).
-  const bool sharded_pd = sharded && am && am->sharded && !(fm && fm->sharded) &&
-                          (o->solver == ADAPROX_S_ADAPTIVE_PRIMAL_DUAL || o->solver == ADAPROX_S_LINESEARCH_PRIMAL_DUAL);
+  // ... and a row-sharded Q of a Quadratic smooth term (dual SVM): gradient rows and value sums are gathered the same way.
+  const bool pd_solver = o->solver == ADAPROX_S_ADAPTIVE_PRIMAL_DUAL || o->solver == ADAPROX_S_LINESEARCH_PRIMAL_DUAL;
+  const bool f_quad_shard = fm && fm->sharded && P.f_kind == ADAPROX_F_QUADRATIC;
+  const bool f_ok = !(fm && fm->sharded) || f_quad_shard;
+  const bool sharded_pd = sharded && f_ok && ((pd_solver && ((am && am->sharded) || f_quad_shard)) ||
+                                              (o->solver == ADAPROX_S_ADAPTIVE_PROXGRAD && f_quad_shard));
   if (sharded_pd) {
     if (!p2p_ready(h, std::max<int64_t>(P.n, 8)))
       return fail(h, ADAPROX_ERR_COMM, "row-sharded primal-dual solve: attach the peer exchange blocks first (adaprox_p2p_export / adaprox_p2p_attach)");
     p2p_fill(h, &P.p2p);
+    P.A_sharded = (am && am->sharded) ? 1 : 0;
+    P.F_sharded = f_quad_shard ? 1 : 0;
   } else if (sharded) {
     return solve_sharded(h, p, o, P, O, fm, am, x0, y0, x_out, y_out, records, res);
   }

@@ -27,12 +27,14 @@ struct DProblem {
   int f_kind, f_ipar;
   double f_c;
   DMat F;                  // matrix of the smooth term
-  const double* fvec;      // b / y / q (local rows for LS / logistic)
+  const double* fvec;      // b / y / q (local rows for LS / logistic; full length for Quadratic)
+  int64_t f_row0;          // Quadratic with a row-sharded Q: F holds rows [f_row0, f_row0 + F.m) of the n x n matrix
   double f_N;              // logistic: global number of samples
   DProx g, h;
   DMat A;                  // linear map of the primal-dual solvers (MAT_NONE: `A = 0`)
   int64_t n, md;           // primal / dual dimension (md: LOCAL rows of A when A is a row shard)
   P2PArgs p2p;             // row-sharded primal-dual solves: in-kernel all-reduce over peer memory (p2p.n <= 1: single GPU)
+  int A_sharded, F_sharded;   // which of the two matrices is a row block (p2p.n > 1 only)
 };
 
 struct DOpts {
@@ -243,11 +245,14 @@ __device__ __forceinline__ void f_phase_B(const DProblem& P, const DWork& W, con
       }
     } break;
     case ADAPROX_F_QUADRATIC:                                       // dual_svm/runme.jl:25-27
-      for (int64_t i = tid; i < P.n; i += nt) {
-        const double temp = zsum(P.F, i), xi = ldcg(x + i);
-        W.r[i] = temp;
+      // (row-sharded Q: this rank owns rows [f_row0, f_row0 + F.m); the sums and the gradient are completed across the
+      //  ranks by the caller.  Unsharded: f_row0 = 0 and F.m = n.)
+      for (int64_t i = tid; i < P.F.m; i += nt) {
+        const int64_t gi = P.f_row0 + i;
+        const double temp = zsum(P.F, i), xi = ldcg(x + gi);
+        W.r[gi] = temp;
         acc[0] = fma(xi, temp, acc[0]);
-        acc[1] = fma(xi, P.fvec[i], acc[1]);
+        acc[1] = fma(xi, P.fvec[gi], acc[1]);
       }
       break;
     case ADAPROX_F_CUBIC: {                                         // cubic_sparse_logreg/runme.jl:27-29
@@ -328,7 +333,10 @@ __device__ __forceinline__ void grad_slice(const DProblem& P, const DWork& W, in
       __syncthreads();
     } break;
     case ADAPROX_F_QUADRATIC:
-      for (int64_t j = j0 + threadIdx.x; j < j1; j += kThreads) out[j] = ldcg(W.r + j) + P.fvec[j];
+      for (int64_t j = j0 + threadIdx.x; j < j1; j += kThreads) {
+        const bool own = (j >= P.f_row0) && (j < P.f_row0 + P.F.m);        // rows of other ranks: 0 (summed across ranks later)
+        out[j] = own ? ldcg(W.r + j) + P.fvec[j] : 0.0;
+      }
       __syncthreads();
       break;
     case ADAPROX_F_ZERO:

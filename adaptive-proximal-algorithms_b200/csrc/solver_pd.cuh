@@ -65,7 +65,10 @@ __global__ void __launch_bounds__(kThreads, 2) k_primal_dual(DProblem P, DOpts O
   // Row-sharded A: this rank holds md = local rows of A, the dual iterate y and A*x are row-local, x and every
   // n-vector are replicated.  A'y and the dual-side sums are combined across the ranks INSIDE this kernel (p2p.cuh); every
   // rank then holds identical bits and the replicated control flow stays in lock step.
-  const bool shardedA = hasA && P.p2p.n > 1;
+  const bool shardedA = hasA && P.p2p.n > 1 && P.A_sharded;
+  // Row-sharded Q of a Quadratic smooth term (dual SVM, dual_svm/runme.jl:19-28): the gradient rows and the two value
+  // sums of this rank are completed across the ranks in the same way.
+  const bool shardedF = P.p2p.n > 1 && P.F_sharded;
   P2PState ps;
   p2p_begin(P.p2p, ps);
   const bool want_obj = O.want_objective != 0;
@@ -103,6 +106,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_primal_dual(DProblem P, DOpts O
     double tot[2];
     grid_totals<2>(W.red, G, SLOT_F0, tot, s_scr);
     grad_slice(P, W, j0, j1, W.gb[gc], tot[1], G);
+    if (shardedF) p2p_allreduce<kThreads>(P.p2p, ps, grid, W.gb[gc], W.gb[gc], P.n);
     if (hasA) gsum_slice(P.A, j0, j1, W.Aty[atc], G);
     if (shardedA) p2p_allreduce<kThreads>(P.p2p, ps, grid, W.Aty[atc], W.Aty[atc], P.n);     // A'y over all row blocks
     double acc[1] = {0.0};
@@ -151,6 +155,10 @@ __global__ void __launch_bounds__(kThreads, 2) k_primal_dual(DProblem P, DOpts O
     grid_totals<2>(W.red, G, SLOT_F0, ftot, s_scr);
     double* grad = W.gb[gc ^ 1];
     grad_slice(P, W, j0, j1, grad, ftot[1], G);
+    if (shardedF) {
+      p2p_allreduce<kThreads>(P.p2p, ps, grid, grad, grad, P.n);            // gather the gradient rows of all ranks
+      p2p_allreduce_scalars<2>(P.p2p, ps, grid, ftot);                      // x'Qx and x'q over all rows
+    }
     {
       double acc[4] = {0.0, 0.0, 0.0, 0.0};
       const double* aty = W.Aty[atc];

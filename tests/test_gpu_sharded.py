@@ -180,3 +180,85 @@ def test_sharded_adapdm_two_gpus(tmp_path):
         y = np.concatenate([R0[hname + "_y"], R1[hname + "_y"]])
         if int(R0[hname + "_it"]) == ito:
             assert np.allclose(R0[hname + "_x"], xo, rtol=1e-6, atol=1e-9) and np.allclose(y, yo, rtol=1e-6, atol=1e-9)
+
+
+# ---------------------------------------------------------------- row-sharded dual SVM
+def _svm_problem():
+    rng = np.random.default_rng(7)
+    N, d = 90, 6
+    X = rng.standard_normal((N, d))
+    w = rng.standard_normal(d)
+    y = np.sign(X @ w + 0.3 * rng.standard_normal(N))
+    y[y == 0] = 1.0
+    Z = y[:, None] * X
+    return Z @ Z.T, -np.ones(N), y                       # dual_svm/runme.jl:47-55: Q, q, labels
+
+
+def _worker_svm(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), LOCAL_RANK=str(rank))
+    import torch.distributed as dist
+    import adaprox_b200 as AdaProx
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    dev = AdaProx.Device(rank)
+    AdaProx.set_default_device(dev)
+    AdaProx.sharding.attach_communicator(dev, dist)
+    assert AdaProx.sharding.attach_p2p(dev, 4096, dist)
+    Q, q, y = _svm_problem()
+    N = Q.shape[0]
+    row0, rows = AdaProx.sharding.shard_rows(N, world, rank)
+    Qs = AdaProx.DeviceMatrix(Q[row0:row0 + rows].copy(), dev=dev)          # this rank's rows of the N x N matrix
+    Qs.set_shard(N, row0)
+    f = AdaProx.Counting(AdaProx.Quadratic(Qs, q))
+    Amat = y[None, :].copy()
+    nA = float(np.linalg.norm(Amat))
+    log = []
+    x, yy, it = AdaProx.adaptive_primal_dual(np.zeros(N), np.zeros(1), f=f, g=AdaProx.IndBox(0.0, 0.1), h=AdaProx.IndZero(),
+                                             A=AdaProx.DeviceMatrix(Amat, dev=dev), rule=AdaProx.OurRule(t=1.0, norm_A=nA), tol=1e-6, maxit=3000, log=log)
+    info = AdaProx.last_solve_info()
+    # AdaPGM on the box-constrained quadratic alone (no equality constraint): the proximal-gradient entry point on a sharded Q
+    log2 = []
+    x2, it2 = AdaProx.adaptive_proxgrad(np.zeros(N), f=AdaProx.Quadratic(Qs, q), g=AdaProx.IndBox(0.0, 0.1), rule=AdaProx.OurRule(gamma=1e-2),
+                                        tol=1e-7, maxit=2000, log=log2)
+    np.savez(out % rank, x=x, y=yy, it=it, gam=np.array([r["gamma"] for r in log]), res=np.array([r["norm_res"] for r in log]),
+             obj=np.array([r["objective"] for r in log]), coll=info["collective"], fe=f.eval_count, ge=f.grad_count,
+             x2=x2, it2=it2, gam2=np.array([r["gamma"] for r in log2]), obj2=np.array([r["objective"] for r in log2]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_dual_svm_two_gpus(tmp_path):
+    """dual_svm/runme.jl:47-59 with the N x N matrix Q row-sharded over 2 GPUs (x replicated): every rank computes its rows of
+    Q x, the gradient rows and the two value sums are gathered inside the persistent kernel over NVLink peer memory."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    from oracle import adaprox_oracle as O
+    out = str(tmp_path / "svm_rank%d.npz")
+    mp.spawn(_worker_svm, args=(2, 32400 + os.getpid() % 500, out), nprocs=2, join=True)
+    R0, R1 = np.load(out % 0), np.load(out % 1)
+    Q, q, y = _svm_problem()
+    N = Q.shape[0]
+    Amat = y[None, :].copy()
+    nA = float(np.linalg.norm(Amat))
+    assert int(R0["coll"]) == 2
+    assert np.array_equal(R0["x"], R1["x"]) and int(R0["it"]) == int(R1["it"]) and np.array_equal(R0["x2"], R1["x2"])
+    fo = O.Counting(O.Quadratic(Q, q))
+    lo = []
+    xo, yo, ito = O.adaptive_primal_dual(np.zeros(N), np.zeros(1), f=fo, g=O.IndBox(0.0, 0.1), h=O.IndZero(), A=Amat,
+                                         rule=O.OurRule(t=1.0, norm_A=nA), tol=1e-6, maxit=3000, log=lo)
+    K = min(40, len(lo), len(R0["gam"]))
+    assert np.allclose(R0["gam"][:K], [r["gamma"] for r in lo[:K]], rtol=1e-11)
+    assert np.allclose(R0["res"][:K], [r["norm_res"] for r in lo[:K]], rtol=1e-9)
+    fin = np.isfinite([r["objective"] for r in lo[:K]])
+    assert np.allclose(R0["obj"][:K][fin], np.array([r["objective"] for r in lo[:K]])[fin], rtol=1e-10)
+    assert abs(int(R0["it"]) - ito) <= max(3, 0.05 * ito)
+    assert (int(R0["fe"]), int(R0["ge"])) == (int(R0["it"]) + 1, int(R0["it"]) + 1)
+    assert abs(fo.f(R0["x"]) - fo.f(xo)) <= 1e-7 * abs(fo.f(xo))
+    lo2 = []
+    xo2, ito2 = O.adaptive_proxgrad(np.zeros(N), f=O.Quadratic(Q, q), g=O.IndBox(0.0, 0.1), rule=O.OurRule(gamma=1e-2), tol=1e-7, maxit=2000, log=lo2)
+    K2 = min(40, len(lo2), len(R0["gam2"]))
+    assert np.allclose(R0["gam2"][:K2], [r["gamma"] for r in lo2[:K2]], rtol=1e-11)
+    assert np.allclose(R0["obj2"][:K2], [r["objective"] for r in lo2[:K2]], rtol=1e-10)
+    assert abs(int(R0["it2"]) - ito2) <= max(3, 0.05 * ito2)
