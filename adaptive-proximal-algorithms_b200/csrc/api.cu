@@ -662,14 +662,19 @@ extern "C" int adaprox_solve(adaprox_handle h, const adaprox_problem* p, const a
   const bool pd_solver = o->solver == ADAPROX_S_ADAPTIVE_PRIMAL_DUAL || o->solver == ADAPROX_S_LINESEARCH_PRIMAL_DUAL;
   const bool f_quad_shard = fm && fm->sharded && P.f_kind == ADAPROX_F_QUADRATIC;
   const bool f_ok = !(fm && fm->sharded) || f_quad_shard;
-  const bool sharded_pd = sharded && f_ok && ((pd_solver && ((am && am->sharded) || f_quad_shard)) ||
-                                              (o->solver == ADAPROX_S_ADAPTIVE_PROXGRAD && f_quad_shard));
+  // ... and the backtracking / Nesterov / aGRAAL baselines on a row-sharded least-squares or Quadratic term.
+  const bool pg_family = o->solver == ADAPROX_S_BACKTRACKING_PROXGRAD || o->solver == ADAPROX_S_BACKTRACKING_NESTEROV ||
+                         o->solver == ADAPROX_S_FIXED_NESTEROV || o->solver == ADAPROX_S_AGRAAL;
+  const bool f_ls_shard = fm && fm->sharded && P.f_kind == ADAPROX_F_LEAST_SQUARES && P.F.kind == MAT_DENSE;
+  const bool sharded_pd = sharded && ((f_ok && pd_solver && ((am && am->sharded) || f_quad_shard)) ||
+                                      (f_ok && o->solver == ADAPROX_S_ADAPTIVE_PROXGRAD && f_quad_shard) ||
+                                      (pg_family && (f_ls_shard || f_quad_shard) && !(am && am->sharded)));
   if (sharded_pd) {
     if (!p2p_ready(h, std::max<int64_t>(P.n, 8)))
       return fail(h, ADAPROX_ERR_COMM, "row-sharded primal-dual solve: attach the peer exchange blocks first (adaprox_p2p_export / adaprox_p2p_attach)");
     p2p_fill(h, &P.p2p);
     P.A_sharded = (am && am->sharded) ? 1 : 0;
-    P.F_sharded = f_quad_shard ? 1 : 0;
+    P.F_sharded = (f_quad_shard || (pg_family && f_ls_shard)) ? 1 : 0;
   } else if (sharded) {
     return solve_sharded(h, p, o, P, O, fm, am, x0, y0, x_out, y_out, records, res);
   }

@@ -8,6 +8,7 @@
 // the device: every CTA derives the same scalars from fixed-order reductions and
 // takes the same branch, so there is no host round trip per trial.
 #pragma once
+#include "p2p.cuh"
 #include "phases.cuh"
 
 namespace adaprox {
@@ -15,9 +16,12 @@ namespace adaprox {
 // f(x) (and optionally the gradient on this CTA's slice).  `x` must be complete
 // and grid-synced.  Returns with all partials consumed; the caller must
 // grid-sync before anything overwrites W.r / the matrix partials again.
+// Row-sharded f (least squares: rows of A and b local; Quadratic: rows of Q local): the value sums and the gradient are
+// completed across the ranks inside the kernel (p2p.cuh); every rank then continues with identical bits.
 __device__ __forceinline__ double eval_f_grid(cg::grid_group& grid, const DProblem& P, const DWork& W, const double* x,
                                               bool want_grad, double* grad_out, int64_t j0, int64_t j1, Sh& sh,
-                                              double* s_scr, int b, int G) {
+                                              double* s_scr, int b, int G, P2PState& ps) {
+  const bool shardedF = P.p2p.n > 1 && P.F_sharded;
   f_phase_A(P, W, x, sh, s_scr, b, G);
   grid.sync();
   f_phase_B(P, W, x, s_scr, b, G);
@@ -28,8 +32,12 @@ __device__ __forceinline__ double eval_f_grid(cg::grid_group& grid, const DProbl
   }
   double tot[2], xx[1] = {0.0};
   grid_totals<2>(W.red, G, SLOT_F0, tot, s_scr);
+  if (shardedF) p2p_allreduce_scalars<2>(P.p2p, ps, grid, tot);
   if (P.f_kind == ADAPROX_F_CUBIC) grid_totals<1>(W.red, G, SLOT_XX0, xx, s_scr);
-  if (want_grad) grad_slice(P, W, j0, j1, grad_out, tot[1], G);
+  if (want_grad) {
+    grad_slice(P, W, j0, j1, grad_out, tot[1], G);
+    if (shardedF) p2p_allreduce<kThreads>(P.p2p, ps, grid, grad_out, grad_out, P.n);
+  }
   return f_value(P, tot[0], tot[1], xx[0]);
 }
 
@@ -42,6 +50,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_proxgrad_family(DProblem P, DOp
   __shared__ unsigned long long s_bars[2 * kStages];
   Sh sh;
   sh_init(sh, dyn_smem, s_scr, s_part, s_bars);
+  P2PState ps;
+  p2p_begin(P.p2p, ps);
   const int64_t tid = (int64_t)b * kThreads + threadIdx.x, nt = (int64_t)G * kThreads;
   int64_t j0, j1;
   cta_slice(P.n, b, G, j0, j1);
@@ -74,7 +84,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_proxgrad_family(DProblem P, DOp
     double* grad = W.gb[0];
     if (nesterov) for (int64_t j = j0 + threadIdx.x; j < j1; j += kThreads) z_prev[j] = x[j];
     double theta = 1.0;                                                          // :68
-    double f_x = eval_f_grid(grid, P, W, x, true, grad, j0, j1, sh, s_scr, b, G);   // :52 / :69
+    double f_x = eval_f_grid(grid, P, W, x, true, grad, j0, j1, sh, s_scr, b, G, ps);   // :52 / :69
     n_eval++; n_grad++;
     int64_t trial_no = 0;
     for (int64_t it = 1; it <= O.maxit; ++it) {
@@ -97,7 +107,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_proxgrad_family(DProblem P, DOp
         block_reduce_store<3>(acc, W.red, G, base, s_scr);
         n_proxg++;
         grid.sync();
-        f_z = eval_f_grid(grid, P, W, z, false, nullptr, j0, j1, sh, s_scr, b, G);   // :37 / :45
+        f_z = eval_f_grid(grid, P, W, z, false, nullptr, j0, j1, sh, s_scr, b, G, ps);   // :37 / :45
         n_eval++;
         double t3[3];
         grid_totals<3>(W.red, G, base, t3, s_scr);
@@ -120,6 +130,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_proxgrad_family(DProblem P, DOp
         double tot[2];
         grid_totals<2>(W.red, G, SLOT_F0, tot, s_scr);
         grad_slice(P, W, j0, j1, grad, tot[1], G);
+        if (P.p2p.n > 1 && P.F_sharded) p2p_allreduce<kThreads>(P.p2p, ps, grid, grad, grad, P.n);
         n_grad++;
         double* t = x; x = z; z = t;
         f_x = f_z;
@@ -135,7 +146,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_proxgrad_family(DProblem P, DOp
         double* t = z_prev; z_prev = z; z = t;                                   // :71
         result = z_prev;
         grid.sync();
-        f_x = eval_f_grid(grid, P, W, x, true, grad, j0, j1, sh, s_scr, b, G);  // :81
+        f_x = eval_f_grid(grid, P, W, x, true, grad, j0, j1, sh, s_scr, b, G, ps);  // :81
         n_eval++; n_grad++;
       }
     }
@@ -161,7 +172,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_proxgrad_family(DProblem P, DOp
       }
       for (int64_t j = j0 + threadIdx.x; j < j1; j += kThreads) z[j] = x[j] + beta * (x[j] - x_prev[j]);   // :129
       grid.sync();
-      eval_f_grid(grid, P, W, z, true, grad, j0, j1, sh, s_scr, b, G);          // :130
+      eval_f_grid(grid, P, W, z, true, grad, j0, j1, sh, s_scr, b, G, ps);          // :130
       n_eval++; n_grad++;
       double acc[2] = {0.0, 0.0};
       for (int64_t j = j0 + threadIdx.x; j < j1; j += kThreads) {               // :131-133 (x_prev <- x, x <- prox)
@@ -182,7 +193,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_proxgrad_family(DProblem P, DOp
       norm_res = sqrt(t2[0]) / gamma;
       double fx = NAN;
       if (want_obj) {                                                            // :134-136, uncounted f(x)
-        fx = eval_f_grid(grid, P, W, x, false, nullptr, j0, j1, sh, s_scr, b, G);
+        fx = eval_f_grid(grid, P, W, x, false, nullptr, j0, j1, sh, s_scr, b, G, ps);
         grid.sync();
       }
       record(it, fx, prox_value_finish(P.g.kind, P.g.lambda, t2[1]));
@@ -197,9 +208,9 @@ __global__ void __launch_bounds__(kThreads, 2) k_proxgrad_family(DProblem P, DOp
     double* grad_prev = W.gb[1];
     for (int64_t j = j0 + threadIdx.x; j < j1; j += kThreads) { x_prev[j] = W.aux[0][j]; x_bar[j] = x[j]; }   // :165
     grid.sync();
-    eval_f_grid(grid, P, W, x, true, grad, j0, j1, sh, s_scr, b, G);            // :166
+    eval_f_grid(grid, P, W, x, true, grad, j0, j1, sh, s_scr, b, G, ps);            // :166
     grid.sync();
-    eval_f_grid(grid, P, W, x_prev, true, grad_prev, j0, j1, sh, s_scr, b, G);  // :167
+    eval_f_grid(grid, P, W, x_prev, true, grad_prev, j0, j1, sh, s_scr, b, G, ps);  // :167
     n_eval = 2; n_grad = 2;
     const double phi = O.phi;
     const double rho = 1.0 / phi + 1.0 / (phi * phi);                            // :172
@@ -242,13 +253,13 @@ __global__ void __launch_bounds__(kThreads, 2) k_proxgrad_family(DProblem P, DOp
       norm_res = sqrt(t3[0]) / gamma;                                            // :182
       double fx = NAN;
       if (want_obj) {
-        fx = eval_f_grid(grid, P, W, x, false, nullptr, j0, j1, sh, s_scr, b, G);
+        fx = eval_f_grid(grid, P, W, x, false, nullptr, j0, j1, sh, s_scr, b, G, ps);
         grid.sync();
       }
       record(it, fx, prox_value_finish(P.g.kind, P.g.lambda, t3[1]));
       result = x;
       if (norm_res <= O.tol) { converged = true; it_done = it; break; }
-      eval_f_grid(grid, P, W, x, true, grad, j0, j1, sh, s_scr, b, G);          // :189
+      eval_f_grid(grid, P, W, x, true, grad, j0, j1, sh, s_scr, b, G, ps);          // :189
       n_eval++; n_grad++;
     }
   }

@@ -262,3 +262,72 @@ def test_sharded_dual_svm_two_gpus(tmp_path):
     assert np.allclose(R0["gam2"][:K2], [r["gamma"] for r in lo2[:K2]], rtol=1e-11)
     assert np.allclose(R0["obj2"][:K2], [r["objective"] for r in lo2[:K2]], rtol=1e-10)
     assert abs(int(R0["it2"]) - ito2) <= max(3, 0.05 * ito2)
+
+
+# ---------------------------------------------------------------- row-sharded backtracking / Nesterov / aGRAAL baselines
+def _worker_pg(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), LOCAL_RANK=str(rank))
+    import torch.distributed as dist
+    import adaprox_b200 as AdaProx
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    dev = AdaProx.Device(rank)
+    AdaProx.set_default_device(dev)
+    AdaProx.sharding.attach_communicator(dev, dist)
+    assert AdaProx.sharding.attach_p2p(dev, 4096, dist)
+    P = AdaProx.synth.planted_lasso(100, 300, 10, 0)
+    Lf = AdaProx.synth.spectral_norm_sq(P["A"], iters=1000, tol=1e-15)
+    g0, n, m = 1.0 / Lf, 300, 100
+    row0, rows = AdaProx.sharding.shard_rows(m, world, rank)
+    A = AdaProx.DeviceMatrix(P["A"][row0:row0 + rows].copy(), dev=dev)
+    A.set_shard(m, row0)
+    b = P["b"][row0:row0 + rows]
+    res = {}
+
+    def run(name, fn, **kw):
+        f = AdaProx.Counting(AdaProx.LinearLeastSquares(A, b))
+        log = []
+        x, it = fn(np.zeros(n), f=f, g=AdaProx.NormL1(1.0), tol=1e-7, maxit=400, log=log, **kw)
+        res[name + "_x"] = x; res[name + "_it"] = it; res[name + "_fe"] = f.eval_count; res[name + "_ge"] = f.grad_count
+        res[name + "_gam"] = np.array([r["gamma"] for r in log]); res[name + "_obj"] = np.array([r["objective"] for r in log])
+        res[name + "_res"] = np.array([r["norm_res"] for r in log]); res[name + "_coll"] = AdaProx.last_solve_info()["collective"]
+
+    run("bt", AdaProx.backtracking_proxgrad, gamma0=g0, xi=1.5)
+    run("btn", AdaProx.backtracking_nesterov, gamma0=g0)
+    run("fn", AdaProx.fixed_nesterov, gamma=g0)
+    run("ag", AdaProx.agraal, x0=np.random.default_rng(3).standard_normal(n), gamma0=g0)
+    np.savez(out % rank, **res)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_pg_baselines_two_gpus(tmp_path):
+    """backtracking_proxgrad / backtracking_nesterov / fixed_nesterov / agraal (src/AdaProx.jl:34-192) on a row-sharded lasso: the
+    value sums of every trial and the gradients are combined inside the persistent kernel; same trial counts as the oracle."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    import adaprox_b200 as AdaProx
+    from oracle import adaprox_oracle as O
+    out = str(tmp_path / "pg_rank%d.npz")
+    mp.spawn(_worker_pg, args=(2, 33400 + os.getpid() % 500, out), nprocs=2, join=True)
+    R0, R1 = np.load(out % 0), np.load(out % 1)
+    P = AdaProx.synth.planted_lasso(100, 300, 10, 0)
+    Lf = AdaProx.synth.spectral_norm_sq(P["A"], iters=1000, tol=1e-15)
+    g0, n = 1.0 / Lf, 300
+    cases = {"bt": (O.backtracking_proxgrad, dict(gamma0=g0, xi=1.5)), "btn": (O.backtracking_nesterov, dict(gamma0=g0)),
+             "fn": (O.fixed_nesterov, dict(gamma=g0)), "ag": (O.agraal, dict(x0=np.random.default_rng(3).standard_normal(n), gamma0=g0))}
+    for name, (fn, kw) in cases.items():
+        assert int(R0[name + "_coll"]) == 2
+        assert np.array_equal(R0[name + "_x"], R1[name + "_x"]) and int(R0[name + "_it"]) == int(R1[name + "_it"])
+        fo = O.Counting(O.LinearLeastSquares(P["A"], P["b"]))
+        lo = []
+        xo, ito = fn(np.zeros(n), f=fo, g=O.NormL1(1.0), tol=1e-7, maxit=400, log=lo, **kw)
+        K = min(30, len(lo), len(R0[name + "_gam"]))
+        assert np.allclose(R0[name + "_gam"][:K], [r["gamma"] for r in lo[:K]], rtol=1e-11), name
+        assert np.allclose(R0[name + "_obj"][:K], [r["objective"] for r in lo[:K]], rtol=1e-10), name
+        assert np.allclose(R0[name + "_res"][:K], [r["norm_res"] for r in lo[:K]], rtol=1e-8), name
+        assert abs(int(R0[name + "_it"]) - ito) <= max(3, 0.05 * ito), name
+        if int(R0[name + "_it"]) == ito:
+            assert (int(R0[name + "_fe"]), int(R0[name + "_ge"])) == (fo.eval_count, fo.grad_count), name    # same backtracking trials
