@@ -11,7 +11,7 @@ from .core import (                                               # noqa: F401
     Device, DeviceMatrix, DeviceVector, default_device, set_default_device,
     Counting, without_counting, is_counting_enabled,
     grad_count, prox_count, mul_count, amul_count, eval_count,
-    LinearLeastSquares, LogisticLoss, Quadratic, Cubic, WorstQuadratic, Simple2DObjective, Simple2DBox,
+    LinearLeastSquares, LogisticLoss, Quadratic, QuadraticGram, Cubic, WorstQuadratic, Simple2DObjective, Simple2DBox,
     Zero, IndZero, NormL1, NormL2, IndBox, Translate, convex_conjugate, prox,
     eval_with_pullback, eval_with_gradient,
     FixedStepsize, MalitskyMishchenkoRule, OurRule, OurRulePlus, stepsize,

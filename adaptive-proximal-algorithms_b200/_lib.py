@@ -53,7 +53,7 @@ class Result(C.Structure):
 
 
 # enum values of include/adaprox.h
-F_ZERO, F_LEAST_SQUARES, F_LOGISTIC, F_QUADRATIC, F_CUBIC, F_WORST_QUADRATIC, F_SIMPLE2D = range(7)
+F_ZERO, F_LEAST_SQUARES, F_LOGISTIC, F_QUADRATIC, F_CUBIC, F_WORST_QUADRATIC, F_SIMPLE2D, F_QUADRATIC_GRAM = range(8)
 P_ZERO, P_IND_ZERO, P_NORM_L1, P_NORM_L2, P_IND_BOX = range(5)
 (S_ADAPTIVE_PRIMAL_DUAL, S_ADAPTIVE_PROXGRAD, S_LINESEARCH_PRIMAL_DUAL, S_BACKTRACKING_PROXGRAD,
  S_BACKTRACKING_NESTEROV, S_FIXED_NESTEROV, S_MALITSKY_POCK, S_AGRAAL) = range(8)

@@ -368,6 +368,21 @@ class Quadratic(_Smooth):
         self.n = self.mat.shape[1]
 
 
+class QuadraticGram(_Smooth):
+    """`Quadratic(Z * Z', q)` of experiments/dual_svm/runme.jl:19-28 given by its factor: the script builds
+    `Q = Dy * X * X' * Dy` (:47-49), i.e. Z = Dy * X (N x d).  `Q * x` is evaluated as `Z * (Z' * x)`: two sweeps over Z
+    (16 N d bytes) instead of one over the N x N matrix (8 N^2 bytes); same value up to rounding.  A row shard of Z
+    (`set_shard`) needs `n` = the global number of rows."""
+    kind = L.F_QUADRATIC_GRAM
+
+    def __init__(self, Z, q, dev=None):
+        self.Z = Z
+        self.q = q
+        self.mat = _as_matrix(Z, dev)
+        self.vec = _as_vector(q, self.mat.dev)
+        self.n = self.vec.len
+
+
 class Cubic(_Smooth):
     """experiments/cubic_sparse_logreg/runme.jl:20-32."""
     kind = L.F_CUBIC

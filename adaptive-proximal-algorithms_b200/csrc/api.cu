@@ -55,8 +55,8 @@ static int get_vec(adaprox_ctx* h, adaprox_id id, int64_t min_len, const double*
 }
 
 template <typename K>
-static int coop_launch(adaprox_ctx* h, K kernel, void** args) {
-  cudaError_t e = cudaLaunchCooperativeKernel((const void*)kernel, dim3(h->grid), dim3(kThreads), args, kRingBytes, h->stream);
+static int coop_launch(adaprox_ctx* h, K kernel, void** args, int grid = 0) {
+  cudaError_t e = cudaLaunchCooperativeKernel((const void*)kernel, dim3(grid > 0 ? grid : h->grid), dim3(kThreads), args, kRingBytes, h->stream);
   if (e != cudaSuccess) return fail(h, ADAPROX_ERR_CUDA, std::string("cooperative launch: ") + cudaGetErrorString(e));
   h->launches++;
   return ADAPROX_OK;
@@ -138,16 +138,20 @@ static int fill_problem(adaprox_ctx* h, const adaprox_problem* p, DProblem* out,
     case ADAPROX_F_LEAST_SQUARES:
     case ADAPROX_F_LOGISTIC:
     case ADAPROX_F_QUADRATIC:
+    case ADAPROX_F_QUADRATIC_GRAM:
     case ADAPROX_F_CUBIC: {
       if ((rc = get_mat(h, p->f_mat, fmat))) return rc;
       P.F = (*fmat)->d;
+      const bool gram = (p->f_kind == ADAPROX_F_QUADRATIC_GRAM);      // F = Z (n x d), any d
       const int64_t ncols = (p->f_kind == ADAPROX_F_LOGISTIC) ? p->n - 1 : p->n;
-      if (P.F.n != ncols) return fail(h, ADAPROX_ERR_INVALID, "f matrix has " + std::to_string(P.F.n) + " columns, expected " + std::to_string(ncols));
+      if (gram && P.F.kind != MAT_DENSE) return fail(h, ADAPROX_ERR_UNSUPPORTED, "QuadraticGram: Z must be a dense matrix");
+      if (!gram && P.F.n != ncols) return fail(h, ADAPROX_ERR_INVALID, "f matrix has " + std::to_string(P.F.n) + " columns, expected " + std::to_string(ncols));
       if ((p->f_kind == ADAPROX_F_QUADRATIC || p->f_kind == ADAPROX_F_CUBIC) && (*fmat)->m_global != p->n)
         return fail(h, ADAPROX_ERR_INVALID, "Q must be square");
+      if (gram && (*fmat)->m_global != p->n) return fail(h, ADAPROX_ERR_INVALID, "QuadraticGram: Z must have n rows");
       if (p->f_kind == ADAPROX_F_CUBIC && (*fmat)->sharded) return fail(h, ADAPROX_ERR_UNSUPPORTED, "Cubic: a row-sharded Q is not supported");
-      if (p->f_kind == ADAPROX_F_QUADRATIC) P.f_row0 = (*fmat)->sharded ? (*fmat)->row0 : 0;
-      vec_len = (p->f_kind == ADAPROX_F_QUADRATIC || p->f_kind == ADAPROX_F_CUBIC) ? p->n : P.F.m;
+      if (p->f_kind == ADAPROX_F_QUADRATIC || gram) P.f_row0 = (*fmat)->sharded ? (*fmat)->row0 : 0;
+      vec_len = (p->f_kind == ADAPROX_F_QUADRATIC || gram || p->f_kind == ADAPROX_F_CUBIC) ? p->n : P.F.m;
       P.f_N = (double)((*fmat)->m_global);
       if (p->f_vec == 0) return fail(h, ADAPROX_ERR_INVALID, "f_vec (b / y / q) is required");
     } break;
@@ -450,11 +454,13 @@ extern "C" int adaprox_eval_f(adaprox_handle h, const adaprox_problem* p, const 
   if (rc) return rc;
   if (fm && fm->sharded) return fail(h, ADAPROX_ERR_UNSUPPORTED, "eval_f on a row shard: use the solver entry points");
   const int64_t mf = std::max<int64_t>(P.F.kind != MAT_NONE ? P.F.m : 0, P.n);
-  if ((rc = ws_reset(h, 2 * ws_size_doubles(P.n) + ws_size_doubles(mf) + ws_size_doubles((int64_t)kMaxRed * h->grid) + ws_size_doubles(4)))) return rc;
+  const int64_t nfu = (P.f_kind == ADAPROX_F_QUADRATIC_GRAM) ? P.F.n : 1;
+  if ((rc = ws_reset(h, 2 * ws_size_doubles(P.n) + ws_size_doubles(mf) + ws_size_doubles(nfu) + ws_size_doubles((int64_t)kMaxRed * h->grid) + ws_size_doubles(4)))) return rc;
   double* dx = ws_doubles(h, P.n);
   double* dg = ws_doubles(h, P.n);
   DWork W{};
   W.r = ws_doubles(h, mf);
+  W.fu = ws_doubles(h, nfu);
   W.red = ws_doubles(h, (int64_t)kMaxRed * h->grid);
   double* scal = ws_doubles(h, 4);
   AP_CUDA(h, cudaMemcpyAsync(dx, x, (size_t)P.n * 8, cudaMemcpyHostToDevice, h->stream));
@@ -556,6 +562,7 @@ static int validate_options(adaprox_ctx* h, const adaprox_problem* p, const adap
 
 // Single-pass fused AdaPGM (solver_fused.cuh): cluster launch sized to full residency.  Returns 1 if the configuration is not
 // eligible (the caller falls through to the two-pass kernel), < 0 on error.
+constexpr int64_t kSmallProblemBytes = 8 << 20;   // fewer matrix bytes than this: latency-bound, one CTA per SM (see solver_grid)
 static int fused_cluster_size(const DProblem& P) { return (int)((P.F.ld + kFCols - 1) / kFCols); }
 static bool fused_eligible(const adaprox_options* o, const DProblem& P) {
   const char* e = std::getenv("ADAPROX_FUSED");
@@ -643,6 +650,28 @@ static void fused_print_probe(const FusedPlan& pl, const char* what) {
   std::fprintf(stderr, "\n");
 }
 
+// CTAs of a persistent solver launch.  Every phase boundary is a grid barrier whose cost grows with the number of CTAs, and
+// every scalar is rebuilt from one partial per CTA: a problem whose matrices are small enough to be latency-bound (a few
+// microseconds per phase) runs faster on fewer CTAs; a streaming problem wants all of them (2 per SM keep ~96 KB of bulk
+// copies in flight per SM).  The matrix partial buffers are sized for h->grid, so any smaller grid is valid.
+// Row-sharded solves always use h->grid: all ranks must reduce the replicated vectors in the same order.
+static int64_t mat_bytes(const DMat& M) {
+  if (M.kind == MAT_DENSE) return M.m * M.ld * 8;
+  if (M.kind == MAT_CSR) return 2 * M.nnz * 12;
+  return 0;
+}
+static int solver_grid(adaprox_ctx* h, const DProblem& P) {
+  if (const char* e = std::getenv("ADAPROX_GRID")) {
+    const int v = std::atoi(e);
+    if (v >= 1) return std::min(v, h->grid);
+  }
+  const int64_t bytes = mat_bytes(P.F) + mat_bytes(P.A);
+  // measured (tools/grid_sweep.py, profiles/r01_grid_sweep.jsonl): 400x1000 lasso (3.2 MB) 38.0 us/iteration on 296 CTAs,
+  // 30.8 on 148, 31.9 on 74, 40.5 on 37; already at 36 MB (rcv1-shaped CSR) and 64 MB (2048x4096 dense) 296 CTAs win.
+  if (bytes < kSmallProblemBytes) return std::min(h->grid, h->sm_count);
+  return h->grid;
+}
+
 extern "C" int adaprox_solve(adaprox_handle h, const adaprox_problem* p, const adaprox_options* o, const double* x0,
                              const double* y0, double* x_out, double* y_out, adaprox_record* records, adaprox_result* res) {
   if (!h || !p || !o || !x0 || !x_out || !res) return fail(h, ADAPROX_ERR_INVALID, "solve: bad arguments");
@@ -660,7 +689,7 @@ extern "C" int adaprox_solve(adaprox_handle h, const adaprox_problem* p, const a
   // kernel itself all-reduces A'y and the dual sums over NVLink peer memory -- needs the exchange blocks (adaprox_p2p_*).
   // ... and a row-sharded Q of a Quadratic smooth term (dual SVM): gradient rows and value sums are gathered the same way.
   const bool pd_solver = o->solver == ADAPROX_S_ADAPTIVE_PRIMAL_DUAL || o->solver == ADAPROX_S_LINESEARCH_PRIMAL_DUAL;
-  const bool f_quad_shard = fm && fm->sharded && P.f_kind == ADAPROX_F_QUADRATIC;
+  const bool f_quad_shard = fm && fm->sharded && (P.f_kind == ADAPROX_F_QUADRATIC || P.f_kind == ADAPROX_F_QUADRATIC_GRAM);
   const bool f_ok = !(fm && fm->sharded) || f_quad_shard;
   // ... and the backtracking / Nesterov / aGRAAL baselines on a row-sharded least-squares or Quadratic term.
   const bool pg_family = o->solver == ADAPROX_S_BACKTRACKING_PROXGRAD || o->solver == ADAPROX_S_BACKTRACKING_NESTEROV ||
@@ -670,7 +699,7 @@ extern "C" int adaprox_solve(adaprox_handle h, const adaprox_problem* p, const a
                                       (f_ok && o->solver == ADAPROX_S_ADAPTIVE_PROXGRAD && f_quad_shard) ||
                                       (pg_family && (f_ls_shard || f_quad_shard) && !(am && am->sharded)));
   if (sharded_pd) {
-    if (!p2p_ready(h, std::max<int64_t>(P.n, 8)))
+    if (!p2p_ready(h, std::max<int64_t>(std::max<int64_t>(P.n, P.f_kind == ADAPROX_F_QUADRATIC_GRAM ? P.F.n : 0), 8)))
       return fail(h, ADAPROX_ERR_COMM, "row-sharded primal-dual solve: attach the peer exchange blocks first (adaprox_p2p_export / adaprox_p2p_attach)");
     p2p_fill(h, &P.p2p);
     P.A_sharded = (am && am->sharded) ? 1 : 0;
@@ -682,7 +711,8 @@ extern "C" int adaprox_solve(adaprox_handle h, const adaprox_problem* p, const a
   const int64_t n = P.n, md = std::max<int64_t>(P.md, 1);
   const int64_t mf = std::max<int64_t>(P.F.kind != MAT_NONE ? P.F.m : 0, n);
   const int64_t nrec = std::min<int64_t>(O.max_records, O.maxit);
-  int G = h->grid;
+  int G = sharded_pd ? h->grid : solver_grid(h, P);
+  const int Gcoop = G;
   bool fused = fused_eligible(o, P);
   FusedPlan fpl;
   if (fused) {
@@ -692,8 +722,9 @@ extern "C" int adaprox_solve(adaprox_handle h, const adaprox_problem* p, const a
   }
   FusedArgs& fa = fpl.fa;
   const int fQ = fpl.Q;
+  const int64_t nfu = (P.f_kind == ADAPROX_F_QUADRATIC_GRAM) ? P.F.n : 1;
   size_t need = (fused ? fused_ws_bytes(fpl) : 0) +
-                11 * ws_size_doubles(n) + 6 * ws_size_doubles(md) + ws_size_doubles(mf) +
+                11 * ws_size_doubles(n) + 6 * ws_size_doubles(md) + ws_size_doubles(mf) + ws_size_doubles(nfu) +
                 ws_size_doubles((int64_t)kMaxRed * G) + ws_size_doubles((nrec * (int64_t)sizeof(adaprox_record) + 7) / 8) +
                 ws_size_doubles((sizeof(DResult) + 7) / 8);
   if ((rc = ws_reset(h, need))) return rc;
@@ -708,6 +739,7 @@ extern "C" int adaprox_solve(adaprox_handle h, const adaprox_problem* p, const a
   for (int k = 0; k < 2; ++k) W.Axb[k] = ws_doubles(h, md);
   W.yout = ws_doubles(h, md);
   W.r = ws_doubles(h, mf);
+  W.fu = ws_doubles(h, nfu);
   W.red = ws_doubles(h, (int64_t)kMaxRed * G);
   W.rec = nrec > 0 ? reinterpret_cast<adaprox_record*>(ws_doubles(h, (nrec * (int64_t)sizeof(adaprox_record) + 7) / 8)) : nullptr;
   W.res = reinterpret_cast<DResult*>(ws_doubles(h, (sizeof(DResult) + 7) / 8));
@@ -746,20 +778,20 @@ extern "C" int adaprox_solve(adaprox_handle h, const adaprox_problem* p, const a
         h->launches++;
         rc = ADAPROX_OK;
       } else {
-        rc = coop_launch(h, k_primal_dual<false>, args);
+        rc = coop_launch(h, k_primal_dual<false>, args, Gcoop);
       }
       break;
     case ADAPROX_S_LINESEARCH_PRIMAL_DUAL:
-      rc = coop_launch(h, k_primal_dual<true>, args);
+      rc = coop_launch(h, k_primal_dual<true>, args, Gcoop);
       break;
     case ADAPROX_S_BACKTRACKING_PROXGRAD:
     case ADAPROX_S_BACKTRACKING_NESTEROV:
     case ADAPROX_S_FIXED_NESTEROV:
     case ADAPROX_S_AGRAAL:
-      rc = coop_launch(h, k_proxgrad_family, args);
+      rc = coop_launch(h, k_proxgrad_family, args, Gcoop);
       break;
     case ADAPROX_S_MALITSKY_POCK:
-      rc = coop_launch(h, k_malitsky_pock, args);
+      rc = coop_launch(h, k_malitsky_pock, args, Gcoop);
       break;
     default:
       return fail(h, ADAPROX_ERR_UNSUPPORTED, "solver has no device kernel yet");

@@ -4,7 +4,7 @@
 // adaprox_eval_f / adaprox_prox_eval exercise exactly the code the persistent
 // solver kernels run.
 #pragma once
-#include "phases.cuh"
+#include "phases_pre.cuh"
 
 namespace adaprox {
 
@@ -44,6 +44,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_ops(OpArgs a, DWork W) {
     gsum_slice(a.M, j0, j1, a.out, G);
   } else if (a.op == OP_EVALF) {
     const DProblem& P = a.P;
+    f_phase_pre(grid, P, W, a.in, sh, b, G, nullptr);
     f_phase_A(P, W, a.in, sh, s_scr, b, G);
     grid.sync();
     f_phase_B(P, W, a.in, s_scr, b, G);

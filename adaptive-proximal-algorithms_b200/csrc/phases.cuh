@@ -57,6 +57,7 @@ struct DWork {
   double* gb[2];           // gradient ring
   double* v; double* Aty[2]; double* yb[2]; double* w; double* Axb[2]; double* r;
   double* aux[3];          // extra n-vectors (proximal-gradient family)
+  double* fu;              // Gram-form Quadratic: u = Z'x (F.n entries), see phases_pre.cuh
   double* red;             // [kMaxRed][G]
   double* xout; double* yout;
   adaprox_record* rec;
@@ -200,19 +201,21 @@ __host__ __device__ inline void rule_step(const DOpts& o, double dgg, double dgx
 
 // ---------------------------------------------------------------------------
 // smooth term: eval_with_pullback split into grid phases
-//   A: matrix pass F*x           (+ |x|^2 partial for the cubic term)
+//   pre: Gram-form Quadratic only: u = Z'x (phases_pre.cuh; two grid barriers of its own)
+//   A: matrix pass F*x           (+ |x|^2 partial for the cubic term; Gram form: Z*u)
 //   B: row-wise finalize -> r (what the pullback multiplies), value partials
 //   C: matrix pass F'*r          (least squares, logistic)
 //   grad_slice: gradient entries of a column slice
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ bool f_has_gemv_n(int k) {
-  return k == ADAPROX_F_LEAST_SQUARES || k == ADAPROX_F_LOGISTIC || k == ADAPROX_F_QUADRATIC || k == ADAPROX_F_CUBIC;
+  return k == ADAPROX_F_LEAST_SQUARES || k == ADAPROX_F_LOGISTIC || k == ADAPROX_F_QUADRATIC || k == ADAPROX_F_CUBIC ||
+         k == ADAPROX_F_QUADRATIC_GRAM;
 }
 __device__ __forceinline__ bool f_has_gemv_t(int k) { return k == ADAPROX_F_LEAST_SQUARES || k == ADAPROX_F_LOGISTIC; }
 
 __device__ __forceinline__ void f_phase_A(const DProblem& P, const DWork& W, const double* x, Sh& sh, double* s_scr,
                                           int b, int G) {
-  if (f_has_gemv_n(P.f_kind)) gemv_n_phase(P.F, x, sh, b, G);
+  if (f_has_gemv_n(P.f_kind)) gemv_n_phase(P.F, P.f_kind == ADAPROX_F_QUADRATIC_GRAM ? W.fu : x, sh, b, G);
   if (P.f_kind == ADAPROX_F_CUBIC) {
     double acc[1] = {0.0};
     const int64_t tid = (int64_t)b * kThreads + threadIdx.x, nt = (int64_t)G * kThreads;
@@ -245,8 +248,9 @@ __device__ __forceinline__ void f_phase_B(const DProblem& P, const DWork& W, con
       }
     } break;
     case ADAPROX_F_QUADRATIC:                                       // dual_svm/runme.jl:25-27
-      // (row-sharded Q: this rank owns rows [f_row0, f_row0 + F.m); the sums and the gradient are completed across the
-      //  ranks by the caller.  Unsharded: f_row0 = 0 and F.m = n.)
+    case ADAPROX_F_QUADRATIC_GRAM:                                  // same with temp = Z*(Z'x): zsum holds Z*u here
+      // (row-sharded Q / Z: this rank owns rows [f_row0, f_row0 + F.m); the sums and the gradient are completed across
+      //  the ranks by the caller.  Unsharded: f_row0 = 0 and F.m = n.)
       for (int64_t i = tid; i < P.F.m; i += nt) {
         const int64_t gi = P.f_row0 + i;
         const double temp = zsum(P.F, i), xi = ldcg(x + gi);
@@ -310,7 +314,8 @@ __device__ __forceinline__ double f_value(const DProblem& P, double s0, double s
   switch (P.f_kind) {
     case ADAPROX_F_LEAST_SQUARES: return 0.5 * norm_sq_jl(s0);              // 0.5 * norm(res)^2
     case ADAPROX_F_LOGISTIC: return -(s0 / P.f_N);                          // -mean(...)
-    case ADAPROX_F_QUADRATIC: return 0.5 * s0 + s1;
+    case ADAPROX_F_QUADRATIC:
+    case ADAPROX_F_QUADRATIC_GRAM: return 0.5 * s0 + s1;
     case ADAPROX_F_CUBIC: { const double nx = sqrt(xx); return (s0 + s1) / 2.0 - nx * nx * nx * P.f_c / 12.0; }
     case ADAPROX_F_WORST_QUADRATIC: return (P.f_c / 4.0) * (s0 / 2.0 - s1);
     case ADAPROX_F_SIMPLE2D: return s0;
@@ -333,6 +338,7 @@ __device__ __forceinline__ void grad_slice(const DProblem& P, const DWork& W, in
       __syncthreads();
     } break;
     case ADAPROX_F_QUADRATIC:
+    case ADAPROX_F_QUADRATIC_GRAM:
       for (int64_t j = j0 + threadIdx.x; j < j1; j += kThreads) {
         const bool own = (j >= P.f_row0) && (j < P.f_row0 + P.F.m);        // rows of other ranks: 0 (summed across ranks later)
         out[j] = own ? ldcg(W.r + j) + P.fvec[j] : 0.0;

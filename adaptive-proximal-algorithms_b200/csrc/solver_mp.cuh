@@ -7,7 +7,7 @@
 // (`eval_with_gradient(f, x)`, :608) -- the same point, bit-identical values.  The kernel
 // evaluates once and counts twice, so the Counting figures match the reference exactly.
 #pragma once
-#include "phases.cuh"
+#include "phases_pre.cuh"
 
 namespace adaprox {
 
@@ -43,6 +43,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_malitsky_pock(DProblem P, DOpts
   int atc = 0;
 
   // ---- prologue: A_x = A*x, At_y = A'*y (:597-598) and f, grad at x0 (first :608) ------------------
+  f_phase_pre(grid, P, W, x_prev, sh, b, G, nullptr);
   gemv_n_phase(P.A, x_prev, sh, b, G);
   f_phase_A(P, W, x_prev, sh, s_scr, b, G);
   grid.sync();
@@ -114,6 +115,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_malitsky_pock(DProblem P, DOpts
       block_reduce_store<3>(acc, W.red, G, base, s_scr);
       n_proxg++;
       grid.sync();
+      f_phase_pre(grid, P, W, x, sh, b, G, nullptr);
       gemv_n_phase(P.A, x, sh, b, G);                             // :561
       f_phase_A(P, W, x, sh, s_scr, b, G);                        // :562
       n_mul++; n_eval++;

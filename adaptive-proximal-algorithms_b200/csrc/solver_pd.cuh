@@ -18,8 +18,7 @@
 //   P6  norm_res, record, convergence; A'*y+ partials            :348-358
 //   P7  slice: A'y, v, x+ = prox_{gamma g}(v)                    :359-361
 #pragma once
-#include "p2p.cuh"
-#include "phases.cuh"
+#include "phases_pre.cuh"
 
 namespace adaprox {
 
@@ -93,6 +92,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_primal_dual(DProblem P, DOpts O
   unsigned flags = 0;
 
   // ---- prologue (:327-332) --------------------------------------------------
+  f_phase_pre(grid, P, W, x, sh, b, G, &ps);
   f_phase_A(P, W, x, sh, s_scr, b, G);
   if (hasA) gemv_n_phase(P.A, x, sh, b, G);
   grid.sync();
@@ -133,6 +133,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_primal_dual(DProblem P, DOpts O
   for (int64_t it = 1; it <= O.maxit; ++it) {
     // ---- P1 ---------------------------------------------------------------
     phase_stamp(W, it, 0);
+    f_phase_pre(grid, P, W, x, sh, b, G, &ps);
     f_phase_A(P, W, x, sh, s_scr, b, G);                                        // :336
     if (hasA) gemv_n_phase(P.A, x, sh, b, G);                                   // :335
     grid.sync();

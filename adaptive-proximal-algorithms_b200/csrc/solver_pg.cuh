@@ -8,8 +8,7 @@
 // the device: every CTA derives the same scalars from fixed-order reductions and
 // takes the same branch, so there is no host round trip per trial.
 #pragma once
-#include "p2p.cuh"
-#include "phases.cuh"
+#include "phases_pre.cuh"
 
 namespace adaprox {
 
@@ -22,6 +21,7 @@ __device__ __forceinline__ double eval_f_grid(cg::grid_group& grid, const DProbl
                                               bool want_grad, double* grad_out, int64_t j0, int64_t j1, Sh& sh,
                                               double* s_scr, int b, int G, P2PState& ps) {
   const bool shardedF = P.p2p.n > 1 && P.F_sharded;
+  f_phase_pre(grid, P, W, x, sh, b, G, &ps);
   f_phase_A(P, W, x, sh, s_scr, b, G);
   grid.sync();
   f_phase_B(P, W, x, s_scr, b, G);

@@ -53,7 +53,10 @@ typedef enum {
   ADAPROX_F_QUADRATIC = 3,      /* dual_svm/runme.jl:19-28: mat=Q (symmetric), vec=q   */
   ADAPROX_F_CUBIC = 4,          /* cubic_sparse_logreg/runme.jl:20-32: mat=Q, vec=q, c */
   ADAPROX_F_WORST_QUADRATIC = 5,/* nesterov_worst_case/runme.jl:14-40: k=ipar, L=c     */
-  ADAPROX_F_SIMPLE2D = 6        /* test/runtests.jl:6-13                               */
+  ADAPROX_F_SIMPLE2D = 6,       /* test/runtests.jl:6-13                               */
+  ADAPROX_F_QUADRATIC_GRAM = 7  /* Quadratic with Q = Z*Z' given by its factor: mat=Z (n x d), vec=q.  dual_svm/runme.jl:47-49
+                                   builds Q = Dy*X*X'*Dy, i.e. Z = Dy*X; Q*x is evaluated as Z*(Z'*x), 16*n*d bytes
+                                   instead of 8*n^2 (same value up to rounding, not bitwise)                  */
 } adaprox_f_kind;
 
 /* ---- nonsmooth terms g, h: ProximalCore / ProximalOperators objects -------- */

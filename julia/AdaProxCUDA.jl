@@ -102,6 +102,7 @@ device_oracle(::ProximalCore.Zero) = (kind = 0, ipar = 0, mat = 0, vec = 0, c = 
 least_squares(A, b) = (kind = 1, ipar = 0, mat = upload(A), vec = upload(b), c = 0.0, n = size(A, 2))   # lasso/runme.jl:16-27
 logistic(X, y) = (kind = 2, ipar = 0, mat = upload(X), vec = upload(y), c = 0.0)        # sparse_logreg/runme.jl:18-39
 quadratic(Q, q) = (kind = 3, ipar = 0, mat = upload(Q), vec = upload(q), c = 0.0)       # dual_svm/runme.jl:19-28
+quadratic_gram(Z, q) = (kind = 7, ipar = 0, mat = upload(Z), vec = upload(q), c = 0.0)  # Quadratic(Z*Z', q) by its factor: dual_svm/runme.jl:47-49 has Z = Dy*X
 cubic(Q, q, c) = (kind = 4, ipar = 0, mat = upload(Q), vec = upload(q), c = Float64(c)) # cubic_sparse_logreg/runme.jl:20-32
 worst_quadratic(k, L) = (kind = 5, ipar = Int(k), mat = 0, vec = 0, c = Float64(L))     # nesterov_worst_case/runme.jl:14-40
 

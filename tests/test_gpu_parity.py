@@ -64,6 +64,12 @@ def _pair(AdaProx, name, rng):
     if name == "quadratic":
         B = rng.standard_normal((70, 70)); Q = B @ B.T; q = rng.standard_normal(70)
         return AdaProx.Quadratic(Q, q), O.Quadratic(Q, q), 70
+    if name == "quadratic_gram":                 # Quadratic(Z Z', q) by its factor; the oracle is the reference's dense-Q form
+        Z = rng.standard_normal((70, 9)); q = rng.standard_normal(70)
+        return AdaProx.QuadraticGram(Z, q), O.Quadratic(Z @ Z.T, q), 70
+    if name == "quadratic_gram_wide":            # d spans three 2048-column chunks, ragged
+        Z = rng.standard_normal((50, 4500)) / 60; q = rng.standard_normal(50)
+        return AdaProx.QuadraticGram(np.asfortranarray(Z), q), O.Quadratic(Z @ Z.T, q), 50
     if name == "cubic":
         B = rng.standard_normal((40, 40)); Q = B @ B.T / 40; q = rng.standard_normal(40)
         return AdaProx.Cubic(Q, q, 0.7), O.Cubic(Q, q, 0.7), 40
@@ -74,7 +80,8 @@ def _pair(AdaProx, name, rng):
     raise KeyError(name)
 
 
-@pytest.mark.parametrize("name", ["ls", "ls_wide", "logistic_csr", "logistic_dense", "quadratic", "cubic", "worst", "simple2d"])
+@pytest.mark.parametrize("name", ["ls", "ls_wide", "logistic_csr", "logistic_dense", "quadratic", "quadratic_gram", "quadratic_gram_wide",
+                                  "cubic", "worst", "simple2d"])
 def test_eval_with_pullback(AdaProx, name):
     rng = np.random.default_rng(5)
     fd, fo, n = _pair(AdaProx, name, rng)
@@ -374,6 +381,53 @@ def test_adapdm_dual_svm(AdaProx):
         assert (fd.eval_count, fd.grad_count, Ad.mul_count, Ad.amul_count) == (itd + 1, itd + 1, itd + 1, itd if ld[-1]["norm_res"] <= 1e-5 else itd + 1)
         assert [r["A_evals"] for r in ld[:5]] == [r["A_evals"] for r in lo[:5]]
         assert [r["At_evals"] for r in ld[:5]] == [r["At_evals"] for r in lo[:5]]
+
+
+def test_dual_svm_gram_form(AdaProx):
+    """dual_svm/runme.jl:47-59 with Q = Z Z' (Z = Dy X) never formed: `QuadraticGram(Z, q)` evaluates Q x as Z (Z' x) in all
+    four persistent kernels.  The checker is the oracle on the reference's dense Q; on the CPU the two forms drift apart by
+    < 1e-13 relative in the first 40 stepsizes (rounding only), identical iteration counts."""
+    X, y = AdaProx.synth.dense_classification(300, 20, 0)
+    Z = y[:, None] * X
+    Q, q, N = Z @ Z.T, -np.ones(300), 300
+    Amat = y[None, :].copy()
+    nA = np.linalg.norm(Amat)
+    fo0 = O.Quadratic(Q, q)
+    for t in (0.1, 1.0):                                            # AdaPDM (k_primal_dual)
+        fd, fo = AdaProx.Counting(AdaProx.QuadraticGram(Z, q)), O.Counting(O.Quadratic(Q, q))
+        ld, lo = [], []
+        xd, yd, itd = AdaProx.adaptive_primal_dual(np.zeros(N), np.zeros(1), f=fd, g=AdaProx.IndBox(0.0, 0.1), h=AdaProx.IndZero(),
+                                                   A=AdaProx.DeviceMatrix(Amat), rule=AdaProx.OurRule(t=t, norm_A=nA), tol=1e-5, maxit=5000, log=ld)
+        xo, yo, ito = O.adaptive_primal_dual(np.zeros(N), np.zeros(1), f=fo, g=O.IndBox(0.0, 0.1), h=O.IndZero(),
+                                             A=Amat, rule=O.OurRule(t=t, norm_A=nA), tol=1e-5, maxit=5000, log=lo)
+        K = 40
+        assert np.allclose([r["gamma"] for r in ld[:K]], [r["gamma"] for r in lo[:K]], rtol=1e-11)
+        assert np.allclose([r["norm_res"] for r in ld[:K]], [r["norm_res"] for r in lo[:K]], rtol=1e-8)
+        assert np.allclose([r["objective"] for r in ld[:K]], [r["objective"] for r in lo[:K]], rtol=1e-10)
+        assert abs(itd - ito) <= max(3, 0.05 * ito)
+        assert abs(fo0(xd) - fo0(xo)) <= 1e-7 * abs(fo0(xo))
+        assert (fd.eval_count, fd.grad_count) == (fo.eval_count + (itd - ito), fo.grad_count + (itd - ito))
+    # AdaPGM, backtracking PG (k_proxgrad_family) and Malitsky-Pock (k_malitsky_pock) on the same term
+    ld, lo = [], []
+    xd, itd = AdaProx.adaptive_proxgrad(np.zeros(N), f=AdaProx.QuadraticGram(Z, q), g=AdaProx.IndBox(0.0, 0.1), rule=AdaProx.OurRule(gamma=1e-2), tol=1e-7, maxit=2000, log=ld)
+    xo, ito = O.adaptive_proxgrad(np.zeros(N), f=O.Quadratic(Q, q), g=O.IndBox(0.0, 0.1), rule=O.OurRule(gamma=1e-2), tol=1e-7, maxit=2000, log=lo)
+    assert np.allclose([r["gamma"] for r in ld[:40]], [r["gamma"] for r in lo[:40]], rtol=1e-11)
+    assert abs(itd - ito) <= max(3, 0.05 * ito) and abs(fo0(xd) - fo0(xo)) <= 1e-9 * abs(fo0(xo))
+    ld, lo = [], []
+    xd, itd = AdaProx.backtracking_proxgrad(np.zeros(N), f=AdaProx.QuadraticGram(Z, q), g=AdaProx.IndBox(0.0, 0.1), gamma0=1.0, tol=1e-7, maxit=300, log=ld)
+    xo, ito = O.backtracking_proxgrad(np.zeros(N), f=O.Quadratic(Q, q), g=O.IndBox(0.0, 0.1), gamma0=1.0, tol=1e-7, maxit=300, log=lo)
+    assert np.allclose([r["gamma"] for r in ld[:30]], [r["gamma"] for r in lo[:30]], rtol=1e-12)
+    assert np.allclose([r["objective"] for r in ld[:30]], [r["objective"] for r in lo[:30]], rtol=1e-10)
+    ld, lo = [], []
+    xd, yd, itd = AdaProx.malitsky_pock(np.zeros(N), np.zeros(1), f=AdaProx.QuadraticGram(Z, q), g=AdaProx.IndBox(0.0, 0.1), h=AdaProx.IndZero(),
+                                        A=AdaProx.DeviceMatrix(Amat), t=1.0, sigma=1.0 / nA, tol=1e-5, maxit=300, log=ld)
+    xo, yo, ito = O.malitsky_pock(np.zeros(N), np.zeros(1), f=O.Quadratic(Q, q), g=O.IndBox(0.0, 0.1), h=O.IndZero(),
+                                  A=Amat, t=1.0, sigma=1.0 / nA, tol=1e-5, maxit=300, log=lo)
+    assert np.allclose([r["gamma"] for r in ld[:30]], [r["gamma"] for r in lo[:30]], rtol=1e-11)
+    assert np.allclose([r["norm_res"] for r in ld[:30]], [r["norm_res"] for r in lo[:30]], rtol=1e-8)
+    # error behaviour: Z must have n rows
+    with pytest.raises(AdaProx.AdaproxError):
+        AdaProx.adaptive_proxgrad(np.zeros(N), f=AdaProx.QuadraticGram(Z[:-1], q), g=AdaProx.IndBox(0.0, 0.1), rule=AdaProx.OurRule(gamma=1e-2), maxit=3)
 
 
 def test_condat_vu(AdaProx):

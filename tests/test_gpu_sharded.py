@@ -183,7 +183,7 @@ def test_sharded_adapdm_two_gpus(tmp_path):
 
 
 # ---------------------------------------------------------------- row-sharded dual SVM
-def _svm_problem():
+def _svm_problem(factor=False):
     rng = np.random.default_rng(7)
     N, d = 90, 6
     X = rng.standard_normal((N, d))
@@ -191,6 +191,8 @@ def _svm_problem():
     y = np.sign(X @ w + 0.3 * rng.standard_normal(N))
     y[y == 0] = 1.0
     Z = y[:, None] * X
+    if factor:
+        return Z
     return Z @ Z.T, -np.ones(N), y                       # dual_svm/runme.jl:47-55: Q, q, labels
 
 
@@ -220,9 +222,23 @@ def _worker_svm(rank, world, port, out):
     log2 = []
     x2, it2 = AdaProx.adaptive_proxgrad(np.zeros(N), f=AdaProx.Quadratic(Qs, q), g=AdaProx.IndBox(0.0, 0.1), rule=AdaProx.OurRule(gamma=1e-2),
                                         tol=1e-7, maxit=2000, log=log2)
+    # Gram form: Z = Dy X split by rows, Q never formed; u = Z'x is all-reduced inside the kernel (d doubles),
+    # then the gradient rows and the value sums as above
+    Z = _svm_problem(factor=True)
+    Zs = AdaProx.DeviceMatrix(Z[row0:row0 + rows].copy(), dev=dev)
+    Zs.set_shard(N, row0)
+    f3 = AdaProx.Counting(AdaProx.QuadraticGram(Zs, q))
+    log3 = []
+    x3, y3, it3 = AdaProx.adaptive_primal_dual(np.zeros(N), np.zeros(1), f=f3, g=AdaProx.IndBox(0.0, 0.1), h=AdaProx.IndZero(),
+                                               A=AdaProx.DeviceMatrix(Amat, dev=dev), rule=AdaProx.OurRule(t=1.0, norm_A=nA), tol=1e-6, maxit=3000, log=log3)
+    coll3 = AdaProx.last_solve_info()["collective"]
+    log4 = []
+    x4, it4 = AdaProx.backtracking_proxgrad(np.zeros(N), f=AdaProx.QuadraticGram(Zs, q), g=AdaProx.IndBox(0.0, 0.1), gamma0=1.0, tol=1e-7, maxit=200, log=log4)
     np.savez(out % rank, x=x, y=yy, it=it, gam=np.array([r["gamma"] for r in log]), res=np.array([r["norm_res"] for r in log]),
              obj=np.array([r["objective"] for r in log]), coll=info["collective"], fe=f.eval_count, ge=f.grad_count,
-             x2=x2, it2=it2, gam2=np.array([r["gamma"] for r in log2]), obj2=np.array([r["objective"] for r in log2]))
+             x2=x2, it2=it2, gam2=np.array([r["gamma"] for r in log2]), obj2=np.array([r["objective"] for r in log2]),
+             x3=x3, it3=it3, gam3=np.array([r["gamma"] for r in log3]), obj3=np.array([r["objective"] for r in log3]), coll3=coll3,
+             fe3=f3.eval_count, x4=x4, it4=it4, gam4=np.array([r["gamma"] for r in log4]), obj4=np.array([r["objective"] for r in log4]))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -262,6 +278,20 @@ def test_sharded_dual_svm_two_gpus(tmp_path):
     assert np.allclose(R0["gam2"][:K2], [r["gamma"] for r in lo2[:K2]], rtol=1e-11)
     assert np.allclose(R0["obj2"][:K2], [r["objective"] for r in lo2[:K2]], rtol=1e-10)
     assert abs(int(R0["it2"]) - ito2) <= max(3, 0.05 * ito2)
+    # Gram form on row shards of Z against the same dense-Q oracle runs (the two forms differ by rounding only)
+    assert int(R0["coll3"]) == 2
+    assert np.array_equal(R0["x3"], R1["x3"]) and int(R0["it3"]) == int(R1["it3"]) and np.array_equal(R0["x4"], R1["x4"])
+    K3 = min(40, len(lo), len(R0["gam3"]))
+    assert np.allclose(R0["gam3"][:K3], [r["gamma"] for r in lo[:K3]], rtol=1e-11)
+    fin3 = np.isfinite([r["objective"] for r in lo[:K3]])
+    assert np.allclose(R0["obj3"][:K3][fin3], np.array([r["objective"] for r in lo[:K3]])[fin3], rtol=1e-10)
+    assert abs(int(R0["it3"]) - ito) <= max(3, 0.05 * ito) and int(R0["fe3"]) == int(R0["it3"]) + 1
+    assert abs(fo.f(R0["x3"]) - fo.f(xo)) <= 1e-7 * abs(fo.f(xo))
+    lo4 = []
+    xo4, ito4 = O.backtracking_proxgrad(np.zeros(N), f=O.Quadratic(Q, q), g=O.IndBox(0.0, 0.1), gamma0=1.0, tol=1e-7, maxit=200, log=lo4)
+    K4 = min(30, len(lo4), len(R0["gam4"]))
+    assert np.allclose(R0["gam4"][:K4], [r["gamma"] for r in lo4[:K4]], rtol=1e-12)
+    assert np.allclose(R0["obj4"][:K4], [r["objective"] for r in lo4[:K4]], rtol=1e-10)
 
 
 # ---------------------------------------------------------------- row-sharded backtracking / Nesterov / aGRAAL baselines

@@ -1,5 +1,5 @@
 """Timings of the other BASELINE.json configs on one GPU (C1 lasso 400x1000, C2 sparse logreg rcv1 shape,
-C3 LAD / sqrt-lasso 50000x2001 with AdaPDM+, dual SVM with AdaPDM).  Prints one JSON line per config.
+C3 LAD / sqrt-lasso 50000x2001 with AdaPDM+, dual SVM with AdaPDM in the dense-Q and the Gram form).  Prints one JSON line per config.
 These are parity-test cases, not the headline bench; numbers go to profiles/."""
 import json
 import os
@@ -87,6 +87,25 @@ def main():
             print(json.dumps(dict(config=f"C3 dual SVM N={N} dense Q AdaPDM t={t}", iterations=it, device_ms=info["solve_ms"],
                                   us_per_iteration=1e3 * info["solve_ms"] / it, hbm_gbs=it * N * N * 8 / (info["solve_ms"] * 1e-3) / 1e9,
                                   final_norm_res=info["final_norm_res"], gen_s=tg + tq)), flush=True)
+    if "svmgram" in which:
+        # the same dual SVM with Q = Z Z' never formed (QuadraticGram, Z = Dy X): two sweeps over Z per iteration (16 N d bytes)
+        # instead of one over Q (8 N^2).  N = 20000 repeats the dense-Q instance above; N = 50000 is BASELINE configs[2]'s size
+        # (the dense Q would be 20 GB and ~4 minutes of host DGEMM to build).
+        for N, d in ((20000, 2000), (50000, 2000)):
+            (X, y), tg = timed(lambda: AdaProx.synth.dense_classification(N, d, 0))
+            Zm = AdaProx.DeviceMatrix(y[:, None] * X)
+            f = AdaProx.QuadraticGram(Zm, -np.ones(N))
+            Amat = AdaProx.DeviceMatrix(y[None, :].copy())
+            for t in (0.1, 1.0):
+                (res, wall) = timed(lambda: AdaProx.adaptive_primal_dual(np.zeros(N), np.zeros(1), f=f, g=AdaProx.IndBox(0.0, 0.1), h=AdaProx.IndZero(),
+                                                                       A=Amat, rule=AdaProx.OurRule(t=t, norm_A=float(np.sqrt(N))), tol=1e-5, maxit=10000))
+                x, yy, it = res
+                info = AdaProx.last_solve_info()
+                print(json.dumps(dict(config=f"C3 dual SVM N={N} d={d} Gram form AdaPDM t={t}", iterations=it, device_ms=info["solve_ms"],
+                                      us_per_iteration=1e3 * info["solve_ms"] / it, hbm_gbs=it * 2 * N * d * 8 / (info["solve_ms"] * 1e-3) / 1e9,
+                                      dense_q_equivalent_gbs=it * N * N * 8 / (info["solve_ms"] * 1e-3) / 1e9,
+                                      final_norm_res=info["final_norm_res"], objective=float(f(x)), e2e_ms=wall * 1e3, gen_s=tg)), flush=True)
+            Zm.free()
     if "c5" in which:
         # BASELINE configs[4]: batched multi-lambda lasso path, 256 lambdas, A 16384 x 8192, FP64 DMMA contractions.
         # Multi-GPU: the lambdas are split over the ranks (no collective), see tools/bench_path_multi.py.
