@@ -312,6 +312,8 @@ extern "C" int adaprox_matrix_upload_csr(adaprox_handle h, int64_t m, int64_t n,
   HostMatrix hm;
   DMat& d = hm.d;
   d.kind = MAT_CSR; d.m = m; d.n = n; d.ld = 0; d.nnz = nnz; d.nchunks = 1; d.rb = 0; d.nrb = 0; d.npad = n;
+  d.lpr_n = csr_lanes_per_row(nnz, m); d.lpr_t = csr_lanes_per_row(nnz, n);
+  if (const char* e = std::getenv("ADAPROX_CSR_LPR")) { const int v = std::atoi(e); if (v == 4 || v == 8 || v == 16 || v == 32) d.lpr_n = d.lpr_t = v; }
   auto up = [&](const void* src, size_t bytes, void** dst) -> cudaError_t {
     cudaError_t e = cudaMalloc(dst, std::max<size_t>(bytes, 8));
     if (e != cudaSuccess) return e;

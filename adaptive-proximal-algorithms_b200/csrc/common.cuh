@@ -33,6 +33,7 @@ struct DMat {
   const int64_t* rowptr; const int* colind; const double* vals;
   const int64_t* t_rowptr; const int* t_colind; const double* t_vals;
   int64_t nnz;
+  int lpr_n, lpr_t;          // CSR: lanes per row of the X*w and X'*r sweeps (csr_lanes_per_row)
   // dense work partition: units = (column chunk c, row block rb), chunk-major
   int nchunks;               // ceil(n / kChunk)
   int rb;                    // rows per unit (multiple of kRowBatch)

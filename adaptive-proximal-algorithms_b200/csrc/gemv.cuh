@@ -182,19 +182,83 @@ __device__ __noinline__ void gemv_t_dense(const DMat& M, const double* r, int b,
 }
 
 // ---------------------------------------------------------------------------
-// CSR: one warp per row, lanes stride over the row's nonzeros.
+// CSR: LPR lanes per row (32 / LPR rows per warp side by side), 4 nonzeros per lane in flight.
+// A row's value is a chain rowptr -> colind -> x[colind] of L2 round trips; with ~30-80 nonzeros per row (rcv1 shape)
+// a full warp per row leaves most lanes idle and serialises the rows of a warp, so LPR is chosen per matrix from the
+// mean row length (csr_lanes_per_row) and each lane issues its 4 index/value loads, then its 4 gathers, together.
+// At 16 lanes per row both rcv1-shaped sweeps move ~2.1 M L2 sectors (0.57 M of CSR data + 1.5 M gathers) in 10.6 / 12.6 us
+// = 6.3 / 5.3 TB/s of L2 sector traffic: bound by the gathers' sector granularity.
+// The summation order (lane, then position, then the xor butterfly) is fixed: reruns are bit-identical.
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ void spmv_rows(int64_t nrows, const int64_t* __restrict__ rowptr, const int* __restrict__ colind,
-                                          const double* __restrict__ vals, const double* x, double* out, int b, int G) {
-  const int lane = threadIdx.x & 31;
+template <int LPR>
+__device__ __forceinline__ void spmv_rows_t(int64_t nrows, const int64_t* __restrict__ rowptr, const int* __restrict__ colind,
+                                            const double* __restrict__ vals, const double* x, double* out, int b, int G) {
+  constexpr int RPW = 32 / LPR;                     // rows per warp side by side
+  constexpr int RU = 1;                             // row groups per warp in flight; 2 measured no faster (11.4 / 13.8 vs 10.6 / 12.6 us):
+                                                    // the sweeps sit at the L2 sector rate (one 32 B sector per gathered double), not on latency
+  const int lane = threadIdx.x & 31, sub = lane / LPR, sl = lane % LPR;
   const int64_t gw = (int64_t)b * kWarps + (threadIdx.x >> 5);
   const int64_t nw = (int64_t)G * kWarps;
-  for (int64_t row = gw; row < nrows; row += nw) {
-    const int64_t k0 = rowptr[row], k1 = rowptr[row + 1];
-    double s = 0.0;
-    for (int64_t k = k0 + lane; k < k1; k += 32) s = fma(vals[k], ldcg(x + colind[k]), s);
-    s = warp_sum(s);
-    if (lane == 0) out[row] = s;
+  for (int64_t base = gw * RPW; base < nrows; base += nw * RPW * RU) {     // warp-uniform trip count
+    int64_t row[RU], k[RU], k1[RU];
+    double s[RU];
+#pragma unroll
+    for (int r = 0; r < RU; ++r) {
+      row[r] = base + r * nw * RPW + sub;
+      const bool valid = row[r] < nrows;
+      k[r] = valid ? rowptr[row[r]] + sl : 0;
+      k1[r] = valid ? rowptr[row[r] + 1] : 0;
+      s[r] = 0.0;
+    }
+    for (;;) {
+      bool any = false;
+#pragma unroll
+      for (int r = 0; r < RU; ++r) any = any || (k[r] < k1[r]);
+      if (!any) break;
+      int c[RU][4]; double v[RU][4], xv[RU][4];
+#pragma unroll
+      for (int r = 0; r < RU; ++r)
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int64_t kk = k[r] + u * LPR;
+          const bool ok = kk < k1[r];
+          c[r][u] = ok ? colind[kk] : 0;
+          v[r][u] = ok ? vals[kk] : 0.0;
+        }
+#pragma unroll
+      for (int r = 0; r < RU; ++r)
+#pragma unroll
+        for (int u = 0; u < 4; ++u) xv[r][u] = (k[r] + u * LPR < k1[r]) ? ldcg(x + c[r][u]) : 0.0;
+#pragma unroll
+      for (int r = 0; r < RU; ++r) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) s[r] = fma(v[r][u], xv[r][u], s[r]);
+        k[r] += 4 * LPR;
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < RU; ++r) {
+      double t = s[r];
+#pragma unroll
+      for (int o = LPR / 2; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+      if (row[r] < nrows && sl == 0) out[row[r]] = t;
+    }
+  }
+}
+// measured on the rcv1 shape (tools/csr_sweep.py, profiles/r01_csr_sweep.md): 16 lanes per row are the fastest for both
+// 75 nonzeros per row (X*w: 11.6 / 10.6 / 15.3 / 18.0 us with 32 / 16 / 8 / 4 lanes) and 32 per row (X'*r: 26.8 / 12.6 / 19.1 / 16.0)
+__host__ __device__ inline int csr_lanes_per_row(int64_t nnz, int64_t nrows) {
+  const int64_t avg = nnz / (nrows > 0 ? nrows : 1);
+  return avg > 192 ? 32 : (avg > 24 ? 16 : (avg > 12 ? 8 : 4));
+}
+__device__ __forceinline__ void spmv_rows(int lpr, int64_t nrows, const int64_t* __restrict__ rowptr, const int* __restrict__ colind,
+                                          const double* __restrict__ vals, const double* x, double* out, int b, int G) {
+  switch (lpr) {
+    case 4: spmv_rows_t<4>(nrows, rowptr, colind, vals, x, out, b, G); break;
+    case 8: spmv_rows_t<8>(nrows, rowptr, colind, vals, x, out, b, G); break;
+    case 16: spmv_rows_t<16>(nrows, rowptr, colind, vals, x, out, b, G); break;
+    default: spmv_rows_t<32>(nrows, rowptr, colind, vals, x, out, b, G); break;
   }
 }
 
@@ -205,13 +269,13 @@ __device__ __forceinline__ void gemv_n_phase(const DMat& M, const double* x, Sh&
   if (M.kind == MAT_DENSE) {
     if (M.path == 1) gemv_n_ring(M, x, sh, b, G);
     else gemv_n_dense(M, x, sh.x, b, G);
-  } else if (M.kind == MAT_CSR) spmv_rows(M.m, M.rowptr, M.colind, M.vals, x, M.zpart, b, G);
+  } else if (M.kind == MAT_CSR) spmv_rows(M.lpr_n, M.m, M.rowptr, M.colind, M.vals, x, M.zpart, b, G);
 }
 __device__ __forceinline__ void gemv_t_phase(const DMat& M, const double* r, Sh& sh, int b, int G) {
   if (M.kind == MAT_DENSE) {
     if (M.path == 1) gemv_t_ring(M, r, sh, b, G);
     else gemv_t_dense(M, r, b, G);
-  } else if (M.kind == MAT_CSR) spmv_rows(M.n, M.t_rowptr, M.t_colind, M.t_vals, r, M.gpart, b, G);
+  } else if (M.kind == MAT_CSR) spmv_rows(M.lpr_t, M.n, M.t_rowptr, M.t_colind, M.t_vals, r, M.gpart, b, G);
 }
 
 // (A*x)_i from the partials (fixed chunk order)
