@@ -305,6 +305,40 @@ __device__ __forceinline__ void f_phase_B(const DProblem& P, const DWork& W, con
   block_reduce_store<2>(acc, W.red, G, SLOT_F0, s_scr);
 }
 
+// Dense F with a single column chunk (n <= 2048) and a transposed pass (least squares, logistic): both sweeps deal the
+// same row blocks to the same CTAs (Segs), so a CTA's A'r sweep consumes exactly the rows of F*x it produced itself.
+// Phases A -> B -> C then need CTA barriers only -- two grid barriers less per evaluation, which is what a small
+// (latency-bound) problem spends its time on.  B has to visit the CTA's own rows instead of a grid-stride loop.
+__device__ __forceinline__ bool f_rows_local(const DProblem& P) {
+  return f_has_gemv_t(P.f_kind) && P.F.kind == MAT_DENSE && P.F.nchunks == 1;
+}
+__device__ __forceinline__ void f_phase_B_local(const DProblem& P, const DWork& W, const double* x, double* s_scr, int b, int G) {
+  double acc[2] = {0.0, 0.0};
+  Segs sg;
+  sg.init(1, P.F.nrb, P.F.rb, P.F.m, b, G);
+  const int64_t r0 = sg.T > 0 ? sg.row0 : 0, r1 = sg.T > 0 ? sg.end0 : 0;
+  __syncthreads();                                                  // this CTA's zpart rows are complete
+  if (P.f_kind == ADAPROX_F_LEAST_SQUARES) {                        // lasso/runme.jl:22
+    for (int64_t i = r0 + threadIdx.x; i < r1; i += kThreads) {
+      const double res = zsum(P.F, i) - P.fvec[i];
+      W.r[i] = res;
+      acc[0] = fma(res, res, acc[0]);
+    }
+  } else {                                                          // logistic, sparse_logreg/runme.jl:24-36
+    const double w_end = ldcg(x + (P.n - 1));
+    for (int64_t i = r0 + threadIdx.x; i < r1; i += kThreads) {
+      const double logits = zsum(P.F, i) + w_end;
+      const double u = 1.0 + exp(-logits);
+      const double yi = P.fvec[i];
+      const double ri = 1.0 / u - yi;
+      W.r[i] = ri;
+      acc[0] += (yi - 1.0) * logits - log(u);
+      acc[1] += ri;
+    }
+  }
+  block_reduce_store<2>(acc, W.red, G, SLOT_F0, s_scr);             // ends with a CTA barrier: r rows visible to phase C
+}
+
 __device__ __forceinline__ void f_phase_C(const DProblem& P, const DWork& W, Sh& sh, int b, int G) {
   if (f_has_gemv_t(P.f_kind)) gemv_t_phase(P.F, W.r, sh, b, G);
 }

@@ -92,13 +92,15 @@ __global__ void __launch_bounds__(kThreads, 2) k_primal_dual(DProblem P, DOpts O
   unsigned flags = 0;
 
   // ---- prologue (:327-332) --------------------------------------------------
+  // rows_local: phases A -> B -> C of f need no grid barrier in between (f_rows_local); A*x still does
+  const bool rows_local = f_rows_local(P);
   f_phase_pre(grid, P, W, x, sh, b, G, &ps);
   f_phase_A(P, W, x, sh, s_scr, b, G);
   if (hasA) gemv_n_phase(P.A, x, sh, b, G);
-  grid.sync();
-  f_phase_B(P, W, x, s_scr, b, G);
+  if (hasA || !rows_local) grid.sync();
+  if (rows_local) f_phase_B_local(P, W, x, s_scr, b, G); else f_phase_B(P, W, x, s_scr, b, G);
   if (hasA) for (int64_t i = tid; i < P.md; i += nt) W.Axb[axc][i] = zsum(P.A, i);
-  grid.sync();
+  if (!rows_local) grid.sync();
   f_phase_C(P, W, sh, b, G);
   if (hasA) gemv_t_phase(P.A, y, sh, b, G);
   grid.sync();
@@ -136,15 +138,15 @@ __global__ void __launch_bounds__(kThreads, 2) k_primal_dual(DProblem P, DOpts O
     f_phase_pre(grid, P, W, x, sh, b, G, &ps);
     f_phase_A(P, W, x, sh, s_scr, b, G);                                        // :336
     if (hasA) gemv_n_phase(P.A, x, sh, b, G);                                   // :335
-    grid.sync();
+    if (hasA || !rows_local) grid.sync();
     // ---- P2 ---------------------------------------------------------------
     phase_stamp(W, it, 1);
-    f_phase_B(P, W, x, s_scr, b, G);
+    if (rows_local) f_phase_B_local(P, W, x, s_scr, b, G); else f_phase_B(P, W, x, s_scr, b, G);
     double* Ax_prev = W.Axb[axc];
     double* Ax = W.Axb[axc ^ 1];
     if (hasA) for (int64_t i = tid; i < P.md; i += nt) Ax[i] = zsum(P.A, i);
     n_eval++; n_mul++;
-    grid.sync();
+    if (!rows_local) grid.sync();
     // ---- P3 ---------------------------------------------------------------
     phase_stamp(W, it, 2);
     f_phase_C(P, W, sh, b, G);

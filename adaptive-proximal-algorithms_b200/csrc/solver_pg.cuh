@@ -22,10 +22,15 @@ __device__ __forceinline__ double eval_f_grid(cg::grid_group& grid, const DProbl
                                               double* s_scr, int b, int G, P2PState& ps) {
   const bool shardedF = P.p2p.n > 1 && P.F_sharded;
   f_phase_pre(grid, P, W, x, sh, b, G, &ps);
-  f_phase_A(P, W, x, sh, s_scr, b, G);
-  grid.sync();
-  f_phase_B(P, W, x, s_scr, b, G);
-  grid.sync();
+  if (f_rows_local(P)) {          // phases A -> B -> C on this CTA's own rows: CTA barriers only
+    f_phase_A(P, W, x, sh, s_scr, b, G);
+    f_phase_B_local(P, W, x, s_scr, b, G);
+  } else {
+    f_phase_A(P, W, x, sh, s_scr, b, G);
+    grid.sync();
+    f_phase_B(P, W, x, s_scr, b, G);
+  }
+  if (!(want_grad && f_rows_local(P))) grid.sync();
   if (want_grad) {
     f_phase_C(P, W, sh, b, G);
     grid.sync();
