@@ -670,7 +670,9 @@ static int solver_grid(adaprox_ctx* h, const DProblem& P) {
   const int64_t bytes = mat_bytes(P.F) + mat_bytes(P.A);
   // measured (tools/grid_sweep.py, profiles/r01_grid_sweep.jsonl): 400x1000 lasso (3.2 MB) 38.0 us/iteration on 296 CTAs,
   // 30.8 on 148, 31.9 on 74, 40.5 on 37; already at 36 MB (rcv1-shaped CSR) and 64 MB (2048x4096 dense) 296 CTAs win.
-  if (bytes < kSmallProblemBytes) return std::min(h->grid, h->sm_count);
+  // The primal-dual loops keep the full grid: their row phases and the one-row tiles of a narrow A want more CTAs
+  // (cpusmall-shaped LAD 8192x13, AdaPDM+: 74.9 us on 296 CTAs, 83.7 on 148; mushrooms-shaped CSR logreg, AdaPGM: 36.9 vs 33.9).
+  if (P.A.kind == MAT_NONE && bytes < kSmallProblemBytes) return std::min(h->grid, h->sm_count);
   return h->grid;
 }
 

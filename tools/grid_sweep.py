@@ -47,6 +47,30 @@ def main():
             Lf = AdaProx.synth.spectral_norm_sq(P["A"], iters=30)
             f, g = AdaProx.LinearLeastSquares(P["A"], P["b"]), AdaProx.NormL1(1.0)
             run(f"lasso {m}x{n} AdaPGM (300 iterations)", lambda: AdaProx.adaptive_proxgrad(np.zeros(n), f=f, g=g, rule=AdaProx.OurRule(gamma=1 / Lf), tol=0.0, maxit=300)[1], grids)
+    if "paper" in which:
+        # shapes of the reference's own experiment datasets (experiments/*/runme.jl main()): mushrooms 8124 x 112 with 21 nonzeros
+        # per row (sparse logreg), cpusmall 8192 x 12 (+ intercept column; LAD with AdaPDM+), svmguide3 1243 x 22 (dual SVM, dense Q)
+        import scipy.sparse as sp
+        rng = np.random.default_rng(0)
+        m, n, k = 8124, 112, 21
+        cols = np.concatenate([rng.choice(n, k, replace=False) for _ in range(m)])
+        X = sp.csr_matrix((np.ones(m * k), cols, np.arange(0, m * k + 1, k)), shape=(m, n))
+        w = rng.standard_normal(n)
+        y = (X @ w + 0.5 * rng.standard_normal(m) > 0).astype(float)
+        f, g = AdaProx.LogisticLoss(X, y), AdaProx.NormL1(1e-3)
+        gam = 4 * m / (X.nnz + m)
+        run("mushrooms-shaped sparse logreg 8124x112 AdaPGM (300 iterations)", lambda: AdaProx.adaptive_proxgrad(np.zeros(n + 1), f=f, g=g, rule=AdaProx.OurRule(gamma=gam), tol=0.0, maxit=300)[1], grids)
+        A = np.hstack([rng.standard_normal((8192, 12)), np.ones((8192, 1))])
+        yv = A @ rng.standard_normal(13) + rng.laplace(size=8192)
+        nA = float(np.linalg.norm(A))
+        Ad = AdaProx.DeviceMatrix(A)
+        kw = dict(f=AdaProx.Zero(), g=AdaProx.NormL1(1.0), h=AdaProx.Translate(AdaProx.NormL1(), -yv), A=Ad, eta=nA, t=1.0, tol=0.0, maxit=300)
+        run("cpusmall-shaped LAD 8192x13 AdaPDM+ (300 iterations)", lambda: AdaProx.adaptive_linesearch_primal_dual(np.zeros(13), np.zeros(8192), **kw)[2], grids)
+        Xs, ys = AdaProx.synth.dense_classification(1243, 22, 0)
+        Z = ys[:, None] * Xs
+        fq = AdaProx.Quadratic(Z @ Z.T, -np.ones(1243))
+        Am = AdaProx.DeviceMatrix(ys[None, :].copy())
+        run("svmguide3-shaped dual SVM N=1243 dense Q AdaPDM (300 iterations)", lambda: AdaProx.adaptive_primal_dual(np.zeros(1243), np.zeros(1), f=fq, g=AdaProx.IndBox(0.0, 0.1), h=AdaProx.IndZero(), A=Am, rule=AdaProx.OurRule(t=1.0, norm_A=float(np.sqrt(1243))), tol=0.0, maxit=300)[2], grids)
     if "lad" in which:
         X, yv = AdaProx.synth.dense_regression(50000, 2000, 0)
         A = np.hstack([X, np.ones((50000, 1))])
