@@ -43,6 +43,23 @@ def test_struct_layouts_match_the_header():
     assert C.sizeof(L.Options) == 4 + 4 + 8 * 18 + 8 + 4 * 5 + 4 + 8 == 192
 
 
+def test_enum_values_match_the_header():
+    """every enumerator of include/adaprox.h has the same value in the ctypes mirror (and in the Julia shim's literal kinds)"""
+    src = open(os.path.join(ROOT, "include", "adaprox.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    enums = {name: int(val) for name, val in re.findall(r"\bADAPROX_((?:F|P|S|RULE)_[A-Z0-9_]+)\s*=\s*(-?\d+)", src)}
+    assert len(enums) == 8 + 5 + 8 + 4
+    for name, val in enums.items():
+        assert getattr(L, name) == val, name
+    flags = {name: int(val) for name, val in re.findall(r"#define ADAPROX_(FLAG_[A-Z_]+)\s+(\d+)u", src)}
+    assert flags and all(getattr(L, k) == v for k, v in flags.items())
+    jl = open(os.path.join(ROOT, "julia", "AdaProxCUDA.jl")).read()
+    for fn, kind in [("least_squares", "F_LEAST_SQUARES"), ("logistic", "F_LOGISTIC"), ("quadratic", "F_QUADRATIC"),
+                     ("quadratic_gram", "F_QUADRATIC_GRAM"), ("cubic", "F_CUBIC"), ("worst_quadratic", "F_WORST_QUADRATIC")]:
+        m = re.search(r"^%s\([^)]*\) = \(kind = (\d+)," % fn, jl, flags=re.M)
+        assert m and int(m.group(1)) == enums[kind], fn
+
+
 def test_no_cpu_fallback_without_a_gpu():
     import torch
     if torch.cuda.is_available():
