@@ -253,15 +253,15 @@ extern "C" int adaprox_matrix_upload_colmajor(adaprox_handle h, const double* A,
   int rc = alloc_dense(h, m, n, hm);
   if (rc) { free_matrix(hm); return rc; }
   double* stage = nullptr;
-  AP_CUDA(h, cudaMalloc(&stage, (size_t)lda * n * 8));
-  cudaError_t e = cudaMemcpyAsync(stage, A, (size_t)lda * n * 8, cudaMemcpyHostToDevice, h->stream);
+  cudaError_t e = cudaMalloc(&stage, (size_t)lda * n * 8);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(stage, A, (size_t)lda * n * 8, cudaMemcpyHostToDevice, h->stream);
   if (e == cudaSuccess) {
     dim3 grid((unsigned)((m + 31) / 32), (unsigned)((hm.d.ld + 31) / 32)), block(32, 8);
     k_colmajor_to_rowmajor<<<grid, block, 0, h->stream>>>(stage, m, n, lda, const_cast<double*>(hm.d.a), hm.d.ld);
     h->launches++;
     e = cudaStreamSynchronize(h->stream);
   }
-  cudaFree(stage);
+  if (stage) cudaFree(stage);
   if (e != cudaSuccess) { free_matrix(hm); return fail(h, ADAPROX_ERR_CUDA, std::string("matrix upload: ") + cudaGetErrorString(e)); }
   const int64_t id = h->next_id++;
   h->mats[id] = hm;
@@ -752,6 +752,7 @@ extern "C" int adaprox_solve(adaprox_handle h, const adaprox_problem* p, const a
   if (fused && (rc = fused_ws_alloc(h, &fpl))) return rc;
   const bool phase_timing = std::getenv("ADAPROX_PHASE_TIMING") != nullptr;
   unsigned long long* d_ts = nullptr;
+  struct DevFree { unsigned long long*& p; ~DevFree() { if (p) cudaFree(p); } } d_ts_guard{d_ts};   // released on every return path
   const int ts_iters = (int)std::min<int64_t>(O.maxit, 64);
   if (phase_timing && ts_iters > 0) {
     AP_CUDA(h, cudaMalloc(&d_ts, (size_t)ts_iters * 8 * sizeof(unsigned long long)));
@@ -813,7 +814,6 @@ extern "C" int adaprox_solve(adaprox_handle h, const adaprox_problem* p, const a
   if (d_ts) {     // phase breakdown of the persistent kernel, averaged over the stamped iterations
     std::vector<unsigned long long> ts((size_t)ts_iters * 8);
     cudaMemcpy(ts.data(), d_ts, ts.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
-    cudaFree(d_ts);
     const int nit = (int)std::min<int64_t>(ts_iters, dr.iters);
     double sum[8] = {0}; int cnt = 0;
     for (int i = 0; i < nit; ++i) {
