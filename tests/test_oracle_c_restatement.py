@@ -1,0 +1,116 @@
+"""The numpy oracle (oracle/adaprox_oracle.py) -- the checker of every GPU parity test -- against a second restatement of
+src/AdaProx.jl:312-364 written independently in plain C (oracle/adaprox_ref.c): no shared code, no BLAS, sequential
+summation.  The two must agree on the stepsize / residual / objective sequences to rounding-level tolerances over a prefix
+(the trajectories are chaotic w.r.t. rounding afterwards), and on the final result."""
+import numpy as np
+import pytest
+
+import adaprox_b200
+from oracle import adaprox_oracle as O
+from oracle import c_ref as R
+
+
+def _prefix(log, hist, K, rtol_gamma=1e-10, rtol_res=1e-8, rtol_obj=1e-10):
+    K = min(K, len(log), len(hist["gamma"]))
+    assert K >= 5
+    assert np.allclose([r["gamma"] for r in log[:K]], hist["gamma"][:K], rtol=rtol_gamma, atol=0)
+    assert np.allclose([r["sigma"] for r in log[:K]], hist["sigma"][:K], rtol=rtol_gamma, atol=0)
+    assert np.allclose([r["norm_res"] for r in log[:K]], hist["norm_res"][:K], rtol=rtol_res, atol=1e-14)
+    obj = np.array([r["objective"] for r in log[:K]])
+    fin = np.isfinite(obj)
+    assert np.array_equal(fin, np.isfinite(hist["objective"][:K]))
+    assert np.allclose(obj[fin], hist["objective"][:K][fin], rtol=rtol_obj, atol=1e-13)
+
+
+@pytest.mark.parametrize("rule", ["our", "mm", "fixed"])
+def test_adapgm_lasso(rule):
+    P = adaprox_b200.synth.planted_lasso(100, 300, 10, 0)
+    Lf = adaprox_b200.synth.spectral_norm_sq(P["A"], iters=1000, tol=1e-15)
+    ro = {"our": O.OurRule(gamma=1 / Lf), "mm": O.MalitskyMishchenkoRule(gamma=1 / Lf), "fixed": O.FixedStepsize(1 / Lf)}[rule]
+    rc = {"our": R.RULE_OUR, "mm": R.RULE_MM, "fixed": R.RULE_FIXED}[rule]
+    log = []
+    xo, ito = O.adaptive_proxgrad(np.zeros(300), f=O.LinearLeastSquares(P["A"], P["b"]), g=O.NormL1(1.0), rule=ro, tol=1e-7, maxit=3000, log=log)
+    xc, _, itc, hist = R.adaptive_primal_dual(np.zeros(300), None, f_kind=R.F_LEAST_SQUARES, F=P["A"], fvec=P["b"], g=R.prox_desc(R.P_NORM_L1, 1.0),
+                                              rule=rc, gamma=1 / Lf, tol=1e-7, maxit=3000, nhist=3000)
+    _prefix(log, hist, 40)
+    assert abs(itc - ito) <= max(3, 0.05 * ito)
+    fo = O.LinearLeastSquares(P["A"], P["b"])
+    oo, oc = fo(xo) + np.abs(xo).sum(), fo(xc) + np.abs(xc).sum()
+    assert abs(oo - oc) <= 1e-10 * abs(oo)
+    if rule != "fixed":                       # fixed-step PGM is still 1e-6 away after 3000 iterations
+        assert abs(oc - P["optimum"]) <= 1e-8 * P["optimum"]
+
+
+def test_adapgm_dense_logistic():
+    rng = np.random.default_rng(1)
+    X = rng.standard_normal((150, 20))
+    y = (rng.random(150) < 0.5).astype(float)
+    gam = 4 * 150 / (np.sum(X * X) + 150)
+    log = []
+    xo, ito = O.adaptive_proxgrad(np.zeros(21), f=O.LogisticLoss(X, y), g=O.NormL1(0.01), rule=O.OurRule(gamma=gam), tol=1e-8, maxit=3000, log=log)
+    xc, _, itc, hist = R.adaptive_primal_dual(np.zeros(21), None, f_kind=R.F_LOGISTIC, F=X, fvec=y, g=R.prox_desc(R.P_NORM_L1, 0.01),
+                                              rule=R.RULE_OUR, gamma=gam, tol=1e-8, maxit=3000, nhist=3000)
+    _prefix(log, hist, 12)                                         # identical to 1e-14 here; near convergence (24 iterations) the
+    _prefix(log, hist, 40, rtol_gamma=1e-8, rtol_res=1e-6)         # differences dx, dgrad cancel and rounding is amplified to ~1e-10
+    assert abs(itc - ito) <= max(3, 0.05 * ito) and np.linalg.norm(xo - xc) <= 1e-6 * max(1.0, np.linalg.norm(xo))
+
+
+@pytest.mark.parametrize("t", [0.1, 1.0])
+def test_adapdm_dual_svm(t):
+    """dual_svm/runme.jl:47-59: f = Quadratic(Q, q), g = IndBox(0, C), h = IndZero(), A = y'."""
+    X, y = adaprox_b200.synth.dense_classification(120, 8, 0)
+    Z = y[:, None] * X
+    Q, q, N = Z @ Z.T, -np.ones(120), 120
+    A = y[None, :].copy()
+    nA = float(np.linalg.norm(A))
+    log = []
+    xo, yo, ito = O.adaptive_primal_dual(np.zeros(N), np.zeros(1), f=O.Quadratic(Q, q), g=O.IndBox(0.0, 0.1), h=O.IndZero(), A=A,
+                                         rule=O.OurRule(t=t, norm_A=nA), tol=1e-6, maxit=5000, log=log)
+    xc, yc, itc, hist = R.adaptive_primal_dual(np.zeros(N), np.zeros(1), f_kind=R.F_QUADRATIC, F=Q, fvec=q, g=R.prox_desc(R.P_IND_BOX, lo=0.0, hi=0.1),
+                                               h=R.prox_desc(R.P_IND_ZERO), A=A, rule=R.RULE_OUR, gamma=1 / (2 * 1.2 * t * nA), t=t, norm_A=nA,
+                                               tol=1e-6, maxit=5000, nhist=5000)
+    _prefix(log, hist, 40)
+    assert abs(itc - ito) <= max(3, 0.05 * ito)
+    fq = O.Quadratic(Q, q)
+    assert abs(fq(xo) - fq(xc)) <= 1e-8 * abs(fq(xo)) and abs(y @ xc) < 1e-4
+
+
+@pytest.mark.parametrize("hname", ["l1", "l2"])
+def test_adapdm_lad_and_sqrt_lasso(hname):
+    """least_absolute_deviation/runme.jl:39-48 and square_root_lasso/runme.jl:41: f = Zero, h = Translate(NormL1 | NormL2, -b)."""
+    rng = np.random.default_rng(2)
+    A = np.hstack([rng.standard_normal((80, 6)), np.ones((80, 1))])
+    b = A @ rng.standard_normal(7) + rng.laplace(size=80)
+    nA = float(np.linalg.norm(A))
+    ho = O.Translate(O.NormL1() if hname == "l1" else O.NormL2(), -b)
+    hc = R.prox_desc(R.P_NORM_L1 if hname == "l1" else R.P_NORM_L2, 1.0, shift=-b)
+    log = []
+    xo, yo, ito = O.adaptive_primal_dual(np.zeros(7), np.zeros(80), f=O.Zero(), g=O.NormL1(0.5), h=ho, A=A, rule=O.OurRule(t=1.0, norm_A=nA),
+                                         tol=1e-6, maxit=4000, log=log)
+    xc, yc, itc, hist = R.adaptive_primal_dual(np.zeros(7), np.zeros(80), f_kind=R.F_ZERO, g=R.prox_desc(R.P_NORM_L1, 0.5), h=hc, A=A,
+                                               rule=R.RULE_OUR, gamma=1 / (2 * 1.2 * nA), t=1.0, norm_A=nA, tol=1e-6, maxit=4000, nhist=4000)
+    _prefix(log, hist, 30)
+    assert abs(itc - ito) <= max(3, 0.05 * ito)
+    oo = log[min(len(log), ito) - 1]["objective"]
+    oc = hist["objective"][min(len(hist["objective"]), itc) - 1]
+    assert abs(oo - oc) <= 1e-7 * abs(oo)
+
+
+def test_condat_vu_fixed_rule():
+    """condat_vu (:367-416) = the generic loop with FixedStepsize(gamma, sqrt(sigma / gamma))."""
+    X, y = adaprox_b200.synth.dense_classification(60, 5, 1)
+    Z = y[:, None] * X
+    Q, q, N = Z @ Z.T, -np.ones(60), 60
+    A = y[None, :].copy()
+    Lf, nA = float(np.linalg.norm(Q)), float(np.linalg.norm(A))
+    log = []
+    xo, yo, ito = O.condat_vu(np.zeros(N), np.zeros(1), f=O.Quadratic(Q, q), g=O.IndBox(0.0, 1.0), h=O.IndZero(), A=A, Lf=Lf, norm_A=nA,
+                              tol=1e-6, maxit=400, log=log)
+    alpha = 1.0 if nA > 5 * Lf else 100 * nA / Lf                                # :398-412
+    gamma, sigma = 1 / (Lf / 2 + nA / alpha), 0.99 / (nA * alpha)
+    xc, yc, itc, hist = R.adaptive_primal_dual(np.zeros(N), np.zeros(1), f_kind=R.F_QUADRATIC, F=Q, fvec=q, g=R.prox_desc(R.P_IND_BOX, lo=0.0, hi=1.0),
+                                               h=R.prox_desc(R.P_IND_ZERO), A=A, rule=R.RULE_FIXED, gamma=gamma, t=np.sqrt(sigma / gamma),
+                                               tol=1e-6, maxit=400, nhist=400)
+    assert itc == ito
+    _prefix(log, hist, 400, rtol_res=1e-7)
+    assert np.allclose(xo, xc, rtol=0, atol=1e-9) and np.allclose(yo, yc, rtol=0, atol=1e-9)
