@@ -6,6 +6,9 @@
  *
  * Follows, line by line:
  *   adaptive_primal_dual            src/AdaProx.jl:312-364   (AdaPGM :418-421 = the same loop with h = Zero(), A = 0, y = zero(x))
+ *   adaptive_linesearch_primal_dual src/AdaProx.jl:463-550   (AdaPDM+)
+ *   backtrack_stepsize, backtracking_proxgrad, backtracking_nesterov :34-84 ; fixed_nesterov :91-142 ; agraal :150-192
+ *   backtrack_stepsize_MP, malitsky_pock                      src/AdaProx.jl:555-629
  *   FixedStepsize / MalitskyMishchenkoRule / OurRule          src/AdaProx.jl:208-273
  *   nan_to_zero                                               src/AdaProx.jl:24
  *   LinearLeastSquares   experiments/lasso/runme.jl:21-25     Quadratic   experiments/dual_svm/runme.jl:24-28
@@ -236,6 +239,274 @@ long ref_adaptive_primal_dual(const ref_problem* p, const double* x0, const doub
   }
   memcpy(x_out, x, (size_t)n * sizeof(double));
   if (y_out) memcpy(y_out, y, (size_t)md * sizeof(double));
+  free(buf);
+  return it_ret;
+}
+
+/* ---- adaptive_linesearch_primal_dual, AdaPDM+ (:463-550) -------------------------------------------------------------
+ * p->gamma must already be resolved (gamma === nothing -> 1 / (2 Theta t eta), :484-486); rule fields other than
+ * t, delta, Theta are unused.  eta, r, R as in the reference.  trials_out (may be NULL): total linesearch trials. */
+long ref_adaptive_linesearch_primal_dual(const ref_problem* p, double eta, double r, double R, const double* x0, const double* y0,
+                                         double* x_out, double* y_out, double* gamma_hist, double* sigma_hist, double* res_hist,
+                                         double* obj_hist, long nhist, long* trials_out) {
+  const long n = p->n, md = p->am;
+  if (!p->A) return -2;
+  const long big = (p->fm > n ? p->fm : n) > md ? (p->fm > n ? p->fm : n) : md;
+  double* buf = (double*)calloc((size_t)(10 * n + 6 * md + 2 * big), sizeof(double));
+  if (!buf) return -1;
+  double *x = buf, *x_prev = x + n, *grad = x_prev + n, *grad_prev = grad + n, *v = grad_prev + n, *At_y = v + n,
+         *pres = At_y + n, *dgr = pres + n, *dx = dgr + n, *At_y_next = dx + n;
+  double *y = At_y_next + n, *A_x = y + md, *A_x_prev = A_x + md, *w = A_x_prev + md, *dres = w + md, *y_next = dres + md;
+  double *tmp = y_next + md, *tmp2 = tmp + big;
+  memcpy(x, x0, (size_t)n * sizeof(double));
+  memcpy(y, y0, (size_t)md * sizeof(double));
+  const double t = p->t, Theta = p->Theta, delta1 = 1.0 + p->delta;               /* :490 */
+  double gamma = p->gamma, gamma_prev = gamma, sigma = t * t * gamma;             /* :491 */
+  long trials = 0;
+  mul(p->A, md, n, x, A_x);                                                       /* :494 */
+  eval_f(p, x, grad, tmp);
+  amul(p->A, md, n, y, At_y);
+  for (long i = 0; i < n; ++i) v[i] = x[i] - gamma * (grad[i] + At_y[i]);         /* :497 */
+  memcpy(x_prev, x, (size_t)n * sizeof(double));
+  memcpy(A_x_prev, A_x, (size_t)md * sizeof(double));
+  memcpy(grad_prev, grad, (size_t)n * sizeof(double));
+  prox(&p->g, v, gamma, x, n);                                                    /* :499 */
+  long it_ret = p->maxit;
+  for (long it = 1; it <= p->maxit; ++it) {
+    mul(p->A, md, n, x, A_x);                                                     /* :502 */
+    const double f_x = eval_f(p, x, grad, tmp);
+    for (long i = 0; i < n; ++i) pres[i] = (v[i] - x[i]) / gamma + grad[i] + At_y[i];                  /* :505 */
+    for (long i = 0; i < n; ++i) { dgr[i] = grad[i] - grad_prev[i]; dx[i] = x[i] - x_prev[i]; }
+    const double dgx = dot(dgr, dx, n);
+    const double C = nan_to_zero(sq(norm2(dgr, n)) / dgx);                        /* :507 */
+    const double L = nan_to_zero(dgx / sq(norm2(dx, n)));                         /* :508 */
+    const double Delta = gamma * L * (gamma * C - 1.0);                           /* :509 */
+    const double xi_bar = (t * t) * (gamma * gamma) * (eta * eta) * (delta1 * delta1);                 /* :510 */
+    const double m4xim1 = 1.0 - 4.0 * xi_bar;                                     /* :511 */
+    eta = R * eta;                                                                /* :513 */
+    for (;;) {                                                                    /* :516-533 */
+      ++trials;
+      const double gamma_next = jl_min(jl_min(gamma * sqrt(1.0 + gamma / gamma_prev), 1.0 / (2.0 * Theta * t * eta)),
+                                       gamma * sqrt(m4xim1 / (2.0 * delta1 * (Delta + sqrt(Delta * Delta + m4xim1 * sq(t * eta * gamma))))));
+      const double rho = gamma_next / gamma;
+      sigma = (t * t) * gamma_next;
+      for (long i = 0; i < md; ++i) w[i] = y[i] + sigma * ((1.0 + rho) * A_x[i] - rho * A_x_prev[i]);
+      prox_conj(&p->h, w, sigma, y_next, tmp2, md);
+      amul(p->A, md, n, y_next, At_y_next);
+      double dn = 0.0, dd = 0.0;
+      for (long j = 0; j < n; ++j) dn += sq(At_y_next[j] - At_y[j]);
+      for (long i = 0; i < md; ++i) dd += sq(y_next[i] - y[i]);
+      if (eta >= sqrt(dn) / sqrt(dd)) {                                           /* :527 */
+        gamma_prev = gamma; gamma = gamma_next;
+        memcpy(y, y_next, (size_t)md * sizeof(double));
+        memcpy(At_y, At_y_next, (size_t)n * sizeof(double));
+        break;
+      }
+      eta *= r;                                                                   /* :532 */
+      if (trials > 100000000L) break;
+    }
+    for (long i = 0; i < md; ++i) dres[i] = (w[i] - y[i]) / sigma - A_x[i];       /* :535 */
+    const double norm_res = sqrt(sq(norm2(pres, n)) + sq(norm2(dres, md)));
+    if (it <= nhist) {
+      if (gamma_hist) gamma_hist[it - 1] = gamma;
+      if (sigma_hist) sigma_hist[it - 1] = sigma;
+      if (res_hist) res_hist[it - 1] = norm_res;
+      if (obj_hist) obj_hist[it - 1] = f_x + prox_value(&p->g, x, n) + prox_value(&p->h, A_x, md);
+    }
+    if (norm_res <= p->tol) { it_ret = it; break; }                               /* :541-543 */
+    for (long i = 0; i < n; ++i) v[i] = x[i] - gamma * (grad[i] + At_y[i]);       /* :545 */
+    memcpy(x_prev, x, (size_t)n * sizeof(double));
+    memcpy(A_x_prev, A_x, (size_t)md * sizeof(double));
+    memcpy(grad_prev, grad, (size_t)n * sizeof(double));
+    prox(&p->g, v, gamma, x, n);                                                  /* :547 */
+  }
+  memcpy(x_out, x, (size_t)n * sizeof(double));
+  memcpy(y_out, y, (size_t)md * sizeof(double));
+  if (trials_out) *trials_out = trials;
+  free(buf);
+  return it_ret;
+}
+
+/* ---- the proximal-gradient baselines --------------------------------------------------------------------------------
+ * which: 0 backtracking_proxgrad (:50-64), 1 backtracking_nesterov (:66-84), 2 fixed_nesterov (:91-142, mu = 0 or > 0),
+ *        3 agraal (:150-192; x_second = the other start point x0, gamma0 <= 0 means `nothing`).
+ * p->gamma = gamma0 (0, 1, 3) / gamma (2).  evals_out[0..1] (may be NULL): f evaluations, gradient evaluations as
+ * Counting would report them (the logged f(x) of fixed_nesterov / agraal is not counted). */
+static double upper_bound(const double* x, double f_x, const double* grad_x, const double* z, double gamma, long n) {   /* :26 */
+  double gd = 0.0, dd = 0.0;
+  for (long i = 0; i < n; ++i) { const double d = z[i] - x[i]; gd += grad_x[i] * d; dd += d * d; }
+  return f_x + gd + 1.0 / (2.0 * gamma) * sq(sqrt(dd));
+}
+long ref_proxgrad_family(const ref_problem* p, int which, double xi, double shrink, double muf, double mug, double theta0,
+                         double gamma_max, double phi, const double* x0, const double* x_second, double* x_out,
+                         double* gamma_hist, double* res_hist, double* obj_hist, long nhist, long* evals_out) {
+  const long n = p->n;
+  const long big = p->fm > n ? p->fm : n;
+  double* buf = (double*)calloc((size_t)(8 * n + big), sizeof(double));
+  if (!buf) return -1;
+  double *x = buf, *z = x + n, *z_prev = z + n, *grad = z_prev + n, *grad2 = grad + n, *u = grad2 + n, *x_bar = u + n, *x_prev = x_bar + n;
+  double* tmp = x_prev + n;
+  long n_eval = 0, n_grad = 0, it_ret = p->maxit;
+  double gamma = p->gamma;
+  memcpy(x, x0, (size_t)n * sizeof(double));
+  double* result = x;
+#define HIST(it, g_, r_, o_) do { if ((it) <= nhist) { if (gamma_hist) gamma_hist[(it) - 1] = (g_); if (res_hist) res_hist[(it) - 1] = (r_); \
+                                                        if (obj_hist) obj_hist[(it) - 1] = (o_); } } while (0)
+  if (which == 0 || which == 1) {
+    memcpy(z, x, (size_t)n * sizeof(double));
+    double theta = 1.0;
+    double f_x = eval_f(p, x, grad, tmp); n_eval++; n_grad++;                     /* :52 / :69 */
+    result = z;
+    for (long it = 1; it <= p->maxit; ++it) {
+      if (which == 1) memcpy(z_prev, z, (size_t)n * sizeof(double));              /* :71 */
+      gamma = (which == 0) ? xi * gamma : gamma;                                  /* :54 / :72 */
+      double f_z;
+      for (;;) {                                                                  /* backtrack_stepsize :34-48 */
+        for (long i = 0; i < n; ++i) u[i] = x[i] - gamma * grad[i];
+        prox(&p->g, u, gamma, z, n);
+        const double ub_z = upper_bound(x, f_x, grad, z, gamma, n);
+        f_z = eval_f(p, z, grad2, tmp); n_eval++;                                 /* value now, pullback (grad2) on demand */
+        if (!(f_z > ub_z)) break;
+        gamma *= shrink;
+        if (gamma < 1e-300) break;
+      }
+      double dd = 0.0;
+      for (long i = 0; i < n; ++i) dd += sq(z[i] - x[i]);
+      const double norm_res = sqrt(dd) / gamma;                                   /* :55 / :73 */
+      HIST(it, gamma, norm_res, f_z + prox_value(&p->g, z, n));
+      if (norm_res <= p->tol) { it_ret = it; break; }
+      if (which == 0) {                                                           /* :60-61 */
+        memcpy(x, z, (size_t)n * sizeof(double)); f_x = f_z;
+        memcpy(grad, grad2, (size_t)n * sizeof(double)); n_grad++;
+      } else {                                                                    /* :78-81 */
+        const double theta_prev = theta;
+        theta = (1.0 + sqrt(1.0 + 4.0 * theta_prev * theta_prev)) / 2.0;
+        for (long i = 0; i < n; ++i) x[i] = z[i] + (theta_prev - 1.0) / theta * (z[i] - z_prev[i]);
+        f_x = eval_f(p, x, grad, tmp); n_eval++; n_grad++;
+      }
+    }
+  } else if (which == 2) {
+    const double mu = muf + mug;                                                  /* :108-117 */
+    const double q = gamma * mu / (1.0 + gamma * mug);
+    double theta = theta0 >= 0.0 ? theta0 : (q > 0.0 ? 1.0 / sqrt(q) : 0.0);
+    memcpy(x_prev, x, (size_t)n * sizeof(double));                                /* :119 */
+    for (long it = 1; it <= p->maxit; ++it) {
+      const double theta_prev = theta;
+      double beta;
+      if (mu == 0.0) {                                                            /* :122-128 */
+        theta = (1.0 + sqrt(1.0 + 4.0 * theta_prev * theta_prev)) / 2.0;
+        beta = (theta_prev - 1.0) / theta;
+      } else {
+        const double a = 1.0 - q * theta_prev * theta_prev;
+        theta = (a + sqrt(a * a + 4.0 * theta_prev * theta_prev)) / 2.0;
+        beta = (theta_prev - 1.0) * (1.0 + gamma * mug - theta * gamma * mu) / theta / (1.0 - gamma * muf);
+      }
+      for (long i = 0; i < n; ++i) z[i] = x[i] + beta * (x[i] - x_prev[i]);       /* :129 */
+      eval_f(p, z, grad, tmp); n_eval++; n_grad++;                                /* :130 */
+      memcpy(x_prev, x, (size_t)n * sizeof(double));                              /* :131 */
+      for (long i = 0; i < n; ++i) u[i] = z[i] - gamma * grad[i];
+      prox(&p->g, u, gamma, x, n);                                                /* :132 */
+      double dd = 0.0;
+      for (long i = 0; i < n; ++i) dd += sq(x[i] - z[i]);
+      const double norm_res = sqrt(dd) / gamma;                                   /* :133 */
+      if (it <= nhist && obj_hist) { const double fx = eval_f(p, x, grad2, tmp); HIST(it, gamma, norm_res, fx + prox_value(&p->g, x, n)); }
+      else HIST(it, gamma, norm_res, NAN);
+      if (norm_res <= p->tol) { it_ret = it; break; }
+    }
+  } else {
+    memcpy(x_prev, x_second, (size_t)n * sizeof(double));                         /* :165 */
+    memcpy(x_bar, x, (size_t)n * sizeof(double));
+    eval_f(p, x, grad, tmp);                                                      /* :166 */
+    eval_f(p, x_prev, grad2, tmp);                                                /* :167 */
+    n_eval = 2; n_grad = 2;
+    const double rho = 1.0 / phi + 1.0 / (phi * phi);                             /* :172 */
+    double theta = 1.0;
+    for (long it = 1; it <= p->maxit; ++it) {
+      double dxx = 0.0, dgg = 0.0;
+      for (long i = 0; i < n; ++i) { dxx += sq(x[i] - x_prev[i]); dgg += sq(grad[i] - grad2[i]); }
+      if (it == 1 && !(p->gamma > 0.0)) gamma = sqrt(dxx) / sqrt(dgg);            /* :168-170 */
+      const double C = sq(sqrt(dxx)) / sq(sqrt(dgg));                             /* :175 */
+      const double gamma_prev = gamma;
+      gamma = jl_min(jl_min(rho * gamma_prev, phi * theta * C / (4.0 * gamma_prev)), gamma_max);       /* :177 */
+      theta = phi * gamma / gamma_prev;                                           /* :178 */
+      for (long i = 0; i < n; ++i) x_bar[i] = ((phi - 1.0) * x[i] + x_bar[i]) / phi;                   /* :179 */
+      memcpy(x_prev, x, (size_t)n * sizeof(double));                              /* :180 */
+      memcpy(grad2, grad, (size_t)n * sizeof(double));
+      for (long i = 0; i < n; ++i) u[i] = x_bar[i] - gamma * grad2[i];
+      prox(&p->g, u, gamma, x, n);                                                /* :181 */
+      double dd = 0.0;
+      for (long i = 0; i < n; ++i) dd += sq(x[i] - x_prev[i]);
+      const double norm_res = sqrt(dd) / gamma;                                   /* :182 */
+      const double fx = eval_f(p, x, grad, tmp);                                  /* value for the record (uncounted) + :189's gradient */
+      HIST(it, gamma, norm_res, fx + prox_value(&p->g, x, n));
+      if (norm_res <= p->tol) { it_ret = it; break; }
+      n_eval++; n_grad++;                                                         /* :189 */
+    }
+  }
+#undef HIST
+  memcpy(x_out, result, (size_t)n * sizeof(double));
+  if (evals_out) { evals_out[0] = n_eval; evals_out[1] = n_grad; }
+  free(buf);
+  return it_ret;
+}
+
+/* ---- malitsky_pock (:555-629) ------------------------------------------------------------------------------------------ */
+long ref_malitsky_pock(const ref_problem* p, double sigma, const double* x0, const double* y0, double* x_out, double* y_out,
+                       double* gamma_hist, double* sigma_hist, double* res_hist, double* obj_hist, long nhist) {
+  const long n = p->n, md = p->am;
+  if (!p->A) return -2;
+  const long big = (p->fm > n ? p->fm : n) > md ? (p->fm > n ? p->fm : n) : md;
+  double* buf = (double*)calloc((size_t)(8 * n + 5 * md + 2 * big), sizeof(double));
+  if (!buf) return -1;
+  double *x = buf, *x_prev = x + n, *grad = x_prev + n, *grad_prev = grad + n, *v = grad_prev + n, *At_y = v + n, *At_y_prev = At_y + n,
+         *pres = At_y_prev + n;
+  double *y = pres + n, *A_x = y + md, *A_x_prev = A_x + md, *w = A_x_prev + md, *dres = w + md;
+  double *tmp = dres + md, *tmp2 = tmp + big;
+  memcpy(x, x0, (size_t)n * sizeof(double));
+  memcpy(y, y0, (size_t)md * sizeof(double));
+  const double t = p->t, theta1 = 1.0;                                            /* :595: theta = one(sigma), never updated */
+  mul(p->A, md, n, x, A_x);                                                       /* :597 */
+  amul(p->A, md, n, y, At_y);                                                     /* :598 */
+  long it_ret = p->maxit;
+  for (long it = 1; it <= p->maxit; ++it) {
+    memcpy(At_y_prev, At_y, (size_t)n * sizeof(double));                          /* :600 */
+    for (long i = 0; i < md; ++i) w[i] = y[i] + sigma * A_x[i];                   /* :601 */
+    prox_conj(&p->h, w, sigma, y, tmp2, md);                                      /* :602 (w and y are distinct buffers) */
+    amul(p->A, md, n, y, At_y);                                                   /* :603 */
+    const double sigma_prev = sigma;                                              /* :605-606 */
+    sigma = sigma * sqrt(1.0 + theta1);
+    const double f_x_prev = eval_f(p, x, grad_prev, tmp);                         /* :608 */
+    memcpy(x_prev, x, (size_t)n * sizeof(double));                                /* :609 */
+    memcpy(A_x_prev, A_x, (size_t)md * sizeof(double));
+    double gamma, f_x;
+    for (;;) {                                                                    /* backtrack_stepsize_MP :555-579 */
+      const double th = sigma / sigma_prev;
+      gamma = t * t * sigma;
+      for (long i = 0; i < n; ++i) v[i] = x_prev[i] - gamma * (((1.0 + th) * At_y[i] - th * At_y_prev[i]) + grad_prev[i]);
+      prox(&p->g, v, gamma, x, n);
+      mul(p->A, md, n, x, A_x);
+      f_x = eval_f(p, x, grad, tmp);
+      double da = 0.0, dxx = 0.0, gd = 0.0;
+      for (long i = 0; i < md; ++i) da += sq(A_x[i] - A_x_prev[i]);
+      for (long i = 0; i < n; ++i) { const double d = x[i] - x_prev[i]; dxx += d * d; gd += grad_prev[i] * d; }
+      const double lhs = gamma * sigma * sq(sqrt(da)) + 2.0 * gamma * (f_x - f_x_prev - gd);
+      if (!(lhs > 0.95 * sq(sqrt(dxx)))) break;
+      sigma /= 2.0;
+      if (sigma < 1e-300) break;
+    }
+    for (long i = 0; i < n; ++i) pres[i] = (v[i] - x[i]) / gamma + grad[i] + At_y[i];                  /* :616 */
+    for (long i = 0; i < md; ++i) dres[i] = (w[i] - y[i]) / sigma_prev - A_x[i];                       /* :617 */
+    const double norm_res = sqrt(sq(norm2(pres, n)) + sq(norm2(dres, md)));
+    if (it <= nhist) {
+      if (gamma_hist) gamma_hist[it - 1] = gamma;
+      if (sigma_hist) sigma_hist[it - 1] = sigma;
+      if (res_hist) res_hist[it - 1] = norm_res;
+      if (obj_hist) obj_hist[it - 1] = f_x + prox_value(&p->g, x, n) + prox_value(&p->h, A_x, md);
+    }
+    if (norm_res <= p->tol) { it_ret = it; break; }
+  }
+  memcpy(x_out, x, (size_t)n * sizeof(double));
+  memcpy(y_out, y, (size_t)md * sizeof(double));
   free(buf);
   return it_ret;
 }

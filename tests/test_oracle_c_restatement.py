@@ -114,3 +114,116 @@ def test_condat_vu_fixed_rule():
     assert itc == ito
     _prefix(log, hist, 400, rtol_res=1e-7)
     assert np.allclose(xo, xc, rtol=0, atol=1e-9) and np.allclose(yo, yc, rtol=0, atol=1e-9)
+
+
+# ---------------------------------------------------------------- AdaPDM+ (:463-550)
+@pytest.mark.parametrize("hname", ["l1", "l2"])
+def test_adapdm_plus(hname):
+    rng = np.random.default_rng(3)
+    A = np.hstack([rng.standard_normal((90, 7)), np.ones((90, 1))])
+    b = A @ rng.standard_normal(8) + rng.laplace(size=90)
+    nA = float(np.linalg.norm(A))
+    ho = O.Translate(O.NormL1() if hname == "l1" else O.NormL2(), -b)
+    hc = R.prox_desc(R.P_NORM_L1 if hname == "l1" else R.P_NORM_L2, 1.0, shift=-b)
+    for eta in (nA, 0.05 * nA):                                     # eta too small on purpose: the linesearch must grow it
+        Ao = O.Counting(A)
+        log = []
+        xo, yo, ito = O.adaptive_linesearch_primal_dual(np.zeros(8), np.zeros(90), f=O.Zero(), g=O.NormL1(0.5), h=ho, A=Ao, eta=eta, t=1.0,
+                                                        tol=1e-6, maxit=3000, log=log)
+        xc, yc, itc, hist, trials = R.adaptive_linesearch_primal_dual(np.zeros(8), np.zeros(90), f_kind=R.F_ZERO, g=R.prox_desc(R.P_NORM_L1, 0.5), h=hc,
+                                                                      A=A, eta=eta, t=1.0, tol=1e-6, maxit=3000, nhist=3000)
+        _prefix(log, hist, 30)
+        assert abs(itc - ito) <= max(3, 0.05 * ito)
+        if itc == ito:                                              # A' is applied once in the prologue and once per linesearch trial
+            assert Ao.amul_count == 1 + trials
+
+
+# ---------------------------------------------------------------- baselines (:34-192)
+def _lasso():
+    P = adaprox_b200.synth.planted_lasso(80, 200, 10, 1)
+    Lf = adaprox_b200.synth.spectral_norm_sq(P["A"], iters=1000, tol=1e-15)
+    return P, Lf
+
+
+def _prefix3(log, hist, K):
+    K = min(K, len(log), len(hist["gamma"]))
+    assert K >= 5
+    assert np.allclose([r["gamma"] for r in log[:K]], hist["gamma"][:K], rtol=1e-12, atol=0)
+    assert np.allclose([r["norm_res"] for r in log[:K]], hist["norm_res"][:K], rtol=1e-8, atol=1e-14)
+    assert np.allclose([r["objective"] for r in log[:K]], hist["objective"][:K], rtol=1e-10, atol=0)
+
+
+@pytest.mark.parametrize("xi", [1.0, 1.5])
+def test_backtracking_proxgrad(xi):
+    P, Lf = _lasso()
+    fo = O.Counting(O.LinearLeastSquares(P["A"], P["b"]))
+    log = []
+    xo, ito = O.backtracking_proxgrad(np.zeros(200), f=fo, g=O.NormL1(1.0), gamma0=5.0 / Lf, xi=xi, tol=1e-7, maxit=1500, log=log)
+    xc, itc, hist, ev = R.proxgrad_family(R.BACKTRACKING_PROXGRAD, np.zeros(200), f_kind=R.F_LEAST_SQUARES, F=P["A"], fvec=P["b"],
+                                          g=R.prox_desc(R.P_NORM_L1, 1.0), gamma=5.0 / Lf, xi=xi, tol=1e-7, maxit=1500, nhist=1500)
+    _prefix3(log, hist, 40)
+    # with xi > 1 every iteration ends on an accept/reject decision `f_z > ub_z` taken near equality: one flipped decision
+    # (rounding) shifts the rest of the run, so only the prefix, the optimum and a loose iteration count are comparable
+    assert abs(itc - ito) <= max(3, (0.05 if xi == 1.0 else 0.15) * ito)
+    fl = O.LinearLeastSquares(P["A"], P["b"])
+    assert abs((fl(xo) + np.abs(xo).sum()) - (fl(xc) + np.abs(xc).sum())) <= 1e-10 * P["optimum"]
+    if itc == ito:
+        assert ev == (fo.eval_count, fo.grad_count)
+
+
+def test_backtracking_nesterov_and_fixed_nesterov():
+    P, Lf = _lasso()
+    fo = O.Counting(O.LinearLeastSquares(P["A"], P["b"]))
+    log = []
+    xo, ito = O.backtracking_nesterov(np.zeros(200), f=fo, g=O.NormL1(1.0), gamma0=5.0 / Lf, tol=1e-7, maxit=1500, log=log)
+    xc, itc, hist, ev = R.proxgrad_family(R.BACKTRACKING_NESTEROV, np.zeros(200), f_kind=R.F_LEAST_SQUARES, F=P["A"], fvec=P["b"],
+                                          g=R.prox_desc(R.P_NORM_L1, 1.0), gamma=5.0 / Lf, tol=1e-7, maxit=1500, nhist=1500)
+    _prefix3(log, hist, 40)
+    assert abs(itc - ito) <= max(3, 0.05 * ito)
+    if itc == ito:
+        assert ev == (fo.eval_count, fo.grad_count)
+    for muf in (0.0, 1e-3):                                         # both branches of the (theta, beta) recursion :122-128
+        fo = O.Counting(O.LinearLeastSquares(P["A"], P["b"]))
+        log = []
+        xo, ito = O.fixed_nesterov(np.zeros(200), f=fo, g=O.NormL1(1.0), gamma=1.0 / Lf, muf=muf, tol=1e-7, maxit=1500, log=log)
+        xc, itc, hist, ev = R.proxgrad_family(R.FIXED_NESTEROV, np.zeros(200), f_kind=R.F_LEAST_SQUARES, F=P["A"], fvec=P["b"],
+                                              g=R.prox_desc(R.P_NORM_L1, 1.0), gamma=1.0 / Lf, muf=muf, tol=1e-7, maxit=1500, nhist=1500)
+        _prefix3(log, hist, 40)
+        assert abs(itc - ito) <= max(3, 0.05 * ito)
+        if itc == ito:
+            assert ev == (fo.eval_count, fo.grad_count)
+
+
+@pytest.mark.parametrize("gamma0", [None, 0.7])
+def test_agraal(gamma0):
+    P, Lf = _lasso()
+    x_second = np.random.default_rng(4).standard_normal(200)
+    g0 = None if gamma0 is None else gamma0 / Lf
+    fo = O.Counting(O.LinearLeastSquares(P["A"], P["b"]))
+    log = []
+    xo, ito = O.agraal(np.zeros(200), f=fo, g=O.NormL1(1.0), x0=x_second, gamma0=g0, tol=1e-7, maxit=1500, log=log)
+    xc, itc, hist, ev = R.proxgrad_family(R.AGRAAL, np.zeros(200), f_kind=R.F_LEAST_SQUARES, F=P["A"], fvec=P["b"], g=R.prox_desc(R.P_NORM_L1, 1.0),
+                                          gamma=0.0 if g0 is None else g0, x_second=x_second, tol=1e-7, maxit=1500, nhist=1500)
+    K = min(30, len(log), len(hist["gamma"]))
+    assert np.allclose([r["gamma"] for r in log[:K]], hist["gamma"][:K], rtol=1e-10, atol=0)
+    assert np.allclose([r["objective"] for r in log[:K]], hist["objective"][:K], rtol=1e-10, atol=0)
+    assert abs(itc - ito) <= max(3, 0.05 * ito)
+    if itc == ito:
+        assert ev == (fo.eval_count, fo.grad_count)
+
+
+# ---------------------------------------------------------------- Malitsky-Pock (:555-629)
+@pytest.mark.parametrize("t", [0.5, 2.0])
+def test_malitsky_pock(t):
+    X, y = adaprox_b200.synth.dense_classification(100, 7, 2)
+    Z = y[:, None] * X
+    Q, q, N = Z @ Z.T, -np.ones(100), 100
+    A = y[None, :].copy()
+    nA = float(np.linalg.norm(A))
+    log = []
+    xo, yo, ito = O.malitsky_pock(np.zeros(N), np.zeros(1), f=O.Quadratic(Q, q), g=O.IndBox(0.0, 0.1), h=O.IndZero(), A=A, sigma=1 / nA, t=t,
+                                  tol=1e-6, maxit=600, log=log)
+    xc, yc, itc, hist = R.malitsky_pock(np.zeros(N), np.zeros(1), f_kind=R.F_QUADRATIC, F=Q, fvec=q, g=R.prox_desc(R.P_IND_BOX, lo=0.0, hi=0.1),
+                                        h=R.prox_desc(R.P_IND_ZERO), A=A, sigma=1 / nA, t=t, tol=1e-6, maxit=600, nhist=600)
+    _prefix(log, hist, 40)
+    assert abs(itc - ito) <= max(3, 0.05 * ito)
