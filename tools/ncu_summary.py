@@ -1,5 +1,5 @@
 """Summarise an .ncu-rep (one kernel) into a small JSON for profiles/: selected raw metrics, warp-stall shares,
-and per-gradient-evaluation DRAM traffic.   python tools/ncu_summary.py REPORT.ncu-rep OUT.json GRAD_EVALS"""
+and per-gradient-evaluation DRAM traffic.   python tools/ncu_summary.py REPORT.ncu-rep OUT.json GRAD_EVALS ["what was captured"]"""
 import csv
 import io
 import json
@@ -25,6 +25,11 @@ KEEP = [
 
 def main():
     rep, out, evals = sys.argv[1], sys.argv[2], float(sys.argv[3])
+    # optional 4th argument: what was captured (default: the bench.py capture of the headline kernel)
+    how = sys.argv[4] if len(sys.argv) > 4 else (
+        "ncu --set full --clock-control none --import-source on, one launch of the persistent kernel "
+        "(bench.py --steps 3 --warmup 3 --no-cpu --power-iters 2: the captured launch is the 3-iteration "
+        "timed solve = 4 gradient evaluations); timings under ncu are not bench values")
     txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(txt)))
     hdr, units, vals = rows[0], rows[1], rows[2]
@@ -48,9 +53,7 @@ def main():
     rd, wr = to_bytes("dram__bytes_read.sum"), to_bytes("dram__bytes_write.sum")
     res["_derived"] = {"gradient_evaluations_in_launch": evals, "dram_bytes_read": rd, "dram_bytes_write": wr,
                        "dram_bytes_per_gradient_eval": (rd + wr) / evals,
-                       "how": "ncu --set full --clock-control none --import-source on, one launch of the persistent kernel "
-                              "(bench.py --steps 3 --warmup 3 --no-cpu --power-iters 2: the captured launch is the 3-iteration "
-                              "timed solve = 4 gradient evaluations); timings under ncu are not bench values"}
+                       "how": how}
     json.dump(res, open(out, "w"), indent=1)
     print(json.dumps(res, indent=1))
 
