@@ -22,7 +22,6 @@ square, ``min`` propagates NaN like Julia's, division by zero yields Inf/NaN.
 """
 from __future__ import annotations
 
-import math
 
 import numpy as np
 

@@ -22,7 +22,6 @@ def AdaProx():
 
 @pytest.fixture(scope="session")
 def lasso_small():
-    import numpy as np
     import adaprox_b200
     P = adaprox_b200.synth.planted_lasso(400, 1000, 5, 0)
     P["Lf"] = adaprox_b200.synth.spectral_norm_sq(P["A"], iters=1000, tol=1e-15)

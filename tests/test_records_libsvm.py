@@ -1,8 +1,6 @@
 """Host-side tooling of SURVEY section 8(f) rows 3-4: the record sink / find_best / is_logstep of
 experiments/logging.jl and the LIBSVM reader of experiments/libsvm.jl.  No GPU."""
 import json
-import math
-import os
 
 import numpy as np
 import pytest
