@@ -9,7 +9,7 @@
  *   adaptive_linesearch_primal_dual src/AdaProx.jl:463-550   (AdaPDM+)
  *   backtrack_stepsize, backtracking_proxgrad, backtracking_nesterov :34-84 ; fixed_nesterov :91-142 ; agraal :150-192
  *   backtrack_stepsize_MP, malitsky_pock                      src/AdaProx.jl:555-629
- *   FixedStepsize / MalitskyMishchenkoRule / OurRule          src/AdaProx.jl:208-273
+ *   FixedStepsize / MalitskyMishchenkoRule / OurRule / OurRulePlus   src/AdaProx.jl:208-308
  *   nan_to_zero                                               src/AdaProx.jl:24
  *   LinearLeastSquares   experiments/lasso/runme.jl:21-25     Quadratic   experiments/dual_svm/runme.jl:24-28
  *   LogisticLoss         experiments/sparse_logreg/runme.jl:23-37          Zero  experiments/least_absolute_deviation/runme.jl:18-21
@@ -24,7 +24,7 @@
 
 enum { F_ZERO = 0, F_LEAST_SQUARES = 1, F_LOGISTIC = 2, F_QUADRATIC = 3 };
 enum { P_ZERO = 0, P_IND_ZERO = 1, P_NORM_L1 = 2, P_NORM_L2 = 3, P_IND_BOX = 4 };
-enum { RULE_FIXED = 0, RULE_MM = 1, RULE_OUR = 2 };
+enum { RULE_FIXED = 0, RULE_MM = 1, RULE_OUR = 2, RULE_OUR_PLUS = 3 };
 
 typedef struct {
   int kind;
@@ -44,6 +44,7 @@ typedef struct {
   double gamma, t, norm_A, delta, Theta;
   double tol;
   long maxit;
+  double xi, nu, r;             /* OurRulePlus (:277-308) */
 } ref_problem;
 
 /* ---- Julia scalar semantics ------------------------------------------------------------------------------------ */
@@ -154,7 +155,7 @@ static double prox_value(const ref_prox* f, const double* x, long n) {
 /* ---- stepsize rules (:208-273); state = (s0, s1) ------------------------------------------------------------------- */
 static void rule_init(const ref_problem* p, double* gamma, double* sigma, double* s0, double* s1) {
   *gamma = p->gamma;
-  *sigma = p->gamma * (p->t * p->t);
+  *sigma = (p->rule == RULE_OUR_PLUS) ? p->gamma : p->gamma * (p->t * p->t);     /* :294-297: (gamma, gamma) */
   if (p->rule == RULE_MM) { *s0 = p->gamma; *s1 = INFINITY; }
   else { *s0 = p->gamma; *s1 = p->gamma; }
 }
@@ -169,8 +170,19 @@ static void rule_step(const ref_problem* p, const double* x1, const double* g1, 
     *gamma = g; *sigma = g * (p->t * p->t); *s0 = g; *s1 = g / gamma_prev;
     return;
   }
-  const double gamma1 = *s0, gamma0 = *s1;                                        /* :258-273 */
-  const double xi = (p->t * p->t) * (gamma1 * gamma1) * (p->norm_A * p->norm_A);
+  const double gamma1 = *s0, gamma0 = *s1;
+  if (p->rule == RULE_OUR_PLUS) {                                                 /* :299-308 */
+    const double dgx2 = dot(dgr, dx, n);
+    const double C2 = nan_to_zero(sq(norm2(dgr, n)) / dgx2);
+    const double L2 = nan_to_zero(dgx2 / sq(norm2(dx, n)));
+    const double D2 = nan_to_zero(1.0 - 2.0 * p->r + gamma1 * L2 * (gamma1 * C2 + 2.0 * (p->r - 1.0)));
+    const double Dpos = D2 > 0.0 ? D2 : 0.0;                                      /* max(D, 0); D is not NaN here */
+    const double g2 = gamma1 * jl_min(sqrt(1.0 / (p->r * (p->nu + p->xi)) + gamma1 / gamma0),
+                                      sqrt((p->nu * (1.0 + p->xi) - 1.0) / (p->nu * (p->nu + p->xi))) / sqrt(Dpos));
+    *gamma = g2; *sigma = g2; *s0 = g2; *s1 = gamma1;
+    return;
+  }
+  const double xi = (p->t * p->t) * (gamma1 * gamma1) * (p->norm_A * p->norm_A);  /* :258-273 */
   const double dgx = dot(dgr, dx, n);
   const double C = nan_to_zero(sq(norm2(dgr, n)) / dgx);
   const double L = nan_to_zero(dgx / sq(norm2(dx, n)));

@@ -9,7 +9,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 F_ZERO, F_LEAST_SQUARES, F_LOGISTIC, F_QUADRATIC = range(4)
 P_ZERO, P_IND_ZERO, P_NORM_L1, P_NORM_L2, P_IND_BOX = range(5)
-RULE_FIXED, RULE_MM, RULE_OUR = range(3)
+RULE_FIXED, RULE_MM, RULE_OUR, RULE_OUR_PLUS = range(4)
 _dp = C.POINTER(C.c_double)
 
 
@@ -20,7 +20,8 @@ class Prox(C.Structure):
 class Problem(C.Structure):
     _fields_ = [("f_kind", C.c_int), ("F", _dp), ("fm", C.c_long), ("fn", C.c_long), ("fvec", _dp), ("g", Prox), ("h", Prox),
                 ("A", _dp), ("am", C.c_long), ("n", C.c_long), ("rule", C.c_int), ("gamma", C.c_double), ("t", C.c_double),
-                ("norm_A", C.c_double), ("delta", C.c_double), ("Theta", C.c_double), ("tol", C.c_double), ("maxit", C.c_long)]
+                ("norm_A", C.c_double), ("delta", C.c_double), ("Theta", C.c_double), ("tol", C.c_double), ("maxit", C.c_long),
+                ("xi", C.c_double), ("nu", C.c_double), ("r", C.c_double)]
 
 
 _lib = None
@@ -49,7 +50,8 @@ def prox_desc(kind, lam=1.0, lo=0.0, hi=0.0, shift=None):
     return Prox(kind, float(lam), float(lo), float(hi), _p(s)), s
 
 
-def _problem(x0, *, f_kind, F, fvec, g, h, A, rule=RULE_FIXED, gamma=0.0, t=1.0, norm_A=0.0, delta=0.0, Theta=1.2, tol=1e-5, maxit=10_000):
+def _problem(x0, *, f_kind, F, fvec, g, h, A, rule=RULE_FIXED, gamma=0.0, t=1.0, norm_A=0.0, delta=0.0, Theta=1.2, tol=1e-5, maxit=10_000,
+             xi=1.0, nu=1.0, r=0.5):
     """builds the C problem struct; returns (Problem, x0, n, md, keepalive)"""
     x0 = np.ascontiguousarray(x0, dtype=np.float64)
     n = x0.shape[0]
@@ -61,7 +63,7 @@ def _problem(x0, *, f_kind, F, fvec, g, h, A, rule=RULE_FIXED, gamma=0.0, t=1.0,
         h = prox_desc(P_ZERO)
     p = Problem(f_kind, _p(Ff), Ff.shape[0] if Ff is not None else 0, Ff.shape[1] if Ff is not None else 0, _p(fv), g[0], h[0],
                 _p(Af), md if Af is not None else 0, n, rule, float(gamma), float(t), float(norm_A), float(delta), float(Theta),
-                float(tol), int(maxit))
+                float(tol), int(maxit), float(xi), float(nu), float(r))
     return p, x0, n, md, (Ff, Af, fv, g, h)
 
 
@@ -71,12 +73,12 @@ def _hist(nhist, maxit, keys):
 
 
 def adaptive_primal_dual(x0, y0, *, f_kind, F=None, fvec=None, g, h=None, A=None, rule, gamma, t=1.0, norm_A=0.0, delta=0.0,
-                         Theta=1.2, tol=1e-5, maxit=10_000, nhist=0):
+                         Theta=1.2, tol=1e-5, maxit=10_000, nhist=0, xi=1.0, nu=1.0, r=0.5):
     """src/AdaProx.jl:312-364 through the C restatement; A=None is `adaptive_proxgrad` (:418-421).
     g, h: (Prox, keepalive) pairs from prox_desc.  Returns (x, y, it, hist) with hist = dict of gamma/sigma/norm_res/objective."""
     lib = load()
     p, x0, n, md, keep = _problem(x0, f_kind=f_kind, F=F, fvec=fvec, g=g, h=h, A=A, rule=rule, gamma=gamma, t=t, norm_A=norm_A,
-                                  delta=delta, Theta=Theta, tol=tol, maxit=maxit)
+                                  delta=delta, Theta=Theta, tol=tol, maxit=maxit, xi=xi, nu=nu, r=r)
     y0 = np.zeros(md) if y0 is None else np.ascontiguousarray(y0, dtype=np.float64)
     x, y = np.empty(n), np.empty(md)
     H, hist = _hist(nhist, maxit, ("gamma", "sigma", "norm_res", "objective"))

@@ -22,12 +22,13 @@ def _prefix(log, hist, K, rtol_gamma=1e-10, rtol_res=1e-8, rtol_obj=1e-10):
     assert np.allclose(obj[fin], hist["objective"][:K][fin], rtol=rtol_obj, atol=1e-13)
 
 
-@pytest.mark.parametrize("rule", ["our", "mm", "fixed"])
+@pytest.mark.parametrize("rule", ["our", "mm", "fixed", "plus"])
 def test_adapgm_lasso(rule):
     P = adaprox_b200.synth.planted_lasso(100, 300, 10, 0)
     Lf = adaprox_b200.synth.spectral_norm_sq(P["A"], iters=1000, tol=1e-15)
-    ro = {"our": O.OurRule(gamma=1 / Lf), "mm": O.MalitskyMishchenkoRule(gamma=1 / Lf), "fixed": O.FixedStepsize(1 / Lf)}[rule]
-    rc = {"our": R.RULE_OUR, "mm": R.RULE_MM, "fixed": R.RULE_FIXED}[rule]
+    ro = {"our": O.OurRule(gamma=1 / Lf), "mm": O.MalitskyMishchenkoRule(gamma=1 / Lf), "fixed": O.FixedStepsize(1 / Lf),
+          "plus": O.OurRulePlus(gamma=1 / Lf)}[rule]                # defined in src/AdaProx.jl:277-308, used by no experiment
+    rc = {"our": R.RULE_OUR, "mm": R.RULE_MM, "fixed": R.RULE_FIXED, "plus": R.RULE_OUR_PLUS}[rule]
     log = []
     xo, ito = O.adaptive_proxgrad(np.zeros(300), f=O.LinearLeastSquares(P["A"], P["b"]), g=O.NormL1(1.0), rule=ro, tol=1e-7, maxit=3000, log=log)
     xc, _, itc, hist = R.adaptive_primal_dual(np.zeros(300), None, f_kind=R.F_LEAST_SQUARES, F=P["A"], fvec=P["b"], g=R.prox_desc(R.P_NORM_L1, 1.0),
