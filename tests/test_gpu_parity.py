@@ -430,6 +430,32 @@ def test_dual_svm_gram_form(AdaProx):
         AdaProx.adaptive_proxgrad(np.zeros(N), f=AdaProx.QuadraticGram(Z[:-1], q), g=AdaProx.IndBox(0.0, 0.1), rule=AdaProx.OurRule(gamma=1e-2), maxit=3)
 
 
+def test_dual_svm_gram_form_full_size(AdaProx):
+    """BASELINE configs[2] size (N = 50000, d = 2000): the Gram-form value and gradient against numpy on the same factor, the
+    affine structure of the gradient, and a short AdaPDM run that stays feasible and decreases the residual."""
+    N, d = 50000, 2000
+    X, y = AdaProx.synth.dense_classification(N, d, 0)
+    Z = y[:, None] * X
+    q = -np.ones(N)
+    f = AdaProx.QuadraticGram(AdaProx.DeviceMatrix(Z), q)
+    rng = np.random.default_rng(11)
+    x = rng.random(N) * 0.1
+    fx, pb = AdaProx.eval_with_pullback(f, x)
+    gx = pb()
+    t = Z @ (Z.T @ x)
+    assert rel(gx, t + q) < 1e-11
+    assert abs(fx - (0.5 * (x @ t) + x @ q)) <= 1e-11 * abs(0.5 * (x @ t) + x @ q)
+    g2 = AdaProx.eval_with_pullback(f, 2.0 * x)[1]()
+    assert rel(g2 - q, 2.0 * (gx - q)) < 1e-12                      # x -> Z Z' x is linear
+    log = []
+    xs, ys, it = AdaProx.adaptive_primal_dual(np.zeros(N), np.zeros(1), f=f, g=AdaProx.IndBox(0.0, 0.1), h=AdaProx.IndZero(),
+                                              A=AdaProx.DeviceMatrix(y[None, :].copy()), rule=AdaProx.OurRule(t=0.1, norm_A=float(np.sqrt(N))),
+                                              tol=1e-5, maxit=300, log=log)
+    assert np.all(xs >= 0) and np.all(xs <= 0.1) and np.all(np.isfinite([r["gamma"] for r in log]))
+    assert log[-1]["norm_res"] < 0.1 * log[0]["norm_res"]
+    assert AdaProx.last_solve_info()["matrix_passes"] == 2
+
+
 def test_condat_vu(AdaProx):
     Q, q, y = _svm(AdaProx, 120, 10, 1)
     N = Q.shape[0]
