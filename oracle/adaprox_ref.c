@@ -522,3 +522,16 @@ long ref_malitsky_pock(const ref_problem* p, double sigma, const double* x0, con
   free(buf);
   return it_ret;
 }
+
+/* ---- ProximalCore.prox(f, x, gamma) -> (y, f(y)) and the same through convex_conjugate(f), one call each (tests) ------- */
+double ref_prox_eval(const ref_prox* f, int conjugate, const double* x, double gamma, double* y, long n) {
+  if (conjugate) {
+    double* tmp = (double*)malloc((size_t)(n > 0 ? n : 1) * sizeof(double));
+    if (!tmp) return NAN;
+    prox_conj(f, x, gamma, y, tmp, n);
+    free(tmp);
+    return NAN;                              /* the solvers never use the value of a conjugate (`y, _ = prox(...)`) */
+  }
+  prox(f, x, gamma, y, n);
+  return prox_value(f, y, n);
+}

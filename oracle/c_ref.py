@@ -152,3 +152,14 @@ def malitsky_pock(x0, y0, *, f_kind, F=None, fvec=None, g, h, A, sigma, t=1.0, t
         raise RuntimeError(f"ref_malitsky_pock failed ({it})")
     k = min(H, it)
     return x, y, int(it), {kk: vv[:k] for kk, vv in hist.items()}
+
+
+def prox_eval(desc, x, gamma, conjugate=False):
+    """ProximalCore.prox(f, x, gamma) -> (y, f(y)); with conjugate=True the prox of convex_conjugate(f) (value: NaN)."""
+    lib = load()
+    lib.ref_prox_eval.restype = C.c_double
+    lib.ref_prox_eval.argtypes = [C.POINTER(Prox), C.c_int, _dp, C.c_double, _dp, C.c_long]
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.empty_like(x)
+    v = lib.ref_prox_eval(C.byref(desc[0]), int(bool(conjugate)), _p(x), float(gamma), _p(y), x.shape[0])
+    return y, v

@@ -228,3 +228,34 @@ def test_malitsky_pock(t):
                                         h=R.prox_desc(R.P_IND_ZERO), A=A, sigma=1 / nA, t=t, tol=1e-6, maxit=600, nhist=600)
     _prefix(log, hist, 40)
     assert abs(itc - ito) <= max(3, 0.05 * ito)
+
+
+# ---------------------------------------------------------------- prox objects, both restatements
+def test_prox_objects_agree():
+    """Every prox object x {plain, Translate} x {itself, convex_conjugate}: the numpy oracle and the C restatement apply the same
+    operations in the same order (Moreau in ProximalCore's order), so they agree to the last bits on random inputs."""
+    rng = np.random.default_rng(5)
+    n = 257
+    shift = rng.standard_normal(n)
+    kinds = [("zero", lambda: O.Zero(), lambda s: R.prox_desc(R.P_ZERO, shift=s)),
+             ("indzero", lambda: O.IndZero(), lambda s: R.prox_desc(R.P_IND_ZERO, shift=s)),
+             ("l1", lambda: O.NormL1(0.7), lambda s: R.prox_desc(R.P_NORM_L1, 0.7, shift=s)),
+             ("l2", lambda: O.NormL2(1.3), lambda s: R.prox_desc(R.P_NORM_L2, 1.3, shift=s)),
+             ("box", lambda: O.IndBox(-0.4, 0.9), lambda s: R.prox_desc(R.P_IND_BOX, lo=-0.4, hi=0.9, shift=s))]
+    for name, mk_o, mk_c in kinds:
+        for translated in (False, True):
+            fo = O.Translate(mk_o(), shift) if translated else mk_o()
+            fc = mk_c(shift if translated else None)
+            for gamma in (0.05, 1.0, 7.5):
+                for scale in (0.1, 3.0):
+                    x = scale * rng.standard_normal(n)
+                    yo, vo = O.prox(fo, x, gamma)
+                    yc, vc = R.prox_eval(fc, x, gamma)
+                    assert np.allclose(yo, yc, rtol=0, atol=1e-15 * max(1.0, np.max(np.abs(x)))), (name, translated, gamma)
+                    # the C entry point reports f evaluated AT y (what the loops log as g(x) / h(A x)); for a translated indicator
+                    # that may differ from the value prox returns (computed before `y .-= b`) by one rounding of (v - b) + b
+                    vo = fo(yc)
+                    assert (np.isinf(vo) and np.isinf(vc)) or abs(vo - vc) <= 1e-13 * max(1.0, abs(vo)), (name, translated, gamma)
+                    yo2, _ = O.prox(O.convex_conjugate(fo), x, gamma)
+                    yc2, _ = R.prox_eval(fc, x, gamma, conjugate=True)
+                    assert np.allclose(yo2, yc2, rtol=0, atol=4e-15 * max(1.0, np.max(np.abs(x)))), (name, translated, gamma, "conj")
