@@ -259,3 +259,60 @@ def test_prox_objects_agree():
                     yo2, _ = O.prox(O.convex_conjugate(fo), x, gamma)
                     yc2, _ = R.prox_eval(fc, x, gamma, conjugate=True)
                     assert np.allclose(yo2, yc2, rtol=0, atol=4e-15 * max(1.0, np.max(np.abs(x)))), (name, translated, gamma, "conj")
+
+
+# ---------------------------------------------------------------- seeded random combinations of f, g, h, A and rule
+def test_random_combinations_of_the_generic_loop():
+    """40 seeded instances of adaptive_primal_dual with random sizes and a random choice of smooth term, prox objects, linear map
+    and stepsize rule: the first 15 stepsizes / residuals of the two restatements agree (rounding only)."""
+    rng = np.random.default_rng(2024)
+    for case in range(40):
+        n, md = int(rng.integers(3, 40)), int(rng.integers(2, 30))
+        fk = rng.choice(["ls", "quad", "zero", "logistic"])
+        if fk == "ls":
+            m = int(rng.integers(2, 50)); F = rng.standard_normal((m, n)); fv = rng.standard_normal(m)
+            fo, fc, Lf = O.LinearLeastSquares(F, fv), dict(f_kind=R.F_LEAST_SQUARES, F=F, fvec=fv), np.linalg.norm(F, 2) ** 2
+        elif fk == "quad":
+            B = rng.standard_normal((n, n)); F = B @ B.T / n; fv = rng.standard_normal(n)
+            fo, fc, Lf = O.Quadratic(F, fv), dict(f_kind=R.F_QUADRATIC, F=F, fvec=fv), np.linalg.norm(F, 2)
+        elif fk == "logistic":
+            m = int(rng.integers(5, 60)); F = rng.standard_normal((m, n - 1)); fv = (rng.random(m) < 0.5).astype(float)
+            fo, fc, Lf = O.LogisticLoss(F, fv), dict(f_kind=R.F_LOGISTIC, F=F, fvec=fv), (np.sum(F * F) + m) / (4 * m)
+        else:
+            fo, fc, Lf = O.Zero(), dict(f_kind=R.F_ZERO), 0.0
+        gk = rng.choice(["l1", "box", "zero"])
+        go, gc = {"l1": (O.NormL1(0.3), R.prox_desc(R.P_NORM_L1, 0.3)), "box": (O.IndBox(-0.5, 0.8), R.prox_desc(R.P_IND_BOX, lo=-0.5, hi=0.8)),
+                  "zero": (O.Zero(), R.prox_desc(R.P_ZERO))}[gk]
+        A = rng.standard_normal((md, n))
+        b = rng.standard_normal(md)
+        hk = rng.choice(["l1t", "l2t", "indzero", "l1"])
+        ho, hc = {"l1t": (O.Translate(O.NormL1(), -b), R.prox_desc(R.P_NORM_L1, 1.0, shift=-b)),
+                  "l2t": (O.Translate(O.NormL2(), -b), R.prox_desc(R.P_NORM_L2, 1.0, shift=-b)),
+                  "indzero": (O.IndZero(), R.prox_desc(R.P_IND_ZERO)), "l1": (O.NormL1(0.5), R.prox_desc(R.P_NORM_L1, 0.5))}[hk]
+        nA = float(np.linalg.norm(A))
+        t = float(rng.choice([0.3, 1.0, 2.5]))
+        rk = rng.choice(["our", "mm", "fixed"])
+        if rk == "our":
+            ro, rc = O.OurRule(t=t, norm_A=nA), dict(rule=R.RULE_OUR, gamma=1 / (2 * 1.2 * t * nA), t=t, norm_A=nA)
+        else:
+            gam = 0.5 / (Lf + nA * max(t, 1.0) + 1e-3)
+            ro = O.MalitskyMishchenkoRule(gamma=gam, t=t) if rk == "mm" else O.FixedStepsize(gam, t)
+            rc = dict(rule=R.RULE_MM if rk == "mm" else R.RULE_FIXED, gamma=gam, t=t)
+        x0, y0 = rng.standard_normal(n), rng.standard_normal(md)
+        log = []
+        O.adaptive_primal_dual(x0, y0, f=fo, g=go, h=ho, A=A, rule=ro, tol=1e-9, maxit=60, log=log)
+        xc, yc, itc, hist = R.adaptive_primal_dual(x0, y0, g=gc, h=hc, A=A, tol=1e-9, maxit=60, nhist=60, **fc, **rc)
+        K = min(15, len(log), len(hist["gamma"]))
+        res0 = np.array([r["norm_res"] for r in log[:K]])
+        grow = np.nonzero(res0 > 10 * res0[0])[0]                  # an unstable (gamma, t) choice: the run diverges and amplifies
+        if len(grow):                                              # rounding exponentially -- compare up to that point only
+            K = max(4, int(grow[0]))
+        tag = (case, fk, gk, hk, rk, t)
+        assert K >= 1, tag
+        go_, gc_ = np.array([r["gamma"] for r in log[:K]]), hist["gamma"][:K]
+        both_nan = np.isnan(go_) & np.isnan(gc_)
+        assert np.allclose(go_[~both_nan], gc_[~both_nan], rtol=1e-9, atol=0), tag
+        ro_, rc_ = np.array([r["norm_res"] for r in log[:K]]), hist["norm_res"][:K]
+        fin = np.isfinite(ro_) & np.isfinite(rc_)
+        assert np.array_equal(np.isfinite(ro_), np.isfinite(rc_)), tag
+        assert np.allclose(ro_[fin], rc_[fin], rtol=1e-7, atol=1e-12), tag
