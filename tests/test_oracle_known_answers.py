@@ -252,3 +252,64 @@ def test_baselines_reach_the_planted_optimum():
     }
     for nm, x in runs.items():
         assert abs(f(x) + g(x) - P["optimum"]) < 1e-8 * P["optimum"], nm
+
+
+# ---------------------------------------------------------------- fixtures produced by the independent C restatement
+def test_numpy_oracle_against_c_restatement_fixtures():
+    """tests/golden/c_restatement_golden.json holds stepsize / residual / objective prefixes computed by oracle/adaprox_ref.c
+    (generator: tests/golden/make_c_golden.py); the numpy oracle must reproduce them.  Needs no compiler."""
+    import importlib.util
+    import json as _json
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    spec = importlib.util.spec_from_file_location("make_c_golden", os.path.join(here, "make_c_golden.py"))
+    try:
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)                                # imports oracle.c_ref (ctypes only; nothing is built or loaded)
+    except Exception as e:                                          # pragma: no cover
+        pytest.skip(f"cannot import the generator: {e}")
+    G = _json.load(open(os.path.join(here, "c_restatement_golden.json")))
+    D = mod.cases()
+    P, Lf = D["P"], D["Lf"]
+
+    def close(a, b, rtol):
+        a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
+        K = min(len(a), len(b))
+        fin = np.isfinite(a[:K]) & np.isfinite(b[:K])
+        return K >= 5 and np.array_equal(np.isfinite(a[:K]), np.isfinite(b[:K])) and np.allclose(a[:K][fin], b[:K][fin], rtol=rtol, atol=1e-13)
+
+    for nm, rule in (("our", O.OurRule(gamma=1 / Lf)), ("mm", O.MalitskyMishchenkoRule(gamma=1 / Lf)), ("plus", O.OurRulePlus(gamma=1 / Lf))):
+        log = []
+        _, it = O.adaptive_proxgrad(np.zeros(300), f=O.LinearLeastSquares(P["A"], P["b"]), g=O.NormL1(1.0), rule=rule, tol=1e-7, maxit=3000, log=log)
+        g = G["lasso_100x300_" + nm]
+        assert close([r["gamma"] for r in log[:30]], g["gamma"], 1e-10) and close([r["norm_res"] for r in log[:30]], g["norm_res"], 1e-8)
+        assert close([r["objective"] for r in log[:30]], g["objective"], 1e-10) and abs(it - g["it"]) <= max(3, 0.05 * g["it"])
+    nA = float(np.linalg.norm(D["A1"]))
+    log = []
+    _, _, it = O.adaptive_primal_dual(np.zeros(120), np.zeros(1), f=O.Quadratic(D["Q"], D["q"]), g=O.IndBox(0.0, 0.1), h=O.IndZero(), A=D["A1"],
+                                      rule=O.OurRule(t=1.0, norm_A=nA), tol=1e-6, maxit=5000, log=log)
+    g = G["dual_svm_120"]
+    assert close([r["gamma"] for r in log[:30]], g["gamma"], 1e-10) and close([r["sigma"] for r in log[:30]], g["sigma"], 1e-10)
+    assert close([r["norm_res"] for r in log[:30]], g["norm_res"], 1e-8) and abs(it - g["it"]) <= max(3, 0.05 * g["it"])
+    nA2 = float(np.linalg.norm(D["A2"]))
+    for hn, hf in (("l1", O.NormL1()), ("l2", O.NormL2())):
+        Ao = O.Counting(D["A2"])
+        log = []
+        _, _, it = O.adaptive_linesearch_primal_dual(np.zeros(7), np.zeros(80), f=O.Zero(), g=O.NormL1(0.5), h=O.Translate(hf, -D["b2"]), A=Ao,
+                                                     eta=0.05 * nA2, t=1.0, tol=1e-6, maxit=3000, log=log)
+        g = G["adapdm_plus_" + hn]
+        assert close([r["gamma"] for r in log[:30]], g["gamma"], 1e-10) and close([r["norm_res"] for r in log[:30]], g["norm_res"], 1e-8)
+        if it == g["it"]:
+            assert Ao.amul_count == 1 + g["trials"]
+    fo = O.Counting(O.LinearLeastSquares(P["A"], P["b"]))
+    log = []
+    _, it = O.backtracking_nesterov(np.zeros(300), f=fo, g=O.NormL1(1.0), gamma0=5.0 / Lf, tol=1e-7, maxit=1500, log=log)
+    g = G["backtracking_nesterov"]
+    assert close([r["gamma"] for r in log[:30]], g["gamma"], 1e-12) and close([r["objective"] for r in log[:30]], g["objective"], 1e-10)
+    if it == g["it"]:
+        assert [fo.eval_count, fo.grad_count] == g["evals"]
+    log = []
+    O.malitsky_pock(np.zeros(120), np.zeros(1), f=O.Quadratic(D["Q"], D["q"]), g=O.IndBox(0.0, 0.1), h=O.IndZero(), A=D["A1"], sigma=1 / nA, t=0.5,
+                    tol=1e-6, maxit=600, log=log)
+    g = G["malitsky_pock"]
+    assert close([r["gamma"] for r in log[:30]], g["gamma"], 1e-10) and close([r["sigma"] for r in log[:30]], g["sigma"], 1e-10)
+    assert close([r["norm_res"] for r in log[:30]], g["norm_res"], 1e-8)
