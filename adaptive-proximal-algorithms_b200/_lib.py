@@ -58,7 +58,7 @@ P_ZERO, P_IND_ZERO, P_NORM_L1, P_NORM_L2, P_IND_BOX = range(5)
 (S_ADAPTIVE_PRIMAL_DUAL, S_ADAPTIVE_PROXGRAD, S_LINESEARCH_PRIMAL_DUAL, S_BACKTRACKING_PROXGRAD,
  S_BACKTRACKING_NESTEROV, S_FIXED_NESTEROV, S_MALITSKY_POCK, S_AGRAAL) = range(8)
 RULE_FIXED, RULE_MM, RULE_OUR, RULE_OUR_PLUS = range(4)
-FLAG_CONVERGED, FLAG_STEP_TOO_SMALL, FLAG_NONFINITE, FLAG_LS_CAP = 1, 2, 4, 8
+FLAG_CONVERGED, FLAG_STEP_TOO_SMALL, FLAG_NONFINITE, FLAG_LS_CAP, FLAG_COMM = 1, 2, 4, 8, 16
 
 # every symbol include/adaprox.h declares: name -> (restype, argtypes)
 _h = C.c_void_p
@@ -86,6 +86,7 @@ SYMBOLS = {
     "adaprox_prox_eval": (C.c_int, [_h, C.POINTER(Prox), c_dp, C.c_int64, C.c_double, c_dp, c_dp]),
     "adaprox_stepsize": (C.c_int, [C.POINTER(Options), C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
                                    c_dp, c_dp, c_dp]),
+    "adaprox_logistic_grad_hessian": (C.c_int, [_h, c_id, c_id, c_dp, c_dp, c_dp]),
     "adaprox_solve": (C.c_int, [_h, C.POINTER(Problem), C.POINTER(Options), c_dp, c_dp, c_dp, c_dp,
                                 C.POINTER(Record), C.POINTER(Result)]),
     "adaprox_solve_lambda_path": (C.c_int, [_h, C.POINTER(Problem), C.POINTER(Options), C.c_int64, c_dp, c_dp, c_dp, c_dp,
@@ -96,6 +97,7 @@ SYMBOLS = {
     "adaprox_comm_info": (C.c_int, [_h, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "adaprox_p2p_export": (C.c_int, [_h, C.c_int64, C.c_void_p]),
     "adaprox_p2p_attach": (C.c_int, [_h, C.c_int, C.c_int, C.c_void_p]),
+    "adaprox_p2p_reset": (C.c_int, [_h]),
     "adaprox_matrix_set_shard": (C.c_int, [_h, c_id, C.c_int64, C.c_int64]),
     "adaprox_time_kernel": (C.c_int, [_h, c_id, C.c_int, C.c_int, c_dp]),
 }

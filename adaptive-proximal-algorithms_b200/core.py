@@ -80,6 +80,10 @@ class Device:
         buf = C.create_string_buffer(handles, 64 * int(nranks))
         self.check(self.lib.adaprox_p2p_attach(self.h, int(nranks), int(rank), buf))
 
+    def p2p_reset(self):
+        """After a sharded solve failed with ADAPROX_ERR_COMM: clear this rank's exchange flags (every rank, then a host barrier)."""
+        self.check(self.lib.adaprox_p2p_reset(self.h))
+
     def close(self):
         if getattr(self, "h", None):
             self.lib.adaprox_destroy(self.h)
@@ -394,6 +398,21 @@ class Cubic(_Smooth):
         self.mat = _as_matrix(Q, dev)
         self.vec = _as_vector(q, self.mat.dev)
         self.n = self.mat.shape[1]
+
+
+def logistic_loss_grad_Hessian(X, y, w, dev=None):
+    """experiments/cubic_sparse_logreg/runme.jl:34-45: ``H, g`` of the logistic loss at ``w`` (intercept last), the setup
+    of the Cubic oracle ``Cubic(H, g, lam)`` (:66-67).  X: dense / scipy.sparse / DeviceMatrix with n columns; H is
+    (n+1) x (n+1), g has n+1 entries.  Computed on the device (csrc/hessian.inl)."""
+    mat = _as_matrix(X, dev)
+    vec = _as_vector(y, mat.dev)
+    n1 = mat.shape[1] + 1
+    w = _vec(w, n1)
+    H = np.empty((n1, n1), dtype=F64)
+    g = np.empty(n1, dtype=F64)
+    mat.dev.check(mat.dev.lib.adaprox_logistic_grad_hessian(mat.dev.h, mat.id, vec.id, _dp(w), _dp(H), _dp(g)))
+    mat.dev.launches += 2
+    return H, g
 
 
 class WorstQuadratic(_Smooth):
@@ -826,6 +845,36 @@ def adaptive_proxgrad_path(X0=None, *, f, lambdas, rule, gamma0=None, tol=1e-5, 
         info.update(gamma_hist=hist[0], res_hist=hist[1], obj_hist=hist[2])
     _last_info.update(dict(flags=info["flags"], solve_ms=res.solve_ms, kernel_launches=int(res.kernel_launches), matrix_passes=2))
     return np.ascontiguousarray(xoT.T), its, info
+
+
+def auto_adaptive_proxgrad(x, *, f, g, gamma=None, tol=1e-5, maxit=100_000, name="AutoAdaPGM", log=None):
+    """src/AdaProx.jl:423-455: two gradient evaluations and one (or two) prox steps estimate the initial stepsize, then
+    AdaPGM with OurRule from the ORIGINAL point.  Every oracle call below is a device call (eval_with_gradient / prox
+    through the C ABI); the loop itself is the persistent kernel.  ``gamma = nothing`` cannot run in the reference
+    (:431 calls ``prox`` without ``g`` -> MethodError) and raises here as well."""
+    x = _vec(x)
+    _, grad_x = eval_with_gradient(f, x)
+    if np.sqrt(np.dot(grad_x, grad_x)) <= tol:                       # :426-428
+        return x, 0
+    if gamma is None:
+        raise TypeError("auto_adaptive_proxgrad: the reference's `gamma = nothing` branch calls prox(x, gamma) without g (src/AdaProx.jl:431): MethodError")
+    assert gamma > 0                                                  # :437
+    gamma = F64(gamma)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        x_prev, grad_x_prev, gamma_prev = x, grad_x, gamma            # :439
+        x, _ = prox(g, x - gamma * grad_x, gamma)                     # :440
+        _, grad_x = eval_with_gradient(f, x)
+        dx = x - x_prev
+        L_ = np.dot(grad_x - grad_x_prev, dx) / np.sqrt(np.dot(dx, dx)) ** 2
+        gamma = np.sqrt(F64(2)) * gamma if L_ == 0 else F64(1) / L_   # :443
+        if gamma_prev / gamma > 1e5:                                  # :445-450
+            x, _ = prox(g, x_prev - gamma * grad_x_prev, gamma)
+            _, grad_x = eval_with_gradient(f, x)
+            dx = x - x_prev
+            L_ = np.dot(grad_x - grad_x_prev, dx) / np.sqrt(np.dot(dx, dx)) ** 2
+            gamma = np.sqrt(F64(2)) * gamma if L_ == 0 else F64(1) / L_
+    rule = OurRule(gamma=float(gamma), t=1, norm_A=0, delta=0, Theta=1.2)      # :452
+    return adaptive_proxgrad(x_prev, f=f, g=g, rule=rule, tol=tol, maxit=maxit, name=name, log=log)
 
 
 def fixed_proxgrad(x, *, f, g, gamma, tol=1e-5, maxit=100_000, name="Fixed stepsize PGM", log=None):

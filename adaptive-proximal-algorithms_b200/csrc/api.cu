@@ -168,6 +168,8 @@ static int fill_problem(adaprox_ctx* h, const adaprox_problem* p, DProblem* out,
   if ((rc = fill_prox(h, p->g, p->n, &P.g))) return rc;
   if (p->A_mat != 0) {
     if ((rc = get_mat(h, p->A_mat, amat))) return rc;
+    if (p->A_mat == p->f_mat)     // the partial buffers (zpart / gpart) belong to the matrix: F'r and A'y would share them in one phase
+      return fail(h, ADAPROX_ERR_UNSUPPORTED, "f and A refer to the same device matrix: upload it a second time for A");
     P.A = (*amat)->d;
     if (P.A.n != p->n) return fail(h, ADAPROX_ERR_INVALID, "A has the wrong number of columns");
     if (P.A.m != p->m_dual) return fail(h, ADAPROX_ERR_INVALID, "A has the wrong number of rows (m_dual)");
@@ -292,6 +294,8 @@ extern "C" int adaprox_matrix_upload_csr(adaprox_handle h, int64_t m, int64_t n,
   if (!h || !rowptr || !out || m <= 0 || n <= 0 || nnz < 0 || (nnz > 0 && (!colind || !vals)))
     return fail(h, ADAPROX_ERR_INVALID, "matrix_upload_csr: bad arguments");
   if (rowptr[0] != 0 || rowptr[m] != nnz) return fail(h, ADAPROX_ERR_INVALID, "matrix_upload_csr: rowptr does not span nnz");
+  for (int64_t i = 0; i < m; ++i)
+    if (rowptr[i] > rowptr[i + 1]) return fail(h, ADAPROX_ERR_INVALID, "matrix_upload_csr: rowptr is not monotone");
   for (int64_t k = 0; k < nnz; ++k)
     if (colind[k] < 0 || colind[k] >= n) return fail(h, ADAPROX_ERR_INVALID, "matrix_upload_csr: column index out of range");
   AP_CUDA(h, cudaSetDevice(h->device));
@@ -528,8 +532,14 @@ static int validate_options(adaprox_ctx* h, const adaprox_problem* p, const adap
                    o->solver == ADAPROX_S_MALITSKY_POCK);
   if (pd && p->A_mat == 0) return fail(h, ADAPROX_ERR_INVALID, "primal-dual solvers need A (use adaptive_proxgrad for A = 0)");
   if (!pd && p->A_mat != 0) return fail(h, ADAPROX_ERR_INVALID, "proximal-gradient solvers take no A");
-  if (p->g.kind == ADAPROX_P_NORM_L2 || p->g.conjugate)
-    return fail(h, ADAPROX_ERR_UNSUPPORTED, "g = NormL2 / conjugate g has no fused kernel");
+  // g = NormL2 or a conjugate g needs one reduction before the prox (src/AdaProx.jl:332,361 accept any prox-able g): the
+  // adaptive primal-dual / proximal-gradient loops have it (solver_pd.cuh primal_step); the comparison baselines do not.
+  const bool pd_loop = (o->solver == ADAPROX_S_ADAPTIVE_PRIMAL_DUAL || o->solver == ADAPROX_S_ADAPTIVE_PROXGRAD ||
+                        o->solver == ADAPROX_S_LINESEARCH_PRIMAL_DUAL);
+  if ((p->g.kind == ADAPROX_P_NORM_L2 || p->g.conjugate) && !pd_loop)
+    return fail(h, ADAPROX_ERR_UNSUPPORTED, "g = NormL2 / conjugate g: supported by adaptive_primal_dual, adaptive_proxgrad, fixed_proxgrad, condat_vu and AdaPDM+ only");
+  if (p->A_mat != 0 && p->h.conjugate && !pd_loop)
+    return fail(h, ADAPROX_ERR_UNSUPPORTED, "h given as a conjugate: supported by adaptive_primal_dual, condat_vu and AdaPDM+ only");
   switch (o->solver) {
     case ADAPROX_S_ADAPTIVE_PRIMAL_DUAL:
     case ADAPROX_S_ADAPTIVE_PROXGRAD:
@@ -566,15 +576,19 @@ static int validate_options(adaprox_ctx* h, const adaprox_problem* p, const adap
 // eligible (the caller falls through to the two-pass kernel), < 0 on error.
 constexpr int64_t kSmallProblemBytes = 8 << 20;   // fewer matrix bytes than this: latency-bound, one CTA per SM (see solver_grid)
 static int fused_cluster_size(const DProblem& P) { return (int)((P.F.ld + kFCols - 1) / kFCols); }
-static bool fused_eligible(const adaprox_options* o, const DProblem& P) {
+// `rows` = the row count the decision is based on: the matrix's own rows on one GPU; for a row shard the GLOBAL rows divided
+// by the number of ranks, so that every rank takes the same decision even when the shards differ by a row (ranks that
+// disagreed would wait for each other in different collectives).  ADAPROX_FUSED is read per process: set it on all ranks.
+static bool fused_eligible(const adaprox_options* o, const DProblem& P, int64_t rows) {
   const char* e = std::getenv("ADAPROX_FUSED");
   if (e && std::strcmp(e, "0") == 0) return false;
   if (o->solver != ADAPROX_S_ADAPTIVE_PROXGRAD || P.f_kind != ADAPROX_F_LEAST_SQUARES || P.F.kind != MAT_DENSE) return false;
+  if (P.g.kind == ADAPROX_P_NORM_L2 || P.g.conjugate) return false;       // needs a reduction before the prox: general kernel
   const bool force = e && std::strcmp(e, "1") == 0;
-  if (!force && P.F.m * P.F.ld < (int64_t)(32 << 20)) return false;        // small problems: the two-pass kernel has more CTAs per column
+  if (!force && rows * P.F.ld < (int64_t)(32 << 20)) return false;         // small problems: the two-pass kernel has more CTAs per column
   return fused_cluster_size(P) <= kFMaxCluster;
 }
-static int fused_config(adaprox_ctx* h, const void* kernel, int C, cudaLaunchConfig_t* cfg, cudaLaunchAttribute* attrs, int* Q) {
+static int fused_config(adaprox_ctx* h, const void* kernel, int C, bool cooperative, cudaLaunchConfig_t* cfg, cudaLaunchAttribute* attrs, int* Q) {
   AP_CUDA(h, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFRingBytes));
   AP_CUDA(h, cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   *cfg = cudaLaunchConfig_t{};
@@ -585,12 +599,21 @@ static int fused_config(adaprox_ctx* h, const void* kernel, int C, cudaLaunchCon
   attrs[0].id = cudaLaunchAttributeClusterDimension;
   attrs[0].val.clusterDim.x = C; attrs[0].val.clusterDim.y = 1; attrs[0].val.clusterDim.z = 1;
   cfg->attrs = attrs;
-  cfg->numAttrs = 1;               // cluster launch only: the kernel carries its own grid barrier (see GridBar)
+  cfg->numAttrs = 1;
   int q = 0;
   cudaError_t e = cudaOccupancyMaxActiveClusters(&q, kernel, cfg);
   if (e != cudaSuccess || q < 1) { cudaGetLastError(); return 1; }
   *Q = q;
   cfg->gridDim = dim3(C * q, 1, 1);
+  // The kernel synchronises the grid with its own arrival-counter barrier (GridBar), so every CTA must be resident:
+  // the persistent single-GPU solve adds the cooperative attribute, which makes the runtime refuse the launch
+  // (cudaErrorCooperativeLaunchTooLarge) instead of letting it spin.  ADAPROX_FUSED_NONCOOP=1: plain cluster launch
+  // (Nsight Compute cannot replay cooperative + cluster); the barrier's spin is bounded either way.
+  if (cooperative && !std::getenv("ADAPROX_FUSED_NONCOOP")) {
+    attrs[1].id = cudaLaunchAttributeCooperative;
+    attrs[1].val.cooperative = 1;
+    cfg->numAttrs = 2;
+  }
   return ADAPROX_OK;
 }
 
@@ -603,10 +626,10 @@ struct FusedPlan {
   FusedArgs fa{};
 };
 // returns 0 = ok, 1 = not possible on this device (fall back to the two-pass kernels), < 0 = error
-static int fused_plan(adaprox_ctx* h, const void* kernel, const DProblem& P, FusedPlan* pl) {
+static int fused_plan(adaprox_ctx* h, const void* kernel, const DProblem& P, bool cooperative, FusedPlan* pl) {
   pl->fa = FusedArgs{};
   pl->fa.C = fused_cluster_size(P);
-  int rc = fused_config(h, kernel, pl->fa.C, &pl->cfg, pl->attrs, &pl->Q);
+  int rc = fused_config(h, kernel, pl->fa.C, cooperative, &pl->cfg, pl->attrs, &pl->Q);
   if (rc) return rc;
   pl->G = pl->fa.C * pl->Q;
   pl->fa.npadf = (int64_t)pl->fa.C * kFCols;
@@ -623,8 +646,8 @@ static int fused_plan(adaprox_ctx* h, const void* kernel, const DProblem& P, Fus
   return 0;
 }
 static size_t fused_ws_bytes(const FusedPlan& pl) {
-  return ws_size_doubles((int64_t)pl.fa.nchunks * pl.fa.npadf) + ws_size_doubles(pl.fa.nchunks) + 2 * ws_size_doubles(1) +
-         ws_size_doubles(4 * 256);
+  return ws_size_doubles((int64_t)pl.fa.nchunks * pl.fa.npadf) + ws_size_doubles(pl.fa.nchunks) + 3 * ws_size_doubles(1) +
+         ws_size_doubles(4 * 256) + ws_size_doubles(5 * kFTraceRows);
 }
 static int fused_ws_alloc(adaprox_ctx* h, FusedPlan* pl) {
   FusedArgs& fa = pl->fa;
@@ -632,16 +655,45 @@ static int fused_ws_alloc(adaprox_ctx* h, FusedPlan* pl) {
   fa.fpart = ws_doubles(h, fa.nchunks);
   fa.bar = reinterpret_cast<unsigned long long*>(ws_doubles(h, 1));
   fa.next = reinterpret_cast<unsigned long long*>(ws_doubles(h, 1));
+  fa.err = reinterpret_cast<int*>(ws_doubles(h, 1));
   AP_CUDA(h, cudaMemsetAsync(fa.bar, 0, 8, h->stream));
   AP_CUDA(h, cudaMemsetAsync(fa.next, 0, 8, h->stream));
+  AP_CUDA(h, cudaMemsetAsync(fa.err, 0, 8, h->stream));
   unsigned long long* lat = reinterpret_cast<unsigned long long*>(ws_doubles(h, 4 * 256));
   if (std::getenv("ADAPROX_FUSED_LAT")) {
     fa.lat = lat;
     AP_CUDA(h, cudaMemsetAsync(fa.lat, 0, 4 * 256 * 8, h->stream));
   }
+  unsigned long long* trace = reinterpret_cast<unsigned long long*>(ws_doubles(h, 5 * kFTraceRows));
+#ifdef ADAPROX_FUSED_TRACE
+  fa.trace = trace;
+  AP_CUDA(h, cudaMemsetAsync(fa.trace, 0, 5 * kFTraceRows * 8, h->stream));
+#else
+  (void)trace;
+#endif
+  return ADAPROX_OK;
+}
+// did a grid barrier of the fused kernel time out?  (GridBar; results are garbage then)
+static int fused_check(adaprox_ctx* h, const FusedPlan& pl) {
+  int e = 0;
+  AP_CUDA(h, cudaMemcpy(&e, pl.fa.err, sizeof(int), cudaMemcpyDeviceToHost));
+  if (e) return fail(h, ADAPROX_ERR_CUDA, "fused sweep kernel: grid barrier timed out (its CTAs were not all resident -- another kernel on this GPU?)");
   return ADAPROX_OK;
 }
 static void fused_print_probe(const FusedPlan& pl, const char* what) {
+#ifdef ADAPROX_FUSED_TRACE
+  if (pl.fa.trace) {        // pipeline timeline of CTA 0, second chunk of the last sweep (SM clock cycles relative to the first issue)
+    std::vector<unsigned long long> T((size_t)5 * kFTraceRows);
+    cudaMemcpy(T.data(), pl.fa.trace, T.size() * 8, cudaMemcpyDeviceToHost);
+    const unsigned long long t0 = T[0];
+    std::fprintf(stderr, "[adaprox %s trace: row issue full dot_done exch_done upd_done (cycles)]\n", what);
+    for (int i = 0; i < kFTraceRows; ++i) {
+      if (!T[(size_t)1 * kFTraceRows + i]) break;
+      std::fprintf(stderr, "T %d %lld %lld %lld %lld %lld\n", i, (long long)(T[i] - t0), (long long)(T[kFTraceRows + i] - t0),
+                   (long long)(T[2 * kFTraceRows + i] - t0), (long long)(T[3 * kFTraceRows + i] - t0), (long long)(T[4 * kFTraceRows + i] - t0));
+    }
+  }
+#endif
   if (!pl.fa.lat) return;
   unsigned long long L4[4 * 256];
   cudaMemcpy(L4, pl.fa.lat, sizeof(L4), cudaMemcpyDeviceToHost);
@@ -717,10 +769,10 @@ extern "C" int adaprox_solve(adaprox_handle h, const adaprox_problem* p, const a
   const int64_t nrec = std::min<int64_t>(O.max_records, O.maxit);
   int G = sharded_pd ? h->grid : solver_grid(h, P);
   const int Gcoop = G;
-  bool fused = fused_eligible(o, P);
+  bool fused = fused_eligible(o, P, P.F.m);
   FusedPlan fpl;
   if (fused) {
-    rc = fused_plan(h, (const void*)k_adapgm_fused, P, &fpl);
+    rc = fused_plan(h, (const void*)k_adapgm_fused, P, true, &fpl);
     if (rc < 0) return rc;
     if (rc == 1) fused = false; else G = fpl.G;
   }
@@ -809,6 +861,7 @@ extern "C" int adaprox_solve(adaprox_handle h, const adaprox_problem* p, const a
   if (y_out && P.md > 0) AP_CUDA(h, cudaMemcpyAsync(y_out, W.yout, (size_t)P.md * 8, cudaMemcpyDeviceToHost, h->stream));
   AP_CUDA(h, cudaStreamSynchronize(h->stream));
   if (fused) fused_print_probe(fpl, "fused");
+  if (fused && (rc = fused_check(h, fpl))) return rc;
   if (records && dr.n_records > 0)
     AP_CUDA(h, cudaMemcpy(records, W.rec, (size_t)dr.n_records * sizeof(adaprox_record), cudaMemcpyDeviceToHost));
   if (d_ts) {     // phase breakdown of the persistent kernel, averaged over the stamped iterations
@@ -887,3 +940,4 @@ extern "C" int adaprox_time_kernel(adaprox_handle h, adaprox_id mat, int which, 
 #include "comm.inl"
 #include "generate.inl"
 #include "path.inl"
+#include "hessian.inl"

@@ -89,7 +89,7 @@ int p2p_check(adaprox_ctx* h) {
   if (!h->comm || !h->comm->p2p.err) return ADAPROX_OK;
   int perr = 0;
   AP_CUDA(h, cudaMemcpy(&perr, h->comm->p2p.err, sizeof(int), cudaMemcpyDeviceToHost));
-  if (perr) return fail(h, ADAPROX_ERR_COMM, "in-kernel all-reduce: a peer rank did not arrive within 5 s");
+  if (perr) return fail(h, ADAPROX_ERR_COMM, "in-kernel all-reduce: a peer rank did not arrive within 5 s (call adaprox_p2p_reset on every rank before the next sharded solve)");
   return ADAPROX_OK;
 }
 
@@ -311,16 +311,18 @@ int solve_sharded(adaprox_ctx* h, const adaprox_problem* p, const adaprox_option
   if (P.f_kind != ADAPROX_F_LEAST_SQUARES && P.f_kind != ADAPROX_F_LOGISTIC)
     return fail(h, ADAPROX_ERR_UNSUPPORTED, "row-sharded solves support least-squares and logistic smooth terms only");
   if (!fm || fm->d.kind == MAT_NONE) return fail(h, ADAPROX_ERR_INVALID, "sharded solve without a matrix");
+  if (P.g.kind == ADAPROX_P_NORM_L2 || P.g.conjugate)
+    return fail(h, ADAPROX_ERR_UNSUPPORTED, "row-sharded AdaPGM: g = NormL2 / conjugate g is not supported (separable g only)");
   DOpts O = Oin;
   const int64_t n = P.n, mf = P.F.m;
   const int64_t nrec = std::min<int64_t>(O.max_records, O.maxit);
   O.max_records = nrec;
   int G = h->grid;
   // dense least squares: the single-pass fused kernel in sweep-only mode replaces k_sh_A .. k_sh_D
-  bool fused = fused_eligible(o, P);
+  bool fused = fused_eligible(o, P, (fm->m_global + h->comm->nranks - 1) / h->comm->nranks);
   FusedPlan fpl;
   if (fused) {
-    int frc = fused_plan(h, (const void*)k_adapgm_fused, P, &fpl);
+    int frc = fused_plan(h, (const void*)k_adapgm_fused, P, false, &fpl);
     if (frc < 0) return frc;
     if (frc == 1) fused = false; else G = fpl.G;
   }
@@ -404,12 +406,14 @@ int solve_sharded(adaprox_ctx* h, const adaprox_problem* p, const adaprox_option
     AP_CUDA(h, cudaMemcpyAsync(live, a.st, sizeof(live), cudaMemcpyDeviceToHost, h->stream));
     AP_CUDA(h, cudaStreamSynchronize(h->stream));
     AP_CUDA(h, cudaGetLastError());
+    if (use_p2p && (rc = p2p_check(h))) return rc;            // a peer was lost: the kernels no longer wait, stop enqueueing
     if (live[enqueued & 1].done || enqueued >= total) finished = true;
   }
   const int cur_idx = (int)(enqueued & 1);          // written by the last k_sh_F
   AP_CUDA(h, cudaEventRecord(h->ev1, h->stream));
   if (use_p2p && (rc = p2p_check(h))) return rc;
   if (fused) fused_print_probe(fpl, "sharded fused");
+  if (fused && (rc = fused_check(h, fpl))) return rc;
   const ShState& cur = live[cur_idx];
   const bool converged = (cur.flags & ADAPROX_FLAG_CONVERGED) != 0;
   // converged at iteration k: x is xb[k % 3]; maxit: the last prox, xb[(maxit + 1) % 3]
@@ -496,6 +500,16 @@ extern "C" int adaprox_p2p_attach(adaprox_handle h, int nranks, int rank, const 
     pp.peer[q] = static_cast<char*>(p);
   }
   pp.nranks = nranks; pp.rank = rank; pp.attached = true;
+  return ADAPROX_OK;
+}
+
+extern "C" int adaprox_p2p_reset(adaprox_handle h) {
+  if (!h) return ADAPROX_ERR_INVALID;
+  if (!h->comm || !h->comm->p2p.local) return adaprox::fail(h, ADAPROX_ERR_COMM, "p2p_reset: no exchange block (adaprox_p2p_export)");
+  AP_CUDA(h, cudaSetDevice(h->device));
+  AP_CUDA(h, cudaStreamSynchronize(h->stream));
+  AP_CUDA(h, cudaMemset(h->comm->p2p.local, 0, adaprox::kP2PFlagBytes));
+  AP_CUDA(h, cudaMemset(h->comm->p2p.err, 0, sizeof(int)));
   return ADAPROX_OK;
 }
 

@@ -8,8 +8,9 @@
 // All ranks run the same kernels on replicated control state, so they perform the same sequence of exchanges; T is
 // carried in registers (P2PState) and is identical everywhere.  Sums are formed in rank order: the same bits on
 // every rank.  Buffer reuse is safe because a rank overwrites buffer T & 1 only after every peer reported that it
-// finished reading exchange T - 1 (hence T - 2).  Spins are bounded (5 s): on timeout *err is set and the caller's
-// results are garbage -- the host checks the flag.
+// finished reading exchange T - 1 (hence T - 2).  Spins are bounded (5 s): on timeout *err is set, later waits return at
+// once, the persistent kernels leave their loop (p2p_failed) and the host returns ADAPROX_ERR_COMM; adaprox_p2p_reset
+// (every rank, then a host barrier) makes the blocks usable again.
 #pragma once
 #include "phases.cuh"      // pulls in p2p_args.cuh
 
@@ -21,13 +22,17 @@ __device__ __forceinline__ void p2p_begin(const P2PArgs& pa, P2PState& st) {
   st.T = 0;
   if (pa.n > 1) asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(st.T) : "l"(pa.flags[pa.rank] + 16) : "memory");
 }
+// Has an exchange of this solve timed out (on this rank)?  Uniform over the grid when read after the last grid barrier of
+// an exchange: the persistent kernels test it at the top of every iteration and leave the loop with ADAPROX_FLAG_COMM.
+__device__ __forceinline__ bool p2p_failed(const P2PArgs& pa) { return pa.n > 1 && *reinterpret_cast<volatile int*>(pa.err) != 0; }
 __device__ __forceinline__ void p2p_wait_ge(const P2PArgs& pa, const unsigned long long* src, unsigned long long v) {
+  if (*reinterpret_cast<volatile int*>(pa.err) != 0) return;       // a peer was lost earlier: never wait again (5 s each otherwise)
   const unsigned long long t0 = globaltimer_ns();
   unsigned long long seen;
   for (unsigned spin = 0;; ++spin) {
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(src) : "memory");
     if (seen >= v) break;
-    if ((spin & 1023u) == 1023u && globaltimer_ns() - t0 > 5000000000ull) { *pa.err = 1; break; }
+    if ((spin & 1023u) == 1023u && globaltimer_ns() - t0 > 5000000000ull) { *reinterpret_cast<volatile int*>(pa.err) = 1; __threadfence(); break; }
   }
 }
 __device__ __forceinline__ double p2p_ld(const double* p) {

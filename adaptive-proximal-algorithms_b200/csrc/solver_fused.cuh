@@ -37,7 +37,32 @@ constexpr int kFStages = 3;
 constexpr int kFStageBytes = kFCols * 8;                  // 64 KB
 constexpr int kFRingBytes = kFStages * kFStageBytes;      // 192 KB dynamic shared memory
 constexpr int kFMaxCluster = 16;
+// Two implementations of the row pipeline (build flag -DADAPROX_FUSED_VARIANT=1|2; measured in profiles/r02_notes.md):
+//   1 (shipped): role-specialised warps -- 8 dot warps and 8 update warps both read the row tile from shared memory; the
+//      two latency chains overlap.  Throughput is bounded by Little's law on the 3 x 64 KB ring: a slot is busy for
+//      copy (2700 cycles under load) + dot (1100) + exchange (900) + update (1500), period = lifetime / 3 = 2150 cycles.
+//   2 (A/B only): every warp does both jobs on its own 16 columns with ONE shared-memory pass per row into registers and
+//      releases the slot right after it.  Same results, but x + accumulators + one row fill the register file, so dot,
+//      exchange and update of a row cannot overlap with the next row: 3000 cycles per row (14.1 vs 11.4 ms per sweep).
+#ifndef ADAPROX_FUSED_VARIANT
+#define ADAPROX_FUSED_VARIANT 1
+#endif
+#if ADAPROX_FUSED_VARIANT == 1
 constexpr int kFDepth = 8;                                // exchange-buffer depth (see fused_pass)
+constexpr int kFXWarps = kFGWarps;                        // warps per CTA that contribute a partial dot per row
+constexpr int kFsumThread = kFGroup;                      // the thread of cluster rank 0 that returns sum r_i^2
+#else
+constexpr int kFDepth = 4;
+constexpr int kFXWarps = kFWarps;
+constexpr int kFsumThread = 0;
+constexpr int kFH2 = kFCols / 2 / kFThreads;              // 8 double2 per thread per row
+#endif
+constexpr int kFTraceRows = 512;
+#ifdef ADAPROX_FUSED_TRACE
+#define FTRACE(cond, k, i) do { if ((cond) && tr != nullptr && (i) < kFTraceRows) tr[(k) * kFTraceRows + (i)] = (unsigned long long)clock64(); } while (0)
+#else
+#define FTRACE(cond, k, i) do { } while (0)
+#endif
 
 struct FusedArgs {
   double* gpartf;      // [nchunks][npadf] per-chunk A'r partials
@@ -56,7 +81,9 @@ struct FusedArgs {
   double* sh_gbuf;
   const int* sh_done;            // the solve has stopped: do nothing
   P2PArgs p2p;                   // in-kernel all-reduce over peer-mapped buffers (p2p.cuh); p2p.n <= 1: ncclAllReduce by the host
+  int* err;                      // set by a CTA whose grid barrier timed out (GridBar); checked by the host after the solve
   unsigned long long* lat;       // optional [grid][4] probe (ADAPROX_FUSED_LAT): chunks taken, sweep ns, -, smid
+  unsigned long long* trace;     // build flag ADAPROX_FUSED_TRACE only: [5][kFTraceRows] clock64 stamps of CTA 0 (issue, full, dot done, exchange complete, update done)
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
@@ -68,7 +95,7 @@ __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.w
 // Control block in static shared memory: full[3] | empty[3] | cfull[8] mbarriers, then the exchange buffers
 // cpart[8][16 ranks][8 warps].  One base register + compile-time offsets address all of it.
 constexpr uint32_t kOffFull = 0, kOffEmpty = 8 * kFStages, kOffCfull = 16 * kFStages, kOffChunk = 16 * kFStages + 8 * kFDepth, kOffCpart = 128;
-constexpr uint32_t kPartStride = kFMaxCluster * kFGWarps * 8;                 // bytes per exchange buffer
+constexpr uint32_t kPartStride = kFMaxCluster * kFXWarps * 8;                 // bytes per exchange buffer
 constexpr int kCtlBytes = kOffCpart + kFDepth * kPartStride;
 static_assert(kOffChunk + 8 <= kOffCpart, "control block layout");
 
@@ -118,7 +145,12 @@ __device__ __forceinline__ void fmbar_wait(uint32_t addr, uint32_t parity) { mba
 // One warp of a role group polls, the other seven park on a hardware named barrier (bar.sync id, 256): parked warps issue
 // nothing (unlike 16 polling warps, which keep the issue slots and the power budget busy) and are released within a few
 // cycles of the poller's arrival (unlike warps suspended by try_wait).  Build flag ADAPROX_FUSED_ALLPOLL restores "every warp polls".
-__device__ __forceinline__ void group_bar(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(kFGroup) : "memory"); }
+#if ADAPROX_FUSED_VARIANT == 1
+constexpr int kFBarThreads = kFGroup;                     // a role group
+#else
+constexpr int kFBarThreads = kFThreads;                   // the whole CTA
+#endif
+__device__ __forceinline__ void group_bar(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(kFBarThreads) : "memory"); }
 #ifndef ADAPROX_FUSED_ALLPOLL
 __device__ __forceinline__ void group_wait(bool poller, int id, uint32_t addr, uint32_t parity) {
   if (poller) fmbar_wait(addr, parity);
@@ -156,9 +188,11 @@ __device__ __forceinline__ double2 lds2v(uint32_t addr) {
 // accumulators (64 registers), one batch of tile data (16), a handful of 32-bit addresses and counters.
 constexpr int kFB = 4;                                    // LDS.128 per batch (16 registers of tile data per thread)
 
+#if ADAPROX_FUSED_VARIANT == 1
 __device__ __noinline__ double fused_pass(const DMat& M, const double* bvec, const double* x, FusedSmem& fs, int C,
-                                           int64_t r0, int nrows, double* gout_row) {
+                                           int64_t r0, int nrows, double* gout_row, unsigned long long* tr = nullptr) {
   const uint32_t ring = fs.ring, ctl = fs.ctl, g0 = fs.count;
+  (void)tr;
   const uint32_t rank = cluster_ctarank();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t col0 = (int64_t)rank * kFCols;
@@ -183,6 +217,7 @@ __device__ __noinline__ double fused_pass(const DMat& M, const double* bvec, con
     const bool sender = lane < C;
     for (int i = 0; i < nrows; ++i) {
       group_wait(warp == 0, 1, ctl + kOffFull + 8 * slot, ph);
+      FTRACE(t == 0, 1, i);
       const uint32_t tile = tile0 + slot * kFStageBytes;
       // batches of kFB x LDS.128 issued back to back: ld.volatile keeps their order and the FMA chains consume the
       // batch in REVERSE, so the whole batch is in flight before the first FMA (ptxas otherwise recycles ONE
@@ -192,7 +227,11 @@ __device__ __noinline__ double fused_pass(const DMat& M, const double* bvec, con
 #pragma unroll
       for (int h = 0; h < kFH; h += kFB) {
 #pragma unroll
+#ifdef ADAPROX_EXP_NO_DOT_LDS
+        for (int k = 0; k < kFB; ++k) av[k] = xr[(h + k + 1) % kFH];          // timing experiment only: no shared-memory reads in the dot warps
+#else
         for (int k = 0; k < kFB; ++k) av[k] = lds2v(tile + (h + k) * kFGroup * 16);
+#endif
 #pragma unroll
         for (int k = kFB - 2; k >= 0; k -= 2) {
           p2 = fma(av[k + 1].x, xr[h + k + 1].x, p2);
@@ -203,6 +242,7 @@ __device__ __noinline__ double fused_pass(const DMat& M, const double* bvec, con
       }
       const double pw = warp_sum((p0 + p1) + (p2 + p3));
       if (sender) st_async_peer(mypart + d * kPartStride, ctl + kOffCfull + 8 * d, (uint32_t)lane, pw);
+      FTRACE(t == 0, 2, i);
       if (++slot == kFStages) { slot = 0; ph ^= 1u; }
       d = (d + 1) % kFDepth;
     }
@@ -227,8 +267,10 @@ __device__ __noinline__ double fused_pass(const DMat& M, const double* bvec, con
     if (leader)
       for (int i = 0; i < kFDepth && i < nrows; ++i) mbar_expect_tx(ctl + kOffCfull + 8 * ((g0 + i) % kFDepth), xbytes);
     uint32_t slot = g0 % kFStages, ph = (g0 / kFStages) & 1u, d = g0 % kFDepth, dph = (g0 / kFDepth) & 1u;
+    int issued = 0; (void)issued;
     auto issue = [&](uint32_t sl, uint32_t par) {    // wait until the update warps left slot sl, then refill it
       fmbar_wait(ctl + kOffEmpty + 8 * sl, par ^ 1u);
+      FTRACE(true, 0, issued); ++issued;
       mbar_expect_tx(ctl + kOffFull + 8 * sl, bytes);
       bulk_g2s(ring + sl * kFStageBytes, src, bytes, ctl + kOffFull + 8 * sl);
       src += ldb;
@@ -250,6 +292,7 @@ __device__ __noinline__ double fused_pass(const DMat& M, const double* bvec, con
       // st.async delivers data and complete_tx through the same path into this CTA's shared memory, so the
       // cta-scope acquire is enough (a cluster-scope acquire compiles to CCTL.IVALL: an L1 flush per row)
       group_wait(warp == kFGWarps, 2, ctl + kOffCfull + 8 * d, dph);
+      FTRACE(leader, 3, i);
       const uint32_t pb = part0 + d * kPartStride;
       const double v0 = (lane < nval) ? lds1(pb) : 0.0;
       const double v1 = (lane + 32 < nval) ? lds1(pb + 256) : 0.0;
@@ -268,7 +311,11 @@ __device__ __noinline__ double fused_pass(const DMat& M, const double* bvec, con
 #pragma unroll
       for (int h = 0; h < kFH; h += kFB) {
 #pragma unroll
+#ifdef ADAPROX_EXP_NO_UPD_LDS
+        for (int k = 0; k < kFB; ++k) av[k] = make_double2(b_cur, rs);          // timing experiment only: no shared-memory reads in the update warps
+#else
         for (int k = 0; k < kFB; ++k) av[k] = lds2v(tile + (h + k) * kFGroup * 16);
+#endif
         __syncwarp();                                           // scheduling fence: the independent FMAs below must not be
                                                                 // hoisted between the loads (one load in flight otherwise)
 #pragma unroll
@@ -279,6 +326,7 @@ __device__ __noinline__ double fused_pass(const DMat& M, const double* bvec, con
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(ctl + kOffEmpty + 8 * slot);
+      FTRACE(leader, 4, i);
       if (producer && i + kFStages < nrows) issue(slot, ph ^ 1u);   // row i + 3 into the slot row i just left
       fsum = fma(rs, rs, fsum);
       if (++slot == kFStages) { slot = 0; ph ^= 1u; }
@@ -295,6 +343,127 @@ __device__ __noinline__ double fused_pass(const DMat& M, const double* bvec, con
   fs.count = (uint32_t)(((uint64_t)g0 + (uint64_t)nrows) % 48u);
   return fsum;
 }
+#else
+// Variant 2.  All 16 warps run the same code; thread t owns the double2 columns k * 512 + t (k = 0 .. 7) of the CTA's
+// 8192-column slice: x (32 registers), the gradient accumulators (32) and ONE row of tile data (32) live in registers.
+// Per row g:
+//   1. warp 0 polls full[g % 3], the other warps park on a named barrier;
+//   2. 8 x LDS.128 bring the thread's 16 columns into registers -- the only shared-memory read of the tile; once the
+//      partial dot (which depends on all of them) exists, lane 0 of every warp arrives on empty[g % 3] and thread 0
+//      refills the slot with row g + 3: a slot is busy for copy + one LDS pass instead of copy + dot + exchange + update;
+//   3. warp partial -> st.async into cpart[g % 4][rank][warp] of every peer (complete_tx on the peer's cfull[g % 4]);
+//   4. warp 1 polls cfull[g % 4]; all warps sum the C * 16 partials in a fixed order (the same bits in every warp of
+//      every CTA of the cluster): r = sum - b[g];
+//   5. acc += tile registers * r.
+// Exchange depth: a warp sends row g + 1 only after it has read the partials of row g, and a peer needs ALL 16 warp
+// partials of row g + 1 from this CTA before it can finish row g + 1 and send row g + 2 -- so buffer g % 4 is never
+// written (row g + 4, or even g + 2) while a warp here still reads row g.  Everything is periodic in g with period
+// lcm(2 * 3, 2 * 4) = 24.
+__device__ __noinline__ double fused_pass(const DMat& M, const double* bvec, const double* x, FusedSmem& fs, int C,
+                                           int64_t r0, int nrows, double* gout_row, unsigned long long* tr = nullptr) {
+  const uint32_t ring = fs.ring, ctl = fs.ctl, g0 = fs.count;
+  (void)tr;
+  const uint32_t rank = cluster_ctarank();
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int64_t col0 = (int64_t)rank * kFCols;
+  double fsum = 0.0;
+
+  double2 xr[kFH2], acc[kFH2];
+  {
+    const int64_t n = M.n;
+#pragma unroll
+    for (int k = 0; k < kFH2; ++k) {
+      const int64_t j = col0 + 2 * (k * kFThreads + t);
+      xr[k].x = (j < n) ? ldcg(x + j) : 0.0;
+      xr[k].y = (j + 1 < n) ? ldcg(x + j + 1) : 0.0;
+      acc[k] = make_double2(0.0, 0.0);
+    }
+  }
+  const int nval = C * kFXWarps;                     // partials per row (<= 256)
+  const uint32_t xbytes = (uint32_t)nval * 8;        // exchange bytes per row per CTA
+  uint32_t bytes;
+  {
+    int64_t width = M.ld - col0;
+    width = width < 0 ? 0 : (width > kFCols ? kFCols : width);
+    bytes = (uint32_t)(width * 8);
+  }
+  const int64_t ldb = M.ld * 8;
+  const char* src = reinterpret_cast<const char*>(M.a + col0 + r0 * M.ld);     // next row to copy (thread 0)
+  uint32_t slot = g0 % kFStages, ph = (g0 / kFStages) & 1u, d = g0 % kFDepth, dph = (g0 / kFDepth) & 1u;
+  auto issue = [&](uint32_t sl, uint32_t par) {      // wait until every warp has left slot sl, then refill it
+    fmbar_wait(ctl + kOffEmpty + 8 * sl, par ^ 1u);
+    mbar_expect_tx(ctl + kOffFull + 8 * sl, bytes);
+    bulk_g2s(ring + sl * kFStageBytes, src, bytes, ctl + kOffFull + 8 * sl);
+    src += ldb;
+  };
+  if (t == 0) {
+    for (int i = 0; i < kFDepth && i < nrows; ++i) mbar_expect_tx(ctl + kOffCfull + 8 * ((g0 + i) % kFDepth), xbytes);
+    uint32_t sl = slot, par = ph;
+    for (int i = 0; i < kFStages && i < nrows; ++i) {
+      FTRACE(true, 0, i);
+      issue(sl, par);
+      if (++sl == kFStages) { sl = 0; par ^= 1u; }
+    }
+  }
+  const uint32_t tile0 = ring + t * 16;
+  const uint32_t mypart = ctl + kOffCpart + (rank * kFXWarps + warp) * 8;
+  const uint32_t part0 = ctl + kOffCpart + lane * 8;
+  const bool sender = lane < C;
+  const double* bp = bvec + r0;
+  double bblk = 0.0;                                 // lane l holds b[r0 + 32 * (i / 32) + l]
+  for (int i = 0; i < nrows; ++i) {
+    if ((i & 31) == 0) bblk = (i + lane < nrows) ? __ldg(bp + i + lane) : 0.0;
+    const double b_cur = __shfl_sync(0xffffffffu, bblk, i & 31);
+    group_wait(warp == 0, 1, ctl + kOffFull + 8 * slot, ph);
+    FTRACE(t == 0, 1, i);
+    const uint32_t tile = tile0 + slot * kFStageBytes;
+    double2 av[kFH2];
+#pragma unroll
+    for (int k = 0; k < kFH2; ++k) av[k] = lds2v(tile + k * kFThreads * 16);
+    // the chains consume the batch in REVERSE order: all eight loads are in flight before the first FMA can issue
+    double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
+#pragma unroll
+    for (int k = kFH2 - 2; k >= 0; k -= 2) {
+      p2 = fma(av[k + 1].x, xr[k + 1].x, p2);
+      p3 = fma(av[k + 1].y, xr[k + 1].y, p3);
+      p0 = fma(av[k].x, xr[k].x, p0);
+      p1 = fma(av[k].y, xr[k].y, p1);
+    }
+    const double pw = warp_sum((p0 + p1) + (p2 + p3));     // depends on all eight loads: the slot is no longer needed
+    if (lane == 0) mbar_arrive(ctl + kOffEmpty + 8 * slot);
+    if (sender) st_async_peer(mypart + d * kPartStride, ctl + kOffCfull + 8 * d, (uint32_t)lane, pw);
+    FTRACE(t == 0, 2, i);
+    if (t == 0 && i + kFStages < nrows) { FTRACE(true, 0, i + kFStages); issue(slot, ph ^ 1u); }   // row i + 3 into the slot row i just left
+    // st.async delivers data and complete_tx through the same path into this CTA's shared memory, so the
+    // cta-scope wait is enough (a cluster-scope acquire compiles to CCTL.IVALL: an L1 flush per row)
+    group_wait(warp == 1, 2, ctl + kOffCfull + 8 * d, dph);
+    FTRACE(t == 0, 3, i);
+    const uint32_t pb = part0 + d * kPartStride;
+    double v[8];                                     // entries of ranks >= C are never written: zeroed once in fused_smem_init
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = lds1(pb + 256 * k);
+    const double rs = warp_sum(((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]))) - b_cur;   // lasso/runme.jl:22  res = A*w - b
+    __syncwarp();
+    if (t == 0 && i + kFDepth < nrows) mbar_expect_tx(ctl + kOffCfull + 8 * d, xbytes);    // arm this buffer for row g + 4
+#pragma unroll
+    for (int k = 0; k < kFH2; ++k) {
+      acc[k].x = fma(av[k].x, rs, acc[k].x);
+      acc[k].y = fma(av[k].y, rs, acc[k].y);
+    }
+    FTRACE(t == 0, 4, i);
+    fsum = fma(rs, rs, fsum);
+    if (++slot == kFStages) { slot = 0; ph ^= 1u; }
+    if (++d == kFDepth) { d = 0; dph ^= 1u; }
+  }
+  double* gout = gout_row + col0;
+#pragma unroll
+  for (int k = 0; k < kFH2; ++k) *reinterpret_cast<double2*>(gout + 2 * (k * kFThreads + t)) = acc[k];
+  if (!(t == kFsumThread && rank == 0)) fsum = 0.0;
+  __syncthreads();
+  fs.count = (uint32_t)(((uint64_t)g0 + (uint64_t)nrows) % 24u);
+  return fsum;
+}
+#endif
 
 // One sweep over the matrix: g = A'(A x - b) as per-chunk partials gpartf[c][cols], fpart[c] = sum of r_i^2 over
 // the rows of chunk c.  Chunks of fa.chunk_rows rows are handed to the clusters DYNAMICALLY (one atomicAdd per
@@ -326,8 +495,12 @@ __device__ __forceinline__ void fused_sweep(const DMat& M, const double* bvec, c
     const int64_t r0 = c * (int64_t)fa.chunk_rows;
     const int64_t left = M.m - r0;
     const int nrows = (int)(left < fa.chunk_rows ? left : fa.chunk_rows);
+#ifdef ADAPROX_FUSED_TRACE
+    const double fv = fused_pass(M, bvec, x, fs, fa.C, r0, nrows, fa.gpartf + c * fa.npadf, (blockIdx.x == 0 && taken == 1) ? fa.trace : nullptr);
+#else
     const double fv = fused_pass(M, bvec, x, fs, fa.C, r0, nrows, fa.gpartf + c * fa.npadf);
-    if (rank == 0 && threadIdx.x == kFGroup) fa.fpart[c] = fv;       // the leader thread of the update warps holds the sum
+#endif
+    if (rank == 0 && threadIdx.x == kFsumThread) fa.fpart[c] = fv;   // the one thread that holds the sum
     ++taken;
     // the next mailbox store happens after this CTA's rank-0 peer finished the chunk, which needs every CTA's
     // last partial dot, which every CTA sends after it has read the mailbox above: no overwrite race
@@ -401,24 +574,35 @@ __device__ __forceinline__ void f_grid_totals(const double* red, int G, int slot
   __syncthreads();
 }
 
-// Grid-wide barrier on a monotonically increasing arrival counter.  The kernel is launched with exactly as many
-// clusters as cudaOccupancyMaxActiveClusters reports (one CTA per SM), so every CTA is resident; it is a plain
-// cluster launch rather than a cooperative one because Nsight Compute cannot replay the cooperative + cluster
-// attribute combination (LaunchFailed), and an unprofilable hot kernel is not acceptable.
+// Grid-wide barrier on a monotonically increasing arrival counter.  The launch is sized by cudaOccupancyMaxActiveClusters
+// (one CTA per SM) and, by default, carries the cooperative attribute next to the cluster dimension, so the runtime
+// guarantees co-residency (api.cu: fused_config; ADAPROX_FUSED_NONCOOP=1 drops the attribute because Nsight Compute cannot
+// replay a cooperative + cluster launch).  The row-sharded sweep-only launches are plain cluster launches.  In both cases
+// the spin is BOUNDED: if the peers do not arrive within kGridBarTimeoutNs (another kernel holding SMs, MPS, a debugger),
+// the CTA sets *err, stops waiting at every later barrier and the host reports ADAPROX_ERR_CUDA instead of hanging.
+constexpr unsigned long long kGridBarTimeoutNs = 10000000000ull;
 struct GridBar {
   unsigned long long* ctr;
   unsigned long long target;
   unsigned int G;
+  int* err;
   __device__ __forceinline__ void sync() {
     __syncthreads();
     if (threadIdx.x == 0) {
       target += G;
       __threadfence();                                   // this CTA's global writes before its arrival
       atomicAdd(ctr, 1ull);
-      unsigned long long seen;
-      do {
+      unsigned long long seen, t0 = 0;
+      for (unsigned spin = 0;; ++spin) {
         asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(ctr) : "memory");
-      } while (seen < target);
+        if (seen >= target) break;
+        if ((spin & 4095u) == 4095u) {
+          if (*reinterpret_cast<volatile int*>(err)) break;                    // somebody already gave up
+          const unsigned long long now = globaltimer_ns();
+          if (t0 == 0) t0 = now;
+          else if (now - t0 > kGridBarTimeoutNs) { *reinterpret_cast<volatile int*>(err) = 1; __threadfence(); break; }
+        }
+      }
     }
     __syncthreads();
   }
@@ -430,7 +614,7 @@ __device__ __forceinline__ void fused_smem_init(FusedSmem& fs, unsigned char* dy
   fs.ctl = smem_u32(s_ctl);
   fs.count = 0;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kFStages; ++s) { mbar_init(fs.ctl + kOffFull + 8 * s, 1); mbar_init(fs.ctl + kOffEmpty + 8 * s, kFGWarps); }
+    for (int s = 0; s < kFStages; ++s) { mbar_init(fs.ctl + kOffFull + 8 * s, 1); mbar_init(fs.ctl + kOffEmpty + 8 * s, kFXWarps); }
     for (int s = 0; s < kFDepth; ++s) mbar_init(fs.ctl + kOffCfull + 8 * s, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -442,6 +626,7 @@ __device__ __forceinline__ void fused_smem_init(FusedSmem& fs, unsigned char* dy
     for (int s = 0; s < kFStages; ++s)
       for (int64_t j = width + threadIdx.x; j < kFCols; j += kFThreads) sts1(fs.ring + s * kFStageBytes + (uint32_t)j * 8, 0.0);
   }
+  for (int j = threadIdx.x; j < (int)(kFDepth * kPartStride / 8); j += kFThreads) sts1(fs.ctl + kOffCpart + j * 8, 0.0);   // exchange buffers
   __syncthreads();
   cluster_arrive();          // every CTA of the cluster has initialised its shared memory before any peer writes into it
   cluster_wait();
@@ -449,7 +634,7 @@ __device__ __forceinline__ void fused_smem_init(FusedSmem& fs, unsigned char* dy
 
 // AdaPGM / fixed-step PGM (src/AdaProx.jl:312-364 with A = 0, h = Zero) around the fused pass.
 __global__ void __launch_bounds__(kFThreads, 1) k_adapgm_fused(DProblem P, DOpts O, DWork W, FusedArgs fa) {
-  GridBar grid{fa.bar, 0ull, gridDim.x};
+  GridBar grid{fa.bar, 0ull, gridDim.x, fa.err};
   const int b = blockIdx.x, G = gridDim.x;
   extern __shared__ __align__(1024) unsigned char dyn_smem[];
   __shared__ __align__(16) unsigned char s_ctl[kCtlBytes];

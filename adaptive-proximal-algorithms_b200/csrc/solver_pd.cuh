@@ -32,15 +32,17 @@ __device__ __forceinline__ void dual_rows(const DProblem& P, const DWork& W, con
                                           double* ynew, double sigma, double l2sum, bool want_h, const double* yold,
                                           double* s_scr, int b, int G, bool linesearch) {
   double acc[3] = {0.0, 0.0, 0.0};
-  const double l2scale = (P.h.kind == ADAPROX_P_NORM_L2) ? prox_l2_scale(P.h.lambda, 1.0 / sigma, l2sum) : 0.0;
+  // h passed as a conjugate (h = phi*): convex_conjugate(h) = phi, so the dual step is the plain prox of the base function
+  const bool h_conj = P.h.conjugate != 0;
+  const double l2scale = (P.h.kind == ADAPROX_P_NORM_L2) ? prox_l2_scale(P.h.lambda, h_conj ? sigma : 1.0 / sigma, l2sum) : 0.0;
   const int64_t tid = (int64_t)b * kThreads + threadIdx.x, nt = (int64_t)G * kThreads;
   for (int64_t i = tid; i < P.md; i += nt) {
     const double wi = ldcg(w + i), axi = ldcg(Ax + i);
-    const double yi = prox_conj_elem(P.h, wi, sigma, i, l2scale);                // :345
+    const double yi = h_conj ? prox_elem(P.h, wi, sigma, i, l2scale) : prox_conj_elem(P.h, wi, sigma, i, l2scale);   // :345
     ynew[i] = yi;
     const double dr = (wi - yi) / sigma - axi;                                   // :347
     acc[0] = fma(dr, dr, acc[0]);
-    if (want_h) acc[1] += prox_value_elem(P.h, axi, i);
+    if (want_h && !h_conj) acc[1] += prox_value_elem(P.h, axi, i);
     if (linesearch) { const double dy = yi - ldcg(yold + i); acc[2] = fma(dy, dy, acc[2]); }
   }
   double a2[2] = {acc[0], acc[1]};
@@ -74,6 +76,37 @@ __global__ void __launch_bounds__(kThreads, 2) k_primal_dual(DProblem P, DOpts O
   const int64_t tid = (int64_t)b * kThreads + threadIdx.x, nt = (int64_t)G * kThreads;
   int64_t j0, j1;
   cta_slice(P.n, b, G, j0, j1);
+
+  // ---- primal step  v = x - gamma (grad + A'y);  x+ = prox_{gamma g}(v)  (:330-332 / :359-361) ----------------------
+  // Separable g: one pass.  g = NormL2 (block soft threshold) needs |v + shift| first, a conjugate g
+  // (ProximalCore's Moreau order) |v / gamma + shift|: one more reduction and grid barrier, only for those.
+  const bool g_conj = P.g.conjugate != 0;
+  const bool g_l2 = (P.g.kind == ADAPROX_P_NORM_L2);
+  auto primal_step = [&](const double* xin, const double* grad_in, const double* aty_in, double gam, double* xn, int gslot) {
+    double l2scale = 0.0;
+    if (g_l2) {
+      double a1[1] = {0.0};
+      for (int64_t j = j0 + threadIdx.x; j < j1; j += kThreads) {
+        const double vj = xin[j] - gam * (grad_in[j] + (aty_in ? aty_in[j] : 0.0));
+        const double z = prox_l2_arg(P.g, g_conj ? vj / gam : vj, j);
+        a1[0] = fma(z, z, a1[0]);
+      }
+      block_reduce_store<1>(a1, W.red, G, SLOT_AUX1, s_scr);
+      grid.sync();
+      double tot[1];
+      grid_totals<1>(W.red, G, SLOT_AUX1, tot, s_scr);
+      l2scale = prox_l2_scale(P.g.lambda, g_conj ? 1.0 / gam : gam, tot[0]);
+    }
+    double acc[1] = {0.0};
+    for (int64_t j = j0 + threadIdx.x; j < j1; j += kThreads) {
+      const double vj = xin[j] - gam * (grad_in[j] + (aty_in ? aty_in[j] : 0.0));
+      W.v[j] = vj;
+      const double xj = g_conj ? prox_conj_elem(P.g, vj, gam, j, l2scale) : prox_elem(P.g, vj, gam, j, l2scale);
+      xn[j] = xj;
+      if (want_obj && !g_conj) acc[0] += prox_value_elem(P.g, xj, j);
+    }
+    block_reduce_store<1>(acc, W.red, G, gslot, s_scr);
+  };
 
   // ---- rule initialisation (:324 / :484-491) ------------------------------
   double gamma, sigma, s0, s1;
@@ -111,17 +144,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_primal_dual(DProblem P, DOpts O
     if (shardedF) p2p_allreduce<kThreads>(P.p2p, ps, grid, W.gb[gc], W.gb[gc], P.n);
     if (hasA) gsum_slice(P.A, j0, j1, W.Aty[atc], G);
     if (shardedA) p2p_allreduce<kThreads>(P.p2p, ps, grid, W.Aty[atc], W.Aty[atc], P.n);     // A'y over all row blocks
-    double acc[1] = {0.0};
-    double* xn = W.xb[1];
-    for (int64_t j = j0 + threadIdx.x; j < j1; j += kThreads) {
-      const double aty = hasA ? W.Aty[atc][j] : 0.0;
-      const double vj = x[j] - gamma * (W.gb[gc][j] + aty);                      // :330
-      W.v[j] = vj;
-      const double xj = prox_elem(P.g, vj, gamma, j, 0.0);                       // :332
-      xn[j] = xj;
-      if (want_obj) acc[0] += prox_value_elem(P.g, xj, j);
-    }
-    block_reduce_store<1>(acc, W.red, G, gval_slot(1), s_scr);
+    primal_step(x, W.gb[gc], hasA ? W.Aty[atc] : nullptr, gamma, W.xb[1], gval_slot(1));     // :330-332
   }
   n_eval = 1; n_grad = 1; n_proxg = 1; n_mul = 1; n_amul = 1;
   grid.sync();
@@ -133,6 +156,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_primal_dual(DProblem P, DOpts O
   bool converged = false;
 
   for (int64_t it = 1; it <= O.maxit; ++it) {
+    if (p2p_failed(P.p2p)) { flags |= ADAPROX_FLAG_COMM; it_done = it - 1; break; }   // a peer rank was lost (uniform: read after a grid barrier)
     // ---- P1 ---------------------------------------------------------------
     phase_stamp(W, it, 0);
     f_phase_pre(grid, P, W, x, sh, b, G, &ps);
@@ -189,7 +213,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_primal_dual(DProblem P, DOpts O
     double xx0[1] = {0.0};
     if (P.f_kind == ADAPROX_F_CUBIC) grid_totals<1>(W.red, G, SLOT_XX0, xx0, s_scr);
     const double f_x = f_value(P, ftot[0], ftot[1], xx0[0]);
-    const double g_x = want_obj ? prox_value_finish(P.g.kind, P.g.lambda, t5[4]) : NAN;
+    const double g_x = (want_obj && !g_conj) ? prox_value_finish(P.g.kind, P.g.lambda, t5[4]) : NAN;   // a ConvexConjugate object is not callable
     const double gamma_old = gamma;                                              // :340
     double dr_sum = 0.0, h_sum = 0.0;
     double* ynew = y;
@@ -204,7 +228,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_primal_dual(DProblem P, DOpts O
         for (int64_t i = tid; i < P.md; i += nt) {
           const double wi = y[i] + sigma * ((1.0 + rho) * Ax[i] - rho * Ax_prev[i]);   // :344
           w[i] = wi;
-          if (h_l2) { const double z = prox_l2_arg(P.h, wi / sigma, i); l2acc[0] = fma(z, z, l2acc[0]); }
+          if (h_l2) { const double z = prox_l2_arg(P.h, P.h.conjugate ? wi : wi / sigma, i); l2acc[0] = fma(z, z, l2acc[0]); }
         }
         double l2tot[1] = {0.0};
         if (h_l2) {
@@ -243,7 +267,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_primal_dual(DProblem P, DOpts O
         for (int64_t i = tid; i < P.md; i += nt) {
           const double wi = y[i] + sigma * ((1.0 + rho) * Ax[i] - rho * Ax_prev[i]);   // :524
           w[i] = wi;
-          if (h_l2) { const double z = prox_l2_arg(P.h, wi / sigma, i); l2acc[0] = fma(z, z, l2acc[0]); }
+          if (h_l2) { const double z = prox_l2_arg(P.h, P.h.conjugate ? wi : wi / sigma, i); l2acc[0] = fma(z, z, l2acc[0]); }
         }
         double l2tot[1] = {0.0};
         if (h_l2) {
@@ -301,7 +325,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_primal_dual(DProblem P, DOpts O
       adaprox_record rc;
       rc.it = it; rc.gamma = gamma; rc.sigma = sigma; rc.norm_res = norm_res;
       rc.f_x = f_x; rc.g_x = g_x;
-      rc.h_Ax = (want_obj && hasA) ? prox_value_finish(P.h.kind, P.h.lambda, h_sum) : (want_obj ? 0.0 : NAN);
+      rc.h_Ax = (want_obj && hasA) ? (P.h.conjugate ? NAN : prox_value_finish(P.h.kind, P.h.lambda, h_sum)) : (want_obj ? 0.0 : NAN);
       rc.f_evals = n_eval; rc.grad_f_evals = n_grad; rc.prox_g_evals = n_proxg; rc.prox_h_evals = n_proxh;
       rc.A_evals = n_mul; rc.At_evals = n_amul;
       W.rec[it - 1] = rc;
@@ -319,19 +343,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_primal_dual(DProblem P, DOpts O
     }
     // ---- P7 (:359-361) ---------------------------------------------------------------
     phase_stamp(W, it, 6);
-    {
-      double acc[1] = {0.0};
-      double* xn = W.xb[(xc + 1) % 3];
-      const double* aty = W.Aty[atc];
-      for (int64_t j = j0 + threadIdx.x; j < j1; j += kThreads) {
-        const double vj = x[j] - gamma * (grad[j] + (hasA ? aty[j] : 0.0));      // :359
-        W.v[j] = vj;
-        const double xj = prox_elem(P.g, vj, gamma, j, 0.0);                     // :361
-        xn[j] = xj;
-        if (want_obj) acc[0] += prox_value_elem(P.g, xj, j);
-      }
-      block_reduce_store<1>(acc, W.red, G, gval_slot(it + 1), s_scr);   // read in P5 of the next iteration
-    }
+    primal_step(x, grad, hasA ? W.Aty[atc] : nullptr, gamma, W.xb[(xc + 1) % 3], gval_slot(it + 1));   // :359-361; g(x+) is read in P5 of the next iteration
     n_proxg++;
     x_prev = x; xc = (xc + 1) % 3; x = W.xb[xc];                                 // :360
     grad_prev = grad; gc ^= 1;

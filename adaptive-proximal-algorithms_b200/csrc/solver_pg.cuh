@@ -93,6 +93,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_proxgrad_family(DProblem P, DOp
     n_eval++; n_grad++;
     int64_t trial_no = 0;
     for (int64_t it = 1; it <= O.maxit; ++it) {
+      if (p2p_failed(P.p2p)) { flags |= ADAPROX_FLAG_COMM; break; }
       // ---- backtrack_stepsize (:34-48) ---------------------------------------------
       gamma = nesterov ? gamma : O.xi * gamma;                                   // :54 / :72
       double f_z = 0.0, g_z = 0.0, dzz = 0.0;
@@ -165,6 +166,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_proxgrad_family(DProblem P, DOp
     double* grad = W.gb[0];
     for (int64_t j = j0 + threadIdx.x; j < j1; j += kThreads) x_prev[j] = x[j];  // :119
     for (int64_t it = 1; it <= O.maxit; ++it) {
+      if (p2p_failed(P.p2p)) { flags |= ADAPROX_FLAG_COMM; break; }
       const double theta_prev = theta;
       double beta;
       if (mu == 0.0) {                                                           // :122-128
@@ -221,6 +223,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_proxgrad_family(DProblem P, DOp
     const double rho = 1.0 / phi + 1.0 / (phi * phi);                            // :172
     double theta = 1.0;
     for (int64_t it = 1; it <= O.maxit; ++it) {
+      if (p2p_failed(P.p2p)) { flags |= ADAPROX_FLAG_COMM; break; }
       const int base = (it & 1) ? SLOT_DR : SLOT_PR;
       double acc[2] = {0.0, 0.0};
       for (int64_t j = j0 + threadIdx.x; j < j1; j += kThreads) {

@@ -18,14 +18,14 @@ import numpy as np
 
 
 def is_logstep(base: int, it: int) -> bool:
-    """logging.jl:13-17: ``scale = floor(Int, log(base, it)); mod(it, base^scale) == 0`` (it >= 1).  The integer
-    power is found exactly instead of through a floating-point logarithm (log(10, 1000) is 2.9999999999999996 in
-    floating point, which would make Julia's own version log every 100th step up to 9999)."""
+    """experiments/logging.jl:13-17, restated as written: ``scale = floor(Int, log(base, it)); step = base^scale;
+    mod(it, step) == 0`` with Julia's ``log(b, x) = log(x) / log(b)`` in Float64.  (The floating-point logarithm of an
+    exact power can land just below the integer -- log(10, 1000) = 2.9999999999999996 gives step 100 instead of 1000 --
+    but an exact power is a multiple of the smaller step too, so the answer is the same as with the exact integer power.)"""
     if it < 1:
-        raise ValueError("is_logstep: it must be >= 1")
-    step = 1
-    while step * base <= it:
-        step *= base
+        raise ValueError("is_logstep: it must be >= 1")               # Julia: DomainError / InexactError from floor(Int, -Inf)
+    scale = math.floor(math.log(it) / math.log(base))
+    step = base ** scale
     return it % step == 0
 
 

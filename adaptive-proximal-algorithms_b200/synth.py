@@ -165,6 +165,14 @@ def sparse_logreg(m=20242, n=47236, seed=0, nnz_lo=40, nnz_hi=112, w_density=0.0
     return rowptr, colind, values, y
 
 
+def logreg_lambda_max(X, y) -> float:
+    """Smallest l1 weight for which w = 0 (intercept 0) is stationary for the feature weights of the logistic loss of
+    sparse_logreg/runme.jl:18-39: |X'(1/2 - y)|_inf / N.  The reference uses lam = 0.01 on data sets whose lambda_max is a
+    few tenths (sparse_logreg/runme.jl:182); configs scale lam as a fraction of this value so the instance is not degenerate."""
+    y = np.asarray(y, dtype=np.float64)
+    return float(np.max(np.abs(X.T @ (0.5 - y))) / y.shape[0])
+
+
 def dense_classification(m=50000, n=2000, seed=0, flip=0.10):
     """X ~ N(0,1)/sqrt(n) (C order) and labels +-1 from a planted hyperplane
     with a fraction ``flip`` of the labels flipped (config C3, dual SVM)."""

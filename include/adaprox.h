@@ -44,6 +44,7 @@ typedef enum {
 #define ADAPROX_FLAG_STEP_TOO_SMALL 2u  /* src/AdaProx.jl:40-42,566-568 @error   */
 #define ADAPROX_FLAG_NONFINITE      4u  /* NaN/Inf stepsize or residual observed */
 #define ADAPROX_FLAG_LS_CAP         8u  /* a linesearch hit its trial cap        */
+#define ADAPROX_FLAG_COMM          16u  /* a peer rank did not show up in an in-kernel exchange; the call returns ADAPROX_ERR_COMM */
 
 /* ---- smooth term f: the experiment scripts' oracle structs ----------------- */
 typedef enum {
@@ -196,13 +197,20 @@ int adaprox_mul(adaprox_handle h, adaprox_id mat, const double* x, double* out);
 int adaprox_amul(adaprox_handle h, adaprox_id mat, const double* y, double* out);
 /* eval_with_pullback + pb()  (src/AdaProx.jl:11-16): f(x) and, if grad != NULL, the gradient. */
 int adaprox_eval_f(adaprox_handle h, const adaprox_problem* p, const double* x, double* f_x, double* grad);
-/* ProximalCore.prox(g, x, gamma) -> (y, g(y)). */
+/* ProximalCore.prox(g, x, gamma) -> (y, g(y)).  For a conjugate (g->conjugate = 1) y is the Moreau prox of g*; *g_y is
+ * then g(y_f) of the BASE function at its inner prox point, not the conjugate's value (no solver uses it: `y, _ = prox(...)`). */
 int adaprox_prox_eval(adaprox_handle h, const adaprox_prox* g, const double* x, int64_t len, double gamma,
                       double* y, double* g_y);
 /* stepsize(rule, state, x1, grad1, x0, grad0)  (src/AdaProx.jl:226,258,299) from the three
  * reductions the kernels fuse: dgg = |dgrad|^2, dgx = <dgrad, dx>, dxx = |dx|^2. */
 int adaprox_stepsize(const adaprox_options* o, double gamma1, double gamma0_or_rho, double dgg, double dgx,
                      double dxx, double* gamma, double* sigma, double* state1);
+
+/* logistic_loss_grad_Hessian(X, y, w) of experiments/cubic_sparse_logreg/runme.jl:34-45 -- the setup that turns a
+ * logistic-regression data set into the Cubic oracle's (Q, q): H_out = [X'RX  X'sb; (X'sb)'  sum(sb)] ((n+1)^2 doubles,
+ * symmetric), g_out = the logistic gradient at w (n+1).  X dense or CSR (n features), y the 0/1 labels, w of length n+1. */
+int adaprox_logistic_grad_hessian(adaprox_handle h, adaprox_id X_mat, adaprox_id y_vec, const double* w,
+                                  double* H_out, double* g_out);
 
 /* ---- solvers ---------------------------------------------------------------- */
 /* x0 (n), y0 (m_dual, may be NULL for proximal gradient) are read; x_out, y_out
@@ -245,6 +253,10 @@ int adaprox_comm_info(adaprox_handle h, int* nranks, int* rank);
  * calls p2p_attach.  All ranks must then issue the same sharded solves in the same order. */
 int adaprox_p2p_export(adaprox_handle h, int64_t n_max, void* ipc_handle64);
 int adaprox_p2p_attach(adaprox_handle h, int nranks, int rank, const void* ipc_handles);
+/* After a sharded solve returned ADAPROX_ERR_COMM (a peer did not arrive within 5 s): clears this rank's exchange flags,
+ * counters and error flag.  Every rank calls it, then the host side synchronises the ranks (no kernel of the failed solve
+ * may still be running anywhere) before the next sharded solve. */
+int adaprox_p2p_reset(adaprox_handle h);
 /* mark a matrix as the local row block [row0, row0+rows) of an m_global-row matrix */
 int adaprox_matrix_set_shard(adaprox_handle h, adaprox_id mat, int64_t m_global, int64_t row0);
 

@@ -29,6 +29,30 @@ F64 = np.float64
 _ERR = dict(divide="ignore", invalid="ignore", over="ignore")
 
 
+class precision:
+    """``with precision(np.longdouble): ...`` runs the SAME restatement with every scalar and every temporary in x87
+    extended precision (64-bit mantissa, eps = 1.1e-19) instead of Float64: callers pass ``longdouble`` arrays and build
+    their rule / prox objects inside the block.  This is not what the reference computes -- it is the yardstick that
+    separates "our rounding" from "their rounding" (hard parts (d)): the Float64 oracle's own distance
+    from the extended-precision trajectory is the intrinsic rounding drift of the algorithm, and a device trajectory
+    that stays inside a small multiple of it is as close to the reference as any Float64 evaluation order can be
+    (oracle/drift.py, tests/test_gpu_parity.py)."""
+
+    def __init__(self, dtype):
+        self.dtype = dtype
+
+    def __enter__(self):
+        global F64
+        self._saved = F64
+        F64 = self.dtype
+        return self
+
+    def __exit__(self, *exc):
+        global F64
+        F64 = self._saved
+        return False
+
+
 # --------------------------------------------------------------------------
 # Julia scalar semantics
 # --------------------------------------------------------------------------
@@ -350,6 +374,8 @@ def convex_conjugate(h):
         return IndZero()
     if isinstance(h, IndZero):
         return Zero()
+    if isinstance(h, ConvexConjugate):      # the biconjugate of a closed convex function is the function itself
+        return h.f
     return ConvexConjugate(h)
 
 
@@ -437,6 +463,21 @@ class Cubic:
 
     def __call__(self, x):
         return self.eval_with_pullback(x)[0]
+
+
+def logistic_loss_grad_Hessian(X, y, w):
+    """experiments/cubic_sparse_logreg/runme.jl:34-45 (setup of the Cubic oracle): returns (H, g)."""
+    y = np.asarray(y, dtype=F64)
+    with np.errstate(**_ERR):
+        probs = 1 / (1 + np.exp(-(X @ w[:-1] + w[-1])))           # sigm.(X * w[1:end-1] .+ w[end])
+        N = y.shape[0]
+        g = np.append((X.T @ (probs - y)) / N, np.mean(probs - y))
+        sb = probs * (1 - probs) / N
+        Xd = X.toarray() if hasattr(X, "toarray") else np.asarray(X)
+        XtR = Xd.T * sb                                            # X' * R, R = diagm(sb)
+        XR = XtR @ np.ones((N, 1))
+        H = np.vstack([np.hstack([XtR @ Xd, XR]), np.hstack([XR.T, [[np.sum(sb)]]])])
+    return H, g
 
 
 class WorstQuadratic:

@@ -10,6 +10,7 @@ import numpy as np
 import pytest
 
 from oracle import adaprox_oracle as O
+from oracle import drift
 
 pytestmark = pytest.mark.gpu
 
@@ -633,14 +634,19 @@ def test_fused_single_pass_matches_two_pass_and_oracle(AdaProx, m, n, pf):
     logo = []
     xo, ito = O.adaptive_proxgrad(np.zeros(n), f=O.LinearLeastSquares(P["A"], P["b"]), g=O.NormL1(1.0), rule=O.OurRule(gamma=1 / Lf),
                                   tol=1e-6, maxit=3000, log=logo)
-    K = 25
-    go = np.array([r["gamma"] for r in logo[:K]])
+    # Free-running stepsize prefix, evidence-based: the distance of the device trajectory from the extended-precision run
+    # of the same algorithm must stay inside 20 x the distance the FLOAT64 oracle itself (and two column permutations of
+    # it: other valid summation orders) has from that run -- the intrinsic rounding drift, oracle/drift.py.  Where that
+    # envelope is below 5e-14 the device is within 1e-12 of the extended-precision run, i.e. north_star's tolerance.
+    K = 40
+    truth = drift.lasso_runs(P["A"], P["b"], 1.0, lambda O_: O_.OurRule(gamma=1 / Lf), K, nperm=2, seed=m + n)
+    env = drift.envelope(truth)
     for mode in ("0", "1"):
         x, it, log, info = runs[mode]
-        gd = np.array([r["gamma"] for r in log[:K]])
-        assert np.max(np.abs(gd[:12] / go[:12] - 1)) < 5e-12, mode   # summation-order sensitivity of the wide instances (6.8e-13 measured)
-        assert np.max(np.abs(gd / go - 1)) < 1e-9, mode
-        assert np.allclose([r["objective"] for r in log[:K]], [r["objective"] for r in logo[:K]], rtol=1e-10)
+        ok, dd, allowed = drift.check_inside([r["gamma"] for r in log[:K]], truth, factor=20.0, floor=1e-12)
+        assert ok, (mode, float(np.max(dd / allowed)), float(dd.max()), float(env.max()))
+        kk = min(len(log), len(logo), 25)
+        assert np.allclose([r["objective"] for r in log[:kk]], [r["objective"] for r in logo[:kk]], rtol=1e-10)
         # runs that hit maxit before converging are compared loosely (the tail of the trajectory is chaotic)
         ftol = 1e-10 if (it < 3000 and ito < 3000) else 1e-3
         assert abs(log[-1]["objective"] - logo[-1]["objective"]) <= ftol * abs(logo[-1]["objective"]), (mode, it, ito)
@@ -711,12 +717,27 @@ def test_lambda_path_matches_per_lambda_solves(AdaProx, m, n, Lc):
     gd, go = info["gamma_hist"][:K], gh[:K]
     live = ~np.isnan(go) & ~np.isnan(gd)
     assert np.array_equal(np.isnan(go[:12]), np.isnan(gd[:12]))                    # the same columns stop at the same early iterations
-    assert np.max(np.abs(gd[live] / go[live] - 1)) < 1e-9
-    assert np.max(np.abs(gd[:10][live[:10]] / go[:10][live[:10]] - 1)) < 5e-12        # 1.6e-12 measured on the widest case
+    # evidence-based drift bound per sampled column (first, middle, last lambda): device vs extended-precision run inside
+    # 20 x the Float64 oracle's own drift envelope (oracle/drift.py), floor 1e-12
+    for j in sorted({0, Lc // 2, Lc - 1}):
+        kj = int(min(K, its[j], itso[j]))
+        if kj < 3:
+            continue
+        truth = drift.lasso_runs(P["A"], P["b"], float(lambdas[j]), lambda O_: O_.OurRule(gamma=1 / Lf), kj, nperm=2, seed=j)
+        ok, dd, allowed = drift.check_inside(info["gamma_hist"][:kj, j], truth, factor=20.0, floor=1e-12)
+        assert ok, (j, float(np.max(dd / allowed)), float(dd.max()))
     od, oo = info["obj_hist"][:K], oh[:K]
     assert np.allclose(od[live], oo[live], rtol=1e-10)
     # stopping iterations agree within the oracle's own rounding sensitivity
-    assert np.all(np.abs(its - itso) <= np.maximum(5, 0.1 * itso)), (its, itso)      # 20 of 354 seen on the widest case
+    assert np.all(np.abs(its - itso) <= np.maximum(5, 0.1 * itso)), (its, itso)      # sanity for every column (20 of 354 seen on the widest case)
+    # ... and evidence-based for the sampled columns: no further from the oracle than the oracle is from itself when the
+    # columns of A are permuted (same algorithm, another Float64 summation order)
+    perm = np.random.default_rng(1).permutation(n)
+    Ap = np.asfortranarray(P["A"][:, perm])
+    for j in sorted({0, Lc // 2, Lc - 1}):
+        _, itp = O.adaptive_proxgrad(np.zeros(n), f=O.LinearLeastSquares(Ap, P["b"]), g=O.NormL1(float(lambdas[j])), rule=O.OurRule(gamma=1 / Lf),
+                                     tol=1e-6, maxit=400)
+        assert abs(int(its[j]) - int(itso[j])) <= max(3, 0.03 * itso[j], 2 * abs(itp - int(itso[j]))), (j, its[j], itso[j], itp)
     # columns that converged on both sides: the minimiser to O(tol), the objective to 1e-9; columns cut off at maxit are
     # compared through the objective only (their trajectories are chaotic w.r.t. rounding)
     conv = (its < 400) & (itso < 400)

@@ -1,0 +1,160 @@
+"""Solver inputs added in round 2, through the C ABI against the CPU oracle: g = NormL2 and a conjugate g in the adaptive
+loops (src/AdaProx.jl:332,361 accept any prox-able g), h passed as a conjugate, auto_adaptive_proxgrad (:423-455), the Cubic
+oracle as a SOLVER input with its logistic_loss_grad_Hessian setup (cubic_sparse_logreg/runme.jl:20-45,66-120)."""
+import numpy as np
+import pytest
+
+from oracle import adaprox_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _gam(log, k=None):
+    return np.array([r["gamma"] for r in (log if k is None else log[:k])])
+
+
+def _ls(AdaProx, m=80, n=120, seed=3):
+    rng = np.random.default_rng(seed)
+    A = np.asfortranarray(rng.standard_normal((m, n)) / np.sqrt(m))
+    b = rng.standard_normal(m)
+    Lf = float(np.linalg.norm(A, 2) ** 2)
+    return A, b, Lf
+
+
+@pytest.mark.parametrize("gname", ["l2", "l2_translated", "conj_l1", "conj_l2", "conj_box"])
+def test_adapgm_with_norml2_and_conjugate_g(AdaProx, gname):
+    A, b, Lf = _ls(AdaProx)
+    n = A.shape[1]
+    rng = np.random.default_rng(5)
+    c = 0.3 * rng.standard_normal(n)
+    gd, go = {
+        "l2": (AdaProx.NormL2(0.8), O.NormL2(0.8)),
+        "l2_translated": (AdaProx.Translate(AdaProx.NormL2(0.5), -c), O.Translate(O.NormL2(0.5), -c)),
+        "conj_l1": (AdaProx.convex_conjugate(AdaProx.NormL1(0.7)), O.convex_conjugate(O.NormL1(0.7))),        # = indicator of the 0.7-box
+        "conj_l2": (AdaProx.convex_conjugate(AdaProx.NormL2(1.5)), O.convex_conjugate(O.NormL2(1.5))),        # = indicator of the 1.5-ball
+        "conj_box": (AdaProx.convex_conjugate(AdaProx.IndBox(-0.2, 0.4)), O.convex_conjugate(O.IndBox(-0.2, 0.4))),   # support function of the box
+    }[gname]
+    x0 = 0.1 * rng.standard_normal(n)
+    fd, fo = AdaProx.Counting(AdaProx.LinearLeastSquares(A, b)), O.Counting(O.LinearLeastSquares(A, b))
+    # a logger would call g(x), which a ConvexConjugate object does not support in the reference: records without objective
+    xd, itd = AdaProx.adaptive_proxgrad(x0, f=fd, g=gd, rule=AdaProx.OurRule(gamma=1 / Lf), tol=1e-8, maxit=4000)
+    xo, ito = O.adaptive_proxgrad(x0, f=fo, g=go, rule=O.OurRule(gamma=1 / Lf), tol=1e-8, maxit=4000)
+    assert abs(itd - ito) <= max(3, 0.05 * ito), (itd, ito)
+    assert np.linalg.norm(xd - xo) <= 1e-6 * max(np.linalg.norm(xo), 1.0)
+    assert fd.eval_count == itd + 1 and fd.grad_count == itd + 1
+    # teacher-free prefix with records where g is callable
+    if not gname.startswith("conj"):
+        logd, logo = [], []
+        AdaProx.adaptive_proxgrad(x0, f=fd, g=gd, rule=AdaProx.OurRule(gamma=1 / Lf), tol=0.0, maxit=25, log=logd)
+        O.adaptive_proxgrad(x0, f=fo, g=go, rule=O.OurRule(gamma=1 / Lf), tol=0.0, maxit=25, log=logo)
+        assert np.max(np.abs(_gam(logd) / _gam(logo) - 1)) < 1e-11
+        assert np.allclose([r["objective"] for r in logd], [r["objective"] for r in logo], rtol=1e-11)
+        assert np.allclose([r["norm_res"] for r in logd], [r["norm_res"] for r in logo], rtol=1e-9)
+    # the comparison baselines have no reduction before their prox: refused, never a silent wrong answer
+    with pytest.raises(AdaProx.AdaproxError):
+        AdaProx.backtracking_proxgrad(x0, f=fd, g=gd, gamma0=1 / Lf, maxit=5)
+
+
+def test_adapdm_with_norml2_g_and_conjugate_h(AdaProx):
+    """AdaPDM with g = NormL2 (one more reduction in the primal step) and h handed over as a conjugate: h = (lam |.|_1)* is the
+    indicator of the lam-box, so convex_conjugate(h) is NormL1 again and the dual step is its plain prox."""
+    rng = np.random.default_rng(8)
+    m, n = 50, 70
+    A = rng.standard_normal((m, n)) / np.sqrt(n)
+    F = np.asfortranarray(rng.standard_normal((40, n)) / np.sqrt(40)); bf = rng.standard_normal(40)
+    nA = float(np.linalg.norm(A, 2))
+    hd = AdaProx.convex_conjugate(AdaProx.NormL1(0.6)); ho = O.convex_conjugate(O.NormL1(0.6))
+    kw = dict(tol=0.0, maxit=40)
+    logd = []
+    xd, yd, itd = AdaProx.adaptive_primal_dual(np.zeros(n), np.zeros(m), f=AdaProx.LinearLeastSquares(F, bf), g=AdaProx.NormL2(0.3), h=hd,
+                                              A=AdaProx.DeviceMatrix(A), rule=AdaProx.OurRule(t=1.0, norm_A=nA), **kw)
+    xo, yo, ito = O.adaptive_primal_dual(np.zeros(n), np.zeros(m), f=O.LinearLeastSquares(F, bf), g=O.NormL2(0.3), h=ho, A=A,
+                                         rule=O.OurRule(t=1.0, norm_A=nA), **kw)
+    assert itd == ito == 40
+    assert np.linalg.norm(xd - xo) <= 1e-10 * np.linalg.norm(xo) and np.linalg.norm(yd - yo) <= 1e-10 * max(np.linalg.norm(yo), 1e-300)
+    # the dual iterate of h* = lam |.|_1 ... its prox is the soft threshold: y is sparse
+    assert np.count_nonzero(yd) == np.count_nonzero(yo)
+
+
+def test_auto_adaptive_proxgrad(AdaProx, lasso_small):
+    P = lasso_small
+    n = 1000
+    for gamma in (1.0 / P["Lf"], 50.0 / P["Lf"], 1e7 / P["Lf"]):       # the last one triggers the "initial guess too large" branch (:445-450)
+        logd, logo = [], []
+        xd, itd = AdaProx.auto_adaptive_proxgrad(np.zeros(n), f=AdaProx.LinearLeastSquares(P["A"], P["b"]), g=AdaProx.NormL1(1.0), gamma=gamma,
+                                                 tol=1e-6, maxit=10_000, log=logd)
+        xo, ito = O.auto_adaptive_proxgrad(np.zeros(n), f=O.LinearLeastSquares(P["A"], P["b"]), g=O.NormL1(1.0), gamma=gamma, tol=1e-6,
+                                           maxit=10_000, log=logo)
+        assert abs(logd[0]["gamma"] / logo[0]["gamma"] - 1) < 1e-12       # the estimated initial stepsize
+        assert np.max(np.abs(_gam(logd, 15) / _gam(logo, 15) - 1)) < 1e-11
+        assert abs(itd - ito) <= max(3, 0.05 * ito)
+        assert abs(logd[-1]["objective"] - logo[-1]["objective"]) <= 1e-10 * abs(logo[-1]["objective"])
+    x, it = AdaProx.auto_adaptive_proxgrad(P["x_star"] * 0, f=AdaProx.LinearLeastSquares(P["A"], 0 * P["b"]), g=AdaProx.NormL1(1.0), gamma=1.0)
+    assert it == 0                                                      # zero gradient at the start: returns at once (:426-428)
+    with pytest.raises(TypeError):
+        AdaProx.auto_adaptive_proxgrad(np.zeros(n), f=AdaProx.LinearLeastSquares(P["A"], P["b"]), g=AdaProx.NormL1(1.0))
+
+
+@pytest.mark.parametrize("sparse", [False, True])
+def test_logistic_loss_grad_hessian(AdaProx, sparse):
+    import scipy.sparse as sp
+    rng = np.random.default_rng(2)
+    m, n = 300, 40
+    X = sp.random(m, n, density=0.2, random_state=4, format="csr") if sparse else rng.standard_normal((m, n))
+    y = (rng.random(m) < 0.4).astype(float)
+    for w in (np.zeros(n + 1), 0.3 * rng.standard_normal(n + 1)):
+        Hd, gd = AdaProx.logistic_loss_grad_Hessian(X, y, w)
+        Ho, go = O.logistic_loss_grad_Hessian(X, y, w)
+        assert Hd.shape == (n + 1, n + 1) and np.max(np.abs(Hd - Ho)) <= 1e-13 * np.max(np.abs(Ho))
+        assert np.max(np.abs(Hd - Hd.T)) <= 1e-15 * np.max(np.abs(Hd))
+        assert np.max(np.abs(gd - go)) <= 1e-13 * np.max(np.abs(go))
+
+
+def test_cubic_subproblem_solvers(AdaProx):
+    """cubic_sparse_logreg/runme.jl:47-160 on a synthetic data set of the mushrooms shape class: Cubic(Q, q, lam) built from the
+    logistic Hessian at 0, g = Zero, gam_init from a random perturbation, then every solver the script runs."""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(0)
+    m, n = 600, 60
+    X = sp.random(m, n, density=0.25, random_state=1, format="csr", data_rvs=lambda k: rng.random(k))
+    y = (rng.random(m) < 0.5).astype(float)
+    n1 = n + 1
+    Qd, qd = AdaProx.logistic_loss_grad_Hessian(X, y, np.zeros(n1))             # :64
+    Qo, qo = O.logistic_loss_grad_Hessian(X, y, np.zeros(n1))
+    assert np.max(np.abs(Qd - Qo)) <= 1e-13 * np.max(np.abs(Qo))
+    lam = 1.0
+    fd_raw, fo_raw = AdaProx.Cubic(Qd, qd, lam), O.Cubic(Qo, qo, lam)
+    x0 = np.zeros(n1)
+    x_pert = x0 + rng.standard_normal(n1)                                       # :71
+    _, g0 = O.eval_with_gradient(fo_raw, x0); _, gp = O.eval_with_gradient(fo_raw, x_pert)
+    gam_init = float(np.linalg.norm(x0 - x_pert) ** 2 / np.dot(g0 - gp, x0 - x_pert))   # :75
+    _, g0d = AdaProx.eval_with_gradient(fd_raw, x0); _, gpd = AdaProx.eval_with_gradient(fd_raw, x_pert)
+    assert abs(float(np.linalg.norm(x0 - x_pert) ** 2 / np.dot(g0d - gpd, x0 - x_pert)) / gam_init - 1) < 1e-12
+    tol, maxit = 1e-5, 1000
+
+    def both(name, **kw):
+        fd, fo = AdaProx.Counting(fd_raw), O.Counting(fo_raw)
+        logd, logo = [], []
+        xd, itd = getattr(AdaProx, name)(x0, f=fd, g=AdaProx.Zero(), tol=tol, maxit=maxit, log=logd, **{k: (v[0] if isinstance(v, tuple) else v) for k, v in kw.items()})
+        xo, ito = getattr(O, name)(x0, f=fo, g=O.Zero(), tol=tol, maxit=maxit, log=logo, **{k: (v[1] if isinstance(v, tuple) else v) for k, v in kw.items()})
+        K = min(20, len(logd), len(logo))
+        assert np.max(np.abs(_gam(logd, K) / _gam(logo, K) - 1)) < 1e-10, name
+        assert abs(itd - ito) <= max(2, 0.03 * ito), (name, itd, ito)
+        assert abs(logd[-1]["objective"] - logo[-1]["objective"]) <= 1e-10 * max(abs(logo[-1]["objective"]), 1e-3), name
+        assert np.linalg.norm(xd - xo) <= 1e-4 * max(np.linalg.norm(xo), 1e-9), name
+        if itd == ito:
+            assert (fd.eval_count, fd.grad_count) == (fo.eval_count, fo.grad_count), name
+        return itd
+
+    both("adaptive_proxgrad", rule=(AdaProx.OurRule(gamma=gam_init), O.OurRule(gamma=gam_init)))                 # :78-86, :122-130
+    both("adaptive_proxgrad", rule=(AdaProx.MalitskyMishchenkoRule(gamma=gam_init), O.MalitskyMishchenkoRule(gamma=gam_init)))   # :112-120
+    for xi in (1, 1.5, 2):
+        both("backtracking_proxgrad", gamma0=gam_init, xi=xi)                                                    # :87-99
+    both("backtracking_nesterov", gamma0=gam_init)                                                               # :101-110
+    fd, fo = AdaProx.Counting(fd_raw), O.Counting(fo_raw)
+    xd, itd = AdaProx.agraal(x0, f=fd, g=AdaProx.Zero(), x0=x_pert, gamma0=gam_init, tol=tol, maxit=maxit)       # :132-142
+    xo, ito = O.agraal(x0, f=fo, g=O.Zero(), x0=x_pert, gamma0=gam_init, tol=tol, maxit=maxit)
+    assert abs(itd - ito) <= max(2, 0.03 * ito) and np.linalg.norm(xd - xo) <= 1e-4 * max(np.linalg.norm(xo), 1e-9)
+    # the minimiser of the cubic model: gradient vanishes
+    _, gsol = O.eval_with_gradient(fo_raw, xd)
+    assert np.linalg.norm(gsol) <= 10 * tol
