@@ -84,3 +84,14 @@ def check_inside(device_series, runs, key="gamma", factor=20.0, floor=1e-12):
     k = min(len(dd), len(env))
     allowed = np.maximum(floor, factor * env[:k])
     return bool(np.all(dd[:k] <= allowed)), dd[:k], allowed
+
+
+def perm_envelope(base, perms):
+    """Float64-only envelope for problems too large for an extended-precision run: running maximum over the iterations of the
+    largest relative distance between the oracle's natural-order run `base` and its permuted-data runs `perms` (same algorithm,
+    other summation orders).  One permutation is a single sample of a heavy-tailed ratio (the stepsize rule divides differences
+    of nearly equal numbers, src/AdaProx.jl:260-268); use three or more."""
+    base = np.asarray(base, dtype=np.float64)
+    d = [np.abs(np.asarray(p, dtype=np.float64)[: len(base)] / base[: len(p)] - 1) for p in perms]
+    k = min(len(x) for x in d)
+    return np.maximum.accumulate(np.max(np.stack([x[:k] for x in d]), axis=0))
