@@ -10,6 +10,7 @@
 #include "solver_pg.cuh"
 #include "solver_mp.cuh"
 #include "solver_fused.cuh"
+#include "solver_resident.cuh"
 #include "comm.hpp"
 
 using namespace adaprox;
@@ -704,6 +705,22 @@ static void fused_print_probe(const FusedPlan& pl, const char* what) {
   std::fprintf(stderr, "\n");
 }
 
+// Small dense least squares: the matrix fits the distributed shared memory of one 16-CTA cluster (solver_resident.cuh).
+// ADAPROX_RESIDENT=0 disables it (A/B against the persistent grid kernel).
+static bool resident_eligible(adaprox_ctx* h, const adaprox_options* o, const DProblem& P, ResidentArgs* ra, size_t* smem) {
+  const char* e = std::getenv("ADAPROX_RESIDENT");
+  if (e && std::strcmp(e, "0") == 0) return false;
+  if (o->solver != ADAPROX_S_ADAPTIVE_PROXGRAD || P.f_kind != ADAPROX_F_LEAST_SQUARES || P.F.kind != MAT_DENSE) return false;
+  if (P.g.kind == ADAPROX_P_NORM_L2 || P.g.conjugate) return false;
+  if (P.F.ld > kRMaxLd || P.n < 1) return false;
+  ra->rows_cap = (int)((P.F.m + kRCluster - 1) / kRCluster);
+  ra->slice = (int)((P.n + kRCluster - 1) / kRCluster);
+  *smem = resident_smem_bytes(ra->rows_cap, P.F.ld);
+  int max_optin = 0;
+  if (cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device) != cudaSuccess) return false;
+  return *smem + 1024 <= (size_t)max_optin;
+}
+
 // CTAs of a persistent solver launch.  Every phase boundary is a grid barrier whose cost grows with the number of CTAs, and
 // every scalar is rebuilt from one partial per CTA: a problem whose matrices are small enough to be latency-bound (a few
 // microseconds per phase) runs faster on fewer CTAs; a streaming problem wants all of them (2 per SM keep ~96 KB of bulk
@@ -754,13 +771,21 @@ extern "C" int adaprox_solve(adaprox_handle h, const adaprox_problem* p, const a
   const bool sharded_pd = sharded && ((f_ok && pd_solver && ((am && am->sharded) || f_quad_shard)) ||
                                       (f_ok && o->solver == ADAPROX_S_ADAPTIVE_PROXGRAD && f_quad_shard) ||
                                       (pg_family && (f_ls_shard || f_quad_shard) && !(am && am->sharded)));
+  // Row-sharded AdaPGM / fixed-step PGM on a dense least-squares shard with the exchange blocks attached: the single-sweep kernel
+  // stays resident for the whole solve and all-reduces inside its loop (solver_fused.cuh, `sharded`): one launch per rank.
+  // ADAPROX_SHARDED_LAUNCHES=1 keeps the round-1 structure (sweep-only launch + two small kernels per iteration) for A/B; without
+  // the exchange blocks (or under ADAPROX_NO_P2P) the split-phase path with ncclAllReduce runs.  All of these are read per process
+  // and must agree on every rank.
+  const bool sharded_fused = sharded && !sharded_pd && f_ls_shard && o->solver == ADAPROX_S_ADAPTIVE_PROXGRAD && h->comm &&
+                             p2p_ready(h, P.n + 2) && !std::getenv("ADAPROX_NO_P2P") && !std::getenv("ADAPROX_SHARDED_LAUNCHES") &&
+                             fused_eligible(o, P, (fm->m_global + comm_nranks(h) - 1) / comm_nranks(h));
   if (sharded_pd) {
     if (!p2p_ready(h, std::max<int64_t>(std::max<int64_t>(P.n, P.f_kind == ADAPROX_F_QUADRATIC_GRAM ? P.F.n : 0), 8)))
       return fail(h, ADAPROX_ERR_COMM, "row-sharded primal-dual solve: attach the peer exchange blocks first (adaprox_p2p_export / adaprox_p2p_attach)");
     p2p_fill(h, &P.p2p);
     P.A_sharded = (am && am->sharded) ? 1 : 0;
     P.F_sharded = (f_quad_shard || (pg_family && f_ls_shard)) ? 1 : 0;
-  } else if (sharded) {
+  } else if (sharded && !sharded_fused) {
     return solve_sharded(h, p, o, P, O, fm, am, x0, y0, x_out, y_out, records, res);
   }
 
@@ -769,17 +794,21 @@ extern "C" int adaprox_solve(adaprox_handle h, const adaprox_problem* p, const a
   const int64_t nrec = std::min<int64_t>(O.max_records, O.maxit);
   int G = sharded_pd ? h->grid : solver_grid(h, P);
   const int Gcoop = G;
-  bool fused = fused_eligible(o, P, P.F.m);
+  ResidentArgs rarg{};
+  size_t rsmem = 0;
+  const bool resident = !sharded && resident_eligible(h, o, P, &rarg, &rsmem);
+  bool fused = sharded_fused || (!resident && !sharded && fused_eligible(o, P, P.F.m));
   FusedPlan fpl;
   if (fused) {
     rc = fused_plan(h, (const void*)k_adapgm_fused, P, true, &fpl);
     if (rc < 0) return rc;
+    if (rc == 1 && sharded_fused) return fail(h, ADAPROX_ERR_CUDA, "row-sharded fused solve: no resident cluster configuration on this device");
     if (rc == 1) fused = false; else G = fpl.G;
   }
   FusedArgs& fa = fpl.fa;
   const int fQ = fpl.Q;
   const int64_t nfu = (P.f_kind == ADAPROX_F_QUADRATIC_GRAM) ? P.F.n : 1;
-  size_t need = (fused ? fused_ws_bytes(fpl) : 0) +
+  size_t need = (fused ? fused_ws_bytes(fpl) : 0) + (sharded_fused ? ws_size_doubles(n + 2) : 0) +
                 11 * ws_size_doubles(n) + 6 * ws_size_doubles(md) + ws_size_doubles(mf) + ws_size_doubles(nfu) +
                 ws_size_doubles((int64_t)kMaxRed * G) + ws_size_doubles((nrec * (int64_t)sizeof(adaprox_record) + 7) / 8) +
                 ws_size_doubles((sizeof(DResult) + 7) / 8);
@@ -802,6 +831,10 @@ extern "C" int adaprox_solve(adaprox_handle h, const adaprox_problem* p, const a
   W.xout = W.aux[2];
   O.max_records = nrec;
   if (fused && (rc = fused_ws_alloc(h, &fpl))) return rc;
+  if (sharded_fused) {
+    fa.sh_gbuf = ws_doubles(h, n + 2);
+    p2p_fill(h, &fa.p2p);
+  }
   const bool phase_timing = std::getenv("ADAPROX_PHASE_TIMING") != nullptr;
   unsigned long long* d_ts = nullptr;
   struct DevFree { unsigned long long*& p; ~DevFree() { if (p) cudaFree(p); } } d_ts_guard{d_ts};   // released on every return path
@@ -829,7 +862,21 @@ extern "C" int adaprox_solve(adaprox_handle h, const adaprox_problem* p, const a
   switch (o->solver) {
     case ADAPROX_S_ADAPTIVE_PRIMAL_DUAL:
     case ADAPROX_S_ADAPTIVE_PROXGRAD:
-      if (fused) {
+      if (resident) {
+        AP_CUDA(h, cudaFuncSetAttribute((const void*)k_adapgm_resident, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
+        AP_CUDA(h, cudaFuncSetAttribute((const void*)k_adapgm_resident, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        cudaLaunchConfig_t cfg{};
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = kRCluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.gridDim = dim3(kRCluster, 1, 1); cfg.blockDim = dim3(kRThreads, 1, 1); cfg.dynamicSmemBytes = rsmem; cfg.stream = h->stream;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        void* rargs[] = {&P, &O, &W, &rarg};
+        cudaError_t e = cudaLaunchKernelExC(&cfg, (const void*)k_adapgm_resident, rargs);
+        if (e != cudaSuccess) return fail(h, ADAPROX_ERR_CUDA, std::string("resident cluster launch: ") + cudaGetErrorString(e));
+        h->launches++;
+        rc = ADAPROX_OK;
+      } else if (fused) {
         cudaError_t e = cudaLaunchKernelExC(&fpl.cfg, (const void*)k_adapgm_fused, fargs);
         if (e != cudaSuccess) return fail(h, ADAPROX_ERR_CUDA, std::string("fused cluster launch: ") + cudaGetErrorString(e));
         h->launches++;
@@ -902,9 +949,9 @@ extern "C" int adaprox_solve(adaprox_handle h, const adaprox_problem* p, const a
   res->n_records = dr.n_records;
   res->final_gamma = dr.final_gamma; res->final_sigma = dr.final_sigma; res->final_norm_res = dr.final_norm_res;
   res->solve_ms = ms; res->kernel_launches = h->launches - launches0;
-  res->matrix_passes = (P.F.kind == MAT_NONE) ? 0 : (fused ? 1 : 2);
-  res->collective = sharded_pd ? 2 : 0;
-  if (sharded_pd && (rc = p2p_check(h))) return rc;
+  res->matrix_passes = (P.F.kind == MAT_NONE) ? 0 : (fused ? 1 : (resident ? 3 : 2));
+  res->collective = (sharded_pd || sharded_fused) ? 2 : 0;
+  if ((sharded_pd || sharded_fused) && (rc = p2p_check(h))) return rc;
   return ADAPROX_OK;
 }
 

@@ -11,6 +11,7 @@ struct P2PArgs;
 void p2p_fill(adaprox_ctx* h, P2PArgs* pa);            // kernel-side view of the peer-mapped exchange blocks (p2p.cuh)
 bool p2p_ready(adaprox_ctx* h, int64_t count);         // attached and large enough for vectors of `count` doubles
 int p2p_check(adaprox_ctx* h);                         // error flag of the bounded spins
+int comm_nranks(adaprox_ctx* h);                       // ranks of the attached communicator (1 without one)
 int comm_setup_kernels();      // opt the split-phase kernels into the ring's dynamic shared memory
 
 int solve_sharded(adaprox_ctx* h, const adaprox_problem* p, const adaprox_options* o, const DProblem& P, const DOpts& O,

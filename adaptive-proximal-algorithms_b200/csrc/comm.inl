@@ -84,6 +84,7 @@ void p2p_fill(adaprox_ctx* h, P2PArgs* pa) {
     pa->flags[q] = reinterpret_cast<unsigned long long*>(pp.peer[q]);
   }
 }
+int comm_nranks(adaprox_ctx* h) { return h->comm ? h->comm->nranks : 1; }
 bool p2p_ready(adaprox_ctx* h, int64_t count) { return h->comm && h->comm->p2p.attached && h->comm->p2p.cap >= count; }
 int p2p_check(adaprox_ctx* h) {
   if (!h->comm || !h->comm->p2p.err) return ADAPROX_OK;

@@ -23,18 +23,30 @@
 namespace adaprox {
 
 constexpr int kGT = 512;                 // threads per CTA of the GEMM kernels
-constexpr int kGBM = 128, kGBK = 16, kGStages = 4;
-constexpr int kGPadK = kGBK + 4;         // 20 doubles: row stride of the k-contiguous tiles
+#ifndef ADAPROX_GEMM_BK
+#define ADAPROX_GEMM_BK 32
+#endif
+// BK doubles of K per stage and CTA barrier.  Wide tile (NT = 4): 32 with a 3-stage ring (216 KB) instead of 16 with 4 stages
+// (160 KB) halves the barriers + ring refills per contraction: 16384 x 8192 x 256 A X 2.37 -> 2.24 ms, A'R 2.29 -> 2.20 ms
+// (profiles/r02_notes.md; -DADAPROX_GEMM_BK=16 restores the round-1 shape).  The narrow tile (NT = 1) keeps 16 x 4 stages:
+// with 32 it lost 12 % on A X (its CTAs are short, the deeper ring matters more than the barrier count).
+constexpr int kGBM = 128;
+constexpr int kGBKWide = ADAPROX_GEMM_BK, kGBKNarrow = 16;
 constexpr int kGPadM = kGBM + 4;         // 132 doubles: row stride of the [k][m] tile of mode 2 (32 B mod 128)
 // NT = 8-column DMMA tiles per warp along N: NT = 4 -> 128 x 128 CTA tile, NT = 1 -> 128 x 32 (narrow batches:
 // the lambdas of one rank when the path is split over 8 GPUs)
 template <int NT> struct GemmCfg {
   static constexpr int BN = 32 * NT;
-  static constexpr int ATile = (kGBM * kGPadK > kGBK * kGPadM) ? kGBM * kGPadK : kGBK * kGPadM;   // doubles
-  static constexpr int BTile = BN * kGPadK;
+  static constexpr int BK = (NT == 4) ? kGBKWide : kGBKNarrow;
+  static constexpr int Stages = (BK >= 32) ? 3 : 4;
+  static constexpr int PadK = BK + 4;                                    // row stride of the k-contiguous tiles (32 B mod 128: conflict-free LDS.64)
+  static constexpr int ChunksK = BK / 2;                                 // 16-byte chunks per k-contiguous tile row
+  static constexpr int ATile = (kGBM * PadK > BK * kGPadM) ? kGBM * PadK : BK * kGPadM;   // doubles
+  static constexpr int BTile = BN * PadK;
   static constexpr int Stage = ATile + BTile;
-  static constexpr int SmemBytes = kGStages * Stage * 8;                 // NT = 4: 163 840 B
+  static constexpr int SmemBytes = Stages * Stage * 8;                   // NT = 4: 221 184 B
 };
+constexpr int kGBK = 16;                 // granularity of the K slabs (both tile shapes are multiples of it)
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
   // 16-byte global -> shared copy; bytes beyond src_bytes (0 or 16) are zero-filled
@@ -70,7 +82,8 @@ struct PathGemmArgs {
 //         k-contiguous.  In both modes the batch is the N dimension, so a narrow batch only needs a narrow N tile.
 template <int MODE, int NT>
 __global__ void __launch_bounds__(kGT, 1) k_path_gemm(PathGemmArgs g) {
-  constexpr int kGBN = GemmCfg<NT>::BN, kGStage = GemmCfg<NT>::Stage;
+  constexpr int kGBN = GemmCfg<NT>::BN, kGStage = GemmCfg<NT>::Stage, kGBK = GemmCfg<NT>::BK, kGStages = GemmCfg<NT>::Stages;
+  constexpr int kGPadK = GemmCfg<NT>::PadK, kGChunksK = GemmCfg<NT>::ChunksK;
   extern __shared__ __align__(16) double gsm[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = warp >> 2, wn = warp & 3;
@@ -97,18 +110,18 @@ __global__ void __launch_bounds__(kGT, 1) k_path_gemm(PathGemmArgs g) {
     const uint32_t sa = smem0 + (uint32_t)(stage * kGStage) * 8;
     const uint32_t sb = sa + GemmCfg<NT>::ATile * 8;
     if (MODE == 1) {
-      // A tile: 128 rows i x 16 doubles (k contiguous) = 128 x 8 chunks of 16 B
+      // A tile: 128 rows i x BK doubles (k contiguous) = 128 x BK/2 chunks of 16 B
 #pragma unroll
       for (int q = 0; q < (kGBM * kGBK / 2) / kGT; ++q) {
         const int ch = tid + q * kGT;
-        const int r = ch >> 3, kc = (ch & 7) * 2;
+        const int r = ch / kGChunksK, kc = (ch % kGChunksK) * 2;
         const int64_t row = m0 + r, k = k0 + kc;
         const bool ok = (row < Mdim) && (k + 2 <= g.lda) && (k < kend);   // the zero padding up to lda may be read
         const double* src = g.A + (ok ? row * g.lda + k : 0);
         cp_async16(sa + (uint32_t)(r * kGPadK + kc) * 8, src, ok ? 16 : 0);
       }
     } else {
-      // A tile: 16 rows (k = row i of A) x 128 columns c (c contiguous) = 16 x 64 chunks
+      // A tile: BK rows (k = row i of A) x 128 columns c (c contiguous) = BK x 64 chunks
 #pragma unroll
       for (int q = 0; q < (kGBK * kGBM / 2) / kGT; ++q) {
         const int ch = tid + q * kGT;
@@ -119,12 +132,12 @@ __global__ void __launch_bounds__(kGT, 1) k_path_gemm(PathGemmArgs g) {
         cp_async16(sa + (uint32_t)(r * kGPadM + cc) * 8, src, ok ? 16 : 0);
       }
     }
-    // B tile: BN rows (columns j of the batch) x 16 doubles, k contiguous
+    // B tile: BN rows (columns j of the batch) x BK doubles, k contiguous
 #pragma unroll
     for (int q = 0; q < (kGBN * kGBK / 2 + kGT - 1) / kGT; ++q) {
       const int ch = tid + q * kGT;
       if (ch >= kGBN * kGBK / 2) break;
-      const int r = ch >> 3, kc = (ch & 7) * 2;
+      const int r = ch / kGChunksK, kc = (ch % kGChunksK) * 2;
       const int64_t col = n0 + r, k = k0 + kc;
       const bool ok = (col < Ndim) && (k + 2 <= ldb) && (k < kend);   // slabs end on even k (multiples of BK, or the padded end)
       const double* src = Bop + (ok ? col * ldb + k : 0);

@@ -694,6 +694,27 @@ __global__ void __launch_bounds__(kFThreads, 1) k_adapgm_fused(DProblem P, DOpts
   unsigned flags = 0;
   int xc = 0, gc = 0;
   double* x = W.xb[0];
+  // Row-sharded solve, persistent form (fa.p2p.n > 1): this rank's matrix is the row block of a larger one.  After the sweep
+  // the shard's partial gradient and value sum (n + 2 doubles) are all-reduced INSIDE this kernel over NVLink peer memory
+  // (p2p.cuh); every rank obtains the same bits, so the replicated stepsize / prox arithmetic below stays in lock step and the
+  // whole sharded solve is ONE launch per rank -- no NCCL, no host, no relaunch per iteration.
+  const bool sharded = fa.p2p.n > 1;
+  P2PState ps;
+  p2p_begin(fa.p2p, ps);
+  // called after the sweep's grid barrier: gradient entries [j0, j1) -> out (this CTA's slice), returns sum of r_i^2 over ALL rows
+  auto finish_gradient = [&](double* out) -> double {
+    if (!sharded) {
+      fused_gradient_slice(fa, j0, j1, out);
+      return fused_fsum(fa, scr);
+    }
+    fused_gradient_slice(fa, j0, j1, fa.sh_gbuf);            // this rank's partial
+    const double f0 = fused_fsum(fa, scr);
+    if (b == 0 && threadIdx.x == 0) { fa.sh_gbuf[P.n] = f0; fa.sh_gbuf[P.n + 1] = 0.0; }
+    grid.sync();                                             // the whole partial vector is in place
+    p2p_allreduce<kFThreads>(fa.p2p, ps, grid, fa.sh_gbuf, fa.sh_gbuf, P.n + 2);
+    for (int64_t j = j0 + threadIdx.x; j < j1; j += kFThreads) out[j] = ldcg(fa.sh_gbuf + j);
+    return ldcg(fa.sh_gbuf + P.n);
+  };
 
   // ---- prologue (:327-332) ----------------------------------------------------------------------------------
   {
@@ -703,7 +724,7 @@ __global__ void __launch_bounds__(kFThreads, 1) k_adapgm_fused(DProblem P, DOpts
   grid.sync();
   phase_stamp(W, 1, 2);
   {
-    fused_gradient_slice(fa, j0, j1, W.gb[gc]);
+    (void)finish_gradient(W.gb[gc]);
     double acc[1] = {0.0};
     double* xn = W.xb[1];
     for (int64_t j = j0 + threadIdx.x; j < j1; j += kFThreads) {
@@ -725,6 +746,7 @@ __global__ void __launch_bounds__(kFThreads, 1) k_adapgm_fused(DProblem P, DOpts
   bool converged = false;
 
   for (int64_t it = 1; it <= O.maxit; ++it) {
+    if (p2p_failed(fa.p2p)) { flags |= ADAPROX_FLAG_COMM; it_done = it - 1; break; }   // a peer rank was lost (uniform: read after a grid barrier)
     phase_stamp(W, it, 0);
     {
       // :336 value + pullback in one sweep
@@ -737,7 +759,7 @@ __global__ void __launch_bounds__(kFThreads, 1) k_adapgm_fused(DProblem P, DOpts
     grid.sync();
     phase_stamp(W, it, 3);
     double* grad = W.gb[gc ^ 1];
-    fused_gradient_slice(fa, j0, j1, grad);
+    const double fsum_all = finish_gradient(grad);
     {
       double acc[4] = {0.0, 0.0, 0.0, 0.0};
       for (int64_t j = j0 + threadIdx.x; j < j1; j += kFThreads) {
@@ -755,7 +777,7 @@ __global__ void __launch_bounds__(kFThreads, 1) k_adapgm_fused(DProblem P, DOpts
     phase_stamp(W, it, 4);
     double t4[4], tg[1] = {0.0}, tf[1];
     f_grid_totals<4>(W.red, G, SLOT_PR, t4, scr);
-    tf[0] = fused_fsum(fa, scr);
+    tf[0] = fsum_all;
     if (want_obj) f_grid_totals<1>(W.red, G, gval_slot(it), tg, scr);
     rule_step(O, t4[1], t4[2], t4[3], gamma, sigma, s0, s1);                    // :341
     norm_res = sqrt(norm_sq_jl(t4[0]));                                         // :348 (dual part is identically zero)

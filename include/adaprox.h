@@ -153,7 +153,9 @@ typedef struct {
   double solve_ms;              /* device time of the solve (CUDA events)                */
   int64_t kernel_launches;      /* library kernels launched by this call                 */
   int64_t matrix_passes;        /* sweeps over the matrix of f per gradient evaluation: 1 = single-pass
-                                   fused A'(Ax-b) kernel, 2 = A*x then A'*r; 0 = f has no matrix        */
+                                   fused A'(Ax-b) kernel, 2 = A*x then A'*r; 0 = f has no matrix;
+                                   3 = the matrix is resident in the shared memory of one cluster for the
+                                   whole solve (small dense least squares): HBM is read once per SOLVE    */
   int64_t collective;           /* row-sharded solves: 1 = ncclAllReduce per iteration, 2 = all-reduce inside the sweep
                                    kernel over NVLink peer memory; 0 = single GPU                       */
 } adaprox_result;

@@ -158,3 +158,54 @@ def test_cubic_subproblem_solvers(AdaProx):
     # the minimiser of the cubic model: gradient vanishes
     _, gsol = O.eval_with_gradient(fo_raw, xd)
     assert np.linalg.norm(gsol) <= 10 * tol
+
+
+# ---------------------------------------------------------------- the cluster-resident small-problem kernel (solver_resident.cuh)
+@pytest.mark.parametrize("m,n", [(400, 1000), (100, 300), (7, 1), (5, 1024), (33, 517), (416, 1024)])
+def test_resident_kernel_matches_grid_kernel_and_oracle(AdaProx, m, n):
+    """Small dense least squares runs with the matrix resident in the shared memory of one 16-CTA cluster.  Shapes: the reference's
+    own lasso sizes (lasso/runme.jl:192-207), fewer rows than CTAs, a single column, the widest row (n = 1024), ragged everything,
+    and the largest matrix that still fits; every stepsize rule; box and translated-l1 prox; maxit = 0 and 1."""
+    import os
+    rng = np.random.default_rng(m * 31 + n)
+    A = np.asfortranarray(rng.standard_normal((m, n)) / np.sqrt(max(m, 2)))
+    b = rng.standard_normal(m)
+    Lf = float(np.linalg.norm(A, 2) ** 2) if min(m, n) > 1 else float(np.sum(A * A))
+    c = 0.1 * rng.standard_normal(n)
+    x0 = 0.05 * rng.standard_normal(n)
+    cases = [("our", AdaProx.NormL1(0.3), O.NormL1(0.3)), ("mm", AdaProx.IndBox(-0.2, 0.5), O.IndBox(-0.2, 0.5)),
+             ("fixed", AdaProx.Translate(AdaProx.NormL1(0.2), -c), O.Translate(O.NormL1(0.2), -c)), ("plus", AdaProx.Zero(), O.Zero())]
+    f = AdaProx.LinearLeastSquares(A, b)
+    for rule, gd, go in cases:
+        mk = {"our": lambda M: M.OurRule(gamma=1 / Lf), "mm": lambda M: M.MalitskyMishchenkoRule(gamma=1 / Lf),
+              "fixed": lambda M: M.FixedStepsize(1 / Lf), "plus": lambda M: M.OurRulePlus(gamma=1 / Lf)}[rule]
+        logo = []
+        xo, ito = O.adaptive_proxgrad(x0, f=O.LinearLeastSquares(A, b), g=go, rule=mk(O), tol=1e-9, maxit=60, log=logo)
+        got = {}
+        for mode in ("1", "0"):
+            os.environ["ADAPROX_RESIDENT"] = mode
+            try:
+                fc = AdaProx.Counting(f)
+                log = []
+                x, it = AdaProx.adaptive_proxgrad(x0, f=fc, g=gd, rule=mk(AdaProx), tol=1e-9, maxit=60, log=log)
+                got[mode] = (x, it, log, AdaProx.last_solve_info()["matrix_passes"], (fc.eval_count, fc.grad_count))
+            finally:
+                os.environ.pop("ADAPROX_RESIDENT", None)
+        assert got["1"][3] == 3 and got["0"][3] == 2, "kernel selection"
+        for mode in ("1", "0"):
+            x, it, log, _, counts = got[mode]
+            assert it == ito and counts == (it + 1, it + 1), (rule, mode, it, ito)
+            k = min(25, len(log))
+            assert np.max(np.abs(_gam(log, k) / _gam(logo, k) - 1)) < 1e-11, (rule, mode)
+            assert np.allclose([r["objective"] for r in log[:k]], [r["objective"] for r in logo[:k]], rtol=1e-11, atol=1e-300), (rule, mode)
+            assert np.allclose([r["norm_res"] for r in log[:k]], [r["norm_res"] for r in logo[:k]], rtol=1e-9, atol=1e-14), (rule, mode)
+            assert np.linalg.norm(x - xo) <= 1e-9 * max(np.linalg.norm(xo), 1e-12), (rule, mode)
+    for maxit in (0, 1):
+        os.environ["ADAPROX_RESIDENT"] = "1"
+        try:
+            x, it = AdaProx.adaptive_proxgrad(x0, f=f, g=AdaProx.NormL1(0.3), rule=AdaProx.OurRule(gamma=1 / Lf), tol=0.0, maxit=maxit)
+        finally:
+            os.environ.pop("ADAPROX_RESIDENT", None)
+        xo, ito = O.adaptive_proxgrad(x0, f=O.LinearLeastSquares(A, b), g=O.NormL1(0.3), rule=O.OurRule(gamma=1 / Lf), tol=0.0, maxit=maxit)
+        assert it == ito == maxit and np.linalg.norm(x - xo) <= 1e-13 * max(np.linalg.norm(xo), 1e-12)
+    f.mat.free()
