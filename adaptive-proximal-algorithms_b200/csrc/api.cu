@@ -710,6 +710,8 @@ static void fused_print_probe(const FusedPlan& pl, const char* what) {
 static bool resident_eligible(adaprox_ctx* h, const adaprox_options* o, const DProblem& P, ResidentArgs* ra, size_t* smem) {
   const char* e = std::getenv("ADAPROX_RESIDENT");
   if (e && std::strcmp(e, "0") == 0) return false;
+  const char* ef = std::getenv("ADAPROX_FUSED");
+  if (ef && std::strcmp(ef, "1") == 0) return false;       // the sweep kernel was requested explicitly
   if (o->solver != ADAPROX_S_ADAPTIVE_PROXGRAD || P.f_kind != ADAPROX_F_LEAST_SQUARES || P.F.kind != MAT_DENSE) return false;
   if (P.g.kind == ADAPROX_P_NORM_L2 || P.g.conjugate) return false;
   if (P.F.ld > kRMaxLd || P.n < 1) return false;

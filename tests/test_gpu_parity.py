@@ -624,6 +624,7 @@ def test_fused_single_pass_matches_two_pass_and_oracle(AdaProx, m, n, pf):
     try:
         for mode in ("0", "1"):
             os.environ["ADAPROX_FUSED"] = mode
+            os.environ["ADAPROX_RESIDENT"] = "0"          # mode 0 = the two-pass grid kernel (the 400 x 1000 case would run cluster-resident)
             f = AdaProx.Counting(f_raw)
             log = []
             x, it = AdaProx.adaptive_proxgrad(np.zeros(n), f=f, g=AdaProx.NormL1(1.0), rule=AdaProx.OurRule(gamma=1 / Lf),
@@ -631,6 +632,7 @@ def test_fused_single_pass_matches_two_pass_and_oracle(AdaProx, m, n, pf):
             runs[mode] = (x, it, log, AdaProx.last_solve_info())
     finally:
         os.environ.pop("ADAPROX_FUSED", None)
+        os.environ.pop("ADAPROX_RESIDENT", None)
     logo = []
     xo, ito = O.adaptive_proxgrad(np.zeros(n), f=O.LinearLeastSquares(P["A"], P["b"]), g=O.NormL1(1.0), rule=O.OurRule(gamma=1 / Lf),
                                   tol=1e-6, maxit=3000, log=logo)
@@ -785,6 +787,7 @@ def test_fused_edge_cases(AdaProx):
         res = {}
         for mode in ("0", "1"):
             os.environ["ADAPROX_FUSED"] = mode
+            os.environ["ADAPROX_RESIDENT"] = "0"          # this test compares the sweep kernel with the two-pass grid kernel
             for k, v in (env or {}).items():
                 os.environ[k] = v
             try:
@@ -794,6 +797,7 @@ def test_fused_edge_cases(AdaProx):
                 res[mode] = (x, it, [r["gamma"] for r in log], [r["objective"] for r in log], AdaProx.last_solve_info()["matrix_passes"])
             finally:
                 os.environ.pop("ADAPROX_FUSED", None)
+                os.environ.pop("ADAPROX_RESIDENT", None)
                 for k in (env or {}):
                     os.environ.pop(k, None)
         return res
