@@ -811,7 +811,7 @@ extern "C" int adaprox_solve(adaprox_handle h, const adaprox_problem* p, const a
   const int fQ = fpl.Q;
   const int64_t nfu = (P.f_kind == ADAPROX_F_QUADRATIC_GRAM) ? P.F.n : 1;
   size_t need = (fused ? fused_ws_bytes(fpl) : 0) + (sharded_fused ? ws_size_doubles(n + 2) : 0) +
-                11 * ws_size_doubles(n) + 6 * ws_size_doubles(md) + ws_size_doubles(mf) + ws_size_doubles(nfu) +
+                9 * ws_size_doubles(n) + 2 * ws_size_doubles(n + 8) + 6 * ws_size_doubles(md) + ws_size_doubles(mf) + ws_size_doubles(nfu) +
                 ws_size_doubles((int64_t)kMaxRed * G) + ws_size_doubles((nrec * (int64_t)sizeof(adaprox_record) + 7) / 8) +
                 ws_size_doubles((sizeof(DResult) + 7) / 8);
   if ((rc = ws_reset(h, need))) return rc;
@@ -819,7 +819,7 @@ extern "C" int adaprox_solve(adaprox_handle h, const adaprox_problem* p, const a
   for (int k = 0; k < 3; ++k) W.xb[k] = ws_doubles(h, n);
   for (int k = 0; k < 2; ++k) W.gb[k] = ws_doubles(h, n);
   W.v = ws_doubles(h, n);
-  for (int k = 0; k < 2; ++k) W.Aty[k] = ws_doubles(h, n);
+  for (int k = 0; k < 2; ++k) W.Aty[k] = ws_doubles(h, n + 8);          // + the row sums that ride along in the sharded exchange
   for (int k = 0; k < 3; ++k) W.aux[k] = ws_doubles(h, n);
   for (int k = 0; k < 2; ++k) W.yb[k] = ws_doubles(h, md);
   W.w = ws_doubles(h, md);

@@ -243,8 +243,21 @@ __global__ void __launch_bounds__(kThreads, 2) k_primal_dual(DProblem P, DOpts O
         grid.sync();
         double t2[2];
         grid_totals<2>(W.red, G, SLOT_DR, t2, s_scr);
-        if (shardedA) p2p_allreduce_scalars<2>(P.p2p, ps, grid, t2);                          // |dual_res|^2, h value
-        dr_sum = t2[0]; h_sum = t2[1];
+        if (!shardedA) {
+          dr_sum = t2[0]; h_sum = t2[1];
+        } else {
+          // Row-sharded A: |dual_res|^2 and the h value are sums over ALL row blocks, and so is A'y+.  One exchange carries
+          // the three of them (n + 2 doubles): A'y+ is formed here, BEFORE the convergence test that src/AdaProx.jl:348-358
+          // runs first -- speculative work on the last iteration only (not counted: see n_amul below), one NVLink round trip
+          // per iteration instead of two.
+          gemv_t_phase(P.A, ynew, sh, b, G);                                          // :358 (speculative)
+          grid.sync();
+          gsum_slice(P.A, j0, j1, W.Aty[atc], G);
+          if (b == 0 && threadIdx.x == 0) { W.Aty[atc][P.n] = t2[0]; W.Aty[atc][P.n + 1] = t2[1]; }
+          grid.sync();
+          p2p_allreduce<kThreads>(P.p2p, ps, grid, W.Aty[atc], W.Aty[atc], P.n + 2);
+          dr_sum = ldcg(W.Aty[atc] + P.n); h_sum = ldcg(W.Aty[atc] + P.n + 1);
+        }
       }
     } else {
       // ---- AdaPDM+ linesearch (:507-533) ----------------------------------------
@@ -258,6 +271,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_primal_dual(DProblem P, DOpts O
       ynew = W.yb[yc ^ 1];
       double* aty_next = W.Aty[atc ^ 1];
       double gamma_next = gamma;
+      double ls_dy = 0.0, ls_dr = 0.0, ls_h = 0.0;
       for (int trial = 0;; ++trial) {
         gamma_next = jl_min(jl_min(gamma * sqrt(1.0 + gamma / gamma_prev_ls), 1.0 / (2.0 * O.Theta * O.t * eta)),
                             gamma * sqrt(m4xim1 / (2.0 * delta1 * (Delta + sqrt(Delta * Delta + m4xim1 * sq(O.t * eta * gamma))))));   // :517-521
@@ -283,7 +297,16 @@ __global__ void __launch_bounds__(kThreads, 2) k_primal_dual(DProblem P, DOpts O
         n_amul++;
         grid.sync();
         gsum_slice(P.A, j0, j1, aty_next, G);
-        if (shardedA) p2p_allreduce<kThreads>(P.p2p, ps, grid, aty_next, aty_next, P.n);      // A'y_next over all row blocks
+        if (shardedA) {
+          // one exchange per trial: A'y_next and the three row sums of this trial (|y+ - y|^2, |dual_res|^2, h value)
+          double td[1], tr[2];
+          grid_totals<1>(W.red, G, SLOT_DY, td, s_scr);
+          grid_totals<2>(W.red, G, SLOT_DR, tr, s_scr);
+          if (b == 0 && threadIdx.x == 0) { aty_next[P.n] = td[0]; aty_next[P.n + 1] = tr[0]; aty_next[P.n + 2] = tr[1]; }
+          grid.sync();
+          p2p_allreduce<kThreads>(P.p2p, ps, grid, aty_next, aty_next, P.n + 3);
+          ls_dy = ldcg(aty_next + P.n); ls_dr = ldcg(aty_next + P.n + 1); ls_h = ldcg(aty_next + P.n + 2);
+        }
         {
           double acc[1] = {0.0};
           const double* aty = W.Aty[atc];
@@ -296,11 +319,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_primal_dual(DProblem P, DOpts O
         grid.sync();
         double tl[2];                               // DY, DATY
         grid_totals<2>(W.red, G, SLOT_DY, tl, s_scr);
-        if (shardedA) {                             // |y_next - y|^2 is a sum over rows; |A'y_next - A'y|^2 is already global
-          double dy[1] = {tl[0]};
-          p2p_allreduce_scalars<1>(P.p2p, ps, grid, dy);
-          tl[0] = dy[0];
-        }
+        if (shardedA) tl[0] = ls_dy;                // |y_next - y|^2 is a sum over all row blocks; |A'y_next - A'y|^2 is already global
         const bool accept = eta >= sqrt(tl[1]) / sqrt(tl[0]);                    // :527
         if (accept || trial >= 200) {
           if (!accept) flags |= ADAPROX_FLAG_LS_CAP;
@@ -312,7 +331,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_primal_dual(DProblem P, DOpts O
       }
       double t2[2];
       grid_totals<2>(W.red, G, SLOT_DR, t2, s_scr);
-      if (shardedA) p2p_allreduce_scalars<2>(P.p2p, ps, grid, t2);
+      if (shardedA) { t2[0] = ls_dr; t2[1] = ls_h; }                             // from the accepted trial's exchange
       dr_sum = t2[0]; h_sum = t2[1];
       atc ^= 1;                                                                  // :529  At_y = At_y_next
     }
@@ -335,11 +354,12 @@ __global__ void __launch_bounds__(kThreads, 2) k_primal_dual(DProblem P, DOpts O
     if (norm_res <= O.tol) { converged = true; it_done = it; break; }            // :354-356
 
     if (hasA && !LINESEARCH) {
-      gemv_t_phase(P.A, y, sh, b, G);                                                // :358
       n_amul++;
-      grid.sync();
-      gsum_slice(P.A, j0, j1, W.Aty[atc], G);
-      if (shardedA) p2p_allreduce<kThreads>(P.p2p, ps, grid, W.Aty[atc], W.Aty[atc], P.n);
+      if (!shardedA) {                                                               // sharded: already done with the scalars above
+        gemv_t_phase(P.A, y, sh, b, G);                                              // :358
+        grid.sync();
+        gsum_slice(P.A, j0, j1, W.Aty[atc], G);
+      }
     }
     // ---- P7 (:359-361) ---------------------------------------------------------------
     phase_stamp(W, it, 6);

@@ -464,9 +464,15 @@ def run_b200(args):
         if not args.nccl:
             AdaProx.sharding.attach_p2p(dev, args.n, dist)       # all-reduce inside the sweep kernel over NVLink peer memory
 
+    def stage(msg):
+        if args.verbose:
+            print(f"[bench rank {rank}] {msg}", file=sys.stderr, flush=True)
+
     parity = None
     if world > 1 and not args.no_parity:
+        stage("sharded_parity ...")
         parity = sharded_parity(AdaProx, dev, dist, world, rank)
+        stage(f"sharded_parity done: {parity.get('pass')}")
 
     m, n = args.m, args.n
     row0, rows = AdaProx.sharding.shard_rows(m, world, rank)
@@ -510,7 +516,9 @@ def run_b200(args):
         return float(t.item())
 
     W, K = max(args.warmup, 3), args.steps
+    stage(f"generated in {t_gen:.1f} s; warm-up ...")
     solve(W, 0.0, False)                                       # warm-up iterations (untimed)
+    stage("timed region ...")
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -642,6 +650,7 @@ def main():
     ap.add_argument("--to-tol", type=float, default=1e-6, help="also report the time to reach norm_res <= tol (BASELINE metric; 0 = skip)")
     ap.add_argument("--tol-maxit", type=int, default=20000)
     ap.add_argument("--reps", type=int, default=5, help="repetitions of the timed K-step solve (the median is reported)")
+    ap.add_argument("--verbose", action="store_true", help="progress markers on stderr")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the configs block (C1, C2, C3, C5 side measurements, N = 1 only)")
     ap.add_argument("--no-parity", action="store_true", help="skip the sharded_parity block (N > 1)")

@@ -121,6 +121,10 @@ function device_prox(g::ProximalOperators.Translate)
     return CProx(p.kind, 0, p.lambda, p.lo, p.hi, p.lo_vec, p.hi_vec, upload(g.b))
 end
 device_prox(c::AdaProx.Counting) = device_prox(c.f)
+function device_prox(c::ProximalCore.ConvexConjugate)          # conjugate flag: Moreau on the device (src/AdaProx.jl:325 applies it to h)
+    p = device_prox(c.f)
+    return CProx(p.kind, 1, p.lambda, p.lo, p.hi, p.lo_vec, p.hi_vec, p.shift)
+end
 
 rule_fields(r::AdaProx.FixedStepsize) = (0, r.gamma, r.t, 0.0, 0.0, 1.2, 1.0, 1.0, 0.5)
 rule_fields(r::AdaProx.MalitskyMishchenkoRule) = (1, r.gamma, r.t, 0.0, 0.0, 1.2, 1.0, 1.0, 0.5)
@@ -204,6 +208,69 @@ function backtracking_nesterov(x0; f, g, gamma0, shrink = 0.5, tol = 1e-5, maxit
 end
 
 
+function fixed_nesterov(x0; f, g, Lf = nothing, muf = 0, mug = 0, gamma = nothing, theta = nothing, tol = 1e-5, maxit = 100_000,
+                        name = "Fixed Nesterov")                                                                       # :91
+    @assert (gamma === nothing) != (Lf === nothing)
+    gamma === nothing && (gamma = 1 / Lf)
+    o = options(5; rule = (0, gamma, 1.0, 0.0, 0.0, 1.2, 1.0, 1.0, 0.5), muf, mug, theta = theta === nothing ? -1.0 : theta, tol, maxit,
+                want = Int32(logging_active()), counting = cflags(f, g, nothing, nothing))
+    xs, _, it = solve(5, x0, nothing; f, g, opts = o, name, pd = false)
+    return xs, it
+end
+function malitsky_pock(x, y; f, g, h, A, sigma, t = 1.0, tol = 1e-5, maxit = 10_000, name = "MP-ls")                    # :581
+    o = options(6; rule = (0, 0.0, t, 0.0, 0.0, 1.2, 1.0, 1.0, 0.5), sigma, tol, maxit, want = Int32(logging_active()), counting = cflags(f, g, h, A))
+    return solve(6, x, y; f, g, h, A, opts = o, name, pd = true)
+end
+function agraal(x1; f, g, x0 = nothing, gamma0 = nothing, gamma_max = 1e6, phi = 1.5, tol = 1e-5, maxit = 100_000, name = "aGRAAL")   # :150
+    x0 === nothing && (x0 = x1 + randn(size(x1)))                                                                     # :162-164
+    o = options(7; rule = (0, gamma0 === nothing ? 0.0 : gamma0, 1.0, 0.0, 0.0, 1.2, 1.0, 1.0, 0.5), gamma_max, phi, tol, maxit,
+                want = Int32(logging_active()), counting = cflags(f, g, nothing, nothing))
+    xs, _, it = solve(7, x1, x0; f, g, opts = o, name, pd = false)      # the second start point travels in the y0 slot
+    return xs, it
+end
+
+# src/AdaProx.jl:423-455: the stepsize estimate is a handful of oracle calls (device calls through eval_f / prox_eval), the loop
+# is the persistent kernel.  `gamma = nothing` cannot run in the reference (:431 calls prox without g) and is not offered.
+function eval_with_gradient(f, x)
+    fo = device_oracle(unwrap(f)); n = length(x)
+    prob = CProblem(fo.kind, fo.ipar, fo.mat, fo.vec, fo.c, noprox(), noprox(), 0, n, 0)
+    fx = Ref{Float64}(0.0); grad = Vector{Float64}(undef, n); xv = Vector{Float64}(x)
+    check(ccall((:adaprox_eval_f, lib), Cint, (Handle, Ref{CProblem}, Ptr{Float64}, Ref{Float64}, Ptr{Float64}), handle(), prob, xv, fx, grad))
+    return fx[], grad
+end
+function prox(g, x, gamma)
+    y = Vector{Float64}(undef, length(x)); gy = Ref{Float64}(0.0); xv = Vector{Float64}(x)
+    check(ccall((:adaprox_prox_eval, lib), Cint, (Handle, Ref{CProx}, Ptr{Float64}, Int64, Float64, Ptr{Float64}, Ref{Float64}),
+                handle(), device_prox(g), xv, length(xv), Float64(gamma), y, gy))
+    return y, gy[]
+end
+function auto_adaptive_proxgrad(x; f, g, gamma, tol = 1e-5, maxit = 100_000, name = "AutoAdaPGM")
+    _, grad_x = eval_with_gradient(f, x)
+    norm(grad_x) <= tol && return x, 0
+    @assert gamma > 0
+    x_prev, grad_x_prev, gamma_prev = x, grad_x, gamma
+    x, _ = prox(g, x - gamma * grad_x, gamma)
+    _, grad_x = eval_with_gradient(f, x)
+    L = dot(grad_x - grad_x_prev, x - x_prev) / norm(x - x_prev)^2
+    gamma = iszero(L) ? sqrt(2) * gamma : 1 / L
+    if gamma_prev / gamma > 1e5
+        x, _ = prox(g, x_prev - gamma * grad_x_prev, gamma)
+        _, grad_x = eval_with_gradient(f, x)
+        L = dot(grad_x - grad_x_prev, x - x_prev) / norm(x - x_prev)^2
+        gamma = iszero(L) ? sqrt(2) * gamma : 1 / L
+    end
+    return adaptive_proxgrad(x_prev; f, g, rule = AdaProx.OurRule(; gamma, t = 1, norm_A = 0, delta = 0, Theta = 1.2), tol, maxit, name)
+end
+
+# cubic_sparse_logreg/runme.jl:34-45 on the device: (H, g) of the logistic loss at w, the setup of Cubic(H, g, lam)
+function logistic_loss_grad_Hessian(X, y, w)
+    n1 = size(X, 2) + 1
+    H = Matrix{Float64}(undef, n1, n1); g = Vector{Float64}(undef, n1); wv = Vector{Float64}(w)
+    check(ccall((:adaprox_logistic_grad_hessian, lib), Cint, (Handle, Id, Id, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                handle(), upload(X), upload(y), wv, H, g))
+    return H, g
+end
+
 # ---- batched multi-lambda lasso path (include/adaprox.h: adaprox_solve_lambda_path) ---------------------------
 # Column j of the result is what `adaptive_proxgrad(X0[:, j]; f, g = NormL1(lambdas[j]), rule, tol, maxit)` returns; the L
 # columns advance together so that A*X and A'*R are FP64 tensor-core contractions.  NOT EXECUTED (no Julia in the build image).
@@ -236,5 +303,8 @@ function attach_p2p(n_max::Integer, nranks::Integer, rank::Integer, allgather::F
     all = allgather(mine)::Vector{UInt8}                      # 64 * nranks bytes
     check(ccall((:adaprox_p2p_attach, lib), Cint, (Handle, Cint, Cint, Ptr{UInt8}), handle(), nranks, rank, all))
 end
+
+# after a sharded solve failed with status -4 (a peer did not arrive): every rank calls this, then a host barrier
+p2p_reset() = check(ccall((:adaprox_p2p_reset, lib), Cint, (Handle,), handle()))
 
 end # module

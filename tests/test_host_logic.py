@@ -60,6 +60,38 @@ def test_enum_values_match_the_header():
         assert m and int(m.group(1)) == enums[kind], fn
 
 
+def test_julia_shim_struct_layouts_match_the_header():
+    """julia/AdaProxCUDA.jl cannot be executed here (no Julia): at least its isbits structs must list the header's fields in the
+    header's order with the matching Julia types, and every `ccall` must name an exported symbol."""
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "adaprox.h")).read(), flags=re.S)
+    jl = open(os.path.join(ROOT, "julia", "AdaProxCUDA.jl")).read()
+    ctype = {"int32_t": "Int32", "uint32_t": "UInt32", "int64_t": "Int64", "adaprox_id": "Id", "double": "Float64",
+             "adaprox_prox": "CProx"}
+
+    def c_fields(name):
+        body = re.search(r"typedef struct \{([^{}]*)\} %s;" % name, hdr).group(1)
+        out = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            ty, names = decl.split(None, 1)
+            out += [(n.strip(), ctype[ty]) for n in names.split(",")]
+        return out
+
+    def jl_fields(name):
+        body = re.search(r"struct %s\n(.*?)\n(?:    \w+\(\) = new|end)" % name, jl, flags=re.S).group(1)
+        return [(m.group(1), m.group(2)) for m in re.finditer(r"(\w+)::(\w+)", body)]
+
+    for cname, jname in [("adaprox_prox", "CProx"), ("adaprox_problem", "CProblem"), ("adaprox_options", "COptions"),
+                         ("adaprox_record", "CRecord"), ("adaprox_result", "CResult")]:
+        cf, jf = c_fields(cname), jl_fields(jname)
+        assert [t for _, t in cf] == [t for _, t in jf], (cname, cf, jf)
+        assert [n for n, _ in cf] == [n for n, _ in jf], (cname, [n for n, _ in cf], [n for n, _ in jf])
+    called = set(re.findall(r"ccall\(\(:(adaprox_\w+), lib\)", jl))
+    assert called and called <= set(L.SYMBOLS), called - set(L.SYMBOLS)
+
+
 def test_no_cpu_fallback_without_a_gpu():
     import torch
     if torch.cuda.is_available():
