@@ -202,6 +202,8 @@ extern "C" int adaprox_create(adaprox_handle* out, int device) {
   h->device = device; h->sm_count = prop.multiProcessorCount; h->cc_major = prop.major; h->cc_minor = prop.minor;
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return ADAPROX_ERR_CUDA; }
   cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1);
+  if (cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking) != cudaSuccess) { delete h; return ADAPROX_ERR_CUDA; }
+  cudaEventCreateWithFlags(&h->ev_h, cudaEventDisableTiming);
   // resident CTAs per SM: the minimum over the persistent kernels
   int per_sm = 2, nb = 0;
   const void* kernels[] = {(const void*)k_primal_dual<false>, (const void*)k_primal_dual<true>, (const void*)k_ops,
@@ -230,6 +232,8 @@ extern "C" int adaprox_destroy(adaprox_handle h) {
   for (auto& kv : h->vecs) cudaFree(kv.second.p);
   if (h->ws) cudaFree(h->ws);
   cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
+  if (h->ev_h) cudaEventDestroy(h->ev_h);
+  if (h->stream2) { cudaStreamSynchronize(h->stream2); cudaStreamDestroy(h->stream2); }
   cudaStreamDestroy(h->stream);
   delete h;
   return ADAPROX_OK;
@@ -633,6 +637,18 @@ static int fused_plan(adaprox_ctx* h, const void* kernel, const DProblem& P, boo
   int rc = fused_config(h, kernel, pl->fa.C, cooperative, &pl->cfg, pl->attrs, &pl->Q);
   if (rc) return rc;
   pl->G = pl->fa.C * pl->Q;
+  // persistent launches (`cooperative`): tagged chunk dispenser, and helper CTAs on the SMs the clusters leave idle -- virtual
+  // clusters of 16 (solver_fused_helper.cuh).  ADAPROX_HELPERS=V overrides (0: none), ADAPROX_HELPER_ROWS=R rows per helper batch.
+  pl->fa.tagged = cooperative ? 1 : 0;
+  pl->fa.hV = 0; pl->fa.hR = 8;
+#if ADAPROX_FUSED_VARIANT == 1
+  if (cooperative && pl->fa.C == kFMaxCluster) {
+    int V = (h->sm_count - pl->G) / kFMaxCluster;
+    if (const char* e = std::getenv("ADAPROX_HELPERS")) V = std::min(V, std::max(0, std::atoi(e)));
+    pl->fa.hV = std::min(V, 4);
+    if (const char* e = std::getenv("ADAPROX_HELPER_ROWS")) pl->fa.hR = std::min(64, std::max(1, std::atoi(e)));
+  }
+#endif
   pl->fa.npadf = (int64_t)pl->fa.C * kFCols;
   // chunk size: k chunks per cluster, k = 8 for long sweeps and 4 for short ones (row shards at N = 8).  A chunk boundary costs a
   // cluster barrier, an atomic, the reload of x and a refill of the 3-slot ring (~10 us); chunks of ceil(m / (Q k)) rows make the
@@ -647,7 +663,8 @@ static int fused_plan(adaprox_ctx* h, const void* kernel, const DProblem& P, boo
   return 0;
 }
 static size_t fused_ws_bytes(const FusedPlan& pl) {
-  return ws_size_doubles((int64_t)pl.fa.nchunks * pl.fa.npadf) + ws_size_doubles(pl.fa.nchunks) + 3 * ws_size_doubles(1) +
+  return ws_size_doubles((int64_t)pl.fa.nchunks * pl.fa.npadf) + ws_size_doubles(pl.fa.nchunks) + 5 * ws_size_doubles(1) + ws_size_doubles(2 + 2 * 4) +
+         ws_size_doubles((int64_t)4 * 2 * 64 * kFMaxCluster * kFGWarps) +
          ws_size_doubles(4 * 256) + ws_size_doubles(5 * kFTraceRows);
 }
 static int fused_ws_alloc(adaprox_ctx* h, FusedPlan* pl) {
@@ -657,6 +674,13 @@ static int fused_ws_alloc(adaprox_ctx* h, FusedPlan* pl) {
   fa.bar = reinterpret_cast<unsigned long long*>(ws_doubles(h, 1));
   fa.next = reinterpret_cast<unsigned long long*>(ws_doubles(h, 1));
   fa.err = reinterpret_cast<int*>(ws_doubles(h, 1));
+  fa.go = reinterpret_cast<unsigned long long*>(ws_doubles(h, 1));
+  fa.done = reinterpret_cast<unsigned long long*>(ws_doubles(h, 1));
+  fa.hsync = reinterpret_cast<unsigned long long*>(ws_doubles(h, 2 + 2 * 4));
+  fa.hxch = ws_doubles(h, (int64_t)4 * 2 * 64 * kFMaxCluster * kFGWarps);
+  AP_CUDA(h, cudaMemsetAsync(fa.go, 0, 8, h->stream));
+  AP_CUDA(h, cudaMemsetAsync(fa.done, 0, 8, h->stream));
+  AP_CUDA(h, cudaMemsetAsync(fa.hsync, 0, (2 + 2 * 4) * 8, h->stream));
   AP_CUDA(h, cudaMemsetAsync(fa.bar, 0, 8, h->stream));
   AP_CUDA(h, cudaMemsetAsync(fa.next, 0, 8, h->stream));
   AP_CUDA(h, cudaMemsetAsync(fa.err, 0, 8, h->stream));
@@ -858,6 +882,8 @@ extern "C" int adaprox_solve(adaprox_handle h, const adaprox_problem* p, const a
   }
   AP_CUDA(h, cudaMemsetAsync(W.red, 0, (size_t)kMaxRed * G * 8, h->stream));
   const int64_t launches0 = h->launches;
+  bool helper_launched = false;
+  AP_CUDA(h, cudaEventRecord(h->ev_h, h->stream));          // workspace initialised (what the helper launch waits for)
   AP_CUDA(h, cudaEventRecord(h->ev0, h->stream));
   void* args[] = {&P, &O, &W};
   void* fargs[] = {&P, &O, &W, &fa};
@@ -882,6 +908,20 @@ extern "C" int adaprox_solve(adaprox_handle h, const adaprox_problem* p, const a
         cudaError_t e = cudaLaunchKernelExC(&fpl.cfg, (const void*)k_adapgm_fused, fargs);
         if (e != cudaSuccess) return fail(h, ADAPROX_ERR_CUDA, std::string("fused cluster launch: ") + cudaGetErrorString(e));
         h->launches++;
+#if ADAPROX_FUSED_VARIANT == 1
+        if (fa.hV > 0) {
+          // helper CTAs beside the clusters: a plain launch on a second stream that only waits for the workspace initialisation (ev_h,
+          // recorded before the main launch); they land on the SMs the resident cluster kernel leaves idle.  Optional by construction
+          // (roll call in the kernel), so a failure to launch them is not an error.
+          if (cudaFuncSetAttribute((const void*)k_adapgm_helper, cudaFuncAttributeMaxDynamicSharedMemorySize, kFRingBytes) == cudaSuccess &&
+              cudaStreamWaitEvent(h->stream2, h->ev_h, 0) == cudaSuccess) {
+            k_adapgm_helper<<<fa.hV * kFMaxCluster, kFThreads, kFRingBytes, h->stream2>>>(P, W, fa);
+            if (cudaGetLastError() == cudaSuccess) { h->launches++; helper_launched = true; }
+          } else {
+            cudaGetLastError();
+          }
+        }
+#endif
         rc = ADAPROX_OK;
       } else {
         rc = coop_launch(h, k_primal_dual<false>, args, Gcoop);
@@ -909,6 +949,7 @@ extern "C" int adaprox_solve(adaprox_handle h, const adaprox_problem* p, const a
   AP_CUDA(h, cudaMemcpyAsync(x_out, W.xout, (size_t)n * 8, cudaMemcpyDeviceToHost, h->stream));
   if (y_out && P.md > 0) AP_CUDA(h, cudaMemcpyAsync(y_out, W.yout, (size_t)P.md * 8, cudaMemcpyDeviceToHost, h->stream));
   AP_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (helper_launched) AP_CUDA(h, cudaStreamSynchronize(h->stream2));     // they leave on the exit tag the main kernel writes last
   if (fused) fused_print_probe(fpl, "fused");
   if (fused && (rc = fused_check(h, fpl))) return rc;
   if (records && dr.n_records > 0)

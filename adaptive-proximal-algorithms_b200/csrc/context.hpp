@@ -29,6 +29,8 @@ struct Comm;   // comm.cu
 struct adaprox_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;    // helper CTAs of the single-sweep kernel run beside it (solver_fused_helper.cuh)
+  cudaEvent_t ev_h = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int sm_count = 0, cc_major = 0, cc_minor = 0;
   int grid = 0;                  // CTAs of every persistent kernel (SMs x resident CTAs)

@@ -81,6 +81,14 @@ struct FusedArgs {
   double* sh_gbuf;
   const int* sh_done;            // the solve has stopped: do nothing
   P2PArgs p2p;                   // in-kernel all-reduce over peer-mapped buffers (p2p.cuh); p2p.n <= 1: ncclAllReduce by the host
+  // Helper CTAs on the SMs no 16-CTA cluster can occupy (k_adapgm_helper, persistent mode only; hV = 0: none).  They take row
+  // chunks from the same dispenser and leave the same per-chunk partials, so the result does not depend on who processed what.
+  int tagged;                    // dispenser protocol: value = (sweep << 32) | index, reset by CTA 0 before the barrier that precedes a sweep
+  int hV, hR;                    // virtual clusters of 16 helper CTAs; rows per helper batch
+  unsigned long long* go;        // sweep whose iterate is complete (written after that barrier); helpers wait for go >= tag
+  unsigned long long* done;      // chunks completed so far, all sweeps, by main clusters and helpers alike
+  unsigned long long* hsync;     // [0] roll call, [1] abort, [2 .. 2 + hV) barrier counters, [2 + hV .. 2 + 2 hV) chunk mailboxes of the virtual clusters
+  double* hxch;                  // [hV][2][hR][16 * 8] partial dots of a helper batch (global memory instead of DSMEM)
   int* err;                      // set by a CTA whose grid barrier timed out (GridBar); checked by the host after the solve
   unsigned long long* lat;       // optional [grid][4] probe (ADAPROX_FUSED_LAT): chunks taken, sweep ns, -, smid
   unsigned long long* trace;     // build flag ADAPROX_FUSED_TRACE only: [5][kFTraceRows] clock64 stamps of CTA 0 (issue, full, dot done, exchange complete, update done)
@@ -480,7 +488,12 @@ __device__ __forceinline__ void fused_sweep(const DMat& M, const double* bvec, c
   int taken = 0;
   for (;;) {
     if (rank == 0 && threadIdx.x == 0) {
-      const long long c = (long long)(atomicAdd(fa.next, 1ull) - base);
+      long long c;
+      if (fa.tagged) {
+        c = (long long)(atomicAdd(fa.next, 1ull) & 0xffffffffull);           // tag = this sweep: reset before the preceding grid barrier
+      } else {
+        c = (long long)(atomicAdd(fa.next, 1ull) - base);
+      }
       for (int p = 0; p < fa.C; ++p) {
         uint32_t raddr;
         asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(mailbox), "r"(p));
@@ -489,6 +502,8 @@ __device__ __forceinline__ void fused_sweep(const DMat& M, const double* bvec, c
     }
     cluster_arrive();          // release: the mailbox stores; acquire: every thread of every CTA sees its mailbox
     cluster_wait();
+    // ... and every peer's gradient stores of the previous chunk are ordered before this point: publish its completion
+    if (fa.tagged && taken > 0 && rank == 0 && threadIdx.x == 0) { __threadfence(); atomicAdd(fa.done, 1ull); }
     long long c;
     asm volatile("ld.volatile.shared.s64 %0, [%1];" : "=l"(c) : "r"(mailbox));
     if (c >= fa.nchunks) break;
@@ -701,6 +716,32 @@ __global__ void __launch_bounds__(kFThreads, 1) k_adapgm_fused(DProblem P, DOpts
   const bool sharded = fa.p2p.n > 1;
   P2PState ps;
   p2p_begin(fa.p2p, ps);
+  // dispenser / helper protocol (fa.tagged): CTA 0 arms the dispenser for sweep s BEFORE the grid barrier that precedes it and
+  // raises `go` AFTER it (the iterate of sweep s is complete then); after a sweep every CTA waits until all chunks are done
+  auto arm_sweep = [&](unsigned long long s_next) {
+    if (fa.tagged && b == 0 && threadIdx.x == 0) asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(fa.next), "l"(s_next << 32) : "memory");
+  };
+  auto release_sweep = [&](unsigned long long s_next) {
+    if (fa.tagged && fa.hV > 0 && b == 0 && threadIdx.x == 0) asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(fa.go), "l"(s_next) : "memory");
+  };
+  auto wait_chunks = [&](unsigned long long sweeps_done) {
+    if (!(fa.tagged && fa.hV > 0)) return;                      // without helpers the grid barrier already covers every chunk
+    if (threadIdx.x == 0) {
+      const unsigned long long want = sweeps_done * (unsigned long long)fa.nchunks;
+      unsigned long long seen, t0 = 0;
+      for (unsigned spin = 0;; ++spin) {
+        asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(fa.done) : "memory");
+        if (seen >= want) break;
+        if ((spin & 4095u) == 4095u) {
+          if (*reinterpret_cast<volatile int*>(fa.err)) break;
+          const unsigned long long now = globaltimer_ns();
+          if (t0 == 0) t0 = now;
+          else if (now - t0 > kGridBarTimeoutNs) { *reinterpret_cast<volatile int*>(fa.err) = 1; __threadfence(); break; }
+        }
+      }
+    }
+    __syncthreads();
+  };
   // called after the sweep's grid barrier: gradient entries [j0, j1) -> out (this CTA's slice), returns sum of r_i^2 over ALL rows
   auto finish_gradient = [&](double* out) -> double {
     if (!sharded) {
@@ -719,9 +760,10 @@ __global__ void __launch_bounds__(kFThreads, 1) k_adapgm_fused(DProblem P, DOpts
   // ---- prologue (:327-332) ----------------------------------------------------------------------------------
   {
     phase_stamp(W, 1, 1);
-    fused_sweep(P.F, P.fvec, x, fs, fa, sweep++);
+    fused_sweep(P.F, P.fvec, x, fs, fa, sweep++);        // sweep 0: dispenser armed and `go` = 0 by the host
   }
   grid.sync();
+  wait_chunks(sweep);
   phase_stamp(W, 1, 2);
   {
     (void)finish_gradient(W.gb[gc]);
@@ -737,7 +779,9 @@ __global__ void __launch_bounds__(kFThreads, 1) k_adapgm_fused(DProblem P, DOpts
     f_block_reduce_store<1>(acc, W.red, G, gval_slot(1), scr);
   }
   n_eval = 1; n_grad = 1; n_proxg = 1;
+  arm_sweep(sweep);
   grid.sync();
+  release_sweep(sweep);
   double* x_prev = W.xb[0];
   x = W.xb[1]; xc = 1;
   double* grad_prev = W.gb[0];
@@ -757,6 +801,7 @@ __global__ void __launch_bounds__(kFThreads, 1) k_adapgm_fused(DProblem P, DOpts
     }
     n_eval++; n_grad++;
     grid.sync();
+    wait_chunks(sweep);
     phase_stamp(W, it, 3);
     double* grad = W.gb[gc ^ 1];
     const double fsum_all = finish_gradient(grad);
@@ -809,8 +854,15 @@ __global__ void __launch_bounds__(kFThreads, 1) k_adapgm_fused(DProblem P, DOpts
     n_proxg++;
     x_prev = x; xc = (xc + 1) % 3; x = W.xb[xc];
     grad_prev = grad; gc ^= 1;
+    arm_sweep(sweep);
     grid.sync();
+    release_sweep(sweep);
     phase_stamp(W, it, 7);
+  }
+  // helpers leave when the dispenser carries the exit tag
+  if (fa.tagged && b == 0 && threadIdx.x == 0) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(fa.next), "l"(0xffffffffull << 32) : "memory");
+    if (fa.hV > 0) asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(fa.go), "l"(~0ull) : "memory");
   }
 
   const int64_t tid = (int64_t)b * kFThreads + threadIdx.x, nt = (int64_t)G * kFThreads;
@@ -830,3 +882,5 @@ __global__ void __launch_bounds__(kFThreads, 1) k_adapgm_fused(DProblem P, DOpts
 }
 
 }  // namespace adaprox
+
+#include "solver_fused_helper.cuh"
