@@ -204,6 +204,13 @@ extern "C" int adaprox_create(adaprox_handle* out, int device) {
   cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1);
   if (cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking) != cudaSuccess) { delete h; return ADAPROX_ERR_CUDA; }
   cudaEventCreateWithFlags(&h->ev_h, cudaEventDisableTiming);
+  if (cudaHostAlloc((void**)&h->resident_host, 64, cudaHostAllocMapped) == cudaSuccess) {
+    *h->resident_host = 0ull;
+    if (cudaHostGetDevicePointer((void**)&h->resident_dev, h->resident_host, 0) != cudaSuccess) h->resident_dev = nullptr;
+  } else {
+    cudaGetLastError();
+    h->resident_host = nullptr;
+  }
   // resident CTAs per SM: the minimum over the persistent kernels
   int per_sm = 2, nb = 0;
   const void* kernels[] = {(const void*)k_primal_dual<false>, (const void*)k_primal_dual<true>, (const void*)k_ops,
@@ -233,6 +240,7 @@ extern "C" int adaprox_destroy(adaprox_handle h) {
   if (h->ws) cudaFree(h->ws);
   cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
   if (h->ev_h) cudaEventDestroy(h->ev_h);
+  if (h->resident_host) cudaFreeHost(h->resident_host);
   if (h->stream2) { cudaStreamSynchronize(h->stream2); cudaStreamDestroy(h->stream2); }
   cudaStreamDestroy(h->stream);
   delete h;
@@ -640,12 +648,17 @@ static int fused_plan(adaprox_ctx* h, const void* kernel, const DProblem& P, boo
   // persistent launches (`cooperative`): tagged chunk dispenser, and helper CTAs on the SMs the clusters leave idle -- virtual
   // clusters of 16 (solver_fused_helper.cuh).  ADAPROX_HELPERS=V overrides (0: none), ADAPROX_HELPER_ROWS=R rows per helper batch.
   pl->fa.tagged = cooperative ? 1 : 0;
-  pl->fa.hV = 0; pl->fa.hR = 8;
+  pl->fa.hV = 0; pl->fa.hR = 16;
 #if ADAPROX_FUSED_VARIANT == 1
   if (cooperative && pl->fa.C == kFMaxCluster) {
+    // Default: as many virtual clusters as fit the SMs the clusters leave idle (2 on B200).  Measured (same box, profiles/r02_notes.md
+    // section 7): 87.2-88.4 vs 84.1-85.5 it/s -- the helpers take ~20 % of the chunks, but the sweep kernel runs into the 1000 W
+    // power cap, so the clusters slow down by most of that.  ADAPROX_HELPERS=0 disables them.
     int V = (h->sm_count - pl->G) / kFMaxCluster;
     if (const char* e = std::getenv("ADAPROX_HELPERS")) V = std::min(V, std::max(0, std::atoi(e)));
-    pl->fa.hV = std::min(V, 4);
+    pl->fa.hV = h->resident_dev ? std::min(V, 4) : 0;
+    pl->fa.resident = h->resident_dev;
+    pl->fa.resident_seq = ++h->solve_seq;
     if (const char* e = std::getenv("ADAPROX_HELPER_ROWS")) pl->fa.hR = std::min(64, std::max(1, std::atoi(e)));
   }
 #endif
@@ -663,7 +676,7 @@ static int fused_plan(adaprox_ctx* h, const void* kernel, const DProblem& P, boo
   return 0;
 }
 static size_t fused_ws_bytes(const FusedPlan& pl) {
-  return ws_size_doubles((int64_t)pl.fa.nchunks * pl.fa.npadf) + ws_size_doubles(pl.fa.nchunks) + 5 * ws_size_doubles(1) + ws_size_doubles(2 + 2 * 4) +
+  return ws_size_doubles((int64_t)pl.fa.nchunks * pl.fa.npadf) + ws_size_doubles(pl.fa.nchunks) + 5 * ws_size_doubles(1) + ws_size_doubles(12) +
          ws_size_doubles((int64_t)4 * 2 * 64 * kFMaxCluster * kFGWarps) +
          ws_size_doubles(4 * 256) + ws_size_doubles(5 * kFTraceRows);
 }
@@ -676,11 +689,11 @@ static int fused_ws_alloc(adaprox_ctx* h, FusedPlan* pl) {
   fa.err = reinterpret_cast<int*>(ws_doubles(h, 1));
   fa.go = reinterpret_cast<unsigned long long*>(ws_doubles(h, 1));
   fa.done = reinterpret_cast<unsigned long long*>(ws_doubles(h, 1));
-  fa.hsync = reinterpret_cast<unsigned long long*>(ws_doubles(h, 2 + 2 * 4));
+  fa.hsync = reinterpret_cast<unsigned long long*>(ws_doubles(h, 12));
   fa.hxch = ws_doubles(h, (int64_t)4 * 2 * 64 * kFMaxCluster * kFGWarps);
   AP_CUDA(h, cudaMemsetAsync(fa.go, 0, 8, h->stream));
   AP_CUDA(h, cudaMemsetAsync(fa.done, 0, 8, h->stream));
-  AP_CUDA(h, cudaMemsetAsync(fa.hsync, 0, (2 + 2 * 4) * 8, h->stream));
+  AP_CUDA(h, cudaMemsetAsync(fa.hsync, 0, 12 * 8, h->stream));
   AP_CUDA(h, cudaMemsetAsync(fa.bar, 0, 8, h->stream));
   AP_CUDA(h, cudaMemsetAsync(fa.next, 0, 8, h->stream));
   AP_CUDA(h, cudaMemsetAsync(fa.err, 0, 8, h->stream));
@@ -913,7 +926,15 @@ extern "C" int adaprox_solve(adaprox_handle h, const adaprox_problem* p, const a
           // helper CTAs beside the clusters: a plain launch on a second stream that only waits for the workspace initialisation (ev_h,
           // recorded before the main launch); they land on the SMs the resident cluster kernel leaves idle.  Optional by construction
           // (roll call in the kernel), so a failure to launch them is not an error.
-          if (cudaFuncSetAttribute((const void*)k_adapgm_helper, cudaFuncAttributeMaxDynamicSharedMemorySize, kFRingBytes) == cudaSuccess &&
+          // Gate: the helpers must not become resident before the cluster kernel is (its 16-CTA clusters need whole GPC slots; helper CTAs
+          // scattered over the GPCs first would keep them from being placed -- seen as a 60 s stall).  The cluster kernel reports through
+          // mapped host memory after its first grid barrier; wait for that (microseconds), at most 2 s.
+          bool up = false;
+          for (long spin = 0; spin < 20000000L; ++spin) {
+            if (*(volatile unsigned long long*)h->resident_host == fa.resident_seq) { up = true; break; }
+            if ((spin & 1023) == 1023 && cudaStreamQuery(h->stream) != cudaErrorNotReady) break;      // the solve is already over (or failed)
+          }
+          if (up && cudaFuncSetAttribute((const void*)k_adapgm_helper, cudaFuncAttributeMaxDynamicSharedMemorySize, kFRingBytes) == cudaSuccess &&
               cudaStreamWaitEvent(h->stream2, h->ev_h, 0) == cudaSuccess) {
             k_adapgm_helper<<<fa.hV * kFMaxCluster, kFThreads, kFRingBytes, h->stream2>>>(P, W, fa);
             if (cudaGetLastError() == cudaSuccess) { h->launches++; helper_launched = true; }
@@ -951,6 +972,12 @@ extern "C" int adaprox_solve(adaprox_handle h, const adaprox_problem* p, const a
   AP_CUDA(h, cudaStreamSynchronize(h->stream));
   if (helper_launched) AP_CUDA(h, cudaStreamSynchronize(h->stream2));     // they leave on the exit tag the main kernel writes last
   if (fused) fused_print_probe(fpl, "fused");
+  if (fused && fa.hV > 0 && std::getenv("ADAPROX_HELPER_STATS")) {
+    unsigned long long hs[12];
+    cudaMemcpy(hs, fa.hsync, sizeof(hs), cudaMemcpyDeviceToHost);
+    std::fprintf(stderr, "[adaprox helpers: V=%d R=%d launched=%d roll=%llu abort=%llu chunks by helpers=%llu of %lld (%d chunks per sweep)]\n", fa.hV, fa.hR,
+                 (int)helper_launched, hs[0], hs[1], hs[10], (long long)(dr.f_evals) * fa.nchunks, fa.nchunks);
+  }
   if (fused && (rc = fused_check(h, fpl))) return rc;
   if (records && dr.n_records > 0)
     AP_CUDA(h, cudaMemcpy(records, W.rec, (size_t)dr.n_records * sizeof(adaprox_record), cudaMemcpyDeviceToHost));

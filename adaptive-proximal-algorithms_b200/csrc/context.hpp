@@ -31,6 +31,9 @@ struct adaprox_ctx {
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;    // helper CTAs of the single-sweep kernel run beside it (solver_fused_helper.cuh)
   cudaEvent_t ev_h = nullptr;
+  unsigned long long* resident_host = nullptr;   // pinned, mapped: the cluster kernel reports "all my CTAs are running" (helper launch gate)
+  unsigned long long* resident_dev = nullptr;
+  unsigned long long solve_seq = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int sm_count = 0, cc_major = 0, cc_minor = 0;
   int grid = 0;                  // CTAs of every persistent kernel (SMs x resident CTAs)

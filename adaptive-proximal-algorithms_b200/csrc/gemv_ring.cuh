@@ -62,6 +62,18 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
 }
 
+// the same with an L2 eviction policy (createpolicy): streaming data that is read once should not displace lines somebody re-reads
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p;
+}
+__device__ __forceinline__ void bulk_g2s_hint(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar, uint64_t policy) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar), "l"(policy) : "memory");
+}
+
 // once per kernel, by all threads
 __device__ __forceinline__ void sh_init(Sh& sh, unsigned char* dyn, double* scr, double* part, unsigned long long* bars) {
   sh.x = reinterpret_cast<double*>(dyn);

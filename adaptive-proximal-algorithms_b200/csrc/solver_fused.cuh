@@ -89,6 +89,8 @@ struct FusedArgs {
   unsigned long long* done;      // chunks completed so far, all sweeps, by main clusters and helpers alike
   unsigned long long* hsync;     // [0] roll call, [1] abort, [2 .. 2 + hV) barrier counters, [2 + hV .. 2 + 2 hV) chunk mailboxes of the virtual clusters
   double* hxch;                  // [hV][2][hR][16 * 8] partial dots of a helper batch (global memory instead of DSMEM)
+  unsigned long long* resident;  // mapped host word: the cluster kernel writes resident_seq once all its CTAs run (gate of the helper launch)
+  unsigned long long resident_seq;
   int* err;                      // set by a CTA whose grid barrier timed out (GridBar); checked by the host after the solve
   unsigned long long* lat;       // optional [grid][4] probe (ADAPROX_FUSED_LAT): chunks taken, sweep ns, -, smid
   unsigned long long* trace;     // build flag ADAPROX_FUSED_TRACE only: [5][kFTraceRows] clock64 stamps of CTA 0 (issue, full, dot done, exchange complete, update done)
@@ -160,8 +162,34 @@ constexpr int kFBarThreads = kFThreads;                   // the whole CTA
 #endif
 __device__ __forceinline__ void group_bar(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(kFBarThreads) : "memory"); }
 #ifndef ADAPROX_FUSED_ALLPOLL
+#ifndef ADAPROX_FUSED_TRYWAIT_NS
+#define ADAPROX_FUSED_TRYWAIT_NS 64
+#endif
+#if ADAPROX_FUSED_TRYWAIT_NS <= 0
+__device__ __forceinline__ void fmbar_wait_hint(uint32_t addr, uint32_t parity) { fmbar_wait(addr, parity); }
+#else
+// The poller of a role group suspends in hardware (mbarrier.try_wait with a SHORT time hint) instead of spinning on test_wait.
+// Alone it changes nothing (84.9 vs 84.5 it/s; hints of 32 ... 5000 ns alike) -- unlike round 1's try_wait WITHOUT a hint,
+// which was 2.3x slower -- but the sweep kernel runs into the 1000 W power cap, and with suspended pollers the helper CTAs turn
+// the freed power into throughput (93.7 vs 84.5 it/s); with spinning pollers they gained nothing.  -DADAPROX_FUSED_TRYWAIT_NS=0
+// restores the spinning poller.
+__device__ __forceinline__ void fmbar_wait_hint(uint32_t addr, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(addr), "r"(parity), "r"((uint32_t)ADAPROX_FUSED_TRYWAIT_NS) : "memory");
+  } while (!ok);
+}
+#endif
 __device__ __forceinline__ void group_wait(bool poller, int id, uint32_t addr, uint32_t parity) {
+#if ADAPROX_FUSED_TRYWAIT_NS > 0
+  if (poller) fmbar_wait_hint(addr, parity);
+#elif defined(ADAPROX_FUSED_POLL_LANE0)
+  // experiment: one LANE polls (the other 31 lanes of the polling warp wait at the warp barrier): fewer active lanes per poll
+  if (poller) { if ((threadIdx.x & 31) == 0) fmbar_wait(addr, parity); __syncwarp(); }
+#else
   if (poller) fmbar_wait(addr, parity);
+#endif
   group_bar(id);
 }
 #else
@@ -276,11 +304,12 @@ __device__ __noinline__ double fused_pass(const DMat& M, const double* bvec, con
       for (int i = 0; i < kFDepth && i < nrows; ++i) mbar_expect_tx(ctl + kOffCfull + 8 * ((g0 + i) % kFDepth), xbytes);
     uint32_t slot = g0 % kFStages, ph = (g0 / kFStages) & 1u, d = g0 % kFDepth, dph = (g0 / kFDepth) & 1u;
     int issued = 0; (void)issued;
+    const uint64_t pol = l2_policy_evict_first();     // the matrix is read once per sweep: do not let it displace what the helper CTAs re-read
     auto issue = [&](uint32_t sl, uint32_t par) {    // wait until the update warps left slot sl, then refill it
       fmbar_wait(ctl + kOffEmpty + 8 * sl, par ^ 1u);
       FTRACE(true, 0, issued); ++issued;
       mbar_expect_tx(ctl + kOffFull + 8 * sl, bytes);
-      bulk_g2s(ring + sl * kFStageBytes, src, bytes, ctl + kOffFull + 8 * sl);
+      bulk_g2s_hint(ring + sl * kFStageBytes, src, bytes, ctl + kOffFull + 8 * sl, pol);
       src += ldb;
     };
     if (producer) {
@@ -709,6 +738,10 @@ __global__ void __launch_bounds__(kFThreads, 1) k_adapgm_fused(DProblem P, DOpts
   unsigned flags = 0;
   int xc = 0, gc = 0;
   double* x = W.xb[0];
+  if (fa.hV > 0) {             // every CTA of this launch is running: the host may launch the helper CTAs now
+    grid.sync();
+    if (b == 0 && threadIdx.x == 0) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(fa.resident), "l"(fa.resident_seq) : "memory");
+  }
   // Row-sharded solve, persistent form (fa.p2p.n > 1): this rank's matrix is the row block of a larger one.  After the sweep
   // the shard's partial gradient and value sum (n + 2 doubles) are all-reduced INSIDE this kernel over NVLink peer memory
   // (p2p.cuh); every rank obtains the same bits, so the replicated stepsize / prox arithmetic below stays in lock step and the

@@ -222,11 +222,12 @@ __global__ void __launch_bounds__(kFThreads, 1) k_adapgm_helper(DProblem P, DWor
         // producer of pass A: lane 0 of the first update warp (the update warps have nothing else to do here)
         uint32_t gg = g;
         const char* src = src0;
+        const uint64_t pol = l2_policy_evict_last();      // these rows come back in pass B
         for (int i = 0; i < nb; ++i) {
           const uint32_t slot = gg % kFStages, ph = (gg / kFStages) & 1u;
-          fmbar_wait(empty0 + 8 * slot, ph ^ 1u);
+          fmbar_wait_hint(empty0 + 8 * slot, ph ^ 1u);
           mbar_expect_tx(full0 + 8 * slot, bytes);
-          bulk_g2s(ring + slot * kFStageBytes, src, bytes, full0 + 8 * slot);
+          bulk_g2s_hint(ring + slot * kFStageBytes, src, bytes, full0 + 8 * slot, pol);
           src += ldb;
           gg = (gg + 1) % 6u;
         }
@@ -273,11 +274,12 @@ __global__ void __launch_bounds__(kFThreads, 1) k_adapgm_helper(DProblem P, DWor
         // producer of pass B: lane 0 of the first dot warp
         uint32_t gg = g;
         const char* src = src0;
+        const uint64_t pol = l2_policy_evict_first();     // last use
         for (int i = 0; i < nb; ++i) {
           const uint32_t slot = gg % kFStages, ph = (gg / kFStages) & 1u;
-          fmbar_wait(empty0 + 8 * slot, ph ^ 1u);
+          fmbar_wait_hint(empty0 + 8 * slot, ph ^ 1u);
           mbar_expect_tx(full0 + 8 * slot, bytes);
-          bulk_g2s(ring + slot * kFStageBytes, src, bytes, full0 + 8 * slot);
+          bulk_g2s_hint(ring + slot * kFStageBytes, src, bytes, full0 + 8 * slot, pol);
           src += ldb;
           gg = (gg + 1) % 6u;
         }
@@ -294,7 +296,7 @@ __global__ void __launch_bounds__(kFThreads, 1) k_adapgm_helper(DProblem P, DWor
       if (tg == 0 && rho == 0) fa.fpart[c] = fsum;
     }
     vb.sync();                                        // (fence + arrival of every CTA after its stores)
-    if (rho == 0 && t == 0) { __threadfence(); atomicAdd(fa.done, 1ull); }
+    if (rho == 0 && t == 0) { __threadfence(); atomicAdd(fa.done, 1ull); atomicAdd(fa.hsync + 10, 1ull); }   // [10]: chunks the helpers processed (statistics)
   }
 }
 

@@ -8,6 +8,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <string>
 
 #define CK(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) { std::fprintf(stderr, "%s: %s\n", #x, cudaGetErrorString(e__)); std::exit(1); } } while (0)
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -52,7 +53,27 @@ __global__ void __launch_bounds__(256, 1) k_stream(const char* __restrict__ src,
   if (acc == 123.456) sink[0] = acc;
 }
 
-int main() {
+// steady mode: ./ingest_probe steady <ctas> <tile_KB> <stages> <lds passes> <seconds>: one configuration back to back (power measurements)
+int main(int argc, char** argv) {
+  if (argc >= 7 && std::string(argv[1]) == "steady") {
+    const int G = std::atoi(argv[2]), tile = std::atoi(argv[3]) * 1024, stages = std::atoi(argv[4]), touch = std::atoi(argv[5]);
+    const double secs = std::atof(argv[6]);
+    const size_t bytes = (size_t)16 << 30;
+    char* d_src; double* d_sink;
+    CK(cudaMalloc(&d_src, bytes)); CK(cudaMemset(d_src, 0, bytes)); CK(cudaMalloc(&d_sink, 8));
+    CK(cudaFuncSetAttribute((const void*)k_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    const int reps = (int)(secs / 0.0025) + 1;
+    CK(cudaEventRecord(e0));
+    for (int r = 0; r < reps; ++r) k_stream<<<G, 256, stages * tile>>>(d_src, (long long)(bytes / tile), tile, stages, touch, d_sink);
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+    std::printf("{\"probe\": \"steady HBM->smem stream\", \"ctas\": %d, \"tile_KB\": %d, \"stages\": %d, \"lds_reads_per_byte\": %d, \"seconds\": %.2f, \"GBps\": %.0f}\n",
+                G, tile / 1024, stages, touch, ms * 1e-3, (double)bytes * reps / (ms * 1e-3) / 1e9);
+    return 0;
+  }
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, 0));
   const int sms = prop.multiProcessorCount;
