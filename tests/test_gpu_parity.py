@@ -654,7 +654,8 @@ def test_fused_single_pass_matches_two_pass_and_oracle(AdaProx, m, n, pf):
         assert abs(log[-1]["objective"] - logo[-1]["objective"]) <= ftol * abs(logo[-1]["objective"]), (mode, it, ito)
         assert abs(it - ito) <= max(3, 0.05 * ito)
         assert [r["f_evals"] for r in log[:5]] == [2, 3, 4, 5, 6]
-    assert runs["1"][3]["kernel_launches"] == 1
+    # one persistent launch for the whole solve (+ the helper CTAs' launch beside it when the cluster size is 16)
+    assert runs["1"][3]["kernel_launches"] == (2 if n > 15 * 8192 else 1)
 
 
 # ---------------------------------------------------------------- LIBSVM file -> CSR upload -> solve -> JSONL records
