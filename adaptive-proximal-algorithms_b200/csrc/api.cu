@@ -655,8 +655,13 @@ static int fused_plan(adaprox_ctx* h, const void* kernel, const DProblem& P, boo
     // section 7): 87.2-88.4 vs 84.1-85.5 it/s -- the helpers take ~20 % of the chunks, but the sweep kernel runs into the 1000 W
     // power cap, so the clusters slow down by most of that.  ADAPROX_HELPERS=0 disables them.
     int V = (h->sm_count - pl->G) / kFMaxCluster;
-    if (const char* e = std::getenv("ADAPROX_HELPERS")) V = std::min(V, std::max(0, std::atoi(e)));
+    // ... for LONG sweeps only: with 8192 rows per GPU (the N = 8 shard) they cost 2 % (686.7 -> 673.4 it/s on one GPU with m = 8192: a helper
+    // chunk takes 1.7x a cluster's, the sweep is 1.4 ms), with 16384 rows they are neutral, with 65536 rows they give +5.5 % (84.3 -> 88.9)
+    if (P.F.m / std::max(pl->Q, 1) < 4096) V = 0;
+    if (const char* e = std::getenv("ADAPROX_HELPERS")) V = std::min((h->sm_count - pl->G) / kFMaxCluster, std::max(0, std::atoi(e)));
     pl->fa.hV = h->resident_dev ? std::min(V, 4) : 0;
+    pl->fa.hHold = (int)(1.7 * pl->Q) + 1;
+    if (const char* e = std::getenv("ADAPROX_HELPER_HOLD")) pl->fa.hHold = std::max(0, std::atoi(e));
     pl->fa.resident = h->resident_dev;
     pl->fa.resident_seq = ++h->solve_seq;
     if (const char* e = std::getenv("ADAPROX_HELPER_ROWS")) pl->fa.hR = std::min(64, std::max(1, std::atoi(e)));

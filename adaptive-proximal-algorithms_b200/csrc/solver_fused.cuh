@@ -85,6 +85,7 @@ struct FusedArgs {
   // chunks from the same dispenser and leave the same per-chunk partials, so the result does not depend on who processed what.
   int tagged;                    // dispenser protocol: value = (sweep << 32) | index, reset by CTA 0 before the barrier that precedes a sweep
   int hV, hR;                    // virtual clusters of 16 helper CTAs; rows per helper batch
+  int hHold;                     // helpers leave the last hHold chunks of a sweep to the clusters (a helper chunk takes ~1.7x as long: no tail)
   unsigned long long* go;        // sweep whose iterate is complete (written after that barrier); helpers wait for go >= tag
   unsigned long long* done;      // chunks completed so far, all sweeps, by main clusters and helpers alike
   unsigned long long* hsync;     // [0] roll call, [1] abort, [2 .. 2 + hV) barrier counters, [2 + hV .. 2 + 2 hV) chunk mailboxes of the virtual clusters

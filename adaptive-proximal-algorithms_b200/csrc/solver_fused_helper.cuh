@@ -120,7 +120,12 @@ __global__ void __launch_bounds__(kFThreads, 1) k_adapgm_helper(DProblem P, DWor
   for (;;) {
     // ---- take a chunk for the whole virtual cluster -------------------------------------------------------------------
     if (rho == 0 && t == 0) {
-      const unsigned long long v = atomicAdd(fa.next, 1ull);
+      // peek first: near the end of a sweep a helper chunk (two passes, ~1.7x a cluster's time) would finish after the clusters
+      // and the whole grid would wait for it -- leave the last hHold chunks to the clusters (reported as "handed out")
+      unsigned long long v;
+      asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(fa.next) : "memory");
+      if ((v >> 32) != kExitTag && (long long)(v & 0xffffffffull) < (long long)fa.nchunks - fa.hHold) v = atomicAdd(fa.next, 1ull);
+      else if ((v >> 32) != kExitTag) v = (v & ~0xffffffffull) | (unsigned long long)fa.nchunks;
       asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(mailbox), "l"(v) : "memory");
     }
     vb.sync();
