@@ -654,8 +654,8 @@ def test_fused_single_pass_matches_two_pass_and_oracle(AdaProx, m, n, pf):
         assert abs(log[-1]["objective"] - logo[-1]["objective"]) <= ftol * abs(logo[-1]["objective"]), (mode, it, ito)
         assert abs(it - ito) <= max(3, 0.05 * ito)
         assert [r["f_evals"] for r in log[:5]] == [2, 3, 4, 5, 6]
-    # one persistent launch for the whole solve (+ the helper CTAs' launch beside it when the cluster size is 16)
-    assert runs["1"][3]["kernel_launches"] == (2 if n > 15 * 8192 else 1)
+    # one persistent launch for the whole solve (the helper CTAs only join sweeps of >= 4096 rows per cluster)
+    assert runs["1"][3]["kernel_launches"] == 1
 
 
 # ---------------------------------------------------------------- LIBSVM file -> CSR upload -> solve -> JSONL records
@@ -821,6 +821,34 @@ def test_fused_edge_cases(AdaProx):
     A = np.zeros((2, n)); A[0, 0] = 1.0; A[1, n - 1] = 2.0; A[0, 5] = 0.5
     R = both(A, np.array([1.0, -1.0]), 0.01, 0.1, 20)
     assert R["1"][4] == 2 and np.array_equal(R["0"][0], R["1"][0])
+
+
+def test_helper_ctas_leave_the_same_bits(AdaProx):
+    """The helper CTAs beside the single-sweep kernel (solver_fused_helper.cuh: virtual clusters on the SMs no 16-CTA cluster can use, partial
+    dots through global memory, rows streamed twice) take chunks from the same dispenser; whoever processes a chunk must leave the same bits.
+    Full cluster width (n = 131072), tiny chunks and batches so that the helpers take part even in a short solve."""
+    import os
+    m, n = 192, 131072
+    P = AdaProx.synth.planted_lasso(m, n, 2000, 6)
+    Lf = AdaProx.synth.spectral_norm_sq(P["A"], iters=50)
+    f = AdaProx.LinearLeastSquares(P["A"], P["b"])
+    got = {}
+    for tag, env in (("off", {"ADAPROX_HELPERS": "0"}), ("on", {"ADAPROX_HELPERS": "2", "ADAPROX_HELPER_HOLD": "0", "ADAPROX_HELPER_ROWS": "3"}),
+                     ("on_b", {"ADAPROX_HELPERS": "1", "ADAPROX_HELPER_HOLD": "2", "ADAPROX_HELPER_ROWS": "16"})):
+        os.environ.update(env, ADAPROX_FUSED="1", ADAPROX_FUSED_CHUNK="4")
+        try:
+            log = []
+            x, it = AdaProx.adaptive_proxgrad(np.zeros(n), f=f, g=AdaProx.NormL1(1.0), rule=AdaProx.OurRule(gamma=1 / Lf), tol=0.0, maxit=300, log=log)
+            got[tag] = (x, [r["gamma"] for r in log], [r["objective"] for r in log], AdaProx.last_solve_info())
+        finally:
+            for k in list(env) + ["ADAPROX_FUSED", "ADAPROX_FUSED_CHUNK"]:
+                os.environ.pop(k, None)
+    assert got["off"][3]["matrix_passes"] == 1 and got["off"][3]["kernel_launches"] == 1
+    assert got["on"][3]["kernel_launches"] == 2                    # the helper launch went out
+    for tag in ("on", "on_b"):
+        assert np.array_equal(got["off"][0], got[tag][0]), tag
+        assert got["off"][1] == got[tag][1] and got["off"][2] == got[tag][2], tag
+    f.mat.free()
 
 
 def test_lambda_path_edge_cases(AdaProx):
