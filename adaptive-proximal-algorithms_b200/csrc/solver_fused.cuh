@@ -107,7 +107,8 @@ __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.w
 // cpart[8][16 ranks][8 warps].  One base register + compile-time offsets address all of it.
 constexpr uint32_t kOffFull = 0, kOffEmpty = 8 * kFStages, kOffCfull = 16 * kFStages, kOffChunk = 16 * kFStages + 8 * kFDepth, kOffCpart = 128;
 constexpr uint32_t kPartStride = kFMaxCluster * kFXWarps * 8;                 // bytes per exchange buffer
-constexpr int kCtlBytes = kOffCpart + kFDepth * kPartStride;
+constexpr uint32_t kOffRs = kOffCpart + kFDepth * kPartStride;                // r_i of the row in exchange buffer d (variant 1, one reducer warp)
+constexpr int kCtlBytes = kOffRs + kFDepth * 8;
 static_assert(kOffChunk + 8 <= kOffCpart, "control block layout");
 
 struct FusedSmem {
@@ -252,6 +253,13 @@ __device__ __noinline__ double fused_pass(const DMat& M, const double* bvec, con
     const uint32_t tile0 = ring + t * 16;
     const uint32_t mypart = ctl + kOffCpart + (rank * kFGWarps + warp) * 8;
     const bool sender = lane < C;
+    // remote addresses of this warp's slot in peer `lane`: mapped once, buffer d is a constant offset (the kernel is power-limited:
+    // every instruction taken out of the per-row loop counts, profiles/r02_notes.md section 7)
+    uint32_t rdata0 = 0, rbar0 = 0;
+    if (sender) {
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rdata0) : "r"(mypart), "r"((uint32_t)lane));
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbar0) : "r"(ctl + kOffCfull), "r"((uint32_t)lane));
+    }
     for (int i = 0; i < nrows; ++i) {
       group_wait(warp == 0, 1, ctl + kOffFull + 8 * slot, ph);
       FTRACE(t == 0, 1, i);
@@ -278,7 +286,9 @@ __device__ __noinline__ double fused_pass(const DMat& M, const double* bvec, con
         }
       }
       const double pw = warp_sum((p0 + p1) + (p2 + p3));
-      if (sender) st_async_peer(mypart + d * kPartStride, ctl + kOffCfull + 8 * d, (uint32_t)lane, pw);
+      if (sender)
+        asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];"
+                     ::"r"(rdata0 + d * kPartStride), "l"(__double_as_longlong(pw)), "r"(rbar0 + 8 * d) : "memory");
       FTRACE(t == 0, 2, i);
       if (++slot == kFStages) { slot = 0; ph ^= 1u; }
       d = (d + 1) % kFDepth;
@@ -325,6 +335,30 @@ __device__ __noinline__ double fused_pass(const DMat& M, const double* bvec, con
     const double* bp = bvec + r0;
     double bblk = 0.0;                               // lane l holds b[r0 + 32 * (i / 32) + l]
     for (int i = 0; i < nrows; ++i) {
+#if !defined(ADAPROX_FUSED_ALLPOLL) && !defined(ADAPROX_FUSED_ALL_REDUCE)
+      // ONE warp per CTA (the poller of the update group) waits for the exchange, sums the C * 8 partials in the fixed order (the same bits
+      // in every CTA of the cluster) and publishes r_i through shared memory before it joins the group barrier: the other seven warps
+      // were executing the identical reduction (22 instructions each per row, ~11 % of the kernel's instruction stream -- and the kernel
+      // is power-limited, profiles/r02_notes.md section 7).  -DADAPROX_FUSED_ALL_REDUCE restores the redundant form.
+      if (warp == kFGWarps) {
+        if ((i & 31) == 0) bblk = (i + lane < nrows) ? __ldg(bp + i + lane) : 0.0;
+        const double b_cur = __shfl_sync(0xffffffffu, bblk, i & 31);
+        // st.async delivers data and complete_tx through the same path into this CTA's shared memory, so the
+        // cta-scope wait is enough (a cluster-scope acquire compiles to CCTL.IVALL: an L1 flush per row)
+        fmbar_wait_hint(ctl + kOffCfull + 8 * d, dph);
+        const uint32_t pb = part0 + d * kPartStride;
+        const double v0 = (lane < nval) ? lds1(pb) : 0.0;
+        const double v1 = (lane + 32 < nval) ? lds1(pb + 256) : 0.0;
+        const double v2 = (lane + 64 < nval) ? lds1(pb + 512) : 0.0;
+        const double v3 = (lane + 96 < nval) ? lds1(pb + 768) : 0.0;
+        if (leader && i + kFDepth < nrows) mbar_expect_tx(ctl + kOffCfull + 8 * d, xbytes);    // arm this buffer for row g + 8
+        const double r1 = warp_sum((v0 + v1) + (v2 + v3)) - b_cur;                            // lasso/runme.jl:22  res = A*w - b
+        if (lane == 0) sts1(ctl + kOffRs + 8 * d, r1);
+      }
+      group_bar(2);                                  // (bar.sync orders the reducer's shared-memory store before the reads below)
+      FTRACE(leader, 3, i);
+      const double rs = lds1(ctl + kOffRs + 8 * d);  // slot d is rewritten 8 rows -- 8 group barriers -- later
+#else
       if ((i & 31) == 0) bblk = (i + lane < nrows) ? __ldg(bp + i + lane) : 0.0;
       const double b_cur = __shfl_sync(0xffffffffu, bblk, i & 31);
       // st.async delivers data and complete_tx through the same path into this CTA's shared memory, so the
@@ -339,6 +373,7 @@ __device__ __noinline__ double fused_pass(const DMat& M, const double* bvec, con
       if (leader && i + kFDepth < nrows) mbar_expect_tx(ctl + kOffCfull + 8 * d, xbytes);    // arm this buffer for row g + 8
       const double rs = warp_sum((v0 + v1) + (v2 + v3)) - b_cur;   // same order in every update warp of the cluster;
                                                                    // lasso/runme.jl:22  res = A*w - b
+#endif
 #ifdef ADAPROX_FUSED_ALLPOLL
       fmbar_wait(ctl + kOffFull + 8 * slot, ph);                 // long complete; makes the bulk-copied tile visible here
 #endif
@@ -366,7 +401,7 @@ __device__ __noinline__ double fused_pass(const DMat& M, const double* bvec, con
       if (lane == 0) mbar_arrive(ctl + kOffEmpty + 8 * slot);
       FTRACE(leader, 4, i);
       if (producer && i + kFStages < nrows) issue(slot, ph ^ 1u);   // row i + 3 into the slot row i just left
-      fsum = fma(rs, rs, fsum);
+      if (warp == kFGWarps) fsum = fma(rs, rs, fsum);               // (only the leader's copy is returned)
       if (++slot == kFStages) { slot = 0; ph ^= 1u; }
       if (++d == kFDepth) { d = 0; dph ^= 1u; }
     }
