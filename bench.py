@@ -9,9 +9,10 @@ the least-squares term, the stepsize rule, the prox step) on the planted lasso
 of lasso/runme.jl:40-77 generated on the device.  N = 1 runs configs[3] at its
 full size, 65536 x 131072 fp64 (68.7 GB, far larger than the 126 MB L2, so no
 L2 flush is needed between iterations).  N > 1 row-shards the same instance
-(strong scaling): per iteration each rank sweeps its shard and the A'r partials
-(n + 2 doubles) are all-reduced -- inside the sweep kernel over NVLink peer
-memory by default, with ncclAllReduce under --nccl.
+(strong scaling): each rank keeps ONE persistent launch of the single-sweep
+kernel for the whole solve and all-reduces the A'r partials (n + 2 doubles)
+inside its iteration loop over NVLink peer memory (--nccl: split-phase launches
+around ncclAllReduce for the A/B).
 
 The default kernel is the single-sweep fused kernel (A is read ONCE per
 iteration: g = A'(Ax - b) per row block while the rows are in shared memory);
@@ -21,9 +22,19 @@ iteration: g = A'(Ax - b) per row block while the rows are in shared memory);
 `value` comes from CUDA events recorded by the library on the stream its kernels
 run on, around a solve of exactly K iterations with everything resident in HBM
 (the solve's prologue -- one more gradient evaluation -- is inside the timed
-region, so the figure is slightly pessimistic).  `e2e` is the same solve timed
-from the caller's side of the C ABI with host buffers: x0 copied in from pinned
-host memory, x and the per-iteration records copied back.
+region, so the figure is slightly pessimistic); the solve is repeated --reps
+times and the median repetition is reported, all samples under `repetitions`.
+`e2e` is the same solve timed from the caller's side of the C ABI with host
+buffers: x0 copied in from pinned host memory, x and the per-iteration records
+copied back.
+
+Also in the default line: `time_to_tol` (the BASELINE metric's time to 1e-6),
+at N > 1 a `sharded_parity` block (configs[0] row-sharded over the N ranks
+against the CPU oracle, before the timed region), at N = 1 a `configs` block
+(configs[0], [1], [2], [4] with their rooflines and the oracle port timed beside
+them) and `cpu_baseline` (the oracle port on a planted row slab of the same
+width, every host thread; measured per-step time and scale factor are separate
+keys, `extrapolated` says so).
 """
 import argparse
 import json

@@ -43,7 +43,7 @@ def main():
         n = 47237
         gam = 4 * 20242 / (va @ va + 20242)            # 4m / ||[X 1]||_F^2  (SURVEY 8d substitute for the m x m Gram)
         f = AdaProx.LogisticLoss(X, y)
-        g = AdaProx.NormL1(0.01)
+        g = AdaProx.NormL1(0.03 * AdaProx.synth.logreg_lambda_max(X, y))     # 0.03 lambda_max: where the reference's lam = 0.01 sits on its own data sets (runme.jl:182)
         AdaProx.adaptive_proxgrad(np.zeros(n), f=f, g=g, rule=AdaProx.OurRule(gamma=gam), tol=1e-7, maxit=50)
         for tol in (1e-6, 1e-7):
             (x, it), wall = timed(lambda: AdaProx.adaptive_proxgrad(np.zeros(n), f=f, g=g, rule=AdaProx.OurRule(gamma=gam), tol=tol, maxit=2000))
