@@ -313,3 +313,26 @@ def test_numpy_oracle_against_c_restatement_fixtures():
     g = G["malitsky_pock"]
     assert close([r["gamma"] for r in log[:30]], g["gamma"], 1e-10) and close([r["sigma"] for r in log[:30]], g["sigma"], 1e-10)
     assert close([r["norm_res"] for r in log[:30]], g["norm_res"], 1e-8)
+
+
+def test_extended_precision_mode_and_drift_envelope():
+    """oracle.precision(np.longdouble) runs the same restatement in x87 extended precision; oracle/drift.py turns the distance of the Float64
+    oracle (natural and permuted summation orders) from that run into the intrinsic-drift envelope the GPU parity tests use."""
+    import adaprox_b200 as AdaProx
+    from oracle import drift
+    P = AdaProx.synth.planted_lasso(60, 150, 5, 1)
+    Lf = AdaProx.synth.spectral_norm_sq(P["A"], iters=500)
+    runs = drift.lasso_runs(P["A"], P["b"], 1.0, lambda O_: O_.OurRule(gamma=1 / Lf), 60, nperm=2, seed=3)
+    assert isinstance(runs["ext"][5]["gamma"], np.longdouble) and isinstance(runs["f64"][5]["gamma"], np.float64)
+    assert O.F64 is np.float64                                     # the mode is restored on exit
+    env = drift.envelope(runs)
+    assert len(env) == 60 and np.all(np.diff(env) >= 0)            # a running maximum
+    assert env[4] < 1e-14 and 1e-12 < env[-1] < 1e-2               # Float64 pins the first iterations, then the trajectories drift apart
+    # a Float64 run is inside its own envelope by construction; a perturbed one (gamma0 changed in the 13th digit) is not for long
+    ok, dd, allowed = drift.check_inside([r["gamma"] for r in runs["perms"][0]], runs, factor=1.0, floor=0.0)
+    assert ok
+    logp = []
+    O.adaptive_proxgrad(np.zeros(150), f=O.LinearLeastSquares(P["A"], P["b"]), g=O.NormL1(1.0), rule=O.OurRule(gamma=(1 / Lf) * (1 + 1e-9)), tol=0.0,
+                        maxit=60, log=logp)
+    ok, dd, allowed = drift.check_inside([r["gamma"] for r in logp], runs, factor=20.0, floor=1e-12)
+    assert not ok
