@@ -224,7 +224,10 @@ __device__ __forceinline__ double2 lds2v(uint32_t addr) {
 // may still be reading rows j-5 .. j-1, so 8 buffers never collide (and phase j-8 of cfull is long complete).
 // Register budget: 512 threads leave 128 registers per thread, so the loop state is kept minimal: x or the
 // accumulators (64 registers), one batch of tile data (16), a handful of 32-bit addresses and counters.
-constexpr int kFB = 4;                                    // LDS.128 per batch (16 registers of tile data per thread)
+#ifndef ADAPROX_FUSED_KFB
+#define ADAPROX_FUSED_KFB 4
+#endif
+constexpr int kFB = ADAPROX_FUSED_KFB;                     // LDS.128 per batch (16 registers of tile data per thread)
 
 #if ADAPROX_FUSED_VARIANT == 1
 __device__ __noinline__ double fused_pass(const DMat& M, const double* bvec, const double* x, FusedSmem& fs, int C,
@@ -389,8 +392,10 @@ __device__ __noinline__ double fused_pass(const DMat& M, const double* bvec, con
 #else
         for (int k = 0; k < kFB; ++k) av[k] = lds2v(tile + (h + k) * kFGroup * 16);
 #endif
+#ifndef ADAPROX_EXP_NO_SYNCWARP
         __syncwarp();                                           // scheduling fence: the independent FMAs below must not be
                                                                 // hoisted between the loads (one load in flight otherwise)
+#endif
 #pragma unroll
         for (int k = kFB - 1; k >= 0; --k) {
           acc[h + k].x = fma(av[k].x, rs, acc[h + k].x);
