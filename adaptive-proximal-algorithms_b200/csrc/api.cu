@@ -63,6 +63,8 @@ static int coop_launch(adaprox_ctx* h, K kernel, void** args, int grid = 0) {
   return ADAPROX_OK;
 }
 
+static constexpr double kL2KeepMB = 0.0;
+
 // choose the work partition of a dense matrix for a grid of G CTAs
 static void plan_dense(DMat& d, int G) {
   d.nchunks = (int)((d.n + kChunk - 1) / kChunk);
@@ -73,6 +75,11 @@ static void plan_dense(DMat& d, int G) {
   d.nrb = (d.m + rb - 1) / rb;
   const char* e = std::getenv("ADAPROX_GEMV");       // "ldg": register-staged loads; default: bulk-copy ring
   d.path = (e && std::strcmp(e, "ldg") == 0) ? 0 : 1;
+  // L2 budget the end of a sweep may pin for the start of the next (gemv.cuh, gemv_n_phase): MB over the whole grid
+  const char* k = std::getenv("ADAPROX_L2_KEEP_MB");
+  const double mb = k ? std::atof(k) : kL2KeepMB;
+  const int64_t tile = std::min<int64_t>(d.ld, kChunk) * 8;
+  d.keep = (mb < 0.0) ? -1 : (int64_t)(mb * 1048576.0 / G / (double)tile);
 }
 
 static int alloc_dense(adaprox_ctx* h, int64_t m, int64_t n, HostMatrix& hm) {
@@ -143,6 +150,7 @@ static int fill_problem(adaprox_ctx* h, const adaprox_problem* p, DProblem* out,
     case ADAPROX_F_CUBIC: {
       if ((rc = get_mat(h, p->f_mat, fmat))) return rc;
       P.F = (*fmat)->d;
+      P.F.slot = 0;
       const bool gram = (p->f_kind == ADAPROX_F_QUADRATIC_GRAM);      // F = Z (n x d), any d
       const int64_t ncols = (p->f_kind == ADAPROX_F_LOGISTIC) ? p->n - 1 : p->n;
       if (gram && P.F.kind != MAT_DENSE) return fail(h, ADAPROX_ERR_UNSUPPORTED, "QuadraticGram: Z must be a dense matrix");
@@ -172,6 +180,7 @@ static int fill_problem(adaprox_ctx* h, const adaprox_problem* p, DProblem* out,
     if (p->A_mat == p->f_mat)     // the partial buffers (zpart / gpart) belong to the matrix: F'r and A'y would share them in one phase
       return fail(h, ADAPROX_ERR_UNSUPPORTED, "f and A refer to the same device matrix: upload it a second time for A");
     P.A = (*amat)->d;
+    P.A.slot = 1;
     if (P.A.n != p->n) return fail(h, ADAPROX_ERR_INVALID, "A has the wrong number of columns");
     if (P.A.m != p->m_dual) return fail(h, ADAPROX_ERR_INVALID, "A has the wrong number of rows (m_dual)");
     if ((rc = fill_prox(h, p->h, p->m_dual, &P.h))) return rc;
@@ -598,7 +607,11 @@ static bool fused_eligible(const adaprox_options* o, const DProblem& P, int64_t 
   if (o->solver != ADAPROX_S_ADAPTIVE_PROXGRAD || P.f_kind != ADAPROX_F_LEAST_SQUARES || P.F.kind != MAT_DENSE) return false;
   if (P.g.kind == ADAPROX_P_NORM_L2 || P.g.conjugate) return false;       // needs a reduction before the prox: general kernel
   const bool force = e && std::strcmp(e, "1") == 0;
-  if (!force && rows * P.F.ld < (int64_t)(32 << 20)) return false;         // small problems: the two-pass kernel has more CTAs per column
+  // Where the single sweep pays (tools/l2_fit_ab.py, us per iteration two-pass / fused, round 2): rows of at least half a 64 KB
+  // stage -- 1000 x 4096: 43.8 / 34.7, 4000 x 4096: 72.3 / 59.0, 300 x 16384: 55.9 / 32.1, 200 x 65536: 60.7 / 39.5,
+  // 8000 x 8192: 185 / 125 -- and not with short rows, where a CTA's stage holds a fraction of a row: 4000 x 1000: 42.8 / 55.7,
+  // 20000 x 1000: 95.4 / 157, 8000 x 2048: 66.7 / 97.2 (1000 x 2048: 36.1 / 34.1, a tie).
+  if (!force && (P.F.ld < kFCols / 2 || rows * P.F.ld * 8 < kSmallProblemBytes)) return false;
   return fused_cluster_size(P) <= kFMaxCluster;
 }
 static int fused_config(adaprox_ctx* h, const void* kernel, int C, bool cooperative, cudaLaunchConfig_t* cfg, cudaLaunchAttribute* attrs, int* Q) {

@@ -265,15 +265,27 @@ __device__ __forceinline__ void spmv_rows(int lpr, int64_t nrows, const int64_t*
 // ---------------------------------------------------------------------------
 // phases
 // ---------------------------------------------------------------------------
+// Sweep direction (dense ring path).  Every CTA streams its own contiguous slab; when a sweep ends, the L2 holds the part of each
+// slab read LAST.  A*x therefore runs in the direction opposite to the previous sweep over the same matrix (its rows are
+// independent, so the bits do not change), A'r always runs first row -> last row (its sums over the rows keep their order):
+// least squares (A*x, A'r per iteration), the Gram form (Z'x, Z*u) and a dense Quadratic (Q*x only) all alternate, and each sweep
+// starts on the tens of MB the previous one left in the 126 MB L2 instead of evicting them before it gets there.
 __device__ __forceinline__ void gemv_n_phase(const DMat& M, const double* x, Sh& sh, int b, int G) {
   if (M.kind == MAT_DENSE) {
-    if (M.path == 1) gemv_n_ring(M, x, sh, b, G);
-    else gemv_n_dense(M, x, sh.x, b, G);
+    if (M.path == 1) {
+#ifdef ADAPROX_SWEEP_ONE_WAY
+      const bool rev = false;
+#else
+      const bool rev = (sh.fwd_last >> M.slot) & 1u;
+#endif
+      gemv_n_ring(M, x, sh, b, G, rev);
+      sh.fwd_last = rev ? (sh.fwd_last & ~(1u << M.slot)) : (sh.fwd_last | (1u << M.slot));
+    } else gemv_n_dense(M, x, sh.x, b, G);
   } else if (M.kind == MAT_CSR) spmv_rows(M.lpr_n, M.m, M.rowptr, M.colind, M.vals, x, M.zpart, b, G);
 }
 __device__ __forceinline__ void gemv_t_phase(const DMat& M, const double* r, Sh& sh, int b, int G) {
   if (M.kind == MAT_DENSE) {
-    if (M.path == 1) gemv_t_ring(M, r, sh, b, G);
+    if (M.path == 1) { gemv_t_ring(M, r, sh, b, G); sh.fwd_last |= 1u << M.slot; }
     else gemv_t_dense(M, r, b, G);
   } else if (M.kind == MAT_CSR) spmv_rows(M.lpr_t, M.n, M.t_rowptr, M.t_colind, M.t_vals, r, M.gpart, b, G);
 }

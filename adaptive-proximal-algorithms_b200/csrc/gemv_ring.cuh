@@ -31,6 +31,7 @@ struct Sh {
   uint32_t full;        // shared-space address of full[0]  (8 B apart)
   uint32_t empty;       // shared-space address of empty[0]
   uint32_t count;       // tiles this CTA has pushed through the ring so far (uniform across the CTA)
+  uint32_t fwd_last;    // bit DMat::slot: the last dense sweep over that matrix ran first row -> last row (see gemv_n_phase)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -84,6 +85,7 @@ __device__ __forceinline__ void sh_init(Sh& sh, unsigned char* dyn, double* scr,
   sh.full = smem_u32(bars);
   sh.empty = smem_u32(bars + kStages);
   sh.count = 0;
+  sh.fwd_last = 0;
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(sh.full + 8 * s, 1); mbar_init(sh.empty + 8 * s, kWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -132,24 +134,42 @@ struct Prod {
   int64_t row, end;
   uint32_t g;            // running ring index of the next tile to issue
   int64_t left;          // tiles still to issue
+  int64_t keep;          // the last `keep` tiles of the sweep are loaded evict_last, the others evict_first; < 0: no hints
+  uint64_t pol_first, pol_last;
+  __device__ __forceinline__ void policies(int64_t keep_tiles) {
+    keep = keep_tiles;
+    if (keep >= 0) { pol_first = l2_policy_evict_first(); pol_last = l2_policy_evict_last(); }
+  }
 };
 
+// rev: the slab is walked last tile -> first tile; p.end is then the first row of the current segment (inclusive)
 __device__ __forceinline__ void prod_issue(Prod& p, const Segs& sg, const double* a, int64_t ld, uint32_t ring, uint32_t full,
-                                           uint32_t empty) {
+                                           uint32_t empty, bool rev = false) {
   const uint32_t s = p.g % kStages, ph = (p.g / kStages) & 1u;
   mbar_wait(empty + 8 * s, ph ^ 1u);
   const int64_t w = ld - (int64_t)p.c * kChunk;
   const uint32_t bytes = (uint32_t)((w < kChunk ? w : kChunk) * 8);
   mbar_expect_tx(full + 8 * s, bytes);
-  bulk_g2s(ring + s * kStageBytes, a + p.row * ld + (int64_t)p.c * kChunk, bytes, full + 8 * s);
+  // What the NEXT sweep over this matrix reads first is what this one reads last (gemv_n_phase): those tiles are asked to stay in
+  // L2, everything else (streamed once, or just re-read from L2) to leave it first.
+  if (p.keep < 0) bulk_g2s(ring + s * kStageBytes, a + p.row * ld + (int64_t)p.c * kChunk, bytes, full + 8 * s);
+  else bulk_g2s_hint(ring + s * kStageBytes, a + p.row * ld + (int64_t)p.c * kChunk, bytes, full + 8 * s,
+                     p.left <= p.keep ? p.pol_last : p.pol_first);
   ++p.g; --p.left;
-  if (++p.row >= p.end) { ++p.c; p.row = 0; p.end = sg.seg_end(p.c); }
+  if (!rev) {
+    if (++p.row >= p.end) { ++p.c; p.row = 0; p.end = sg.seg_end(p.c); }
+  } else if (--p.row < p.end) {
+    --p.c; p.row = sg.seg_end(p.c) - 1; p.end = sg.seg_begin(p.c);
+  }
 }
 
 // ---------------------------------------------------------------------------
 // A*x partials: zpart[c][row] = sum over the chunk
+// rev: the CTA walks its slab from the last tile to the first.  A row's value does not depend on the order the rows are
+// visited in (one fixed-order sum of kWarps warp partials per row), so both directions leave the same bits; what changes is
+// which end of the slab is still in L2 from the previous sweep over the same matrix (gemv_n_phase picks the direction).
 // ---------------------------------------------------------------------------
-__device__ __noinline__ void gemv_n_ring(const DMat& M, const double* x, Sh& sh, int b, int G) {
+__device__ __noinline__ void gemv_n_ring(const DMat& M, const double* x, Sh& sh, int b, int G, bool rev) {
   constexpr int kH = kV / 2;
   // descriptors into registers (nothing below may alias them)
   const double* const a = M.a;
@@ -162,11 +182,15 @@ __device__ __noinline__ void gemv_n_ring(const DMat& M, const double* x, Sh& sh,
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint32_t g = sh.count;                  // ring index of the next tile to consume
   Prod p;
-  p.c = sg.c0; p.row = sg.row0; p.end = sg.end0; p.g = g; p.left = sg.T;
+  p.g = g; p.left = sg.T; p.policies(M.keep);
+  if (!rev) { p.c = sg.c0; p.row = sg.row0; p.end = sg.end0; }
+  else { p.c = sg.c1; p.row = sg.seg_end(sg.c1) - 1; p.end = sg.seg_begin(sg.c1); }
   if (threadIdx.x == 0)
-    for (int k = 0; k < kStages - 1 && p.left > 0; ++k) prod_issue(p, sg, a, ld, ring, full, empty);
+    for (int k = 0; k < kStages - 1 && p.left > 0; ++k) prod_issue(p, sg, a, ld, ring, full, empty, rev);
 
-  for (int c = sg.c0; c <= sg.c1; ++c) {
+  const int nc = sg.c1 - sg.c0 + 1;
+  for (int ci = 0; ci < nc; ++ci) {
+    const int c = rev ? sg.c1 - ci : sg.c0 + ci;
     const int64_t col0 = (int64_t)c * kChunk;
     double2 xr[kH];
     bool ok[kH];
@@ -178,10 +202,10 @@ __device__ __noinline__ void gemv_n_ring(const DMat& M, const double* x, Sh& sh,
       xr[k].y = (j + 1 < n) ? ldcg(x + j + 1) : 0.0;
     }
     const int64_t rbeg = sg.seg_begin(c), rend = sg.seg_end(c);
-    for (int64_t blk = rbeg; blk < rend; blk += kPartRows) {
-      const int nrows = (int)((rend - blk < kPartRows) ? (rend - blk) : kPartRows);
+    for (int64_t done = 0; done < rend - rbeg; done += kPartRows) {   // tile q of the block: row rbeg+done+q, or rend-1-done-q
+      const int nrows = (int)((rend - rbeg - done < kPartRows) ? (rend - rbeg - done) : kPartRows);
       for (int q = 0; q < nrows; ++q) {
-        if (threadIdx.x == 0 && p.left > 0) prod_issue(p, sg, a, ld, ring, full, empty);
+        if (threadIdx.x == 0 && p.left > 0) prod_issue(p, sg, a, ld, ring, full, empty, rev);
         const uint32_t s = g % kStages, ph = (g / kStages) & 1u;
         mbar_wait(full + 8 * s, ph);
         const uint32_t tile = ring + s * kStageBytes + threadIdx.x * 16;
@@ -204,7 +228,8 @@ __device__ __noinline__ void gemv_n_ring(const DMat& M, const double* x, Sh& sh,
         double sum = 0.0;
 #pragma unroll
         for (int w = 0; w < kWarps; ++w) sum += lds1(part + (threadIdx.x * kWarps + w) * 8);
-        zpart[(int64_t)c * m + blk + threadIdx.x] = sum;
+        const int64_t row = rev ? rend - 1 - done - threadIdx.x : rbeg + done + threadIdx.x;
+        zpart[(int64_t)c * m + row] = sum;
       }
       __syncthreads();
     }
@@ -227,7 +252,7 @@ __device__ __noinline__ void gemv_t_ring(const DMat& M, const double* r, Sh& sh,
   const int lane = threadIdx.x & 31;
   uint32_t g = sh.count;
   Prod p;
-  p.c = sg.c0; p.row = sg.row0; p.end = sg.end0; p.g = g; p.left = sg.T;
+  p.c = sg.c0; p.row = sg.row0; p.end = sg.end0; p.g = g; p.left = sg.T; p.policies(M.keep);
   if (threadIdx.x == 0)
     for (int k = 0; k < kStages - 1 && p.left > 0; ++k) prod_issue(p, sg, a, ld, ring, full, empty);
 
