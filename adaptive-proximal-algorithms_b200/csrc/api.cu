@@ -1020,6 +1020,14 @@ extern "C" int adaprox_solve(adaprox_handle h, const adaprox_problem* p, const a
         std::fprintf(stderr, " %.0f|%.0f", (double)(t[3] - t[0]) * 1e-3, (double)(t[7] - t[3]) * 1e-3);
       }
       std::fprintf(stderr, "\n");
+      double f3[3] = {0, 0, 0}; int fc = 0;
+      for (int i = 1; i < nit; ++i) {                       // stamps 0, 3, 4, 7 of the fused loop; the first iteration is left out
+        const unsigned long long* t = &ts[(size_t)i * 8];
+        if (!t[0] || !t[3] || !t[4] || !t[7]) continue;
+        f3[0] += (double)(t[3] - t[0]) * 1e-3; f3[1] += (double)(t[4] - t[3]) * 1e-3; f3[2] += (double)(t[7] - t[4]) * 1e-3; ++fc;
+      }
+      if (fc) std::fprintf(stderr, "[adaprox fused, mean of %d iterations, us: sweep + grid barrier %.1f | gradient slice + 4 sums + grid barrier %.1f | stepsize, record, prox, grid barrier %.1f]\n",
+                           fc, f3[0] / fc, f3[1] / fc, f3[2] / fc);
     }
     if (cnt && !fused) {
       const char* names[7] = {"P1 F*x (+A*x)", "P2 rows/residual", "P3 F'*r", "P4 grad+reductions", "P5 stepsize/dual", "P6 record/A'y", "P7 prox step"};
