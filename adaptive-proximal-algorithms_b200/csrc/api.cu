@@ -80,6 +80,7 @@ static void plan_dense(DMat& d, int G) {
   const double mb = k ? std::atof(k) : kL2KeepMB;
   const int64_t tile = std::min<int64_t>(d.ld, kChunk) * 8;
   d.keep = (mb < 0.0) ? -1 : (int64_t)(mb * 1048576.0 / G / (double)tile);
+  d.alternate = std::getenv("ADAPROX_SWEEP_ONE_WAY") ? 0 : 1;
 }
 
 static int alloc_dense(adaprox_ctx* h, int64_t m, int64_t n, HostMatrix& hm) {

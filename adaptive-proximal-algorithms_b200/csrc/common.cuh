@@ -44,6 +44,7 @@ struct DMat {
   int64_t npad;              // n rounded up to kChunk
   int path;                  // dense passes: 1 = bulk-copy shared-memory ring (default), 0 = register-staged LDG.128
   int64_t keep;              // ring path: tiles per CTA a sweep leaves in L2 for the next one (evict_last), < 0: no eviction hints
+  int alternate;             // ring path: A*x runs against the direction of the previous sweep (0: ADAPROX_SWEEP_ONE_WAY=1, A/B and tests)
   int slot;                  // 0 = the matrix of f, 1 = the linear map A (index of the sweep-direction bit in Sh::fwd_last)
 };
 

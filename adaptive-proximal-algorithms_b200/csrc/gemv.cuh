@@ -273,11 +273,7 @@ __device__ __forceinline__ void spmv_rows(int lpr, int64_t nrows, const int64_t*
 __device__ __forceinline__ void gemv_n_phase(const DMat& M, const double* x, Sh& sh, int b, int G) {
   if (M.kind == MAT_DENSE) {
     if (M.path == 1) {
-#ifdef ADAPROX_SWEEP_ONE_WAY
-      const bool rev = false;
-#else
-      const bool rev = (sh.fwd_last >> M.slot) & 1u;
-#endif
+      const bool rev = M.alternate && ((sh.fwd_last >> M.slot) & 1u);
       gemv_n_ring(M, x, sh, b, G, rev);
       sh.fwd_last = rev ? (sh.fwd_last & ~(1u << M.slot)) : (sh.fwd_last | (1u << M.slot));
     } else gemv_n_dense(M, x, sh.x, b, G);

@@ -6,6 +6,8 @@ trajectory is chaotic w.r.t. summation order, so whole runs are
 compared by (a) single-call operator parity, (b) the free-running prefix of the
 trajectory, (c) final objective / iterate / iteration count.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -455,6 +457,50 @@ def test_dual_svm_gram_form_full_size(AdaProx):
     assert np.all(xs >= 0) and np.all(xs <= 0.1) and np.all(np.isfinite([r["gamma"] for r in log]))
     assert log[-1]["norm_res"] < 0.1 * log[0]["norm_res"]
     assert AdaProx.last_solve_info()["matrix_passes"] == 2
+
+
+def test_sweep_direction_and_eviction_hints_leave_the_same_bits(AdaProx):
+    """gemv.cuh / gemv_ring.cuh: A*x runs against the direction of the previous sweep over the same matrix and the ring's bulk
+    copies carry an L2 evict_first policy.  Neither may change a bit: the Gram-form dual SVM (Z'x forward, Z*u reversed, one chunk)
+    and LAD with AdaPDM+ on a 3-chunk matrix (A*x alternating, A'y forward) under every switch."""
+    rng = np.random.default_rng(5)
+    N, d = 3000, 700
+    X = rng.standard_normal((N, d)) / np.sqrt(d)
+    ysv = np.where(rng.random(N) < 0.5, -1.0, 1.0)
+    m, n = 1500, 4500
+    Al = rng.standard_normal((m, n)) / np.sqrt(n)
+    bl = Al @ np.where(rng.random(n) < 0.05, rng.standard_normal(n), 0.0) + rng.laplace(scale=0.1, size=m)
+
+    def solve():
+        out = []
+        Zm = AdaProx.DeviceMatrix(ysv[:, None] * X)                 # the switches are read when a matrix is uploaded
+        Am = AdaProx.DeviceMatrix(ysv[None, :].copy())
+        log = []
+        xs, ys, it = AdaProx.adaptive_primal_dual(np.zeros(N), np.zeros(1), f=AdaProx.QuadraticGram(Zm, -np.ones(N)), g=AdaProx.IndBox(0.0, 0.1),
+                                                  h=AdaProx.IndZero(), A=Am, rule=AdaProx.OurRule(t=0.1, norm_A=float(np.sqrt(N))),
+                                                  tol=0.0, maxit=80, log=log)
+        out += [xs.tobytes(), ys.tobytes(), np.array([r["gamma"] for r in log]).tobytes(), np.array([r["norm_res"] for r in log]).tobytes()]
+        Zm.free(); Am.free()
+        Ad = AdaProx.DeviceMatrix(Al)
+        log = []
+        xs, ys, it = AdaProx.adaptive_linesearch_primal_dual(np.zeros(n), np.zeros(m), f=AdaProx.Zero(), g=AdaProx.NormL1(0.5),
+                                                             h=AdaProx.Translate(AdaProx.NormL1(), -bl), A=Ad, eta=float(np.linalg.norm(Al)), t=1.0,
+                                                             tol=0.0, maxit=60, log=log)
+        out += [xs.tobytes(), ys.tobytes(), np.array([r["gamma"] for r in log]).tobytes(), np.array([r["norm_res"] for r in log]).tobytes()]
+        Ad.free()
+        return out
+
+    runs = {}
+    for name, env in (("shipped", {}), ("one_way", {"ADAPROX_SWEEP_ONE_WAY": "1"}), ("no_hints", {"ADAPROX_L2_KEEP_MB": "-1"}),
+                      ("keep_tail", {"ADAPROX_L2_KEEP_MB": "1"})):
+        os.environ.update(env)
+        try:
+            runs[name] = solve()
+        finally:
+            for k in env:
+                os.environ.pop(k, None)
+    for name in ("one_way", "no_hints", "keep_tail"):
+        assert runs[name] == runs["shipped"], name
 
 
 def test_condat_vu(AdaProx):

@@ -1,9 +1,10 @@
-# dense ring sweeps: alternating direction (shipped) vs every sweep first row -> last row (-DADAPROX_SWEEP_ONE_WAY), each with the
-# stream loaded evict_first (shipped, ADAPROX_L2_KEEP_MB=0) and without eviction hints (-1); same box
-for lib in "" build_ab/libadaprox_oneway.so; do
+# dense ring sweeps: A*x against the direction of the previous sweep (shipped) vs every sweep first row -> last row
+# (ADAPROX_SWEEP_ONE_WAY=1), each with the stream loaded evict_first (shipped, ADAPROX_L2_KEEP_MB=0) and without eviction hints (-1); same box
+for ow in "" 1; do
  for mb in 0 -1; do
-  echo "== ${lib:-shipped} ADAPROX_L2_KEEP_MB=$mb"
-  ADAPROX_L2_KEEP_MB=$mb ADAPROX_LIB=${lib:+$PWD/$lib} python tools/bench_configs.py ${CONFIGS:-lad svm svmgram} 2>&1 | python -c "
+  if [ -n "$ow" ]; then label="one way"; else label="alternating"; fi
+  echo "== $label ADAPROX_L2_KEEP_MB=$mb"
+  env ${ow:+ADAPROX_SWEEP_ONE_WAY=1} ADAPROX_L2_KEEP_MB=$mb python tools/bench_configs.py ${CONFIGS:-lad svm svmgram} 2>&1 | python -c "
 import json,sys
 for l in sys.stdin:
     if l.startswith('{'):
