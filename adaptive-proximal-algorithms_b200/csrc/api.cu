@@ -11,6 +11,7 @@
 #include "solver_mp.cuh"
 #include "solver_fused.cuh"
 #include "solver_resident.cuh"
+#include "solver_gridres.cuh"
 #include "comm.hpp"
 
 using namespace adaprox;
@@ -779,6 +780,37 @@ static bool resident_eligible(adaprox_ctx* h, const adaprox_options* o, const DP
   return *smem + 1024 <= (size_t)max_optin;
 }
 
+// Dense least squares with short rows that fits the shared memory of all SMs together (solver_gridres.cuh): the reference's
+// 500 x 1000 and 4000 x 1000 lasso runs.  ADAPROX_GRIDRES=0 disables it (A/B against the persistent grid kernel).
+static bool gridres_eligible(adaprox_ctx* h, const adaprox_options* o, const DProblem& P, GridResArgs* ga, size_t* smem) {
+  const char* e = std::getenv("ADAPROX_GRIDRES");
+  if (e && std::strcmp(e, "0") == 0) return false;
+  const char* ef = std::getenv("ADAPROX_FUSED");
+  if (ef && std::strcmp(ef, "1") == 0) return false;       // the sweep kernel was requested explicitly
+  if (o->solver != ADAPROX_S_ADAPTIVE_PROXGRAD || P.f_kind != ADAPROX_F_LEAST_SQUARES || P.F.kind != MAT_DENSE) return false;
+  if (P.g.kind == ADAPROX_P_NORM_L2 || P.g.conjugate) return false;
+  if (P.F.ld > kGMaxLd || P.n < 1 || P.F.m < 1) return false;
+  const int G = h->sm_count;
+  if (G < 1 || G > h->grid || G > 32 * kGMaxP) return false;   // the matrix's partial buffer has h->grid rows
+  ga->rows_cap = (int)((P.F.m + G - 1) / G);
+  ga->slice = (int)((P.n + G - 1) / G);
+  ga->row_ctas = (int)((P.F.m + ga->rows_cap - 1) / ga->rows_cap);
+  if (ga->slice > kGWarps) return false;
+  int max_optin = 0;
+  if (cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device) != cudaSuccess) return false;
+  // the CTA's copy of x sits in shared memory when the rows leave room for it (4000 x 1000: 28 rows of 8064 B leave 6.6 KB), else in global memory
+  ga->x_in_smem = gridres_smem_bytes(ga->rows_cap, P.F.ld, true) + 1024 <= (size_t)max_optin ? 1 : 0;
+  *smem = gridres_smem_bytes(ga->rows_cap, P.F.ld, ga->x_in_smem != 0);
+  if (*smem + 1024 > (size_t)max_optin) return false;
+  int per_sm = 0;
+  if (cudaFuncSetAttribute((const void*)k_adapgm_gridres, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*smem) != cudaSuccess ||
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)k_adapgm_gridres, kGThreads, *smem) != cudaSuccess || per_sm < 1) {
+    cudaGetLastError();
+    return false;
+  }
+  return true;
+}
+
 // CTAs of a persistent solver launch.  Every phase boundary is a grid barrier whose cost grows with the number of CTAs, and
 // every scalar is rebuilt from one partial per CTA: a problem whose matrices are small enough to be latency-bound (a few
 // microseconds per phase) runs faster on fewer CTAs; a streaming problem wants all of them (2 per SM keep ~96 KB of bulk
@@ -855,7 +887,11 @@ extern "C" int adaprox_solve(adaprox_handle h, const adaprox_problem* p, const a
   ResidentArgs rarg{};
   size_t rsmem = 0;
   const bool resident = !sharded && resident_eligible(h, o, P, &rarg, &rsmem);
-  bool fused = sharded_fused || (!resident && !sharded && fused_eligible(o, P, P.F.m));
+  GridResArgs garg{};
+  size_t gsmem = 0;
+  const bool gridres = !sharded && !resident && gridres_eligible(h, o, P, &garg, &gsmem);
+  bool fused = sharded_fused || (!resident && !gridres && !sharded && fused_eligible(o, P, P.F.m));
+  if (gridres) G = std::max(G, h->sm_count);
   FusedPlan fpl;
   if (fused) {
     rc = fused_plan(h, (const void*)k_adapgm_fused, P, true, &fpl);
@@ -866,7 +902,9 @@ extern "C" int adaprox_solve(adaprox_handle h, const adaprox_problem* p, const a
   FusedArgs& fa = fpl.fa;
   const int fQ = fpl.Q;
   const int64_t nfu = (P.f_kind == ADAPROX_F_QUADRATIC_GRAM) ? P.F.n : 1;
+  const int64_t gr_x = gridres ? (garg.x_in_smem ? 1 : (int64_t)h->sm_count * P.F.ld) : 1;
   size_t need = (fused ? fused_ws_bytes(fpl) : 0) + (sharded_fused ? ws_size_doubles(n + 2) : 0) +
+                (gridres ? ws_size_doubles(P.F.ld) + ws_size_doubles(h->sm_count) + ws_size_doubles(gr_x) : 0) +
                 9 * ws_size_doubles(n) + 2 * ws_size_doubles(n + 8) + 6 * ws_size_doubles(md) + ws_size_doubles(mf) + ws_size_doubles(nfu) +
                 ws_size_doubles((int64_t)kMaxRed * G) + ws_size_doubles((nrec * (int64_t)sizeof(adaprox_record) + 7) / 8) +
                 ws_size_doubles((sizeof(DResult) + 7) / 8);
@@ -889,6 +927,11 @@ extern "C" int adaprox_solve(adaprox_handle h, const adaprox_problem* p, const a
   W.xout = W.aux[2];
   O.max_records = nrec;
   if (fused && (rc = fused_ws_alloc(h, &fpl))) return rc;
+  if (gridres) {
+    garg.gfull = ws_doubles(h, P.F.ld);
+    garg.fpart = ws_doubles(h, h->sm_count);
+    garg.xpriv = ws_doubles(h, gr_x);
+  }
   if (sharded_fused) {
     fa.sh_gbuf = ws_doubles(h, n + 2);
     p2p_fill(h, &fa.p2p);
@@ -934,6 +977,12 @@ extern "C" int adaprox_solve(adaprox_handle h, const adaprox_problem* p, const a
         void* rargs[] = {&P, &O, &W, &rarg};
         cudaError_t e = cudaLaunchKernelExC(&cfg, (const void*)k_adapgm_resident, rargs);
         if (e != cudaSuccess) return fail(h, ADAPROX_ERR_CUDA, std::string("resident cluster launch: ") + cudaGetErrorString(e));
+        h->launches++;
+        rc = ADAPROX_OK;
+      } else if (gridres) {
+        void* gargs[] = {&P, &O, &W, &garg};
+        cudaError_t e = cudaLaunchCooperativeKernel((const void*)k_adapgm_gridres, dim3(h->sm_count), dim3(kGThreads), gargs, gsmem, h->stream);
+        if (e != cudaSuccess) return fail(h, ADAPROX_ERR_CUDA, std::string("grid-resident cooperative launch: ") + cudaGetErrorString(e));
         h->launches++;
         rc = ADAPROX_OK;
       } else if (fused) {
@@ -1031,7 +1080,9 @@ extern "C" int adaprox_solve(adaprox_handle h, const adaprox_problem* p, const a
                            fc, f3[0] / fc, f3[1] / fc, f3[2] / fc);
     }
     if (cnt && !fused) {
-      const char* names[7] = {"P1 F*x (+A*x)", "P2 rows/residual", "P3 F'*r", "P4 grad+reductions", "P5 stepsize/dual", "P6 record/A'y", "P7 prox step"};
+      const char* names_pd[7] = {"P1 F*x (+A*x)", "P2 rows/residual", "P3 F'*r", "P4 grad+reductions", "P5 stepsize/dual", "P6 record/A'y", "P7 prox step"};
+      const char* names_gr[7] = {"passes 1+2", "grid barrier 1", "gradient entries", "grid barrier 2", "load gradient + 5 sums", "stepsize + record", "prox step"};
+      const char** names = gridres ? names_gr : names_pd;
       std::fprintf(stderr, "[adaprox phase timing] %d iterations, us per iteration:", cnt);
       for (int k = 0; k < 7; ++k) std::fprintf(stderr, " %s=%.1f", names[k], sum[k] / cnt);
       std::fprintf(stderr, " total=%.1f\n", sum[7] / cnt);
@@ -1046,7 +1097,7 @@ extern "C" int adaprox_solve(adaprox_handle h, const adaprox_problem* p, const a
   res->n_records = dr.n_records;
   res->final_gamma = dr.final_gamma; res->final_sigma = dr.final_sigma; res->final_norm_res = dr.final_norm_res;
   res->solve_ms = ms; res->kernel_launches = h->launches - launches0;
-  res->matrix_passes = (P.F.kind == MAT_NONE) ? 0 : (fused ? 1 : (resident ? 3 : 2));
+  res->matrix_passes = (P.F.kind == MAT_NONE) ? 0 : (fused ? 1 : (resident ? 3 : (gridres ? 4 : 2)));
   res->collective = (sharded_pd || sharded_fused) ? 2 : 0;
   if ((sharded_pd || sharded_fused) && (rc = p2p_check(h))) return rc;
   return ADAPROX_OK;

@@ -237,8 +237,9 @@ __device__ __forceinline__ void sh_phase_F(const ShArgs& a, long long it, R red)
     double t4[4], tg[1] = {0.0};
     red.template totals<4>(a.W.red, G, SLOT_PR, t4);
     if (O.want_objective) red.template totals<1>(a.W.red, G, gval_slot(it), tg);
+    const double gamma_prev = gamma;
     rule_step(O, t4[1], t4[2], t4[3], gamma, sigma, s0, s1);
-    const double norm_res = sqrt(norm_sq_jl(t4[0]));
+    const double norm_res = sqrt(norm_sq_jl(t4[0]) + adapgm_dual_res_sq(gamma, gamma_prev, sigma));   // :348 (dual part: 0, or NaN -- phases.cuh)
     nx.norm_res = norm_res;
     if (!(gamma == gamma) || !(norm_res == norm_res) || isinf(gamma)) nx.flags |= ADAPROX_FLAG_NONFINITE;
     if (b == 0 && threadIdx.x == 0 && a.W.rec != nullptr && it <= O.max_records) {

@@ -364,8 +364,9 @@ __global__ void __launch_bounds__(kPT, 2) k_path_step(PathStepArgs a) {
       s_bc[threadIdx.x] = s;
     }
     __syncthreads();
+    const double gamma_prev = gamma;
     rule_step(a.O, s_bc[1], s_bc[2], s_bc[3], gamma, sigma, s0, s1);     // :341
-    norm_res = sqrt(norm_sq_jl(s_bc[0]));                                // :348
+    norm_res = sqrt(norm_sq_jl(s_bc[0]) + adapgm_dual_res_sq(gamma, gamma_prev, sigma));   // :348 (dual part: 0, or NaN -- phases.cuh)
     if (norm_res <= a.O.tol) stop = true;                                // :354
   }
   // objective of the record: f(x) + lambda |x|_1

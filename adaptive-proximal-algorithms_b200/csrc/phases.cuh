@@ -156,6 +156,18 @@ __host__ __device__ inline void rule_init(const DOpts& o, double& gamma, double&
   }
 }
 
+// AdaPGM is AdaPDM with A = 0 (a scalar), y = zero(x), h = Zero (src/AdaProx.jl:418-421).  Its dual residual (:344-347)
+//   w = y + sigma * ((1 + rho) * A_x - rho * A_x_prev),  y+ = prox(IndZero) = 0,  dual_res = (w - y+) / sigma - A_x
+// is zero -- unless the new sigma or rho = gamma / gamma_prev is not finite (or sigma = 0): then 0 * Inf / 0 * NaN / 0 / 0 make
+// every entry NaN, norm_res (:348) is NaN, the test :354 fails and the next v = x - gamma * grad carries the NaN into x.  The
+// kernels without a dual vector reproduce that with the same arithmetic on one entry.  Returns (entry of dual_res)^2.
+__host__ __device__ inline double adapgm_dual_res_sq(double gamma, double gamma_prev, double sigma) {
+  const double rho = gamma / gamma_prev;                                                       // :342
+  const double w = 0.0 + sigma * ((1.0 + rho) * 0.0 - rho * 0.0);                              // :344
+  const double d = (w - 0.0) / sigma - 0.0;                                                    // :347
+  return d * d;
+}
+
 // dgg = sum (dgrad)^2, dgx = <dgrad, dx>, dxx = sum (dx)^2
 __host__ __device__ inline void rule_step(const DOpts& o, double dgg, double dgx, double dxx, double& gamma,
                                           double& sigma, double& s0, double& s1) {

@@ -898,8 +898,9 @@ __global__ void __launch_bounds__(kFThreads, 1) k_adapgm_fused(DProblem P, DOpts
     f_grid_totals<4>(W.red, G, SLOT_PR, t4, scr);
     tf[0] = fsum_all;
     if (want_obj) f_grid_totals<1>(W.red, G, gval_slot(it), tg, scr);
+    const double gamma_prev = gamma;
     rule_step(O, t4[1], t4[2], t4[3], gamma, sigma, s0, s1);                    // :341
-    norm_res = sqrt(norm_sq_jl(t4[0]));                                         // :348 (dual part is identically zero)
+    norm_res = sqrt(norm_sq_jl(t4[0]) + adapgm_dual_res_sq(gamma, gamma_prev, sigma));   // :348 (dual part: 0, or NaN -- phases.cuh)
     if (!(gamma == gamma) || !(norm_res == norm_res) || isinf(gamma)) flags |= ADAPROX_FLAG_NONFINITE;
     if (b == 0 && threadIdx.x == 0 && W.rec != nullptr && it <= O.max_records) {
       adaprox_record rc;

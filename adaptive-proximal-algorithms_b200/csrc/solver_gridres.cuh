@@ -1,0 +1,274 @@
+// solver_gridres.cuh -- AdaPGM / fixed-step PGM (src/AdaProx.jl:312-364 with A = 0, h = Zero) on a dense least-squares
+// term whose matrix fits the shared memory of ALL SMs together (148 x ~225 KB = 33 MB), rows of at most 1024 columns.
+//
+// The reference's own lasso runs (lasso/runme.jl:191-195) are 100 x 300, 500 x 1000 and 4000 x 1000.  The first fits one
+// cluster (solver_resident.cuh); the other two (4 MB, 32 MB) do not, and in the persistent grid kernel they spend their
+// iteration on seven short phases (28 / 43 us per iteration: the matrix is L2-resident, the sweeps themselves are a few
+// microseconds).  Here the grid keeps the matrix in shared memory for the whole solve, exactly as the cluster kernel does,
+// exchanges through global memory (L2), and needs TWO grid barriers per iteration:
+//   * CTA b owns rows [b R, (b+1) R) in its shared memory (loaded once) and a full copy of the iterate;
+//   * pass 1 (one warp per row, x in registers): r_i = <A[i,:], x> - b_i;  pass 2 (thread = 2 columns, no reduction): this
+//     CTA's partial gradient, written to its row of the matrix's partial buffer;
+//   * grid barrier;  warp w of CTA b owns column b S + w: the partials of all row-owning CTAs in CTA order (each lane a fixed
+//     subsequence, then the shuffle tree) -> one entry of the gradient in global memory;
+//   * grid barrier;  EVERY CTA loads the whole gradient (8 KB) and repeats the rest of the iteration for all n columns: the
+//     four stepsize sums of src/AdaProx.jl:338,260-261 (fixed order: the same bits in every CTA), the stepsize rule, the
+//     convergence test, the prox step.  The new iterate never leaves the CTA, so there is no third barrier.
+// No atomics, every sum has a fixed order: reruns are bit-identical.  Limits: ld <= 1024 (a row fits one warp's registers, a
+// thread owns two columns), ceil(m / G) rows of A per CTA in shared memory, ceil(n / G) <= 16 gradient entries per CTA, G <= 256.
+#pragma once
+#include <cooperative_groups.h>
+
+#include "phases.cuh"
+
+namespace adaprox {
+
+constexpr int kGThreads = 512;
+constexpr int kGWarps = kGThreads / 32;
+constexpr int kGMaxLd = 1024;
+constexpr int kGLaneV = kGMaxLd / 2 / 32;                 // 16 double2 per lane per row (pass 1)
+constexpr int kGMaxP = 8;                                 // partials per lane in a grid-wide sum: G <= 32 * kGMaxP
+constexpr int kGSums = 5;                                 // |primal_res|^2, |dgrad|^2, <dgrad, dx>, |dx|^2, g(x)
+
+struct GridResArgs {
+  int rows_cap;            // rows per CTA: ceil(m / G)
+  int slice;               // gradient entries reduced per CTA: ceil(n / G) <= kGWarps
+  int row_ctas;            // CTAs that own at least one row: ceil(m / rows_cap)
+  int x_in_smem;           // the CTA's copy of x lives in shared memory (else in xpriv: the last row did not leave room)
+  double* gfull;           // [ld]     the gradient of the iteration
+  double* fpart;           // [G]      per-CTA sums of r_i^2
+  double* xpriv;           // [G][ld]  per-CTA copies of x when !x_in_smem
+};
+
+__host__ __device__ inline size_t gridres_smem_bytes(int64_t rows_cap, int64_t ld, bool x_in_smem) {
+  return (size_t)8 * (size_t)(rows_cap * ld + 2 * rows_cap + kGWarps + kGWarps * 8 + 16 + (x_in_smem ? ld : 0));
+}
+
+__global__ void __launch_bounds__(kGThreads, 1) k_adapgm_gridres(DProblem P, DOpts O, DWork W, GridResArgs ga) {
+  cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+  extern __shared__ __align__(1024) unsigned char dyn_smem[];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int b = blockIdx.x, G = gridDim.x;
+  const int64_t m = P.F.m, n = P.n, ld = P.F.ld;
+  const int ldv = (int)(ld / 2);                           // double2 per row (<= 512)
+  const int R = ga.rows_cap, S = ga.slice, GR = ga.row_ctas;
+  const int64_t row0 = (int64_t)b * R;
+  const int rows = (int)(row0 >= m ? 0 : (m - row0 < R ? m - row0 : R));
+  double* As = reinterpret_cast<double*>(dyn_smem);       // [R][ld]
+  double* r_loc = As + (size_t)R * ld;                     // [R]
+  double* b_loc = r_loc + R;                               // [R]
+  double* wpart = b_loc + R;                               // [kGWarps]      per-warp sums of r_i^2
+  double* spart = wpart + kGWarps;                         // [kGWarps][8]   per-warp partials of the kGSums sums
+  double* totals = spart + kGWarps * 8;                    // [8] the sums; [8] = sum of r_i^2 over the grid (CTA 0)
+  double* xs = ga.x_in_smem ? totals + 16 : ga.xpriv + (int64_t)b * ld;    // [ld] this CTA's copy of the iterate
+  double* gpart_all = P.F.gpart;                           // [G][npad] partial gradients
+  const int64_t npad = P.F.npad;
+  const bool want_obj = O.want_objective != 0;
+
+  // thread t owns the columns c0 = 2 t and c0 + 1 in pass 2 and in the vector part of the iteration
+  const int64_t c0 = 2 * (int64_t)t;
+  const bool own0 = (t < ldv) && (c0 < n), own1 = (t < ldv) && (c0 + 1 < n);
+  double2 x_t = make_double2(0.0, 0.0), xprev_t = x_t, gprev_t = x_t, v_t = x_t;
+
+  // ---- load this CTA's rows, b and x0 ------------------------------------------------------------------------------
+  {
+    const double2* src = reinterpret_cast<const double2*>(P.F.a + row0 * ld);
+    double2* dst = reinterpret_cast<double2*>(As);
+    const int64_t cnt = (int64_t)rows * ldv;
+    for (int64_t k = t; k < cnt; k += kGThreads) dst[k] = ld_stream(reinterpret_cast<const double*>(src + k));
+    for (int i = t; i < R; i += kGThreads) { b_loc[i] = i < rows ? P.fvec[row0 + i] : 0.0; r_loc[i] = 0.0; }
+    if (t < 16) totals[t] = 0.0;
+    if (own0) x_t.x = W.xb[0][c0];
+    if (own1) x_t.y = W.xb[0][c0 + 1];
+    if (t < ldv) reinterpret_cast<double2*>(xs)[t] = x_t;             // columns n .. ld-1 hold zeros
+  }
+  __syncthreads();
+
+  double gamma, sigma, s0, s1;
+  rule_init(O, gamma, sigma, s0, s1);
+  int64_t n_eval = 0, n_grad = 0, n_proxg = 0, n_rec = 0;
+  unsigned flags = 0;
+  double norm_res = INFINITY;
+  int64_t it_done = O.maxit;
+  bool converged = false;
+
+  // gradient evaluation at xs: this CTA's partial gradient -> gpart_all[b][:], its sum of r_i^2 -> fpart[b]
+  auto local_gradient = [&]() {
+    double2 xr[kGLaneV];
+#pragma unroll
+    for (int k = 0; k < kGLaneV; ++k) {
+      const int idx = lane + 32 * k;
+      xr[k] = idx < ldv ? reinterpret_cast<const double2*>(xs)[idx] : make_double2(0.0, 0.0);
+    }
+    double fw = 0.0;
+    for (int i = warp; i < rows; i += kGWarps) {          // pass 1: one warp per row
+      const double2* row = reinterpret_cast<const double2*>(As + (size_t)i * ld);
+      double p0 = 0.0, p1 = 0.0;
+#pragma unroll
+      for (int k = 0; k < kGLaneV; ++k) {
+        const int idx = lane + 32 * k;
+        if (idx < ldv) { const double2 a = row[idx]; p0 = fma(a.x, xr[k].x, p0); p1 = fma(a.y, xr[k].y, p1); }
+      }
+      const double res = warp_sum(p0 + p1) - b_loc[i];                          // lasso/runme.jl:22
+      if (lane == 0) r_loc[i] = res;
+      fw = fma(res, res, fw);
+    }
+    if (lane == 0) wpart[warp] = fw;
+    __syncthreads();
+    if (t < ldv && b < GR) {                               // pass 2: thread t owns double2 column t, no reduction
+      double2 acc = make_double2(0.0, 0.0);
+      for (int i = 0; i < rows; ++i) {
+        const double ri = r_loc[i];
+        const double2 a = reinterpret_cast<const double2*>(As + (size_t)i * ld)[t];
+        acc.x = fma(a.x, ri, acc.x); acc.y = fma(a.y, ri, acc.y);              // :23
+      }
+      *reinterpret_cast<double2*>(gpart_all + (int64_t)b * npad + c0) = acc;
+    }
+    if (t == 0) {
+      double fs = 0.0;
+#pragma unroll
+      for (int w = 0; w < kGWarps; ++w) fs += wpart[w];
+      ga.fpart[b] = fs;
+    }
+  };
+  // after the first barrier: warp w reduces gradient entry b S + w (lane l the CTAs l, l + 32, ... in order, then the shuffle
+  // tree); the last warp of CTA 0 sums the value partials for the record the same way
+  auto reduce_slice = [&]() {
+    const int64_t j = (int64_t)b * S + warp;
+    if (warp < S && j < n) {
+      double v[kGMaxP];
+#pragma unroll
+      for (int q = 0; q < kGMaxP; ++q) { const int p = lane + 32 * q; v[q] = p < GR ? ldcg(gpart_all + (int64_t)p * npad + j) : 0.0; }
+      double s = 0.0;
+#pragma unroll
+      for (int q = 0; q < kGMaxP; ++q) s += v[q];
+      s = warp_sum(s);
+      if (lane == 0) ga.gfull[j] = s;
+    }
+    if (b == 0 && warp == kGWarps - 1) {
+      double v[kGMaxP];
+#pragma unroll
+      for (int q = 0; q < kGMaxP; ++q) { const int p = lane + 32 * q; v[q] = p < G ? ldcg(ga.fpart + p) : 0.0; }
+      double s = 0.0;
+#pragma unroll
+      for (int q = 0; q < kGMaxP; ++q) s += v[q];
+      s = warp_sum(s);
+      if (lane == 0) totals[8] = s;
+    }
+  };
+  // after the second barrier: this thread's two gradient entries
+  auto load_gradient = [&]() -> double2 {
+    double2 g = make_double2(0.0, 0.0);
+    if (t < ldv) { g = ldcg2(ga.gfull + c0); if (!own0) g.x = 0.0; if (!own1) g.y = 0.0; }
+    return g;
+  };
+  // kGSums per-thread terms -> totals[0 .. kGSums): warp tree, then the warps in order; identical in every CTA
+  auto block_sums = [&](const double (&a)[kGSums]) {
+#pragma unroll
+    for (int k = 0; k < kGSums; ++k) {
+      const double s = warp_sum(a[k]);
+      if (lane == 0) spart[warp * 8 + k] = s;
+    }
+    __syncthreads();
+    if (t < kGSums) {
+      double s = 0.0;
+#pragma unroll
+      for (int w = 0; w < kGWarps; ++w) s += spart[w * 8 + t];
+      totals[t] = s;
+    }
+    __syncthreads();
+  };
+  auto prox_step = [&](const double2 g) {
+    if (t < ldv) {
+      v_t.x = x_t.x - gamma * g.x; v_t.y = x_t.y - gamma * g.y;                 // :330 / :359
+      double2 xn = make_double2(0.0, 0.0);
+      if (own0) xn.x = prox_elem(P.g, v_t.x, gamma, c0, 0.0);                   // :332 / :361
+      if (own1) xn.y = prox_elem(P.g, v_t.y, gamma, c0 + 1, 0.0);
+      xprev_t = x_t; gprev_t = g; x_t = xn;
+      reinterpret_cast<double2*>(xs)[t] = xn;
+    }
+    __syncthreads();                                       // xs complete (shared memory, or this CTA's own global copy)
+  };
+
+  // ---- prologue (:327-332) ---------------------------------------------------------------------------------------------
+  {
+    local_gradient();
+    grid.sync();                                          // all partial gradients are in place
+    reduce_slice();
+    grid.sync();                                          // the gradient is complete
+    n_eval = 1; n_grad = 1;
+    prox_step(load_gradient());
+    n_proxg = 1;
+  }
+
+  for (int64_t it = 1; it <= O.maxit; ++it) {
+    phase_stamp(W, it, 0);                                // ADAPROX_PHASE_TIMING=1: CTA 0's clock at the phase boundaries
+    local_gradient();                                     // :336 value + pullback
+    n_eval++; n_grad++;
+    phase_stamp(W, it, 1);
+    grid.sync();                                          // barrier 1
+    phase_stamp(W, it, 2);
+    reduce_slice();
+    phase_stamp(W, it, 3);
+    grid.sync();                                          // barrier 2
+    phase_stamp(W, it, 4);
+    const double2 g = load_gradient();
+    {
+      double a[kGSums] = {0.0, 0.0, 0.0, 0.0, 0.0};
+      if (own0) {
+        const double pr = (v_t.x - x_t.x) / gamma + g.x;                        // :338 (old gamma)
+        const double dg = g.x - gprev_t.x, dx = x_t.x - xprev_t.x;
+        a[0] = pr * pr; a[1] = dg * dg; a[2] = dg * dx; a[3] = dx * dx;
+        if (want_obj) a[4] = prox_value_elem(P.g, x_t.x, c0);
+      }
+      if (own1) {
+        const double pr = (v_t.y - x_t.y) / gamma + g.y;
+        const double dg = g.y - gprev_t.y, dx = x_t.y - xprev_t.y;
+        a[0] = fma(pr, pr, a[0]); a[1] = fma(dg, dg, a[1]); a[2] = fma(dg, dx, a[2]); a[3] = fma(dx, dx, a[3]);
+        if (want_obj) a[4] += prox_value_elem(P.g, x_t.y, c0 + 1);
+      }
+      // Measured, not understood: without this CTA barrier between the loads / divisions above and the shuffle trees below the phase
+      // takes 6.2 us instead of 0.7 us (500 x 1000: 15.7 -> 9.5 us per iteration, profiles/r02_notes.md section 12).
+      __syncthreads();
+      block_sums(a);
+    }
+    phase_stamp(W, it, 5);
+    const double gamma_prev = gamma;
+    rule_step(O, totals[1], totals[2], totals[3], gamma, sigma, s0, s1);        // :341
+    norm_res = sqrt(norm_sq_jl(totals[0]) + adapgm_dual_res_sq(gamma, gamma_prev, sigma));   // :348 (dual part: 0, or NaN -- phases.cuh)
+    if (!(gamma == gamma) || !(norm_res == norm_res) || isinf(gamma)) flags |= ADAPROX_FLAG_NONFINITE;
+    if (b == 0 && t == 0 && W.rec != nullptr && it <= O.max_records) {
+      adaprox_record rc;
+      rc.it = it; rc.gamma = gamma; rc.sigma = sigma; rc.norm_res = norm_res;
+      rc.f_x = 0.5 * norm_sq_jl(totals[8]);
+      rc.g_x = want_obj ? prox_value_finish(P.g.kind, P.g.lambda, totals[4]) : NAN;
+      rc.h_Ax = want_obj ? 0.0 : NAN;
+      rc.f_evals = n_eval; rc.grad_f_evals = n_grad; rc.prox_g_evals = n_proxg; rc.prox_h_evals = 0;
+      rc.A_evals = 0; rc.At_evals = 0;
+      W.rec[it - 1] = rc;
+    }
+    if (it <= O.max_records) n_rec = it;
+    if (norm_res <= O.tol) { converged = true; it_done = it; break; }           // :354-356 (uniform over the grid: same bits everywhere)
+    phase_stamp(W, it, 6);
+    prox_step(g);
+    n_proxg++;
+    phase_stamp(W, it, 7);
+  }
+
+  if (b == 0) {                                            // converged: the iterate whose gradient was just evaluated; maxit: the last prox
+    if (own0) W.xout[c0] = x_t.x;
+    if (own1) W.xout[c0 + 1] = x_t.y;
+  }
+  if (b == 0 && t == 0) {
+    DResult r;
+    r.iters = it_done;
+    r.flags = flags | (converged ? ADAPROX_FLAG_CONVERGED : 0u);
+    r.xbuf = 0;
+    r.f_evals = n_eval; r.grad_f_evals = n_grad; r.prox_g_evals = n_proxg; r.prox_h_evals = 0;
+    r.A_evals = 0; r.At_evals = 0; r.n_records = n_rec;
+    r.final_gamma = gamma; r.final_sigma = sigma; r.final_norm_res = norm_res;
+    *W.res = r;
+  }
+}
+
+}  // namespace adaprox

@@ -338,7 +338,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_primal_dual(DProblem P, DOpts O
 
     // ---- P6: residual, record, convergence (:348-356) ----------------------------
     phase_stamp(W, it, 5);
-    norm_res = sqrt(norm_sq_jl(t5[0]) + (hasA ? norm_sq_jl(dr_sum) : 0.0));
+    norm_res = sqrt(norm_sq_jl(t5[0]) + (hasA ? norm_sq_jl(dr_sum) : adapgm_dual_res_sq(gamma, gamma_old, sigma)));   // no dual vector: 0 or NaN (phases.cuh)
     if (!(gamma == gamma) || !(norm_res == norm_res) || isinf(gamma)) flags |= ADAPROX_FLAG_NONFINITE;
     if (b == 0 && threadIdx.x == 0 && W.rec != nullptr && it <= O.max_records) {
       adaprox_record rc;

@@ -224,8 +224,9 @@ __global__ void __launch_bounds__(kRThreads, 1) k_adapgm_resident(DProblem P, DO
     }
     cluster_sync_all();                                   // barrier 2
     cluster_totals();
+    const double gamma_prev = gamma;
     rule_step(O, totals[1], totals[2], totals[3], gamma, sigma, s0, s1);        // :341
-    norm_res = sqrt(norm_sq_jl(totals[0]));                                     // :348 (dual part identically zero)
+    norm_res = sqrt(norm_sq_jl(totals[0]) + adapgm_dual_res_sq(gamma, gamma_prev, sigma));   // :348 (dual part: 0, or NaN -- phases.cuh)
     if (!(gamma == gamma) || !(norm_res == norm_res) || isinf(gamma)) flags |= ADAPROX_FLAG_NONFINITE;
     if (rank == 0 && t == 0 && W.rec != nullptr && it <= O.max_records) {
       adaprox_record rc;

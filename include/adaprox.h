@@ -155,7 +155,8 @@ typedef struct {
   int64_t matrix_passes;        /* sweeps over the matrix of f per gradient evaluation: 1 = single-pass
                                    fused A'(Ax-b) kernel, 2 = A*x then A'*r; 0 = f has no matrix;
                                    3 = the matrix is resident in the shared memory of one cluster for the
-                                   whole solve (small dense least squares): HBM is read once per SOLVE    */
+                                   whole solve (small dense least squares): HBM is read once per SOLVE;
+                                   4 = the same with the rows spread over the shared memory of all SMs    */
   int64_t collective;           /* row-sharded solves: 1 = ncclAllReduce per iteration, 2 = all-reduce inside the sweep
                                    kernel over NVLink peer memory; 0 = single GPU                       */
 } adaprox_result;

@@ -167,6 +167,52 @@ def test_resident_kernel_matches_grid_kernel_and_oracle(AdaProx, m, n):
     """Small dense least squares runs with the matrix resident in the shared memory of one 16-CTA cluster.  Shapes: the reference's
     own lasso sizes (lasso/runme.jl:192-207), fewer rows than CTAs, a single column, the widest row (n = 1024), ragged everything,
     and the largest matrix that still fits; every stepsize rule; box and translated-l1 prox; maxit = 0 and 1."""
+    _small_ls_kernel_check(AdaProx, m, n, {"ADAPROX_RESIDENT": "1"}, {"ADAPROX_RESIDENT": "0", "ADAPROX_GRIDRES": "0"}, 3)
+
+
+# ---------------------------------------------------------------- the grid-resident kernel (solver_gridres.cuh)
+@pytest.mark.parametrize("m,n", [(500, 1000), (4000, 1000), (120, 40), (1, 1024), (3000, 517), (4100, 1024), (4144, 1000)])
+def test_grid_resident_kernel_matches_grid_kernel_and_oracle(AdaProx, m, n):
+    """Dense least squares with rows of at most 1024 columns that fits the shared memory of all SMs together: the reference's 500 x 1000 and
+    4000 x 1000 lasso runs (lasso/runme.jl:191-195), more CTAs than rows, one row, ragged shapes, the widest row with every CTA full
+    (4100 x 1024: 28 rows of 8 KB per CTA), 148 x 28 rows exactly; same checks as the cluster-resident kernel."""
+    _small_ls_kernel_check(AdaProx, m, n, {"ADAPROX_RESIDENT": "0", "ADAPROX_GRIDRES": "1"}, {"ADAPROX_RESIDENT": "0", "ADAPROX_GRIDRES": "0"}, 4)
+
+
+def test_nonfinite_stepsize_reaches_the_residual_like_the_reference(AdaProx):
+    """src/AdaProx.jl:342-348 with A = 0, h = Zero: once the rule returns a NaN stepsize (Malitsky-Mishchenko on an iterate the box keeps
+    in place: dx = 0, L = 0 / 0), w = y + sigma * (...) * 0 is NaN, so norm_res is NaN, the test :354 never fires and x turns NaN -- although
+    the primal residual alone is exactly 0 at that point.  Every AdaPGM kernel has to do the same, not stop with 'converged'."""
+    import os
+    m, n = 149, 3
+    rng = np.random.default_rng(m * 31 + n)
+    A = np.asfortranarray(rng.standard_normal((m, n)) / np.sqrt(m))
+    b = rng.standard_normal(m)
+    Lf = float(np.linalg.norm(A, 2) ** 2)
+    rng.standard_normal(n)
+    x0 = 0.05 * rng.standard_normal(n)
+    logo = []
+    xo, ito = O.adaptive_proxgrad(x0, f=O.LinearLeastSquares(A, b), g=O.IndBox(-0.2, 0.5), rule=O.MalitskyMishchenkoRule(gamma=1 / Lf), tol=1e-9, maxit=12, log=logo)
+    assert ito == 12 and np.all(np.isnan(xo)) and np.isnan(logo[1]["norm_res"]) and np.isfinite(logo[0]["norm_res"])   # the instance is the degenerate one
+    f = AdaProx.LinearLeastSquares(A, b)
+    for env, passes in (({"ADAPROX_RESIDENT": "1"}, 3), ({"ADAPROX_RESIDENT": "0", "ADAPROX_GRIDRES": "1"}, 4),
+                        ({"ADAPROX_RESIDENT": "0", "ADAPROX_GRIDRES": "0"}, 2), ({"ADAPROX_FUSED": "1"}, 1)):
+        os.environ.update(env)
+        try:
+            log = []
+            x, it = AdaProx.adaptive_proxgrad(x0, f=f, g=AdaProx.IndBox(-0.2, 0.5), rule=AdaProx.MalitskyMishchenkoRule(gamma=1 / Lf), tol=1e-9, maxit=12, log=log)
+            assert AdaProx.last_solve_info()["matrix_passes"] == passes, env
+        finally:
+            for k_ in env:
+                os.environ.pop(k_, None)
+        assert it == 12 and np.all(np.isnan(x)), (env, it, x)
+        assert np.array_equal(np.isnan([r["norm_res"] for r in log]), np.isnan([r["norm_res"] for r in logo])), env
+        assert np.array_equal(np.isnan([r["gamma"] for r in log]), np.isnan([r["gamma"] for r in logo])), env
+        assert abs(log[0]["norm_res"] - logo[0]["norm_res"]) <= 1e-12 * logo[0]["norm_res"]
+    f.mat.free()
+
+
+def _small_ls_kernel_check(AdaProx, m, n, env_on, env_off, passes_on):
     import os
     rng = np.random.default_rng(m * 31 + n)
     A = np.asfortranarray(rng.standard_normal((m, n)) / np.sqrt(max(m, 2)))
@@ -178,6 +224,7 @@ def test_resident_kernel_matches_grid_kernel_and_oracle(AdaProx, m, n):
              ("fixed", AdaProx.Translate(AdaProx.NormL1(0.2), -c), lambda pm: O.Translate(O.NormL1(0.2), -c[pm])), ("plus", AdaProx.Zero(), lambda pm: O.Zero())]
     f = AdaProx.LinearLeastSquares(A, b)
     gscale = float(np.linalg.norm(A.T @ (A @ x0 - b))) + 1e-300      # residuals are compared down to 1e-12 of the initial gradient
+    fscale = 0.5 * float(np.sum((A @ x0 - b) ** 2))                   # ... objectives down to 1e-13 of the value at x0 (one row: the first step lands on 0)
     ident = np.arange(n)
     for rule, gd, mkg in cases:
         mk = {"our": lambda M: M.OurRule(gamma=1 / Lf), "mm": lambda M: M.MalitskyMishchenkoRule(gamma=1 / Lf),
@@ -194,16 +241,17 @@ def test_resident_kernel_matches_grid_kernel_and_oracle(AdaProx, m, n):
         kenv = min(len(logo), min(len(g_) for g_ in gperms))
         env = drift.perm_envelope(_gam(logo, kenv), [g_[:kenv] for g_ in gperms]) if kenv > 0 else np.zeros(0)
         got = {}
-        for mode in ("1", "0"):
-            os.environ["ADAPROX_RESIDENT"] = mode
+        for mode, env_ in (("1", env_on), ("0", env_off)):
+            os.environ.update(env_)
             try:
                 fc = AdaProx.Counting(f)
                 log = []
                 x, it = AdaProx.adaptive_proxgrad(x0, f=fc, g=gd, rule=mk(AdaProx), tol=1e-9, maxit=60, log=log)
                 got[mode] = (x, it, log, AdaProx.last_solve_info()["matrix_passes"], (fc.eval_count, fc.grad_count))
             finally:
-                os.environ.pop("ADAPROX_RESIDENT", None)
-        assert got["1"][3] == 3 and got["0"][3] == 2, "kernel selection"
+                for k_ in env_:
+                    os.environ.pop(k_, None)
+        assert got["1"][3] == passes_on and got["0"][3] == 2, ("kernel selection", got["1"][3], got["0"][3])
         for mode in ("1", "0"):
             x, it, log, _, counts = got[mode]
             assert abs(it - ito) <= 1 and counts == (it + 1, it + 1), (rule, mode, it, ito)
@@ -213,16 +261,18 @@ def test_resident_kernel_matches_grid_kernel_and_oracle(AdaProx, m, n):
             k10 = min(k, 10)
             # (absolute floor relative to the first value: on underdetermined instances the objective runs to 0 through cancellation)
             assert np.allclose([r["objective"] for r in log[:k10]], [r["objective"] for r in logo[:k10]], rtol=1e-10,
-                               atol=1e-13 * abs(logo[0]["objective"])), (rule, mode)
+                               atol=1e-13 * max(abs(logo[0]["objective"]), fscale)), (rule, mode)
             assert np.allclose([r["norm_res"] for r in log[:k10]], [r["norm_res"] for r in logo[:k10]], rtol=1e-9,
                                atol=1e-12 * gscale), (rule, mode)
             assert np.linalg.norm(x - xo) <= 1e-6 * max(np.linalg.norm(xo), 1e-12), (rule, mode)
     for maxit in (0, 1):
-        os.environ["ADAPROX_RESIDENT"] = "1"
+        os.environ.update(env_on)
         try:
             x, it = AdaProx.adaptive_proxgrad(x0, f=f, g=AdaProx.NormL1(0.3), rule=AdaProx.OurRule(gamma=1 / Lf), tol=0.0, maxit=maxit)
+            assert AdaProx.last_solve_info()["matrix_passes"] == passes_on
         finally:
-            os.environ.pop("ADAPROX_RESIDENT", None)
+            for k_ in env_on:
+                os.environ.pop(k_, None)
         xo, ito = O.adaptive_proxgrad(x0, f=O.LinearLeastSquares(A, b), g=O.NormL1(0.3), rule=O.OurRule(gamma=1 / Lf), tol=0.0, maxit=maxit)
         assert it == ito == maxit and np.linalg.norm(x - xo) <= 1e-13 * max(np.linalg.norm(xo), 1e-12)
     f.mat.free()
