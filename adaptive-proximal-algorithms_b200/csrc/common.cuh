@@ -172,6 +172,21 @@ __device__ __forceinline__ void block_reduce_store(double (&v)[K], double* red, 
   __syncthreads();
 }
 
+// sum of p[b * stride] over b = lane, lane + 32, ... < count, added in that order.  The loads are issued eight at a time: written
+// as `s += ldcg(...)` in a loop, each addition waits for its own L2 round trip (~0.7 us) before the next load is even issued --
+// ten of them in a row for the 296 partials of one scalar.  Same order of additions as the plain loop, so the same bits.
+__device__ __forceinline__ double lane_strided_sum(const double* p, int count, int64_t stride, int lane) {
+  double s = 0.0;
+  for (int b0 = lane; b0 < count; b0 += 256) {
+    double v[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { const int b = b0 + 32 * q; v[q] = b < count ? ldcg(p + (int64_t)b * stride) : 0.0; }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) if (b0 + 32 * q < count) s += v[q];
+  }
+  return s;
+}
+
 // Sum the per-CTA partials of K slots in a fixed order; every thread of every
 // CTA obtains bit-identical totals.  Must follow a grid-wide sync (or a kernel
 // boundary) after the block_reduce_store that produced the partials.
@@ -179,10 +194,7 @@ template <int K>
 __device__ __forceinline__ void grid_totals(const double* red, int G, int slot0, double (&out)[K], double* s_scratch) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int k = warp; k < K; k += kWarps) {
-    const double* p = red + (int64_t)(slot0 + k) * G;
-    double s = 0.0;
-    for (int b = lane; b < G; b += 32) s += ldcg(p + b);
-    s = warp_sum(s);
+    const double s = warp_sum(lane_strided_sum(red + (int64_t)(slot0 + k) * G, G, 1, lane));
     if (lane == 0) s_scratch[k] = s;
   }
   __syncthreads();

@@ -290,7 +290,13 @@ __device__ __forceinline__ void gemv_t_phase(const DMat& M, const double* r, Sh&
 __device__ __forceinline__ double zsum(const DMat& M, int64_t i) {
   if (M.kind == MAT_CSR) return ldcg(M.zpart + i);
   double s = 0.0;
-  for (int c = 0; c < M.nchunks; ++c) s += ldcg(M.zpart + (int64_t)c * M.m + i);
+  for (int c0 = 0; c0 < M.nchunks; c0 += 8) {             // loads eight at a time, additions in chunk order
+    double v[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v[q] = c0 + q < M.nchunks ? ldcg(M.zpart + (int64_t)(c0 + q) * M.m + i) : 0.0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) if (c0 + q < M.nchunks) s += v[q];
+  }
   return s;
 }
 
@@ -317,8 +323,18 @@ __device__ __forceinline__ void gsum_slice(const DMat& M, int64_t j0, int64_t j1
         cur_c = c;
       }
       double s = 0.0;
-      for (int bb = blo; bb <= bhi; ++bb)
-        if (unit_begin(U, bb + 1, G) > unit_begin(U, bb, G)) s += ldcg(M.gpart + (int64_t)bb * M.npad + j);
+      for (int b0 = blo; b0 <= bhi; b0 += 8) {            // loads eight at a time, additions in CTA order (common.cuh: lane_strided_sum)
+        double v[8];
+        bool has[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int bb = b0 + q;
+          has[q] = bb <= bhi && unit_begin(U, bb + 1, G) > unit_begin(U, bb, G);
+          v[q] = has[q] ? ldcg(M.gpart + (int64_t)bb * M.npad + j) : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) if (has[q]) s += v[q];
+      }
       out[j] = s;
     }
   } else {
@@ -328,8 +344,18 @@ __device__ __forceinline__ void gsum_slice(const DMat& M, int64_t j0, int64_t j1
       const int blo = unit_owner(U, (int64_t)c * M.nrb, G);
       const int bhi = unit_owner(U, (int64_t)(c + 1) * M.nrb - 1, G);
       double s = 0.0;
-      for (int bb = blo + lane; bb <= bhi; bb += 32)
-        if (unit_begin(U, bb + 1, G) > unit_begin(U, bb, G)) s += ldcg(M.gpart + (int64_t)bb * M.npad + j);
+      for (int b0 = blo + lane; b0 <= bhi; b0 += 256) {
+        double v[8];
+        bool has[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int bb = b0 + 32 * q;
+          has[q] = bb <= bhi && unit_begin(U, bb + 1, G) > unit_begin(U, bb, G);
+          v[q] = has[q] ? ldcg(M.gpart + (int64_t)bb * M.npad + j) : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) if (has[q]) s += v[q];
+      }
       s = warp_sum(s);
       if (lane == 0) out[j] = s;
     }

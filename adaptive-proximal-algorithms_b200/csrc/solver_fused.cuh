@@ -614,9 +614,7 @@ __device__ __forceinline__ void fused_gradient_slice(const FusedArgs& fa, int64_
 __device__ __forceinline__ double fused_fsum(const FusedArgs& fa, uint32_t scr) {
   const int lane = threadIdx.x & 31;
   if (threadIdx.x < 32) {
-    double s = 0.0;
-    for (int c = lane; c < fa.nchunks; c += 32) s += ldcg(fa.fpart + c);
-    s = warp_sum(s);
+    const double s = warp_sum(lane_strided_sum(fa.fpart, fa.nchunks, 1, lane));
     if (lane == 0) sts1(scr, s);
   }
   __syncthreads();
@@ -647,10 +645,7 @@ template <int K>
 __device__ __forceinline__ void f_grid_totals(const double* red, int G, int slot0, double (&out)[K], uint32_t scr) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int k = warp; k < K; k += kFWarps) {
-    const double* p = red + (int64_t)(slot0 + k) * G;
-    double s = 0.0;
-    for (int b = lane; b < G; b += 32) s += ldcg(p + b);
-    s = warp_sum(s);
+    const double s = warp_sum(lane_strided_sum(red + (int64_t)(slot0 + k) * G, G, 1, lane));
     if (lane == 0) sts1(scr + k * 8, s);
   }
   __syncthreads();

@@ -671,6 +671,7 @@ def test_fused_single_pass_matches_two_pass_and_oracle(AdaProx, m, n, pf):
         for mode in ("0", "1"):
             os.environ["ADAPROX_FUSED"] = mode
             os.environ["ADAPROX_RESIDENT"] = "0"          # mode 0 = the two-pass grid kernel (the 400 x 1000 case would run cluster-resident)
+            os.environ["ADAPROX_GRIDRES"] = "0"           # ... or grid-resident
             f = AdaProx.Counting(f_raw)
             log = []
             x, it = AdaProx.adaptive_proxgrad(np.zeros(n), f=f, g=AdaProx.NormL1(1.0), rule=AdaProx.OurRule(gamma=1 / Lf),
@@ -679,6 +680,7 @@ def test_fused_single_pass_matches_two_pass_and_oracle(AdaProx, m, n, pf):
     finally:
         os.environ.pop("ADAPROX_FUSED", None)
         os.environ.pop("ADAPROX_RESIDENT", None)
+        os.environ.pop("ADAPROX_GRIDRES", None)
     logo = []
     xo, ito = O.adaptive_proxgrad(np.zeros(n), f=O.LinearLeastSquares(P["A"], P["b"]), g=O.NormL1(1.0), rule=O.OurRule(gamma=1 / Lf),
                                   tol=1e-6, maxit=3000, log=logo)
@@ -835,6 +837,7 @@ def test_fused_edge_cases(AdaProx):
         for mode in ("0", "1"):
             os.environ["ADAPROX_FUSED"] = mode
             os.environ["ADAPROX_RESIDENT"] = "0"          # this test compares the sweep kernel with the two-pass grid kernel
+            os.environ["ADAPROX_GRIDRES"] = "0"
             for k, v in (env or {}).items():
                 os.environ[k] = v
             try:
@@ -845,6 +848,7 @@ def test_fused_edge_cases(AdaProx):
             finally:
                 os.environ.pop("ADAPROX_FUSED", None)
                 os.environ.pop("ADAPROX_RESIDENT", None)
+                os.environ.pop("ADAPROX_GRIDRES", None)
                 for k in (env or {}):
                     os.environ.pop(k, None)
         return res

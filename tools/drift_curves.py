@@ -27,7 +27,7 @@ out = {"instance": "planted lasso 400x1000 (configs[0]), AdaPGM OurRule gamma0 =
        "float64_envelope_running_max": drift.envelope(truth).tolist()}
 f, g = AdaProx.LinearLeastSquares(P["A"], P["b"]), AdaProx.NormL1(1.0)
 for name, env in (("device_cluster_resident", {}), ("device_single_sweep", {"ADAPROX_FUSED": "1"}),
-                  ("device_two_pass_grid", {"ADAPROX_RESIDENT": "0", "ADAPROX_FUSED": "0"})):
+                  ("device_two_pass_grid", {"ADAPROX_RESIDENT": "0", "ADAPROX_GRIDRES": "0", "ADAPROX_FUSED": "0"})):
     os.environ.update(env)
     try:
         log = []
