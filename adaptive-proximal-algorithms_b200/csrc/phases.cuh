@@ -162,6 +162,9 @@ __host__ __device__ inline void rule_init(const DOpts& o, double& gamma, double&
 // every entry NaN, norm_res (:348) is NaN, the test :354 fails and the next v = x - gamma * grad carries the NaN into x.  The
 // kernels without a dual vector reproduce that with the same arithmetic on one entry.  Returns (entry of dual_res)^2.
 __host__ __device__ inline double adapgm_dual_res_sq(double gamma, double gamma_prev, double sigma) {
+  // ordinary values: rho and 1 + rho are finite, sigma is finite and not 0, every product below is a zero -- skip the two divisions
+  // (they sit on the serial scalar path of a 7 us iteration).  NaN fails every comparison and takes the exact path.
+  if (fabs(gamma) <= 1e150 && fabs(gamma_prev) >= 1e-150 && fabs(sigma) <= 1.7e308 && sigma != 0.0) return 0.0;
   const double rho = gamma / gamma_prev;                                                       // :342
   const double w = 0.0 + sigma * ((1.0 + rho) * 0.0 - rho * 0.0);                              // :344
   const double d = (w - 0.0) / sigma - 0.0;                                                    // :347
