@@ -1,5 +1,5 @@
 """One small workload per kernel family, for `ncu -k <kernel>` captures (profiles/r02_ncu_*.json):
-    python tools/profile_kernels.py resident | c2 | pgfamily | mp | path | lad
+    python tools/profile_kernels.py resident | gridres | c2 | pgfamily | mp | path | lad
 Each prints one JSON line with the device time of the solve (NOT a bench value when run under ncu)."""
 import json
 import sys
@@ -18,6 +18,12 @@ def main():
         Lf = AdaProx.synth.spectral_norm_sq(P["A"], iters=1000, tol=1e-15)
         x, it = AdaProx.adaptive_proxgrad(np.zeros(1000), f=AdaProx.LinearLeastSquares(P["A"], P["b"]), g=AdaProx.NormL1(1.0),
                                           rule=AdaProx.OurRule(gamma=1 / Lf), tol=0.0, maxit=2000)
+    elif which == "gridres":         # k_adapgm_gridres: the largest lasso instance of lasso/runme.jl:191-195
+        P = AdaProx.synth.planted_lasso(4000, 1000, 10, 0)
+        Lf = AdaProx.synth.spectral_norm_sq(P["A"], iters=100)
+        x, it = AdaProx.adaptive_proxgrad(np.zeros(1000), f=AdaProx.LinearLeastSquares(P["A"], P["b"]), g=AdaProx.NormL1(1.0),
+                                          rule=AdaProx.OurRule(gamma=1 / Lf), tol=0.0, maxit=2000)
+        assert AdaProx.last_solve_info()["matrix_passes"] == 4
     elif which == "c2":              # k_primal_dual<false> with the CSR sweeps (spmv_rows): configs[1]
         import scipy.sparse as sp
         m, n = 20242, 47236

@@ -15,6 +15,7 @@ MNEMONICS = ["UBLKCP", "SYNCS", "STAS", "UCGABAR", "CCTL", "MAPA", "LDS", "STS",
 KERNELS = {
     "k_adapgm_fused": ("single-sweep AdaPGM kernel (solver_fused.cuh): bulk-copy ring, DSMEM exchange", r"STAS", 70, 40),
     "k_adapgm_resident": ("cluster-resident AdaPGM kernel (solver_resident.cuh): DSMEM reduce / broadcast, cluster barriers", r"UCGABAR_ARV", 60, 30),
+    "k_adapgm_gridres": ("grid-resident AdaPGM kernel (solver_gridres.cuh): rows in shared memory, partial gradients through L2, two grid barriers", r"LDG\.E\.128\.STRONG\.GPU|LDG\.E\.128", 60, 40),
     "k_primal_dual": ("persistent primal-dual kernel (solver_pd.cuh): bulk-copy ring GEMV phases", r"UBLKCP", 30, 60),
     "k_path_gemm": ("lambda-path contraction (path_gemm.cuh): fp64 tensor-core MMA from a cp.async ring", r"DMMA", 40, 60),
     "k_proxgrad_family": ("backtracking / Nesterov / aGRAAL kernel (solver_pg.cuh)", r"UBLKCP", 20, 40),
