@@ -348,6 +348,24 @@ def configs_block(AdaProx, peak_hbm):
         "kernel": info.get("kernel", "persistent"), "launches": info["kernel_launches"],
         "roofline": {"bound": "latency (3.2 MB matrix, L2/SMEM resident)", "achieved_l2_gbs": 2 * 8 * 400 * 1000 / (us * 1e-6) / 1e9, "frac": None},
         "cpu_port": {"us_per_iteration": 1e6 * dt / ito, "time_to_tol_ms": 1e3 * dt}}
+    # the other two sizes of the reference's lasso experiment (lasso/runme.jl:191-195, pfactor 10): grid-resident kernel
+    for (mm, nn) in ((500, 1000), (4000, 1000)):
+        P = AdaProx.synth.planted_lasso(mm, nn, 10, 0)
+        Lf = AdaProx.synth.spectral_norm_sq(P["A"], iters=300, tol=1e-13)
+        f, g = AdaProx.LinearLeastSquares(P["A"], P["b"]), AdaProx.NormL1(1.0)
+        AdaProx.adaptive_proxgrad(np.zeros(nn), f=f, g=g, rule=AdaProx.OurRule(gamma=1 / Lf), tol=1e-7, maxit=200)
+        x, it = AdaProx.adaptive_proxgrad(np.zeros(nn), f=f, g=g, rule=AdaProx.OurRule(gamma=1 / Lf), tol=1e-7, maxit=2000)
+        info = AdaProx.last_solve_info()
+        Kc = 300
+        dt, _ = cpu_time(lambda: O.adaptive_proxgrad(np.zeros(nn), f=O.LinearLeastSquares(P["A"], P["b"]), g=O.NormL1(1.0),
+                                                     rule=O.OurRule(gamma=1 / Lf), tol=0.0, maxit=Kc))
+        us = 1e3 * info["solve_ms"] / it
+        out[f"lasso_{mm}x{nn}_adapgm"] = {
+            "iterations": int(it), "tol": 1e-7, "maxit": 2000, "us_per_iteration": us, "iters_per_s": 1e6 / us, "time_ms": info["solve_ms"],
+            "matrix_passes_code": int(info["matrix_passes"]), "launches": info["kernel_launches"], "final_norm_res": info["final_norm_res"],
+            "roofline": {"bound": "latency (matrix resident in the shared memory of all SMs; two grid barriers per iteration)", "frac": None},
+            "cpu_port": {"us_per_iteration": 1e6 * dt / Kc, "sample": f"{Kc} iterations, numpy/OpenBLAS dgemv"}}
+        f.mat.free()
     # C2 -------------------------------------------------------------------------------------------------------
     m, n = 20242, 47236
     rp, ci, va, y = AdaProx.synth.sparse_logreg(m, n, 0)
