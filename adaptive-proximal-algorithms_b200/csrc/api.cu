@@ -889,7 +889,7 @@ extern "C" int adaprox_solve(adaprox_handle h, const adaprox_problem* p, const a
   const bool resident = !sharded && resident_eligible(h, o, P, &rarg, &rsmem);
   GridResArgs garg{};
   size_t gsmem = 0;
-  const bool gridres = !sharded && !resident && gridres_eligible(h, o, P, &garg, &gsmem);
+  bool gridres = !sharded && !resident && gridres_eligible(h, o, P, &garg, &gsmem);
   bool fused = sharded_fused || (!resident && !gridres && !sharded && fused_eligible(o, P, P.F.m));
   if (gridres) G = std::max(G, h->sm_count);
   FusedPlan fpl;
@@ -982,9 +982,16 @@ extern "C" int adaprox_solve(adaprox_handle h, const adaprox_problem* p, const a
       } else if (gridres) {
         void* gargs[] = {&P, &O, &W, &garg};
         cudaError_t e = cudaLaunchCooperativeKernel((const void*)k_adapgm_gridres, dim3(h->sm_count), dim3(kGThreads), gargs, gsmem, h->stream);
-        if (e != cudaSuccess) return fail(h, ADAPROX_ERR_CUDA, std::string("grid-resident cooperative launch: ") + cudaGetErrorString(e));
-        h->launches++;
-        rc = ADAPROX_OK;
+        if (e == cudaSuccess) {
+          h->launches++;
+          rc = ADAPROX_OK;
+        } else {
+          // one CTA per SM with all of its shared memory: refused (cudaErrorCooperativeLaunchTooLarge) when something else holds SMs.
+          // The persistent grid kernel needs far less per SM; the workspace above covers it.
+          cudaGetLastError();
+          gridres = false;
+          rc = coop_launch(h, k_primal_dual<false>, args, Gcoop);
+        }
       } else if (fused) {
         cudaError_t e = cudaLaunchKernelExC(&fpl.cfg, (const void*)k_adapgm_fused, fargs);
         if (e != cudaSuccess) return fail(h, ADAPROX_ERR_CUDA, std::string("fused cluster launch: ") + cudaGetErrorString(e));
