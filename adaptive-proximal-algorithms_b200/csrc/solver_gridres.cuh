@@ -227,9 +227,14 @@ __global__ void __launch_bounds__(kGThreads, 1) k_adapgm_gridres(DProblem P, DOp
         a[0] = fma(pr, pr, a[0]); a[1] = fma(dg, dg, a[1]); a[2] = fma(dg, dx, a[2]); a[3] = fma(dx, dx, a[3]);
         if (want_obj) a[4] += prox_value_elem(P.g, x_t.y, c0 + 1);
       }
-      // Measured, not understood: without this CTA barrier between the loads / divisions above and the shuffle trees below the phase
-      // takes 6.2 us instead of 0.7 us (500 x 1000: 15.7 -> 9.5 us per iteration, profiles/r02_notes.md section 12).
-      __syncthreads();
+      // Warp 0 leaves cooperative_groups' grid.sync() diverged (its thread 0 polled the arrival counter), and ptxas cannot prove
+      // convergence across the predicated blocks above: without a convergence point here the 50 SHFL of the five shuffle trees are
+      // emitted a second time behind BRA.DIV / WARPSYNC guards (SASS: 224 SHFL, 121 WARPSYNC instead of 174 / 71) and the diverged
+      // warp takes that path -- 6.2 us for this phase instead of 1.2 us (500 x 1000: 15.7 vs 8.2 us per iteration, measured;
+      // __syncwarp and a CTA barrier do equally well; -DADAPROX_EXP_GR_NO_PRESYNC removes it for the A/B).
+#ifndef ADAPROX_EXP_GR_NO_PRESYNC
+      __syncwarp();
+#endif
       block_sums(a);
     }
     phase_stamp(W, it, 5);
