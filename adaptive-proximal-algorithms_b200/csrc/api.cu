@@ -782,12 +782,21 @@ static bool resident_eligible(adaprox_ctx* h, const adaprox_options* o, const DP
 
 // Dense least squares with short rows that fits the shared memory of all SMs together (solver_gridres.cuh): the reference's
 // 500 x 1000 and 4000 x 1000 lasso runs.  ADAPROX_GRIDRES=0 disables it (A/B against the persistent grid kernel).
+static const void* gridres_kernel(int solver) {
+  switch (solver) {
+    case ADAPROX_S_ADAPTIVE_PROXGRAD: return (const void*)k_adapgm_gridres<0>;
+    case ADAPROX_S_FIXED_NESTEROV: return (const void*)k_adapgm_gridres<1>;
+    case ADAPROX_S_AGRAAL: return (const void*)k_adapgm_gridres<2>;
+    default: return nullptr;
+  }
+}
 static bool gridres_eligible(adaprox_ctx* h, const adaprox_options* o, const DProblem& P, GridResArgs* ga, size_t* smem) {
   const char* e = std::getenv("ADAPROX_GRIDRES");
   if (e && std::strcmp(e, "0") == 0) return false;
   const char* ef = std::getenv("ADAPROX_FUSED");
   if (ef && std::strcmp(ef, "1") == 0) return false;       // the sweep kernel was requested explicitly
-  if (o->solver != ADAPROX_S_ADAPTIVE_PROXGRAD || P.f_kind != ADAPROX_F_LEAST_SQUARES || P.F.kind != MAT_DENSE) return false;
+  const void* kernel = gridres_kernel(o->solver);          // AdaPGM / fixed-step PGM, fixed_nesterov, agraal
+  if (!kernel || P.f_kind != ADAPROX_F_LEAST_SQUARES || P.F.kind != MAT_DENSE || P.A.kind != MAT_NONE) return false;
   if (P.g.kind == ADAPROX_P_NORM_L2 || P.g.conjugate) return false;
   if (P.F.ld > kGMaxLd || P.n < 1 || P.F.m < 1) return false;
   const int G = h->sm_count;
@@ -803,8 +812,8 @@ static bool gridres_eligible(adaprox_ctx* h, const adaprox_options* o, const DPr
   *smem = gridres_smem_bytes(ga->rows_cap, P.F.ld, ga->x_in_smem != 0);
   if (*smem + 1024 > (size_t)max_optin) return false;
   int per_sm = 0;
-  if (cudaFuncSetAttribute((const void*)k_adapgm_gridres, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*smem) != cudaSuccess ||
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)k_adapgm_gridres, kGThreads, *smem) != cudaSuccess || per_sm < 1) {
+  if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*smem) != cudaSuccess ||
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kGThreads, *smem) != cudaSuccess || per_sm < 1) {
     cudaGetLastError();
     return false;
   }
@@ -904,7 +913,7 @@ extern "C" int adaprox_solve(adaprox_handle h, const adaprox_problem* p, const a
   const int64_t nfu = (P.f_kind == ADAPROX_F_QUADRATIC_GRAM) ? P.F.n : 1;
   const int64_t gr_x = gridres ? (garg.x_in_smem ? 1 : (int64_t)h->sm_count * P.F.ld) : 1;
   size_t need = (fused ? fused_ws_bytes(fpl) : 0) + (sharded_fused ? ws_size_doubles(n + 2) : 0) +
-                (gridres ? ws_size_doubles(P.F.ld) + ws_size_doubles(h->sm_count) + ws_size_doubles(gr_x) : 0) +
+                (gridres ? ws_size_doubles(P.F.ld) + 2 * ws_size_doubles(h->sm_count) + ws_size_doubles(gr_x) : 0) +
                 9 * ws_size_doubles(n) + 2 * ws_size_doubles(n + 8) + 6 * ws_size_doubles(md) + ws_size_doubles(mf) + ws_size_doubles(nfu) +
                 ws_size_doubles((int64_t)kMaxRed * G) + ws_size_doubles((nrec * (int64_t)sizeof(adaprox_record) + 7) / 8) +
                 ws_size_doubles((sizeof(DResult) + 7) / 8);
@@ -930,6 +939,7 @@ extern "C" int adaprox_solve(adaprox_handle h, const adaprox_problem* p, const a
   if (gridres) {
     garg.gfull = ws_doubles(h, P.F.ld);
     garg.fpart = ws_doubles(h, h->sm_count);
+    garg.fpart2 = ws_doubles(h, h->sm_count);
     garg.xpriv = ws_doubles(h, gr_x);
   }
   if (sharded_fused) {
@@ -981,7 +991,7 @@ extern "C" int adaprox_solve(adaprox_handle h, const adaprox_problem* p, const a
         rc = ADAPROX_OK;
       } else if (gridres) {
         void* gargs[] = {&P, &O, &W, &garg};
-        cudaError_t e = cudaLaunchCooperativeKernel((const void*)k_adapgm_gridres, dim3(h->sm_count), dim3(kGThreads), gargs, gsmem, h->stream);
+        cudaError_t e = cudaLaunchCooperativeKernel(gridres_kernel(o->solver), dim3(h->sm_count), dim3(kGThreads), gargs, gsmem, h->stream);
         if (e == cudaSuccess) {
           h->launches++;
           rc = ADAPROX_OK;
@@ -1030,7 +1040,18 @@ extern "C" int adaprox_solve(adaprox_handle h, const adaprox_problem* p, const a
     case ADAPROX_S_BACKTRACKING_NESTEROV:
     case ADAPROX_S_FIXED_NESTEROV:
     case ADAPROX_S_AGRAAL:
-      rc = coop_launch(h, k_proxgrad_family, args, Gcoop);
+      rc = 1;
+      if (gridres) {            // fixed_nesterov / agraal on a small dense least-squares term: the grid-resident form (solver_gridres.cuh)
+        void* gargs[] = {&P, &O, &W, &garg};
+        if (cudaLaunchCooperativeKernel(gridres_kernel(o->solver), dim3(h->sm_count), dim3(kGThreads), gargs, gsmem, h->stream) == cudaSuccess) {
+          h->launches++;
+          rc = ADAPROX_OK;
+        } else {
+          cudaGetLastError();
+          gridres = false;
+        }
+      }
+      if (rc == 1) rc = coop_launch(h, k_proxgrad_family, args, Gcoop);
       break;
     case ADAPROX_S_MALITSKY_POCK:
       rc = coop_launch(h, k_malitsky_pock, args, Gcoop);

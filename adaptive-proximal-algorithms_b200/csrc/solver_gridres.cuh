@@ -14,6 +14,8 @@
 //   * grid barrier;  EVERY CTA loads the whole gradient (8 KB) and repeats the rest of the iteration for all n columns: the
 //     four stepsize sums of src/AdaProx.jl:338,260-261 (fixed order: the same bits in every CTA), the stepsize rule, the
 //     convergence test, the prox step.  The new iterate never leaves the CTA, so there is no third barrier.
+// MODE 1 / 2 run the two comparison methods of the lasso experiment that need no linesearch -- fixed_nesterov (src/AdaProx.jl:91-142)
+// and agraal (:150-192) -- through the same passes and barriers (solver_pg.cuh holds their general grid form).
 // No atomics, every sum has a fixed order: reruns are bit-identical.  Limits: ld <= 1024 (a row fits one warp's registers, a
 // thread owns two columns), ceil(m / G) rows of A per CTA in shared memory, ceil(n / G) <= 16 gradient entries per CTA, G <= 256.
 #pragma once
@@ -36,7 +38,8 @@ struct GridResArgs {
   int row_ctas;            // CTAs that own at least one row: ceil(m / rows_cap)
   int x_in_smem;           // the CTA's copy of x lives in shared memory (else in xpriv: the last row did not leave room)
   double* gfull;           // [ld]     the gradient of the iteration
-  double* fpart;           // [G]      per-CTA sums of r_i^2
+  double* fpart;           // [G]      per-CTA sums of r_i^2 (gradient evaluations)
+  double* fpart2;          // [G]      the same for the value-only evaluations of MODE 1 / 2 (f(x) of the record)
   double* xpriv;           // [G][ld]  per-CTA copies of x when !x_in_smem
 };
 
@@ -44,6 +47,7 @@ __host__ __device__ inline size_t gridres_smem_bytes(int64_t rows_cap, int64_t l
   return (size_t)8 * (size_t)(rows_cap * ld + 2 * rows_cap + kGWarps + kGWarps * 8 + 16 + (x_in_smem ? ld : 0));
 }
 
+template <int MODE>      // 0: AdaPGM / fixed-step PGM, 1: fixed_nesterov, 2: agraal
 __global__ void __launch_bounds__(kGThreads, 1) k_adapgm_gridres(DProblem P, DOpts O, DWork W, GridResArgs ga) {
   cooperative_groups::grid_group grid = cooperative_groups::this_grid();
   extern __shared__ __align__(1024) unsigned char dyn_smem[];
@@ -131,6 +135,48 @@ __global__ void __launch_bounds__(kGThreads, 1) k_adapgm_gridres(DProblem P, DOp
       ga.fpart[b] = fs;
     }
   };
+  // value only (pass 1) at xs: this CTA's sum of r_i^2 -> fpart2[b]
+  auto local_value = [&]() {
+    double2 xr[kGLaneV];
+#pragma unroll
+    for (int k = 0; k < kGLaneV; ++k) {
+      const int idx = lane + 32 * k;
+      xr[k] = idx < ldv ? reinterpret_cast<const double2*>(xs)[idx] : make_double2(0.0, 0.0);
+    }
+    double fw = 0.0;
+    for (int i = warp; i < rows; i += kGWarps) {
+      const double2* row = reinterpret_cast<const double2*>(As + (size_t)i * ld);
+      double p0 = 0.0, p1 = 0.0;
+#pragma unroll
+      for (int k = 0; k < kGLaneV; ++k) {
+        const int idx = lane + 32 * k;
+        if (idx < ldv) { const double2 a = row[idx]; p0 = fma(a.x, xr[k].x, p0); p1 = fma(a.y, xr[k].y, p1); }
+      }
+      const double res = warp_sum(p0 + p1) - b_loc[i];
+      fw = fma(res, res, fw);
+    }
+    if (lane == 0) wpart[warp] = fw;
+    __syncthreads();
+    if (t == 0) {
+      double fs = 0.0;
+#pragma unroll
+      for (int w = 0; w < kGWarps; ++w) fs += wpart[w];
+      ga.fpart2[b] = fs;
+    }
+  };
+  // CTA 0, last warp: the G value partials in CTA order -> totals[8]
+  auto value_total = [&](const double* part) {
+    if (b == 0 && warp == kGWarps - 1) {
+      double v[kGMaxP];
+#pragma unroll
+      for (int q = 0; q < kGMaxP; ++q) { const int p = lane + 32 * q; v[q] = p < G ? ldcg(part + p) : 0.0; }
+      double s = 0.0;
+#pragma unroll
+      for (int q = 0; q < kGMaxP; ++q) s += v[q];
+      s = warp_sum(s);
+      if (lane == 0) totals[8] = s;
+    }
+  };
   // after the first barrier: warp w reduces gradient entry b S + w (lane l the CTAs l, l + 32, ... in order, then the shuffle
   // tree); the last warp of CTA 0 sums the value partials for the record the same way
   auto reduce_slice = [&]() {
@@ -145,16 +191,7 @@ __global__ void __launch_bounds__(kGThreads, 1) k_adapgm_gridres(DProblem P, DOp
       s = warp_sum(s);
       if (lane == 0) ga.gfull[j] = s;
     }
-    if (b == 0 && warp == kGWarps - 1) {
-      double v[kGMaxP];
-#pragma unroll
-      for (int q = 0; q < kGMaxP; ++q) { const int p = lane + 32 * q; v[q] = p < G ? ldcg(ga.fpart + p) : 0.0; }
-      double s = 0.0;
-#pragma unroll
-      for (int q = 0; q < kGMaxP; ++q) s += v[q];
-      s = warp_sum(s);
-      if (lane == 0) totals[8] = s;
-    }
+    if (MODE == 0) value_total(ga.fpart);
   };
   // after the second barrier: this thread's two gradient entries
   auto load_gradient = [&]() -> double2 {
@@ -190,74 +227,209 @@ __global__ void __launch_bounds__(kGThreads, 1) k_adapgm_gridres(DProblem P, DOp
     __syncthreads();                                       // xs complete (shared memory, or this CTA's own global copy)
   };
 
-  // ---- prologue (:327-332) ---------------------------------------------------------------------------------------------
-  {
-    local_gradient();
-    grid.sync();                                          // all partial gradients are in place
-    reduce_slice();
-    grid.sync();                                          // the gradient is complete
-    n_eval = 1; n_grad = 1;
-    prox_step(load_gradient());
-    n_proxg = 1;
+  if constexpr (MODE == 0) {
+    // ---- prologue (:327-332) ---------------------------------------------------------------------------------------------
+    {
+      local_gradient();
+      grid.sync();                                          // all partial gradients are in place
+      reduce_slice();
+      grid.sync();                                          // the gradient is complete
+      n_eval = 1; n_grad = 1;
+      prox_step(load_gradient());
+      n_proxg = 1;
+    }
+
+    for (int64_t it = 1; it <= O.maxit; ++it) {
+      phase_stamp(W, it, 0);                                // ADAPROX_PHASE_TIMING=1: CTA 0's clock at the phase boundaries
+      local_gradient();                                     // :336 value + pullback
+      n_eval++; n_grad++;
+      phase_stamp(W, it, 1);
+      grid.sync();                                          // barrier 1
+      phase_stamp(W, it, 2);
+      reduce_slice();
+      phase_stamp(W, it, 3);
+      grid.sync();                                          // barrier 2
+      phase_stamp(W, it, 4);
+      const double2 g = load_gradient();
+      {
+        double a[kGSums] = {0.0, 0.0, 0.0, 0.0, 0.0};
+        if (own0) {
+          const double pr = (v_t.x - x_t.x) / gamma + g.x;                        // :338 (old gamma)
+          const double dg = g.x - gprev_t.x, dx = x_t.x - xprev_t.x;
+          a[0] = pr * pr; a[1] = dg * dg; a[2] = dg * dx; a[3] = dx * dx;
+          if (want_obj) a[4] = prox_value_elem(P.g, x_t.x, c0);
+        }
+        if (own1) {
+          const double pr = (v_t.y - x_t.y) / gamma + g.y;
+          const double dg = g.y - gprev_t.y, dx = x_t.y - xprev_t.y;
+          a[0] = fma(pr, pr, a[0]); a[1] = fma(dg, dg, a[1]); a[2] = fma(dg, dx, a[2]); a[3] = fma(dx, dx, a[3]);
+          if (want_obj) a[4] += prox_value_elem(P.g, x_t.y, c0 + 1);
+        }
+        // Warp 0 leaves cooperative_groups' grid.sync() diverged (its thread 0 polled the arrival counter), and ptxas cannot prove
+        // convergence across the predicated blocks above: without a convergence point here the 50 SHFL of the five shuffle trees are
+        // emitted a second time behind BRA.DIV / WARPSYNC guards (SASS: 224 SHFL, 121 WARPSYNC instead of 174 / 71) and the diverged
+        // warp takes that path -- 6.2 us for this phase instead of 1.2 us (500 x 1000: 15.7 vs 8.2 us per iteration, measured;
+        // __syncwarp and a CTA barrier do equally well; -DADAPROX_EXP_GR_NO_PRESYNC removes it for the A/B).
+  #ifndef ADAPROX_EXP_GR_NO_PRESYNC
+        __syncwarp();
+  #endif
+        block_sums(a);
+      }
+      phase_stamp(W, it, 5);
+      const double gamma_prev = gamma;
+      rule_step(O, totals[1], totals[2], totals[3], gamma, sigma, s0, s1);        // :341
+      norm_res = sqrt(norm_sq_jl(totals[0]) + adapgm_dual_res_sq(gamma, gamma_prev, sigma));   // :348 (dual part: 0, or NaN -- phases.cuh)
+      if (!(gamma == gamma) || !(norm_res == norm_res) || isinf(gamma)) flags |= ADAPROX_FLAG_NONFINITE;
+      if (b == 0 && t == 0 && W.rec != nullptr && it <= O.max_records) {
+        adaprox_record rc;
+        rc.it = it; rc.gamma = gamma; rc.sigma = sigma; rc.norm_res = norm_res;
+        rc.f_x = 0.5 * norm_sq_jl(totals[8]);
+        rc.g_x = want_obj ? prox_value_finish(P.g.kind, P.g.lambda, totals[4]) : NAN;
+        rc.h_Ax = want_obj ? 0.0 : NAN;
+        rc.f_evals = n_eval; rc.grad_f_evals = n_grad; rc.prox_g_evals = n_proxg; rc.prox_h_evals = 0;
+        rc.A_evals = 0; rc.At_evals = 0;
+        W.rec[it - 1] = rc;
+      }
+      if (it <= O.max_records) n_rec = it;
+      if (norm_res <= O.tol) { converged = true; it_done = it; break; }           // :354-356 (uniform over the grid: same bits everywhere)
+      phase_stamp(W, it, 6);
+      prox_step(g);
+      n_proxg++;
+      phase_stamp(W, it, 7);
+    }
   }
 
-  for (int64_t it = 1; it <= O.maxit; ++it) {
-    phase_stamp(W, it, 0);                                // ADAPROX_PHASE_TIMING=1: CTA 0's clock at the phase boundaries
-    local_gradient();                                     // :336 value + pullback
-    n_eval++; n_grad++;
-    phase_stamp(W, it, 1);
-    grid.sync();                                          // barrier 1
-    phase_stamp(W, it, 2);
+  // ---- the two comparison methods: shared pieces --------------------------------------------------------------------------
+  // full gradient at the point the owning threads hold in `at`: xs <- at, passes, two grid barriers, this thread's two entries
+  auto gradient_at = [&](const double2 at) -> double2 {
+    if (t < ldv) reinterpret_cast<double2*>(xs)[t] = at;
+    __syncthreads();
+    local_gradient();
+    grid.sync();
     reduce_slice();
-    phase_stamp(W, it, 3);
-    grid.sync();                                          // barrier 2
-    phase_stamp(W, it, 4);
-    const double2 g = load_gradient();
-    {
-      double a[kGSums] = {0.0, 0.0, 0.0, 0.0, 0.0};
-      if (own0) {
-        const double pr = (v_t.x - x_t.x) / gamma + g.x;                        // :338 (old gamma)
-        const double dg = g.x - gprev_t.x, dx = x_t.x - xprev_t.x;
-        a[0] = pr * pr; a[1] = dg * dg; a[2] = dg * dx; a[3] = dx * dx;
-        if (want_obj) a[4] = prox_value_elem(P.g, x_t.x, c0);
-      }
-      if (own1) {
-        const double pr = (v_t.y - x_t.y) / gamma + g.y;
-        const double dg = g.y - gprev_t.y, dx = x_t.y - xprev_t.y;
-        a[0] = fma(pr, pr, a[0]); a[1] = fma(dg, dg, a[1]); a[2] = fma(dg, dx, a[2]); a[3] = fma(dx, dx, a[3]);
-        if (want_obj) a[4] += prox_value_elem(P.g, x_t.y, c0 + 1);
-      }
-      // Warp 0 leaves cooperative_groups' grid.sync() diverged (its thread 0 polled the arrival counter), and ptxas cannot prove
-      // convergence across the predicated blocks above: without a convergence point here the 50 SHFL of the five shuffle trees are
-      // emitted a second time behind BRA.DIV / WARPSYNC guards (SASS: 224 SHFL, 121 WARPSYNC instead of 174 / 71) and the diverged
-      // warp takes that path -- 6.2 us for this phase instead of 1.2 us (500 x 1000: 15.7 vs 8.2 us per iteration, measured;
-      // __syncwarp and a CTA barrier do equally well; -DADAPROX_EXP_GR_NO_PRESYNC removes it for the A/B).
-#ifndef ADAPROX_EXP_GR_NO_PRESYNC
-      __syncwarp();
-#endif
-      block_sums(a);
-    }
-    phase_stamp(W, it, 5);
-    const double gamma_prev = gamma;
-    rule_step(O, totals[1], totals[2], totals[3], gamma, sigma, s0, s1);        // :341
-    norm_res = sqrt(norm_sq_jl(totals[0]) + adapgm_dual_res_sq(gamma, gamma_prev, sigma));   // :348 (dual part: 0, or NaN -- phases.cuh)
-    if (!(gamma == gamma) || !(norm_res == norm_res) || isinf(gamma)) flags |= ADAPROX_FLAG_NONFINITE;
+    grid.sync();
+    return load_gradient();
+  };
+  // f at the point in `at`, NOT counted (the objective of a record: `without_counting`, src/AdaProx.jl:134-136 / :183-185);
+  // one more grid barrier.  The value is complete in CTA 0 only, which writes the records.
+  auto value_at = [&](const double2 at) -> double {
+    if (t < ldv) reinterpret_cast<double2*>(xs)[t] = at;
+    __syncthreads();
+    local_value();
+    grid.sync();
+    value_total(ga.fpart2);
+    __syncthreads();
+    return f_value(P, totals[8], 0.0, 0.0);
+  };
+  auto record = [&](int64_t it, double objective_f, double objective_g) {
     if (b == 0 && t == 0 && W.rec != nullptr && it <= O.max_records) {
       adaprox_record rc;
-      rc.it = it; rc.gamma = gamma; rc.sigma = sigma; rc.norm_res = norm_res;
-      rc.f_x = 0.5 * norm_sq_jl(totals[8]);
-      rc.g_x = want_obj ? prox_value_finish(P.g.kind, P.g.lambda, totals[4]) : NAN;
-      rc.h_Ax = want_obj ? 0.0 : NAN;
+      rc.it = it; rc.gamma = gamma; rc.sigma = NAN; rc.norm_res = norm_res;
+      rc.f_x = objective_f; rc.g_x = objective_g; rc.h_Ax = 0.0;
       rc.f_evals = n_eval; rc.grad_f_evals = n_grad; rc.prox_g_evals = n_proxg; rc.prox_h_evals = 0;
       rc.A_evals = 0; rc.At_evals = 0;
       W.rec[it - 1] = rc;
     }
     if (it <= O.max_records) n_rec = it;
-    if (norm_res <= O.tol) { converged = true; it_done = it; break; }           // :354-356 (uniform over the grid: same bits everywhere)
-    phase_stamp(W, it, 6);
-    prox_step(g);
-    n_proxg++;
-    phase_stamp(W, it, 7);
+  };
+  // prox of (p - gamma g) for this thread's two columns; adds |prox - ref|^2 to a[0] and g(prox) to a[1]
+  auto prox_pair = [&](const double2 p, const double2 g, const double2 ref, double (&a)[kGSums]) -> double2 {
+    double2 xn = make_double2(0.0, 0.0);
+    if (own0) {
+      xn.x = prox_elem(P.g, p.x - gamma * g.x, gamma, c0, 0.0);
+      const double d = xn.x - ref.x;
+      a[0] = fma(d, d, a[0]);
+      a[1] += prox_value_elem(P.g, xn.x, c0);
+    }
+    if (own1) {
+      xn.y = prox_elem(P.g, p.y - gamma * g.y, gamma, c0 + 1, 0.0);
+      const double d = xn.y - ref.y;
+      a[0] = fma(d, d, a[0]);
+      a[1] += prox_value_elem(P.g, xn.y, c0 + 1);
+    }
+    return xn;
+  };
+
+  if constexpr (MODE == 1) {                               // fixed_nesterov, src/AdaProx.jl:91-142 (grid form: solver_pg.cuh)
+    sigma = NAN;
+    gamma = O.gamma;
+    const double mu = O.muf + O.mug;                                             // :108-117
+    const double q = gamma * mu / (1.0 + gamma * O.mug);
+    double theta = O.theta >= 0.0 ? O.theta : (q > 0.0 ? 1.0 / sqrt(q) : 0.0);
+    xprev_t = x_t;                                                               // :119
+    for (int64_t it = 1; it <= O.maxit; ++it) {
+      const double theta_prev = theta;
+      double beta;
+      if (mu == 0.0) {                                                           // :122-128
+        theta = (1.0 + sqrt(1.0 + 4.0 * theta_prev * theta_prev)) / 2.0;
+        beta = (theta_prev - 1.0) / theta;
+      } else {
+        const double a_ = 1.0 - q * theta_prev * theta_prev;
+        theta = (a_ + sqrt(a_ * a_ + 4.0 * theta_prev * theta_prev)) / 2.0;
+        beta = (theta_prev - 1.0) * (1.0 + gamma * O.mug - theta * gamma * mu) / theta / (1.0 - gamma * O.muf);
+      }
+      double2 z = make_double2(0.0, 0.0);
+      if (own0) z.x = x_t.x + beta * (x_t.x - xprev_t.x);                        // :129
+      if (own1) z.y = x_t.y + beta * (x_t.y - xprev_t.y);
+      const double2 g = gradient_at(z);                                          // :130
+      n_eval++; n_grad++;
+      double a[kGSums] = {0.0, 0.0, 0.0, 0.0, 0.0};
+      const double2 xn = prox_pair(z, g, z, a);                                  // :131-133
+      __syncwarp();
+      block_sums(a);
+      n_proxg++;
+      xprev_t = x_t; x_t = xn;
+      norm_res = sqrt(totals[0]) / gamma;
+      const double g_x = prox_value_finish(P.g.kind, P.g.lambda, totals[1]);
+      const double fx = want_obj ? value_at(x_t) : NAN;                          // :134-136
+      record(it, fx, g_x);
+      if (norm_res <= O.tol) { converged = true; it_done = it; break; }
+    }
+    if (!(gamma == gamma) || !(norm_res == norm_res)) flags |= ADAPROX_FLAG_NONFINITE;
+  }
+
+  if constexpr (MODE == 2) {                               // agraal, src/AdaProx.jl:150-192; W.aux[0] holds the second start point x0
+    sigma = NAN;
+    gamma = O.gamma;
+    double2 xbar_t = x_t, g_t, gp_t;
+    xprev_t = make_double2(own0 ? W.aux[0][c0] : 0.0, own1 ? W.aux[0][c0 + 1] : 0.0);   // :165
+    g_t = gradient_at(x_t);                                                      // :166
+    gp_t = gradient_at(xprev_t);                                                 // :167
+    n_eval = 2; n_grad = 2;
+    const double phi = O.phi;
+    const double rho = 1.0 / phi + 1.0 / (phi * phi);                            // :172
+    double theta = 1.0;
+    for (int64_t it = 1; it <= O.maxit; ++it) {
+      double a[kGSums] = {0.0, 0.0, 0.0, 0.0, 0.0};
+      if (own0) { const double dx = x_t.x - xprev_t.x, dg = g_t.x - gp_t.x; a[0] = dx * dx; a[1] = dg * dg; }
+      if (own1) { const double dx = x_t.y - xprev_t.y, dg = g_t.y - gp_t.y; a[0] = fma(dx, dx, a[0]); a[1] = fma(dg, dg, a[1]); }
+      __syncwarp();
+      block_sums(a);
+      const double sxx = totals[0], sgg = totals[1];
+      if (it == 1 && !(O.gamma > 0.0)) gamma = sqrt(sxx) / sqrt(sgg);            // :168-170
+      const double C = norm_sq_jl(sxx) / norm_sq_jl(sgg);                        // :175
+      const double gamma_prev = gamma;
+      gamma = jl_min(jl_min(rho * gamma_prev, phi * theta * C / (4.0 * gamma_prev)), O.gamma_max);   // :177
+      theta = phi * gamma / gamma_prev;                                          // :178
+      double2 xb = make_double2(0.0, 0.0);
+      if (own0) xb.x = ((phi - 1.0) * x_t.x + xbar_t.x) / phi;                   // :179
+      if (own1) xb.y = ((phi - 1.0) * x_t.y + xbar_t.y) / phi;
+      xbar_t = xb;
+      double a2[kGSums] = {0.0, 0.0, 0.0, 0.0, 0.0};
+      const double2 xn = prox_pair(xb, g_t, x_t, a2);                            // :181
+      __syncwarp();
+      block_sums(a2);
+      n_proxg++;
+      xprev_t = x_t; x_t = xn; gp_t = g_t;                                       // :180
+      norm_res = sqrt(totals[0]) / gamma;                                        // :182
+      const double g_x = prox_value_finish(P.g.kind, P.g.lambda, totals[1]);
+      const double fx = want_obj ? value_at(x_t) : NAN;                          // :183-185
+      record(it, fx, g_x);
+      if (norm_res <= O.tol) { converged = true; it_done = it; break; }
+      g_t = gradient_at(x_t);                                                    // :189
+      n_eval++; n_grad++;
+    }
+    if (!(gamma == gamma) || !(norm_res == norm_res)) flags |= ADAPROX_FLAG_NONFINITE;
   }
 
   if (b == 0) {                                            // converged: the iterate whose gradient was just evaluated; maxit: the last prox

@@ -179,6 +179,63 @@ def test_grid_resident_kernel_matches_grid_kernel_and_oracle(AdaProx, m, n):
     _small_ls_kernel_check(AdaProx, m, n, {"ADAPROX_RESIDENT": "0", "ADAPROX_GRIDRES": "1"}, {"ADAPROX_RESIDENT": "0", "ADAPROX_GRIDRES": "0"}, 4)
 
 
+@pytest.mark.parametrize("m,n", [(500, 1000), (120, 40), (4000, 1000)])
+def test_grid_resident_nesterov_and_agraal(AdaProx, m, n):
+    """fixed_nesterov (src/AdaProx.jl:91-142) and agraal (:150-192) on a small dense least-squares term run in the grid-resident
+    kernel (MODE 1 / 2 of solver_gridres.cuh).  Against the oracle and against the general grid kernel (ADAPROX_GRIDRES=0): stepsizes,
+    residuals, objectives of the records, counters (the logged f(x) is not counted), with and without records, maxit = 0 / 1."""
+    import os
+    P = AdaProx.synth.planted_lasso(m, n, 10, 0)
+    Lf = float(np.linalg.norm(P["A"], 2) ** 2)
+    g0 = 1.0 / Lf
+    xs0 = np.random.default_rng(3).standard_normal(n)
+    calls = {"nesterov": (lambda M, f, g, **kw: M.fixed_nesterov(np.zeros(n), f=f, g=g, gamma=g0, **kw)),
+             "nesterov_mu": (lambda M, f, g, **kw: M.fixed_nesterov(np.zeros(n), f=f, g=g, gamma=g0, muf=0.05 * Lf, **kw)),
+             "agraal": (lambda M, f, g, **kw: M.agraal(np.zeros(n), f=f, g=g, x0=xs0, gamma0=g0, **kw)),
+             "agraal_auto": (lambda M, f, g, **kw: M.agraal(np.zeros(n), f=f, g=g, x0=xs0, **kw))}
+    fd_raw = AdaProx.LinearLeastSquares(P["A"], P["b"])
+    for name, call in calls.items():
+        fo = O.Counting(O.LinearLeastSquares(P["A"], P["b"]))
+        lo = []
+        xo, ito = call(O, fo, O.NormL1(1.0), tol=1e-7, maxit=150, log=lo)
+        got = {}
+        for mode in ("1", "0"):
+            os.environ["ADAPROX_GRIDRES"] = mode
+            try:
+                fd = AdaProx.Counting(fd_raw)
+                ld = []
+                xd, itd = call(AdaProx, fd, AdaProx.NormL1(1.0), tol=1e-7, maxit=150, log=ld)
+                passes = AdaProx.last_solve_info()["matrix_passes"]
+                xq, itq = call(AdaProx, fd_raw, AdaProx.NormL1(1.0), tol=1e-7, maxit=150)          # no records: no value-only evaluations
+                got[mode] = (xd, itd, ld, passes, (fd.eval_count, fd.grad_count), xq, itq)
+            finally:
+                os.environ.pop("ADAPROX_GRIDRES", None)
+        assert got["1"][3] == 4 and got["0"][3] == 2, (name, got["1"][3], got["0"][3])
+        for mode in ("1", "0"):
+            xd, itd, ld, _, counts, xq, itq = got[mode]
+            K = min(30, len(ld), len(lo))
+            assert abs(itd - ito) <= max(2, 0.03 * ito), (name, mode, itd, ito)
+            assert counts == (fo.eval_count, fo.grad_count) or itd != ito, (name, mode, counts)
+            assert np.allclose([r["gamma"] for r in ld[:K]], [r["gamma"] for r in lo[:K]], rtol=1e-11), (name, mode)
+            assert np.allclose([r["objective"] for r in ld[:K]], [r["objective"] for r in lo[:K]], rtol=1e-10), (name, mode)
+            assert np.allclose([r["norm_res"] for r in ld[:K]], [r["norm_res"] for r in lo[:K]], rtol=1e-8), (name, mode)
+            assert [r["f_evals"] for r in ld[:K]] == [r["f_evals"] for r in lo[:K]], (name, mode)
+            assert np.linalg.norm(xd - xo) <= 1e-4 * np.linalg.norm(xo), (name, mode)     # 150 iterations of a free-running trajectory (cf. test_cubic_*: 1e-4)
+            assert itq == itd and np.array_equal(xq, xd), (name, mode, "records must not change the iterates")
+    for maxit in (0, 1):
+        os.environ["ADAPROX_GRIDRES"] = "1"
+        try:
+            xd, itd = AdaProx.agraal(np.zeros(n), f=fd_raw, g=AdaProx.NormL1(1.0), x0=xs0, gamma0=g0, tol=0.0, maxit=maxit)
+            xn, itn = AdaProx.fixed_nesterov(np.zeros(n), f=fd_raw, g=AdaProx.NormL1(1.0), gamma=g0, tol=0.0, maxit=maxit)
+        finally:
+            os.environ.pop("ADAPROX_GRIDRES", None)
+        xo, ito = O.agraal(np.zeros(n), f=O.LinearLeastSquares(P["A"], P["b"]), g=O.NormL1(1.0), x0=xs0, gamma0=g0, tol=0.0, maxit=maxit)
+        xno, itno = O.fixed_nesterov(np.zeros(n), f=O.LinearLeastSquares(P["A"], P["b"]), g=O.NormL1(1.0), gamma=g0, tol=0.0, maxit=maxit)
+        assert itd == ito == maxit and np.linalg.norm(xd - xo) <= 1e-12 * max(np.linalg.norm(xo), 1e-12)
+        assert itn == itno == maxit and np.linalg.norm(xn - xno) <= 1e-12 * max(np.linalg.norm(xno), 1e-12)
+    fd_raw.mat.free()
+
+
 def test_nonfinite_stepsize_reaches_the_residual_like_the_reference(AdaProx):
     """src/AdaProx.jl:342-348 with A = 0, h = Zero: once the rule returns a NaN stepsize (Malitsky-Mishchenko on an iterate the box keeps
     in place: dx = 0, L = 0 / 0), w = y + sigma * (...) * 0 is NaN, so norm_res is NaN, the test :354 never fires and x turns NaN -- although
