@@ -787,6 +787,8 @@ static const void* gridres_kernel(int solver) {
     case ADAPROX_S_ADAPTIVE_PROXGRAD: return (const void*)k_adapgm_gridres<0>;
     case ADAPROX_S_FIXED_NESTEROV: return (const void*)k_adapgm_gridres<1>;
     case ADAPROX_S_AGRAAL: return (const void*)k_adapgm_gridres<2>;
+    case ADAPROX_S_BACKTRACKING_PROXGRAD: return (const void*)k_adapgm_gridres<3>;
+    case ADAPROX_S_BACKTRACKING_NESTEROV: return (const void*)k_adapgm_gridres<4>;
     default: return nullptr;
   }
 }
@@ -795,7 +797,7 @@ static bool gridres_eligible(adaprox_ctx* h, const adaprox_options* o, const DPr
   if (e && std::strcmp(e, "0") == 0) return false;
   const char* ef = std::getenv("ADAPROX_FUSED");
   if (ef && std::strcmp(ef, "1") == 0) return false;       // the sweep kernel was requested explicitly
-  const void* kernel = gridres_kernel(o->solver);          // AdaPGM / fixed-step PGM, fixed_nesterov, agraal
+  const void* kernel = gridres_kernel(o->solver);          // AdaPGM / fixed-step PGM, fixed_nesterov, agraal, the two backtracking methods
   if (!kernel || P.f_kind != ADAPROX_F_LEAST_SQUARES || P.F.kind != MAT_DENSE || P.A.kind != MAT_NONE) return false;
   if (P.g.kind == ADAPROX_P_NORM_L2 || P.g.conjugate) return false;
   if (P.F.ld > kGMaxLd || P.n < 1 || P.F.m < 1) return false;
@@ -913,7 +915,7 @@ extern "C" int adaprox_solve(adaprox_handle h, const adaprox_problem* p, const a
   const int64_t nfu = (P.f_kind == ADAPROX_F_QUADRATIC_GRAM) ? P.F.n : 1;
   const int64_t gr_x = gridres ? (garg.x_in_smem ? 1 : (int64_t)h->sm_count * P.F.ld) : 1;
   size_t need = (fused ? fused_ws_bytes(fpl) : 0) + (sharded_fused ? ws_size_doubles(n + 2) : 0) +
-                (gridres ? ws_size_doubles(P.F.ld) + 2 * ws_size_doubles(h->sm_count) + ws_size_doubles(gr_x) : 0) +
+                (gridres ? ws_size_doubles(P.F.ld) + ws_size_doubles(h->sm_count) + ws_size_doubles(2 * h->sm_count) + ws_size_doubles(gr_x) : 0) +
                 9 * ws_size_doubles(n) + 2 * ws_size_doubles(n + 8) + 6 * ws_size_doubles(md) + ws_size_doubles(mf) + ws_size_doubles(nfu) +
                 ws_size_doubles((int64_t)kMaxRed * G) + ws_size_doubles((nrec * (int64_t)sizeof(adaprox_record) + 7) / 8) +
                 ws_size_doubles((sizeof(DResult) + 7) / 8);
@@ -939,7 +941,7 @@ extern "C" int adaprox_solve(adaprox_handle h, const adaprox_problem* p, const a
   if (gridres) {
     garg.gfull = ws_doubles(h, P.F.ld);
     garg.fpart = ws_doubles(h, h->sm_count);
-    garg.fpart2 = ws_doubles(h, h->sm_count);
+    garg.fpart2 = ws_doubles(h, 2 * h->sm_count);
     garg.xpriv = ws_doubles(h, gr_x);
   }
   if (sharded_fused) {
@@ -1041,7 +1043,7 @@ extern "C" int adaprox_solve(adaprox_handle h, const adaprox_problem* p, const a
     case ADAPROX_S_FIXED_NESTEROV:
     case ADAPROX_S_AGRAAL:
       rc = 1;
-      if (gridres) {            // fixed_nesterov / agraal on a small dense least-squares term: the grid-resident form (solver_gridres.cuh)
+      if (gridres) {            // the comparison methods on a small dense least-squares term: the grid-resident form (solver_gridres.cuh)
         void* gargs[] = {&P, &O, &W, &garg};
         if (cudaLaunchCooperativeKernel(gridres_kernel(o->solver), dim3(h->sm_count), dim3(kGThreads), gargs, gsmem, h->stream) == cudaSuccess) {
           h->launches++;

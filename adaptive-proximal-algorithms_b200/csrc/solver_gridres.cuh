@@ -39,7 +39,7 @@ struct GridResArgs {
   int x_in_smem;           // the CTA's copy of x lives in shared memory (else in xpriv: the last row did not leave room)
   double* gfull;           // [ld]     the gradient of the iteration
   double* fpart;           // [G]      per-CTA sums of r_i^2 (gradient evaluations)
-  double* fpart2;          // [G]      the same for the value-only evaluations of MODE 1 / 2 (f(x) of the record)
+  double* fpart2;          // [2][G]   the same for the value-only evaluations of MODE 1-4 (records, linesearch trials), alternating
   double* xpriv;           // [G][ld]  per-CTA copies of x when !x_in_smem
 };
 
@@ -47,7 +47,7 @@ __host__ __device__ inline size_t gridres_smem_bytes(int64_t rows_cap, int64_t l
   return (size_t)8 * (size_t)(rows_cap * ld + 2 * rows_cap + kGWarps + kGWarps * 8 + 16 + (x_in_smem ? ld : 0));
 }
 
-template <int MODE>      // 0: AdaPGM / fixed-step PGM, 1: fixed_nesterov, 2: agraal
+template <int MODE>      // 0: AdaPGM / fixed-step PGM, 1: fixed_nesterov, 2: agraal, 3: backtracking_proxgrad, 4: backtracking_nesterov
 __global__ void __launch_bounds__(kGThreads, 1) k_adapgm_gridres(DProblem P, DOpts O, DWork W, GridResArgs ga) {
   cooperative_groups::grid_group grid = cooperative_groups::this_grid();
   extern __shared__ __align__(1024) unsigned char dyn_smem[];
@@ -96,47 +96,8 @@ __global__ void __launch_bounds__(kGThreads, 1) k_adapgm_gridres(DProblem P, DOp
   int64_t it_done = O.maxit;
   bool converged = false;
 
-  // gradient evaluation at xs: this CTA's partial gradient -> gpart_all[b][:], its sum of r_i^2 -> fpart[b]
-  auto local_gradient = [&]() {
-    double2 xr[kGLaneV];
-#pragma unroll
-    for (int k = 0; k < kGLaneV; ++k) {
-      const int idx = lane + 32 * k;
-      xr[k] = idx < ldv ? reinterpret_cast<const double2*>(xs)[idx] : make_double2(0.0, 0.0);
-    }
-    double fw = 0.0;
-    for (int i = warp; i < rows; i += kGWarps) {          // pass 1: one warp per row
-      const double2* row = reinterpret_cast<const double2*>(As + (size_t)i * ld);
-      double p0 = 0.0, p1 = 0.0;
-#pragma unroll
-      for (int k = 0; k < kGLaneV; ++k) {
-        const int idx = lane + 32 * k;
-        if (idx < ldv) { const double2 a = row[idx]; p0 = fma(a.x, xr[k].x, p0); p1 = fma(a.y, xr[k].y, p1); }
-      }
-      const double res = warp_sum(p0 + p1) - b_loc[i];                          // lasso/runme.jl:22
-      if (lane == 0) r_loc[i] = res;
-      fw = fma(res, res, fw);
-    }
-    if (lane == 0) wpart[warp] = fw;
-    __syncthreads();
-    if (t < ldv && b < GR) {                               // pass 2: thread t owns double2 column t, no reduction
-      double2 acc = make_double2(0.0, 0.0);
-      for (int i = 0; i < rows; ++i) {
-        const double ri = r_loc[i];
-        const double2 a = reinterpret_cast<const double2*>(As + (size_t)i * ld)[t];
-        acc.x = fma(a.x, ri, acc.x); acc.y = fma(a.y, ri, acc.y);              // :23
-      }
-      *reinterpret_cast<double2*>(gpart_all + (int64_t)b * npad + c0) = acc;
-    }
-    if (t == 0) {
-      double fs = 0.0;
-#pragma unroll
-      for (int w = 0; w < kGWarps; ++w) fs += wpart[w];
-      ga.fpart[b] = fs;
-    }
-  };
-  // value only (pass 1) at xs: this CTA's sum of r_i^2 -> fpart2[b]
-  auto local_value = [&]() {
+  // pass 1 at xs (one warp per row, x in registers): r_loc[i] = <A[i,:], x> - b_i, this CTA's sum of r_i^2 -> fdst[b]
+  auto pass1 = [&](double* fdst) {
     double2 xr[kGLaneV];
 #pragma unroll
     for (int k = 0; k < kGLaneV; ++k) {
@@ -152,7 +113,8 @@ __global__ void __launch_bounds__(kGThreads, 1) k_adapgm_gridres(DProblem P, DOp
         const int idx = lane + 32 * k;
         if (idx < ldv) { const double2 a = row[idx]; p0 = fma(a.x, xr[k].x, p0); p1 = fma(a.y, xr[k].y, p1); }
       }
-      const double res = warp_sum(p0 + p1) - b_loc[i];
+      const double res = warp_sum(p0 + p1) - b_loc[i];                          // lasso/runme.jl:22
+      if (lane == 0) r_loc[i] = res;
       fw = fma(res, res, fw);
     }
     if (lane == 0) wpart[warp] = fw;
@@ -161,12 +123,29 @@ __global__ void __launch_bounds__(kGThreads, 1) k_adapgm_gridres(DProblem P, DOp
       double fs = 0.0;
 #pragma unroll
       for (int w = 0; w < kGWarps; ++w) fs += wpart[w];
-      ga.fpart2[b] = fs;
+      fdst[b] = fs;
     }
   };
-  // CTA 0, last warp: the G value partials in CTA order -> totals[8]
-  auto value_total = [&](const double* part) {
-    if (b == 0 && warp == kGWarps - 1) {
+  // pass 2 from r_loc (thread t owns double2 column t, no reduction): this CTA's partial gradient -> gpart_all[b][:]
+  auto pass2 = [&]() {
+    if (t < ldv && b < GR) {
+      double2 acc = make_double2(0.0, 0.0);
+      for (int i = 0; i < rows; ++i) {
+        const double ri = r_loc[i];
+        const double2 a = reinterpret_cast<const double2*>(As + (size_t)i * ld)[t];
+        acc.x = fma(a.x, ri, acc.x); acc.y = fma(a.y, ri, acc.y);              // :23
+      }
+      *reinterpret_cast<double2*>(gpart_all + (int64_t)b * npad + c0) = acc;
+    }
+  };
+  // value + pullback at xs; value partial -> fpart[b]
+  auto local_gradient = [&]() { pass1(ga.fpart); pass2(); };
+  // value-only evaluations (records of MODE 1 / 2, linesearch trials of MODE 3 / 4) alternate between two partial buffers: a CTA
+  // may start the next one while another still reads this one's partials (one grid barrier apart, not two)
+  unsigned vcount = 0;
+  // last warp (of CTA 0, or of every CTA): the G value partials in CTA order -> totals[8]
+  auto value_total = [&](const double* part, bool all) {
+    if ((all || b == 0) && warp == kGWarps - 1) {
       double v[kGMaxP];
 #pragma unroll
       for (int q = 0; q < kGMaxP; ++q) { const int p = lane + 32 * q; v[q] = p < G ? ldcg(part + p) : 0.0; }
@@ -191,7 +170,8 @@ __global__ void __launch_bounds__(kGThreads, 1) k_adapgm_gridres(DProblem P, DOp
       s = warp_sum(s);
       if (lane == 0) ga.gfull[j] = s;
     }
-    if (MODE == 0) value_total(ga.fpart);
+    if (MODE == 0) value_total(ga.fpart, false);
+    if (MODE == 4) value_total(ga.fpart, true);
   };
   // after the second barrier: this thread's two gradient entries
   auto load_gradient = [&]() -> double2 {
@@ -311,13 +291,14 @@ __global__ void __launch_bounds__(kGThreads, 1) k_adapgm_gridres(DProblem P, DOp
     return load_gradient();
   };
   // f at the point in `at`, NOT counted (the objective of a record: `without_counting`, src/AdaProx.jl:134-136 / :183-185);
-  // one more grid barrier.  The value is complete in CTA 0 only, which writes the records.
-  auto value_at = [&](const double2 at) -> double {
+  // one more grid barrier.  `all`: every CTA obtains the value (linesearch), else only CTA 0, which writes the records.
+  auto value_at = [&](const double2 at, bool all) -> double {
+    double* part = ga.fpart2 + (size_t)(vcount++ & 1u) * G;
     if (t < ldv) reinterpret_cast<double2*>(xs)[t] = at;
     __syncthreads();
-    local_value();
+    pass1(part);
     grid.sync();
-    value_total(ga.fpart2);
+    value_total(part, all);
     __syncthreads();
     return f_value(P, totals[8], 0.0, 0.0);
   };
@@ -381,7 +362,7 @@ __global__ void __launch_bounds__(kGThreads, 1) k_adapgm_gridres(DProblem P, DOp
       xprev_t = x_t; x_t = xn;
       norm_res = sqrt(totals[0]) / gamma;
       const double g_x = prox_value_finish(P.g.kind, P.g.lambda, totals[1]);
-      const double fx = want_obj ? value_at(x_t) : NAN;                          // :134-136
+      const double fx = want_obj ? value_at(x_t, false) : NAN;                   // :134-136
       record(it, fx, g_x);
       if (norm_res <= O.tol) { converged = true; it_done = it; break; }
     }
@@ -423,13 +404,86 @@ __global__ void __launch_bounds__(kGThreads, 1) k_adapgm_gridres(DProblem P, DOp
       xprev_t = x_t; x_t = xn; gp_t = g_t;                                       // :180
       norm_res = sqrt(totals[0]) / gamma;                                        // :182
       const double g_x = prox_value_finish(P.g.kind, P.g.lambda, totals[1]);
-      const double fx = want_obj ? value_at(x_t) : NAN;                          // :183-185
+      const double fx = want_obj ? value_at(x_t, false) : NAN;                   // :183-185
       record(it, fx, g_x);
       if (norm_res <= O.tol) { converged = true; it_done = it; break; }
       g_t = gradient_at(x_t);                                                    // :189
       n_eval++; n_grad++;
     }
     if (!(gamma == gamma) || !(norm_res == norm_res)) flags |= ADAPROX_FLAG_NONFINITE;
+  }
+
+  double2 res_t = x_t;                                     // MODE 3 / 4: the last accepted point
+  if constexpr (MODE == 3 || MODE == 4) {                  // backtracking_proxgrad (:50-64) / backtracking_nesterov (:66-84); grid form: solver_pg.cuh
+    constexpr bool nesterov = (MODE == 4);
+    sigma = NAN;
+    gamma = O.gamma;
+    double2 zprev_t = x_t;                                                       // :67
+    double theta = 1.0;                                                          // :68
+    double2 g_t = gradient_at(x_t);                                              // :52 / :69
+    // f(x) from the same evaluation: every CTA needs it for the sufficient-decrease test
+    if (!nesterov) value_total(ga.fpart, true);                                  // (MODE 4: reduce_slice already did)
+    __syncthreads();
+    double f_x = f_value(P, totals[8], 0.0, 0.0);
+    n_eval = 1; n_grad = 1;
+    for (int64_t it = 1; it <= O.maxit; ++it) {
+      gamma = nesterov ? gamma : O.xi * gamma;                                   // :54 / :72
+      double f_z = 0.0, g_z = 0.0, dzz = 0.0;
+      double2 z = make_double2(0.0, 0.0);
+      for (;;) {                                                                 // backtrack_stepsize (:34-48)
+        double a[kGSums] = {0.0, 0.0, 0.0, 0.0, 0.0};
+        z = make_double2(0.0, 0.0);
+        if (own0) {
+          z.x = prox_elem(P.g, x_t.x - gamma * g_t.x, gamma, c0, 0.0);           // :35 / :43
+          const double d = z.x - x_t.x;
+          a[0] = g_t.x * d; a[1] = d * d; a[2] = prox_value_elem(P.g, z.x, c0);
+        }
+        if (own1) {
+          z.y = prox_elem(P.g, x_t.y - gamma * g_t.y, gamma, c0 + 1, 0.0);
+          const double d = z.y - x_t.y;
+          a[0] = fma(g_t.y, d, a[0]); a[1] = fma(d, d, a[1]); a[2] += prox_value_elem(P.g, z.y, c0 + 1);
+        }
+        __syncwarp();
+        block_sums(a);
+        n_proxg++;
+        const double gd = totals[0];
+        dzz = totals[1];
+        g_z = prox_value_finish(P.g.kind, P.g.lambda, totals[2]);
+        f_z = value_at(z, true);                                                 // :37 / :45
+        n_eval++;
+        const double ub_z = f_x + gd + 1.0 / (2.0 * gamma) * norm_sq_jl(dzz);    // :26
+        if (!(f_z > ub_z)) break;                                                // :38
+        gamma *= O.shrink;                                                       // :39
+        if (gamma < 1e-12) flags |= ADAPROX_FLAG_STEP_TOO_SMALL;                 // :40-42 (the reference keeps looping)
+        if (gamma < 1e-300) break;
+      }
+      norm_res = sqrt(dzz) / gamma;                                              // :55 / :73
+      record(it, f_z, g_z);
+      res_t = z;
+      if (norm_res <= O.tol) { converged = true; it_done = it; break; }          // :57 / :75
+      if (!nesterov) {
+        pass2();                                                                 // :60-61  grad_x = pb(): r_loc still holds the residual of z
+        grid.sync();
+        reduce_slice();
+        grid.sync();
+        g_t = load_gradient();
+        n_grad++;
+        x_t = z; f_x = f_z;
+      } else {
+        const double theta_prev = theta;                                         // :78-80
+        theta = (1.0 + sqrt(1.0 + 4.0 * theta_prev * theta_prev)) / 2.0;
+        const double beta = (theta_prev - 1.0) / theta;
+        if (own0) x_t.x = z.x + beta * (z.x - zprev_t.x);
+        if (own1) x_t.y = z.y + beta * (z.y - zprev_t.y);
+        zprev_t = z;                                                             // :71
+        g_t = gradient_at(x_t);                                                  // :81 (reduce_slice leaves f(x) in totals[8] of every CTA)
+        __syncthreads();
+        f_x = f_value(P, totals[8], 0.0, 0.0);
+        n_eval++; n_grad++;
+      }
+    }
+    if (!(gamma == gamma) || !(norm_res == norm_res)) flags |= ADAPROX_FLAG_NONFINITE;
+    x_t = res_t;
   }
 
   if (b == 0) {                                            // converged: the iterate whose gradient was just evaluated; maxit: the last prox

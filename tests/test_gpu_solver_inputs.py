@@ -181,8 +181,8 @@ def test_grid_resident_kernel_matches_grid_kernel_and_oracle(AdaProx, m, n):
 
 @pytest.mark.parametrize("m,n", [(500, 1000), (120, 40), (4000, 1000)])
 def test_grid_resident_nesterov_and_agraal(AdaProx, m, n):
-    """fixed_nesterov (src/AdaProx.jl:91-142) and agraal (:150-192) on a small dense least-squares term run in the grid-resident
-    kernel (MODE 1 / 2 of solver_gridres.cuh).  Against the oracle and against the general grid kernel (ADAPROX_GRIDRES=0): stepsizes,
+    """fixed_nesterov (src/AdaProx.jl:91-142), agraal (:150-192), backtracking_proxgrad (:50-64) and backtracking_nesterov (:66-84) on a
+    small dense least-squares term run in the grid-resident kernel (MODE 1-4 of solver_gridres.cuh).  Against the oracle and against the general grid kernel (ADAPROX_GRIDRES=0): stepsizes,
     residuals, objectives of the records, counters (the logged f(x) is not counted), with and without records, maxit = 0 / 1."""
     import os
     P = AdaProx.synth.planted_lasso(m, n, 10, 0)
@@ -192,7 +192,10 @@ def test_grid_resident_nesterov_and_agraal(AdaProx, m, n):
     calls = {"nesterov": (lambda M, f, g, **kw: M.fixed_nesterov(np.zeros(n), f=f, g=g, gamma=g0, **kw)),
              "nesterov_mu": (lambda M, f, g, **kw: M.fixed_nesterov(np.zeros(n), f=f, g=g, gamma=g0, muf=0.05 * Lf, **kw)),
              "agraal": (lambda M, f, g, **kw: M.agraal(np.zeros(n), f=f, g=g, x0=xs0, gamma0=g0, **kw)),
-             "agraal_auto": (lambda M, f, g, **kw: M.agraal(np.zeros(n), f=f, g=g, x0=xs0, **kw))}
+             "agraal_auto": (lambda M, f, g, **kw: M.agraal(np.zeros(n), f=f, g=g, x0=xs0, **kw)),
+             "backtracking_xi1": (lambda M, f, g, **kw: M.backtracking_proxgrad(np.zeros(n), f=f, g=g, gamma0=10 * g0, xi=1.0, **kw)),
+             "backtracking_xi2": (lambda M, f, g, **kw: M.backtracking_proxgrad(np.zeros(n), f=f, g=g, gamma0=g0, xi=2.0, **kw)),
+             "backtracking_nesterov": (lambda M, f, g, **kw: M.backtracking_nesterov(np.zeros(n), f=f, g=g, gamma0=10 * g0, **kw))}
     fd_raw = AdaProx.LinearLeastSquares(P["A"], P["b"])
     for name, call in calls.items():
         fo = O.Counting(O.LinearLeastSquares(P["A"], P["b"]))
@@ -220,6 +223,8 @@ def test_grid_resident_nesterov_and_agraal(AdaProx, m, n):
             assert np.allclose([r["objective"] for r in ld[:K]], [r["objective"] for r in lo[:K]], rtol=1e-10), (name, mode)
             assert np.allclose([r["norm_res"] for r in ld[:K]], [r["norm_res"] for r in lo[:K]], rtol=1e-8), (name, mode)
             assert [r["f_evals"] for r in ld[:K]] == [r["f_evals"] for r in lo[:K]], (name, mode)
+            assert [r["grad_f_evals"] for r in ld[:K]] == [r["grad_f_evals"] for r in lo[:K]], (name, mode)
+            assert [r["prox_g_evals"] for r in ld[:K]] == [r["prox_g_evals"] for r in lo[:K]], (name, mode)
             assert np.linalg.norm(xd - xo) <= 1e-4 * np.linalg.norm(xo), (name, mode)     # 150 iterations of a free-running trajectory (cf. test_cubic_*: 1e-4)
             assert itq == itd and np.array_equal(xq, xd), (name, mode, "records must not change the iterates")
     for maxit in (0, 1):
