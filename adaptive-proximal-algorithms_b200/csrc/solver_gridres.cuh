@@ -14,8 +14,9 @@
 //   * grid barrier;  EVERY CTA loads the whole gradient (8 KB) and repeats the rest of the iteration for all n columns: the
 //     four stepsize sums of src/AdaProx.jl:338,260-261 (fixed order: the same bits in every CTA), the stepsize rule, the
 //     convergence test, the prox step.  The new iterate never leaves the CTA, so there is no third barrier.
-// MODE 1 / 2 run the two comparison methods of the lasso experiment that need no linesearch -- fixed_nesterov (src/AdaProx.jl:91-142)
-// and agraal (:150-192) -- through the same passes and barriers (solver_pg.cuh holds their general grid form).
+// MODE 1-4 run the comparison methods of the lasso experiment through the same passes and barriers (solver_pg.cuh holds their general
+// grid form): fixed_nesterov (src/AdaProx.jl:91-142), agraal (:150-192), backtracking_proxgrad (:50-64), backtracking_nesterov (:66-84).
+// A linesearch trial is a value-only pass 1 plus ONE grid barrier; the accepted trial's residual is reused for the pullback.
 // No atomics, every sum has a fixed order: reruns are bit-identical.  Limits: ld <= 1024 (a row fits one warp's registers, a
 // thread owns two columns), ceil(m / G) rows of A per CTA in shared memory, ceil(n / G) <= 16 gradient entries per CTA, G <= 256.
 #pragma once
