@@ -336,3 +336,26 @@ def test_extended_precision_mode_and_drift_envelope():
                         maxit=60, log=logp)
     ok, dd, allowed = drift.check_inside([r["gamma"] for r in logp], runs, factor=20.0, floor=1e-12)
     assert not ok
+
+
+def test_adapgm_nan_stepsize_reaches_norm_res_through_the_dual_residual():
+    """src/AdaProx.jl:342-348 with A = 0, h = Zero (AdaPGM, :418-421): when the rule returns NaN (Malitsky-Mishchenko with dx = 0:
+    L = 0 / 0), w = y + sigma * ((1 + rho) * A_x - rho * A_x_prev) is NaN although A_x = 0, so dual_res and norm_res are NaN, the
+    stopping test never fires and the next v = x - gamma * grad makes x NaN -- even though the primal residual alone is exactly 0.
+    The restatement has to behave the same way (the device kernels are tested against it on this instance)."""
+    m, n = 149, 3
+    rng = np.random.default_rng(m * 31 + n)
+    A = np.asfortranarray(rng.standard_normal((m, n)) / np.sqrt(m))
+    b = rng.standard_normal(m)
+    Lf = float(np.linalg.norm(A, 2) ** 2)
+    rng.standard_normal(n)
+    x0 = 0.05 * rng.standard_normal(n)
+    log = []
+    x, it = O.adaptive_proxgrad(x0, f=O.LinearLeastSquares(A, b), g=O.IndBox(-0.2, 0.5), rule=O.MalitskyMishchenkoRule(gamma=1 / Lf),
+                                tol=1e-9, maxit=12, log=log)
+    assert it == 12 and np.all(np.isnan(x))
+    assert np.isfinite(log[0]["norm_res"]) and np.isfinite(log[0]["gamma"])
+    assert all(np.isnan(r["norm_res"]) and np.isnan(r["gamma"]) for r in log[1:])
+    # the same instance with a rule that cannot return NaN stops at the stationary point the box holds it in
+    x2, it2 = O.adaptive_proxgrad(x0, f=O.LinearLeastSquares(A, b), g=O.IndBox(-0.2, 0.5), rule=O.FixedStepsize(1 / Lf), tol=1e-9, maxit=12)
+    assert it2 <= 3 and np.all(np.isfinite(x2)) and np.all((x2 == -0.2) | (x2 == 0.5) | ((x2 > -0.2) & (x2 < 0.5)))
