@@ -316,3 +316,25 @@ def test_random_combinations_of_the_generic_loop():
         fin = np.isfinite(ro_) & np.isfinite(rc_)
         assert np.array_equal(np.isfinite(ro_), np.isfinite(rc_)), tag
         assert np.allclose(ro_[fin], rc_[fin], rtol=1e-7, atol=1e-12), tag
+
+
+def test_nan_stepsize_takes_the_same_course_in_both_restatements():
+    """The degenerate AdaPGM instance of test_oracle_known_answers (Malitsky-Mishchenko, box keeps the iterate in place: gamma = NaN from
+    the second iteration on): both restatements carry the NaN through w = y + sigma * (...) * 0 into norm_res and x, neither stops."""
+    m, n = 149, 3
+    rng = np.random.default_rng(m * 31 + n)
+    A = np.asfortranarray(rng.standard_normal((m, n)) / np.sqrt(m))
+    b = rng.standard_normal(m)
+    Lf = float(np.linalg.norm(A, 2) ** 2)
+    rng.standard_normal(n)
+    x0 = 0.05 * rng.standard_normal(n)
+    log = []
+    xo, ito = O.adaptive_proxgrad(x0, f=O.LinearLeastSquares(A, b), g=O.IndBox(-0.2, 0.5), rule=O.MalitskyMishchenkoRule(gamma=1 / Lf),
+                                  tol=1e-9, maxit=12, log=log)
+    xc, _, itc, hist = R.adaptive_primal_dual(x0, None, f_kind=R.F_LEAST_SQUARES, F=A, fvec=b, g=R.prox_desc(R.P_IND_BOX, lo=-0.2, hi=0.5),
+                                              rule=R.RULE_MM, gamma=1 / Lf, tol=1e-9, maxit=12, nhist=12)
+    assert ito == itc == 12 and np.all(np.isnan(xo)) and np.all(np.isnan(xc))
+    for key in ("gamma", "norm_res"):
+        a = np.array([r[key] for r in log])
+        assert np.array_equal(np.isnan(a), np.isnan(hist[key][:12])) and np.isnan(a[1:]).all() and np.isfinite(a[0])
+        assert abs(a[0] - hist[key][0]) <= 1e-12 * abs(a[0])
